@@ -1,0 +1,350 @@
+"""dzoptimization.jl_b200 -- host-side mirror of DZOptimization.jl's optimizer API over the
+sm_100a CUDA library ``csrc/libdzopt_b200.so`` (C ABI: ``include/dzopt.h``).
+
+The reference is Julia; Julia is not installed where this is built or run, so the host
+side above the C ABI is Python with the reference's names, argument order and error
+behaviour (the Julia ``ccall`` wrapper a maintainer would ship is ``julia/DZOptimizationB200.jl``).
+
+    reference (README.md:33-41)                      this module
+    -------------------------------------------     -------------------------------------------
+    opt = BFGSOptimizer(f, g!, x0, 1.0)             opt = BFGSOptimizer(f, g_, x0, 1.0)
+    while !opt.has_converged[]                      while not opt.has_converged[()]:
+        step!(opt)                                      step_(opt)
+    opt.current_objective_value[]                   opt.current_objective_value[()]
+    opt.current_point                               opt.current_point
+
+Julia closures cannot run on the device: ``f``/``g_``/constraint are the *device versions* of
+``legacy/ExampleFunctions.jl`` exported from :mod:`ExampleFunctions` below (tokens that select
+a compiled device objective).  Passing an arbitrary Python callable raises ``TypeError``.
+
+There is no CPU fallback: importing works anywhere, constructing an optimizer without the
+CUDA library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import _capi
+
+__all__ = [
+    "BFGSOptimizer", "GradientDescentOptimizer", "QuadraticLineSearch", "step_",
+    "ExampleFunctions", "NULL_CONSTRAINT", "SPHERE_CONSTRAINT", "StepType",
+    "DZOptError", "lib", "lib_path",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "csrc", "libdzopt_b200.so")
+_lib = None
+
+# include/dzopt.h constants
+OBJ_ROSENBROCK, OBJ_RIESZ = 1, 2
+CONSTRAINT_NONE, CONSTRAINT_SPHERE = 0, 1
+ORDER_SEQUENTIAL, ORDER_TREE = 0, 1
+SMALL_N_MAX = 32
+
+
+class DZOptError(RuntimeError):
+    """A negative status from the C ABI (the reference raises AssertionError for the same
+    conditions: legacy/DZOptimization.jl:771,773)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"dzopt error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load (once) and return the CUDA library.  Fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path):
+            raise DZOptError(-6, f"{lib_path} not built; run `python __graft_entry__.py build` "
+                                 "(there is no CPU fallback)")
+        raw = C.CDLL(lib_path, mode=C.RTLD_GLOBAL)
+        _lib = _capi.bind(_capi._DevAlias(raw), cpu=False)
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise DZOptError(rc, lib().dzo_last_error().decode())
+
+
+def set_tuning(key: str, value: int):
+    _check(lib().dzo_set_tuning(key.encode(), int(value)))
+
+
+def _dp(a):
+    return a.ctypes.data_as(_capi.c_double_p)
+
+
+# ------------------------------------------------------------------------------------------
+# Device objectives: tokens standing for legacy/ExampleFunctions.jl functions.
+class _DeviceFunction:
+    def __init__(self, name, objective, role):
+        self.name, self.objective, self.role = name, objective, role
+
+    def __repr__(self):
+        return f"<device {self.role} {self.name}>"
+
+
+class _Constraint:
+    def __init__(self, name, cid):
+        self.name, self.cid = name, cid
+
+    def __repr__(self):
+        return f"<device constraint {self.name}>"
+
+
+#: ``x -> true`` (the reference's NULL_CONSTRAINT, legacy/DZOptimization.jl:384,759)
+NULL_CONSTRAINT = _Constraint("NULL_CONSTRAINT", CONSTRAINT_NONE)
+#: normalise every point to the unit sphere (SURVEY.md 8.0 [GLUE]); selects the tangent
+#: projection of the gradient (legacy/ExampleFunctions.jl:361-374)
+SPHERE_CONSTRAINT = _Constraint("SPHERE_CONSTRAINT", CONSTRAINT_SPHERE)
+
+ExampleFunctions = SimpleNamespace(
+    #: legacy/ExampleFunctions.jl:10-15; for n > 2 the extended (pairwise) form
+    rosenbrock_function=_DeviceFunction("rosenbrock_function", OBJ_ROSENBROCK, "objective"),
+    #: legacy/ExampleFunctions.jl:17-24
+    rosenbrock_gradient_=_DeviceFunction("rosenbrock_gradient!", OBJ_ROSENBROCK, "gradient"),
+    #: legacy/ExampleFunctions.jl:30-45
+    riesz_energy=_DeviceFunction("riesz_energy", OBJ_RIESZ, "objective"),
+    #: legacy/ExampleFunctions.jl:47-83
+    riesz_gradient_=_DeviceFunction("riesz_gradient!", OBJ_RIESZ, "gradient"),
+)
+
+
+class StepType:
+    """@enum StepType, legacy/DZOptimization.jl:727-731"""
+    NullStep, GradientDescentStep, BFGSStep = 0, 1, 2
+
+
+class QuadraticLineSearch:
+    """legacy/DZOptimization.jl:181-188"""
+
+    def __init__(self, max_increases: int = 0):
+        self.max_increases = int(max_increases)
+
+
+def _resolve(objective_function, gradient_function_, constraint_function_):
+    if not isinstance(objective_function, _DeviceFunction) or objective_function.role != "objective":
+        raise TypeError("objective_function must be a device objective from ExampleFunctions "
+                        "(host callables cannot run inside the CUDA step!)")
+    if not isinstance(gradient_function_, _DeviceFunction) or gradient_function_.role != "gradient":
+        raise TypeError("gradient_function! must be a device gradient from ExampleFunctions")
+    if objective_function.objective != gradient_function_.objective:
+        raise TypeError("objective and gradient belong to different example functions")
+    if not isinstance(constraint_function_, _Constraint):
+        raise TypeError("constraint_function! must be NULL_CONSTRAINT or SPHERE_CONSTRAINT")
+    return objective_function.objective, constraint_function_.cid
+
+
+def _layout(initial_point, objective, batched):
+    """numpy (C order) -> the reference's column-major layout.
+
+    Julia ``x0::Array{T,N}`` column-major <-> numpy C-order with reversed axes:
+      Rosenbrock vector of n          : shape (n,)            batch of them: (batch, n)
+      Riesz ``dim x N`` Matrix         : shape (N, dim)        batch of them: (batch, N, dim)
+    """
+    a = np.ascontiguousarray(initial_point, dtype=np.float64)
+    base_ndim = 2 if objective == OBJ_RIESZ else 1
+    if batched:
+        if a.ndim != base_ndim + 1:
+            raise ValueError(f"batched initial point must have {base_ndim + 1} dimensions")
+        batch = a.shape[0]
+        pshape = a.shape[1:]
+    else:
+        if a.ndim != base_ndim:
+            raise ValueError(f"initial point must have {base_ndim} dimension(s)")
+        batch = 1
+        pshape = a.shape
+    n = int(np.prod(pshape))
+    dim = int(pshape[-1]) if objective == OBJ_RIESZ else 0
+    return a, n, batch, pshape, dim
+
+
+class _Optimizer:
+    _prefix = ""
+
+    def _vec(self, getter):
+        out = np.empty((self._batch,) + self._pshape if self._batched else self._pshape, dtype=np.float64)
+        _check(getattr(lib(), f"dzo_{self._prefix}_{getter}")(self._h, _dp(out)))
+        return out
+
+    def _scalar(self, getter, dtype=np.float64, ptr=_capi.c_double_p):
+        out = np.empty(self._batch, dtype=dtype)
+        _check(getattr(lib(), f"dzo_{self._prefix}_{getter}")(self._h, out.ctypes.data_as(ptr)))
+        # reference scalars are 0-dim Arrays read with `[]`; numpy 0-dim arrays read with `[()]`
+        return out if self._batched else out.reshape(())
+
+    # fields shared by both optimizers
+    @property
+    def current_point(self): return self._vec("get_point")
+    @property
+    def current_gradient(self): return self._vec("get_gradient")
+    @property
+    def delta_point(self): return self._vec("get_delta_point")
+    @property
+    def delta_gradient(self): return self._vec("get_delta_gradient")
+    @property
+    def next_step_direction(self): return self._vec("get_direction")
+    @property
+    def current_objective_value(self): return self._scalar("get_objective")
+    @property
+    def last_step_length(self): return self._scalar("get_step_length")
+    @property
+    def iteration_count(self): return self._scalar("get_iteration_count", np.int64, _capi.c_i64_p)
+    @property
+    def has_terminated(self):
+        return self._scalar("get_terminated", np.uint8, _capi.c_u8_p).astype(bool)
+    #: README.md:38 spelling of has_terminated
+    has_converged = has_terminated
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(getattr(lib(), f"dzo_{self._prefix}_set_stream")(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def step(self, k: int = 1):
+        _check(getattr(lib(), f"dzo_{self._prefix}_step")(self._h, int(k)))
+        return self
+
+    def step_async(self, k: int = 1):
+        _check(getattr(lib(), f"dzo_{self._prefix}_step_async")(self._h, int(k)))
+        return self
+
+    def sync(self):
+        _check(getattr(lib(), f"dzo_{self._prefix}_sync")(self._h))
+        return self
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            getattr(lib(), f"dzo_{self._prefix}_destroy")(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BFGSOptimizer(_Optimizer):
+    """struct BFGSOptimizer, legacy/DZOptimization.jl:733-751.
+
+    ``BFGSOptimizer(f, g_, x0, step)`` (:753-760) or ``BFGSOptimizer(f, g_, c_, x0, step)``
+    (:762-810).  ``batched=True`` treats the leading axis of x0 as independent problems
+    (README.md:12 "run multiple optimizers in parallel").  ``shard=(rank, nranks, nccl_id)``
+    row-shards one large-n inverse Hessian over GPUs (one process per GPU).
+    """
+    _prefix = "bfgs"
+
+    def __init__(self, objective_function, gradient_function_, *args, batched=False, device=0,
+                 shard=None):
+        if len(args) == 2:
+            constraint_function_, (initial_point, initial_step_length) = NULL_CONSTRAINT, args
+        elif len(args) == 3:
+            constraint_function_, initial_point, initial_step_length = args
+        else:
+            raise TypeError("BFGSOptimizer(f, g!, [c!,] x0, initial_step_length)")
+        obj, cid = _resolve(objective_function, gradient_function_, constraint_function_)
+        a, n, batch, pshape, dim = _layout(initial_point, obj, batched)
+        self._batched, self._batch, self._pshape, self._n = batched, batch, pshape, n
+        self._h = None
+        h = C.c_void_p()
+        if shard is None:
+            _check(lib().dzo_bfgs_create(C.byref(h), obj, cid, dim, n, batch, _dp(a),
+                                         float(initial_step_length), int(device)))
+        else:
+            rank, nranks, nccl_id = shard
+            if batched:
+                raise ValueError("row sharding applies to a single large-n problem")
+            idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+            _check(lib().dzo_bfgs_create_sharded(C.byref(h), obj, cid, dim, n, _dp(a),
+                                                 float(initial_step_length), int(device),
+                                                 int(rank), int(nranks), idbuf))
+        self._h = h
+
+    @property
+    def last_step_type(self): return self._scalar("get_step_type", np.int32, _capi.c_i32_p)
+
+    def inverse_hessian(self, problem: int = 0):
+        """approximate_inverse_hessian (:746) of one problem as an (n, n) array.  It is bitwise
+        symmetric, so the column-major device matrix and this C-order view coincide."""
+        r0, r1 = self.row_range
+        out = np.empty((self._n, r1 - r0), dtype=np.float64)  # column-major rows x n
+        _check(lib().dzo_bfgs_get_inverse_hessian(self._h, int(problem), _dp(out)))
+        return out.T  # (rows, n): out.T[i, j] = H[r0 + i, j]
+
+    @property
+    def approximate_inverse_hessian(self): return self.inverse_hessian(0)
+
+    @property
+    def row_range(self):
+        r0, r1 = C.c_int64(), C.c_int64()
+        _check(lib().dzo_bfgs_info(self._h, None, None, None, C.byref(r0), C.byref(r1)))
+        return r0.value, r1.value
+
+    @property
+    def summation_order(self):
+        o = C.c_int()
+        _check(lib().dzo_bfgs_info(self._h, None, None, C.byref(o), None, None))
+        return o.value
+
+    def count_active(self) -> int:
+        c = C.c_int64()
+        _check(lib().dzo_bfgs_count_active(self._h, C.byref(c)))
+        return c.value
+
+    def set_state(self, point, inverse_hessian, delta_point, delta_gradient, last_step_length,
+                  last_step_type, iteration_count):
+        """Resume from saved fields (README.md:11); semantics of the rebuilding constructor
+        legacy/DZOptimization.jl:819-862 (f, g and H*g are recomputed)."""
+        f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+        x, Hm, dx, dg = f64(point), f64(inverse_hessian), f64(delta_point), f64(delta_gradient)
+        # numpy (n,n) C-order of a symmetric matrix == column-major; for generality transpose
+        Hm = np.ascontiguousarray(np.swapaxes(Hm.reshape((-1, self._n, self._n)), 1, 2))
+        L = f64(np.atleast_1d(last_step_length))
+        t = np.ascontiguousarray(np.atleast_1d(last_step_type), dtype=np.int32)
+        it = np.ascontiguousarray(np.atleast_1d(iteration_count), dtype=np.int64)
+        _check(lib().dzo_bfgs_set_state(self._h, _dp(x), _dp(Hm), _dp(dx), _dp(dg), _dp(L),
+                                        t.ctypes.data_as(_capi.c_i32_p),
+                                        it.ctypes.data_as(_capi.c_i64_p)))
+        return self
+
+
+class GradientDescentOptimizer(_Optimizer):
+    """struct GradientDescentOptimizer, legacy/DZOptimization.jl:305-327.
+
+    ``GradientDescentOptimizer(f, g_, line_search, x0, step)`` (:377-390) or
+    ``GradientDescentOptimizer(c_, f, g_, line_search, x0, step)`` (:330-337; note the
+    constraint comes FIRST in this constructor, unlike BFGSOptimizer)."""
+    _prefix = "gd"
+
+    def __init__(self, *args, batched=False, device=0):
+        if len(args) == 5:
+            constraint_function_ = NULL_CONSTRAINT
+            objective_function, gradient_function_, line_search, initial_point, step = args
+        elif len(args) == 6:
+            constraint_function_, objective_function, gradient_function_, line_search, initial_point, step = args
+        else:
+            raise TypeError("GradientDescentOptimizer([c!,] f, g!, line_search!, x0, initial_step_length)")
+        if not isinstance(line_search, QuadraticLineSearch):
+            raise TypeError("line_search_function! must be a QuadraticLineSearch")
+        obj, cid = _resolve(objective_function, gradient_function_, constraint_function_)
+        a, n, batch, pshape, dim = _layout(initial_point, obj, batched)
+        self._batched, self._batch, self._pshape, self._n = batched, batch, pshape, n
+        self._h = None
+        h = C.c_void_p()
+        _check(lib().dzo_gd_create(C.byref(h), obj, cid, dim, n, batch, _dp(a), float(step),
+                                   line_search.max_increases, int(device)))
+        self._h = h
+
+    @property
+    def delta_objective_value(self): return self._scalar("get_delta_objective")
+
+
+def step_(opt):
+    """step!(opt) -- legacy/DZOptimization.jl:393, :891.  Returns opt (:448, :993)."""
+    return opt.step(1)

@@ -1,0 +1,429 @@
+"""Independent pure-Python restatement of the same reference path (small cases only).
+
+TEST INFRASTRUCTURE.  Written from the Julia sources (legacy/DZOptimization.jl,
+legacy/Kernels.jl, legacy/ExampleFunctions.jl, legacy/PCG.jl) separately from
+oracle/dzo_oracle.c, with Python floats (IEEE binary64, no FMA), so that a transcription
+slip in either restatement shows up as a bitwise mismatch in tests/test_oracle.py.
+It also generates the committed fixtures in tests/golden/ (tests/golden/make_golden.py).
+"""
+import math
+
+INF = float("inf")
+TREE_WIDTH = 4096
+GEMV_CHUNK = 1024
+RIESZ_SEG = 128
+CAP = 4096
+MASK64 = (1 << 64) - 1
+
+
+# ------------------------------------------------------------------ legacy/PCG.jl
+def pcg_fill(count, seed):
+    def advance(s):  # :7-8
+        return (0x5851F42D4C957F2D * s + 0x14057B7EF767814F) & MASK64
+
+    def extract(s):  # :11-12  bitrotate(x, -k) == rotate right by k
+        v = (((s >> 18) ^ s) >> 27) & 0xFFFFFFFF
+        k = s >> 59
+        return ((v >> k) | (v << (32 - k))) & 0xFFFFFFFF if k else v
+
+    state = advance((0x14057B7EF767814F + seed) & MASK64)  # :16
+    out = []
+    for _ in range(count):
+        out.append(2.3283064365386962890625E-10 * extract(state))  # :18
+        state = advance(state)
+    return out
+
+
+# ------------------------------------------------------------------ summation orders
+def _tree_combine(p):
+    for bit in (4, 3, 2, 1, 0, 5, 6, 7, 8, 9, 10, 11):
+        m = 1 << bit
+        for v in range(TREE_WIDTH):
+            if not v & m:
+                p[v] = p[v] + p[v | m]
+    return p[0]
+
+
+def ksum(terms, tree, owner=lambda k: k):
+    """Sum an iterable of terms: left-to-right (legacy/Kernels.jl:12-20) or canonical tree."""
+    if not tree:
+        r = 0.0
+        for t in terms:
+            r += t
+        return r
+    p = [0.0] * TREE_WIDTH
+    for k, t in enumerate(terms):
+        p[owner(k) % TREE_WIDTH] += t
+    return _tree_combine(p)
+
+
+def dot(v, w, tree=False):
+    return ksum((a * b for a, b in zip(v, w)), tree, owner=lambda e: e // 2)
+
+
+def norm2(x, tree=False):
+    return dot(x, x, tree)
+
+
+def gemv(H, v, tree=False):
+    """H[i][j]; row sums with j ascending (stand-in for LinearAlgebra.mul!)."""
+    n = len(v)
+    chunk = GEMV_CHUNK if tree else max(n, 1)
+    out = []
+    for i in range(n):
+        acc = None
+        for c0 in range(0, n, chunk):
+            part = 0.0
+            for j in range(c0, min(c0 + chunk, n)):
+                part += H[i][j] * v[j]
+            acc = part if acc is None else acc + part
+        out.append(acc)
+    return out
+
+
+# ------------------------------------------------------------------ legacy/ExampleFunctions.jl
+class Rosenbrock:
+    """:10-24, extended over consecutive pairs [GLUE, SURVEY.md 8.0]"""
+
+    def __init__(self, tree=False):
+        self.tree = tree
+
+    def constraint(self, x):
+        return True
+
+    def f(self, v):
+        def term(k):
+            x, y = v[2 * k], v[2 * k + 1]
+            t1 = 1 - x
+            t2 = y - x * x
+            return t1 * t1 + 100 * (t2 * t2)
+        return ksum((term(k) for k in range(len(v) // 2)), self.tree)
+
+    def g(self, g, v):
+        for k in range(len(v) // 2):
+            x, y = v[2 * k], v[2 * k + 1]
+            t1 = 1 - x
+            t2 = y - x * x
+            g[2 * k] = -2 * t1 - 400 * x * t2
+            g[2 * k + 1] = 200 * t2
+
+
+class Riesz:
+    """:30-83 on a dim x N column-major matrix stored flat (point j at [j*dim, (j+1)*dim))."""
+
+    def __init__(self, dim, sphere=False, tree=False):
+        self.dim, self.sphere, self.tree = dim, sphere, tree
+
+    def constraint(self, x):
+        if self.sphere:  # [GLUE] normalise every column
+            d = self.dim
+            for j in range(len(x) // d):
+                s = 0.0
+                for k in range(d):
+                    s += x[j * d + k] * x[j * d + k]
+                inv = 1.0 / math.sqrt(s)
+                for k in range(d):
+                    x[j * d + k] *= inv
+        return True
+
+    def _rsqrt_dist(self, p, i, j):
+        d = self.dim
+        dist_sq = 0.0
+        for k in range(d):
+            dist = p[i * d + k] - p[j * d + k]
+            dist_sq += dist * dist
+        return dist_sq
+
+    def f(self, p):
+        d = self.dim
+        npts = len(p) // d
+        if not self.tree:  # :34-43
+            result = 0.0
+            for j in range(1, npts):
+                for i in range(j):
+                    result += 1.0 / math.sqrt(self._rsqrt_dist(p, i, j))
+            return result
+        rows = []
+        for j in range(npts):
+            ej = 0.0
+            for s0 in range(0, j, RIESZ_SEG):
+                seg = 0.0
+                for i in range(s0, min(s0 + RIESZ_SEG, j)):
+                    seg += 1.0 / math.sqrt(self._rsqrt_dist(p, i, j))
+                ej = seg if s0 == 0 else ej + seg
+            rows.append(ej)
+        return ksum(rows, True)
+
+    def g(self, g, p):
+        d = self.dim
+        npts = len(p) // d
+        seg = RIESZ_SEG if self.tree else npts
+        for j in range(npts):
+            acc = [0.0] * d
+            for s0 in range(0, npts, seg):
+                part = [0.0] * d
+                for i in range(s0, min(s0 + seg, npts)):
+                    if i == j:
+                        continue
+                    dist_sq = self._rsqrt_dist(p, i, j)
+                    inv_dist = 1.0 / math.sqrt(dist_sq)
+                    inv_dist_cubed = inv_dist / dist_sq
+                    for k in range(d):
+                        part[k] += (p[i * d + k] - p[j * d + k]) * inv_dist_cubed
+                acc = part if s0 == 0 else [a + b for a, b in zip(acc, part)]
+            for k in range(d):
+                g[j * d + k] = acc[k]
+            if self.sphere:  # :361-374
+                overlap = 0.0
+                for k in range(d):
+                    overlap += p[j * d + k] * g[j * d + k]
+                for k in range(d):
+                    g[j * d + k] -= overlap * p[j * d + k]
+
+
+# ------------------------------------------------------------------ line search
+class Ray:
+    """LineSearchEvaluator (:12-46) with sign=+1; the BFGS functor [GLUE] with sign=-1."""
+
+    def __init__(self, fn, x, direction, sign):
+        self.fn, self.x, self.dir, self.sign = fn, x, direction, sign
+        self.new = list(x)
+        self.ref = list(x)
+
+    def move(self, t):
+        a = self.sign * t
+        changed = False
+        for i in range(len(self.x)):
+            nw = self.x[i] + a * self.dir[i]
+            changed |= (self.x[i] != nw)
+            self.new[i] = nw
+        return changed
+
+    def __call__(self, t):  # :25-46
+        self.move(t)
+        if not self.fn.constraint(self.new):
+            return INF
+        return self.fn.f(self.new)
+
+
+def find_three_point_bracket(lse, f0, t1, max_increases):  # :49-172
+    if not math.isfinite(f0):
+        return (0.0, f0, 0.0, f0)
+    if not math.isfinite(t1) or t1 == 0.0:  # [GLUE]
+        return (0.0, f0, 0.0, f0)
+    if all(s == 0.0 for s in lse.dir):  # :71-85
+        return (0.0, f0, 0.0, f0)
+    step_size = t1
+    point_changed = lse.move(step_size)
+    step_is_small = False
+    cap = CAP
+    while not point_changed:  # :91-101
+        step_size += step_size
+        step_is_small = True
+        point_changed = lse.move(step_size)
+        cap -= 1
+        if cap == 0:
+            return (0.0, f0, 0.0, f0)
+    is_feasible = lse.fn.constraint(lse.new)  # :104
+    if step_is_small:
+        if not is_feasible:
+            return (0.0, f0, 0.0, f0)
+        if lse.x == lse.new:  # :119
+            return (0.0, f0, 0.0, f0)
+    f1 = lse.fn.f(lse.new) if is_feasible else INF  # :126
+    if f1 <= f0:  # :130
+        lse.ref = list(lse.new)
+        num_increases = 0
+        cap = CAP
+        while True:
+            double_step_size = step_size + step_size
+            num_increases += 1
+            f2 = lse(double_step_size)
+            cap -= 1
+            if ((max_increases > 0 and num_increases >= max_increases) or not math.isfinite(f2)
+                    or f2 > f1 or lse.new == lse.ref or cap == 0):
+                return (step_size, f1, double_step_size, f2)
+            step_size = double_step_size
+            f1 = f2
+            lse.ref = list(lse.new)
+    else:  # :157-171
+        cap = CAP
+        while True:
+            half_step_size = 0.5 * step_size
+            f2 = lse(half_step_size)
+            cap -= 1
+            if f2 <= f0 or cap == 0:
+                return (half_step_size, f2, step_size, f1)
+            step_size = half_step_size
+            f1 = f2
+
+
+def quadratic_line_search(lse, f0, t1=1.0, max_increases=0):  # :191-216
+    x1, f1, x2, f2 = find_three_point_bracket(lse, f0, t1, max_increases)
+    xb, fb = 0.0, f0
+    if f1 < fb:
+        xb, fb = x1, f1
+    if f2 < fb:
+        xb, fb = x2, f2
+    delta_1 = f0 - f1
+    delta_2 = f2 - f1
+    sum_deltas = delta_1 + delta_2
+    if delta_1 >= 0.0 and delta_2 >= 0.0 and sum_deltas > 0.0:
+        twice_delta_1 = delta_1 + delta_1
+        delta_ratio = (twice_delta_1 + sum_deltas) / (sum_deltas + sum_deltas)
+        xq = delta_ratio * x1
+        fq = lse(xq)
+        if fq < fb:
+            xb, fb = xq, fq
+    return xb, fb
+
+
+# ------------------------------------------------------------------ BFGS (:725-994)
+NullStep, GradientDescentStep, BFGSStep = 0, 1, 2
+
+
+class BFGSOptimizer:
+    def __init__(self, fn, x0, initial_step_length, tree=False):  # :762-810
+        self.fn, self.tree = fn, tree
+        n = len(x0)
+        self.iteration_count = 0
+        self.has_terminated = False
+        self.current_point = list(x0)
+        assert fn.constraint(self.current_point)
+        self.current_objective_value = fn.f(self.current_point)
+        assert not math.isnan(self.current_objective_value)
+        self.current_gradient = [0.0] * n
+        fn.g(self.current_gradient, self.current_point)
+        self.delta_point = [0.0] * n
+        self.delta_gradient = [0.0] * n
+        self.last_step_length = initial_step_length
+        self.last_step_type = NullStep
+        self.H = [[1.0 if i == j else 0.0 for j in range(n)] for i in range(n)]
+        self.next_step_direction = list(self.current_gradient)
+
+    def update_inverse_hessian(self, step_length, step_direction, delta_gradient):  # :864-889
+        n = len(step_direction)
+        overlap = dot(step_direction, delta_gradient, self.tree)
+        inv = 1.0 / overlap
+        for i in range(n):
+            step_direction[i] *= inv
+        scratch = gemv(self.H, delta_gradient, self.tree)
+        delta_norm = step_length * overlap + dot(delta_gradient, scratch, self.tree)
+        for j in range(n):
+            sj, tj = step_direction[j], scratch[j]
+            for i in range(n):
+                self.H[i][j] += (delta_norm * (step_direction[i] * sj)
+                                 - (scratch[i] * sj + step_direction[i] * tj))
+
+    def step(self):  # :891-994
+        if self.has_terminated:
+            return self
+        fn, n = self.fn, len(self.current_point)
+        point, gradient, d = self.current_point, self.current_gradient, self.next_step_direction
+        f0 = self.current_objective_value
+        step_length = self.last_step_length
+        grad_norm = math.sqrt(norm2(gradient, self.tree))
+        grad_step_length, grad_obj = quadratic_line_search(
+            Ray(fn, point, gradient, -1.0), f0, _div(step_length, grad_norm))
+        bfgs_norm = math.sqrt(norm2(d, self.tree))
+        bfgs_step_length, bfgs_obj = quadratic_line_search(
+            Ray(fn, point, d, -1.0), f0, _div(step_length, bfgs_norm))
+        if bfgs_obj < f0 and not (bfgs_obj > grad_obj):
+            self.current_objective_value = bfgs_obj
+            self.last_step_length = bfgs_step_length * bfgs_norm
+            self.last_step_type = BFGSStep
+            self.iteration_count += 1
+            self._move(-bfgs_step_length, d)
+            self.update_inverse_hessian(-bfgs_step_length, d, self.delta_gradient)
+            d[:] = gemv(self.H, gradient, self.tree)
+        elif grad_obj < f0:
+            self.current_objective_value = grad_obj
+            self.last_step_length = grad_step_length * grad_norm
+            self.last_step_type = GradientDescentStep
+            self.iteration_count += 1
+            self._move(-grad_step_length, gradient)
+            self.H = [[1.0 if i == j else 0.0 for j in range(n)] for i in range(n)]
+            d[:] = gradient
+        else:
+            self.has_terminated = True
+        return self
+
+    def _move(self, alpha, direction):  # :943-950 / :971-978
+        n = len(self.current_point)
+        point, gradient = self.current_point, self.current_gradient
+        for i in range(n):
+            self.delta_point[i] = -point[i]
+            self.delta_gradient[i] = -gradient[i]
+        step = [alpha * direction[i] for i in range(n)]  # direction may alias gradient
+        for i in range(n):
+            point[i] += step[i]
+        assert self.fn.constraint(point)
+        self.fn.g(gradient, point)
+        for i in range(n):
+            self.delta_point[i] += point[i]
+            self.delta_gradient[i] += gradient[i]
+
+
+def _div(a, b):
+    """IEEE a / b (Python raises on b == 0; Julia returns Inf/NaN)."""
+    if b == 0.0:
+        return math.nan if (a == 0.0 or math.isnan(a)) else math.copysign(INF, a) * math.copysign(1.0, b)
+    return a / b
+
+
+# ------------------------------------------------------------------ gradient descent (:305-449)
+class GradientDescentOptimizer:
+    def __init__(self, fn, x0, initial_step_length, max_increases=0, tree=False):  # :330-374
+        self.fn, self.tree, self.max_increases = fn, tree, max_increases
+        n = len(x0)
+        self.current_point = list(x0)
+        assert fn.constraint(self.current_point)
+        self.delta_point = [0.0] * n
+        self.current_objective_value = fn.f(self.current_point)
+        self.delta_objective_value = 0.0
+        self.current_gradient = [0.0] * n
+        fn.g(self.current_gradient, self.current_point)
+        self.delta_gradient = [0.0] * n
+        self.last_step_length = 0.0
+        inv_gradient_norm = _div(1.0, math.sqrt(norm2(self.current_gradient, tree)))
+        self.next_step_direction = [0.0] * n
+        if math.isfinite(inv_gradient_norm):
+            a = -initial_step_length * inv_gradient_norm
+            self.next_step_direction = [gi * a for gi in self.current_gradient]
+        self.iteration_count = 0
+        self.has_terminated = (not math.isfinite(self.current_objective_value)
+                               or not math.isfinite(inv_gradient_norm))
+
+    def step(self):  # :393-449
+        if self.has_terminated:
+            return self
+        n = len(self.current_point)
+        x, d, g = self.current_point, self.next_step_direction, self.current_gradient
+        step_size, objective_value = quadratic_line_search(
+            Ray(self.fn, x, d, +1.0), self.current_objective_value, 1.0, self.max_increases)
+        if step_size == 0.0 or not (objective_value < self.current_objective_value):
+            self.has_terminated = True
+            return self
+        self.iteration_count += 1
+        self.delta_point = list(x)
+        for i in range(n):
+            x[i] += step_size * d[i]
+        assert self.fn.constraint(x)
+        for i in range(n):
+            self.delta_point[i] = x[i] - self.delta_point[i]
+        step_length = math.sqrt(norm2(self.delta_point, self.tree))
+        self.last_step_length = step_length
+        self.delta_objective_value = objective_value - self.current_objective_value
+        self.current_objective_value = objective_value
+        self.delta_gradient = list(g)
+        self.fn.g(g, x)
+        for i in range(n):
+            self.delta_gradient[i] = g[i] - self.delta_gradient[i]
+        inv_gradient_norm = _div(1.0, math.sqrt(norm2(g, self.tree)))
+        if not math.isfinite(inv_gradient_norm):
+            self.has_terminated = True
+            return self
+        a = -step_length * inv_gradient_norm
+        for i in range(n):
+            d[i] = a * g[i]
+        return self
