@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- batched BFGS step! throughput (BASELINE.json configs[1]) + n=16384 step! roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (N=1): 1,000,000 independent extended-Rosenbrock problems, n=16, x0 = 4u-2 with u from
+the reference's PCG (legacy/PCG.jl, seed 2024+rank), initial step 1.0.  One "step" = one step!
+call on every problem of the batch = ONE launch of bfgs_batched_step_kernel.  For N>1 every rank
+holds its own 1M problems (weak scaling, no collective on the data path).
+
+Numbers on the JSON line
+  value     active problem-steps/s, state resident in HBM, CUDA events on the launching stream
+  e2e       the README loop through the public API with HOST buffers: constructor from pinned
+            host x0 (H2D) + K x [step!; read has_converged[] and current_objective_value[] (D2H)]
+  roofline  bfgs_batched_step_kernel against the measured HBM copy bandwidth
+  large_n   n=16384 single-problem step! (configs[2]): ms per BFGS-type step, achieved GB/s of
+            the 24 n^2-byte step and of its two n^2 kernels against the same peak
+  cpu_baseline  the CPU oracle (a port of the reference: the reference itself is commented-out
+            Julia and no Julia exists here) on all host threads, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SMALL = 16
+BATCH = 1_000_000
+LARGE_N = 16384
+METRIC = "batched BFGS problem-steps/s (1M x n=16)"
+UNIT = "problem-steps/s"
+# algorithmic bytes of one batched problem-step: read x,g,d,H + f,L,iter,term;
+# write x,g,d,dx,dg,H + f,L,iter,type
+BYTES_PER_PROBLEM_STEP = (3 * N_SMALL * 8 + N_SMALL * N_SMALL * 8 + 25) + (5 * N_SMALL * 8 + N_SMALL * N_SMALL * 8 + 28)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_mod():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    oracle.build()
+    return oracle
+
+
+def x0_batch(orc, batch, seed):
+    return (4.0 * orc.pcg_fill(batch * N_SMALL, seed) - 2.0).reshape(batch, N_SMALL)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_leg(orc, steps, warmup, sample_batch):
+    """Oracle (port of the reference path) on every host thread; bounded sample of the workload."""
+    threads = os.cpu_count() or 1
+    x0 = x0_batch(orc, sample_batch, 2024)
+    ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0, 1.0, order=orc.SEQ, nthreads=threads)
+    ref.step(warmup)
+    active0 = ref.count_active()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        done += ref.count_active()
+        ref.step(1)
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{sample_batch} of the {BATCH} problems (same PCG stream), {steps} step! calls after {warmup} warm-up, "
+                      f"{active0} active at start; oracle/dzo_oracle.c, OpenMP over problems",
+            "seconds": dt, "ms_per_step": 1e3 * dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc = oracle_mod()
+    sample = 100_000
+    leg = cpu_leg(orc, args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batched BFGS 1,000,000 x n=16 extended Rosenbrock (BASELINE configs[1])",
+                   "sample_batch": sample, "note": "reference = CPU oracle port (Julia reference is dead code; no Julia here)"},
+        "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    distributed = world > 1
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import dzopt_b200 as dz
+    EF = dz.ExampleFunctions
+    orc = oracle_mod()  # input generator (PCG) and, on rank 0, the cpu_baseline leg
+    peak, peak_src = load_peaks()
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if not distributed:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if not distributed:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    x0 = x0_batch(orc, BATCH, 2024 + rank)
+    x0_pinned = torch.from_numpy(x0).pin_memory()
+    x0_host = x0_pinned.numpy()
+    stream = torch.cuda.Stream()      # a real (non-default) stream: handle 0 would mean "the handle's own stream"
+    torch.cuda.set_stream(stream)
+
+    # ---- device-resident throughput: K step! calls, one kernel launch each
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
+                           device=local_rank)
+    opt.set_stream(stream.cuda_stream)
+    opt.step(W)
+    # per-step active counts are read AFTER the timed region from iteration counts, not inside it
+    it0 = opt.iteration_count.copy()
+    done0 = opt.has_converged.copy()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(K):
+            opt.step_async(1)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ms)
+    it1 = opt.iteration_count
+    done1 = opt.has_converged
+    # a problem active at the start of a step either moved (iteration +1) or terminated in that step
+    problem_steps = float((it1 - it0).sum() + (done1 & ~done0).sum())
+    total_problem_steps = sum_over_ranks(problem_steps)
+    value = total_problem_steps / (ms * 1e-3)
+    kernel_ms = ms / K
+    achieved = BYTES_PER_PROBLEM_STEP * problem_steps / K / (kernel_ms * 1e-3) / 1e9
+    active_frac = problem_steps / (K * BATCH)
+    opt.close()
+
+    # ---- end to end through the public API with host buffers
+    barrier()
+    barrier()
+    t1 = time.perf_counter()
+    e2 = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
+                          device=local_rank)           # H2D of x0 inside the timed region
+    e2.step(W)                                          # same starting state as the device-timed arm
+    flags = obj = None
+    for _ in range(K):
+        dz.step_(e2)
+        flags = e2.has_converged                        # D2H, what `while !opt.has_converged[]` reads
+        obj = e2.current_objective_value                # D2H
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t1
+    # every step! of an active problem either moves it (iteration_count + 1) or terminates it; the
+    # warm-up steps of this arm are inside its timed region and count as work too
+    e2e_steps_total = float(e2.iteration_count.sum() + flags.sum())
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = sum_over_ranks(e2e_steps_total) / e2e_s
+    h2d = x0.nbytes / (K + W)
+    d2h = (flags.nbytes + obj.nbytes)
+    e2.close()
+
+    # ---- large-n step! (configs[2]) and its two n^2 kernels, rank 0 only at N=1
+    large = None
+    if rank == 0 and not args.skip_large:
+        large = bench_large(dz, orc, torch, stream, peak, local_rank)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cpu = cpu_leg(orc, K, W, args.cpu_sample)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "batched BFGS 1,000,000 x n=16 extended Rosenbrock per GPU (BASELINE configs[1])",
+                       "batch_per_gpu": BATCH, "n": N_SMALL, "initial_step_length": 1.0,
+                       "l2": "state per GPU = 2.9 GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
+                       "active_fraction_in_timed_region": active_frac,
+                       "parallelism": f"independent problems, {world} GPU(s), no collective"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "BFGSOptimizer(host x0) + W+K x [step!; has_converged[]; current_objective_value[]] via the C ABI"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "kernel": "bfgs_batched_step_kernel<16>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_problem_step": BYTES_PER_PROBLEM_STEP},
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if large:
+            line["large_n"] = large
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def bench_large(dz, orc, torch, stream, peak, device):
+    import ctypes as C
+    EF = dz.ExampleFunctions
+    n = LARGE_N
+    x0 = 4.0 * orc.pcg_fill(n, 1) - 2.0
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, device=device)
+    opt.set_stream(stream.cuda_stream)
+    opt.step(3)
+    times, types = [], []
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        opt.step_async(1)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+        types.append(int(opt.last_step_type[()]))
+    opt.close()
+    bf = [t for t, ty in zip(times, types) if ty == dz.StepType.BFGSStep]
+    out = {"n": n, "steps_timed": len(times), "bfgs_steps": len(bf)}
+    if bf:
+        ms = float(np.mean(bf))
+        gbs = 24.0 * n * n / (ms * 1e-3) / 1e9
+        out.update({"ms_per_bfgs_step": ms, "steps_per_s": 1e3 / ms, "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
+                    "algorithmic_bytes_per_step": 24 * n * n})
+    ms = C.c_float()
+    for which, name, nbytes in ((1, "gemv_kernel", 8), (2, "update_gemv_kernel", 16), (3, "identity_kernel", 8)):
+        rc = dz.lib().dzo_bench_kernel(which, n, 10, 0, C.byref(ms), device)
+        if rc == 0:
+            g = nbytes * n * n / (ms.value * 1e-3) / 1e9
+            out[name] = {"ms": ms.value, "achieved_gbs": g, "frac_of_peak": g / peak}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-large", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=50_000)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,449 @@
+// batched_bfgs.cuh -- batched small-n BFGS: many independent optimizers, one per lane group.
+//
+// Implements, per problem, exactly SURVEY.md 8.0 / legacy/DZOptimization.jl:762-810 (ctor) and
+// :891-994 (step!) with SEQUENTIAL summation order (legacy/Kernels.jl:12-20), so results are
+// bitwise equal to the sequential oracle.
+//
+// Mapping (DESIGN.md "batched kernel"): LPP lanes per problem (n <= LPP, LPP in {2,..,32});
+// lane r owns element r of every vector and ROW r of approximate_inverse_hessian in
+// registers.  A CTA of 256 threads holds 256/LPP problems.  The inverse Hessians of a CTA are
+// staged through shared memory by 1-D bulk async copies (TMA, cp.async.bulk + mbarrier) that
+// are issued before the two line searches and waited on only when the rank-2 update needs
+// them, and are written back by bulk stores.  All cross-lane traffic is warp shuffles or
+// group-private shared-memory broadcast buffers; there is no __syncthreads in the step.
+#pragma once
+#include "common.cuh"
+
+namespace dzo {
+
+struct BatchedArgs {
+    double *x, *g, *d, *dx, *dg, *H, *f, *L;
+    long long* iter;
+    int* type;
+    unsigned char* term;
+    unsigned long long* probes;  // optional statistics (may be null): objective evaluations
+    int n;
+    long long batch;
+    int ksteps;
+};
+
+constexpr int kBatchedThreads = 256;
+constexpr int kBcBufs = 5;  // 2 rotating reduction buffers + 3 vector broadcast buffers
+
+template <int LPP>
+struct Group {
+    int r;          // element / row owned by this lane
+    int n;
+    unsigned mask;  // lanes of this problem
+    bool act;       // r < n
+    double* bc;     // kBcBufs * LPP doubles, private to the group
+    int flip;       // rotating reduction buffer
+    unsigned long long probes;
+
+    DZO_DEVINL void sync() const { __syncwarp(mask); }
+    DZO_DEVINL bool all(bool p) const { return __all_sync(mask, p || !act) != 0; }
+    DZO_DEVINL bool any(bool p) const { return __any_sync(mask, p && act) != 0; }
+    DZO_DEVINL double* vbuf(int k) const { return bc + (2 + k) * LPP; }
+
+    // Kernels.dot / norm2 order: result = 0; result += v[i], i ascending (legacy/Kernels.jl:12-20)
+    DZO_DEVINL double seq_sum(double v) {
+        double* b = bc + flip * LPP;
+        flip ^= 1;
+        if (act) b[r] = v;
+        sync();
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < LPP; ++j)
+            if (j < n) acc += b[j];
+        return acc;
+    }
+};
+
+// ----------------------------------------------------------------------------- objectives
+// Extended Rosenbrock, legacy/ExampleFunctions.jl:10-24 per consecutive pair.
+struct RosenbrockSmall {
+    template <int LPP>
+    static DZO_DEVINL double eval(Group<LPP>& G, double w) {
+        const double y = __shfl_down_sync(G.mask, w, 1, LPP);
+        const double t1 = 1 - w;
+        const double t2 = y - w * w;
+        const double term = t1 * t1 + 100 * (t2 * t2);
+        double* b = G.bc + G.flip * LPP;
+        G.flip ^= 1;
+        if (G.act && !(G.r & 1)) b[G.r >> 1] = term;
+        G.sync();
+        G.probes++;
+        double acc = 0.0;
+        const int m = G.n >> 1;
+#pragma unroll
+        for (int k = 0; k < LPP / 2; ++k)
+            if (k < m) acc += b[k];
+        return acc;
+    }
+    template <int LPP>
+    static DZO_DEVINL double grad(const Group<LPP>& G, double w) {
+        const double up = __shfl_down_sync(G.mask, w, 1, LPP);  // element r+1
+        const double dn = __shfl_up_sync(G.mask, w, 1, LPP);    // element r-1
+        if (!(G.r & 1)) {
+            const double t1 = 1 - w;
+            const double t2 = up - w * w;
+            return -2 * t1 - 400 * w * t2;
+        }
+        const double t2 = w - dn * dn;
+        return 200 * t2;
+    }
+};
+
+// ----------------------------------------------------------------------------- line search
+// quadratic_line_search(functor, f0, t1): find_three_point_bracket (legacy/DZOptimization.jl
+// :49-172, first trial step t1) + QuadraticLineSearch (:191-216), along w = x + (-t)*dir
+// (sign from :945,:973).  Control flow is uniform across the lanes of a group.
+template <int LPP, class Obj>
+DZO_DEVINL void group_line_search(Group<LPP>& G, double x, double dir, double f0, double t1, double& t_best,
+                                  double& f_best) {
+    double x1 = 0.0, f1 = f0, x2 = 0.0, f2 = f0;
+    do {
+        if (!isfinite(f0)) break;                                  // :64-66
+        if (!isfinite(t1) || t1 == 0.0) break;                     // [GLUE]
+        if (G.all(dir == 0.0)) break;                              // :71-85
+        double step = t1;
+        double w = x + (-step) * dir;                              // :73-80
+        bool changed = G.any(x != w);
+        bool small = false;
+        int cap = DZO_LINESEARCH_CAP;
+        bool capped = false;
+        while (!changed) {                                         // :91-101
+            step += step;
+            small = true;
+            w = x + (-step) * dir;
+            changed = G.any(x != w);
+            if (--cap == 0) { capped = true; break; }
+        }
+        if (capped) break;
+        if (small && G.all(x == w)) break;                         // :107-123 (constraint is the identity)
+        double fa = Obj::eval(G, w);                               // :126
+        if (fa <= f0) {                                            // :130
+            double ref = w;                                        // :136
+            cap = DZO_LINESEARCH_CAP;
+            for (;;) {                                             // :143-156
+                const double ds = step + step;
+                w = x + (-ds) * dir;
+                const double fb = Obj::eval(G, w);
+                const bool same = G.all(w == ref);
+                --cap;
+                if (!isfinite(fb) || fb > fa || same || cap == 0) {
+                    x1 = step; f1 = fa; x2 = ds; f2 = fb;
+                    break;
+                }
+                step = ds; fa = fb; ref = w;
+            }
+        } else {                                                   // :157-171
+            cap = DZO_LINESEARCH_CAP;
+            for (;;) {
+                const double hs = 0.5 * step;
+                w = x + (-hs) * dir;
+                const double fb = Obj::eval(G, w);
+                --cap;
+                if (fb <= f0 || cap == 0) {
+                    x1 = hs; f1 = fb; x2 = step; f2 = fa;
+                    break;
+                }
+                step = hs; fa = fb;
+            }
+        }
+    } while (0);
+    double xb = 0.0, fb = f0;                                      // :196-202
+    if (f1 < fb) { xb = x1; fb = f1; }
+    if (f2 < fb) { xb = x2; fb = f2; }
+    const double delta_1 = f0 - f1;                                // :203-205
+    const double delta_2 = f2 - f1;
+    const double sum_deltas = delta_1 + delta_2;
+    if (delta_1 >= 0.0 && delta_2 >= 0.0 && sum_deltas > 0.0) {    // :206-214
+        const double twice_delta_1 = delta_1 + delta_1;
+        const double delta_ratio = (twice_delta_1 + sum_deltas) / (sum_deltas + sum_deltas);
+        const double xq = delta_ratio * x1;
+        const double w = x + (-xq) * dir;
+        const double fq = Obj::eval(G, w);
+        if (fq < fb) { xb = xq; fb = fq; }
+    }
+    t_best = xb;
+    f_best = fb;
+}
+
+// ----------------------------------------------------------------------------- constructor kernel
+// BFGSOptimizer(f, g!, x0, L0)  legacy/DZOptimization.jl:762-810.  x already holds copy(x0).
+template <int LPP, class Obj>
+__global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_init_kernel(BatchedArgs A, double initial_step_length) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PPC = kBatchedThreads / LPP;
+    double* bc_all = reinterpret_cast<double*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int gi = threadIdx.x / LPP;
+    Group<LPP> G;
+    G.r = threadIdx.x % LPP;
+    G.n = A.n;
+    G.act = G.r < A.n;
+    G.mask = (LPP == 32) ? 0xffffffffu : (((1u << LPP) - 1u) << (lane - (lane % LPP)));
+    G.bc = bc_all + gi * (kBcBufs * LPP);
+    G.flip = 0;
+    G.probes = 0;
+    const long long p = (long long)blockIdx.x * PPC + gi;
+    if (p >= A.batch) return;
+    const int n = A.n;
+    const double x = G.act ? A.x[p * n + G.r] : 0.0;
+    const double f0 = Obj::eval(G, x);                              // :772
+    const double g = Obj::grad(G, x);                               // :775-776
+    if (G.act) {
+        A.g[p * n + G.r] = g;
+        A.d[p * n + G.r] = g;                                       // :784 next_step_direction = copy(gradient)
+        A.dx[p * n + G.r] = 0.0;                                    // :777
+        A.dg[p * n + G.r] = 0.0;                                    // :778
+        double* Hp = A.H + p * n * n;                               // :781-783 identity_matrix!
+        for (int j = 0; j < n; ++j) Hp[G.r + j * n] = (j == G.r) ? 1.0 : 0.0;
+    }
+    if (G.r == 0) {
+        A.f[p] = f0;
+        A.L[p] = initial_step_length;                               // :779
+        A.iter[p] = 0;                                              // :767
+        A.type[p] = DZO_STEP_NULL;                                  // :780
+        A.term[p] = 0;                                              // :768
+    }
+}
+
+// ----------------------------------------------------------------------------- step! kernel
+template <int LPP, class Obj>
+__global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kernel(BatchedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PPC = kBatchedThreads / LPP;
+    const int n = A.n;
+    const int nn = n * n;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* sH_all = reinterpret_cast<double*>(smem_raw + 16);
+    double* bc_all = sH_all + PPC * nn;
+
+    const int lane = threadIdx.x & 31;
+    const int gi = threadIdx.x / LPP;
+    Group<LPP> G;
+    G.r = threadIdx.x % LPP;
+    G.n = n;
+    G.act = G.r < n;
+    G.mask = (LPP == 32) ? 0xffffffffu : (((1u << LPP) - 1u) << (lane - (lane % LPP)));
+    G.bc = bc_all + gi * (kBcBufs * LPP);
+    G.flip = 0;
+    G.probes = 0;
+    const int r = G.r;
+    double* sH = sH_all + gi * nn;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, PPC);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const long long p = (long long)blockIdx.x * PPC + gi;
+    const bool valid = p < A.batch;
+    bool term = valid ? (A.term[p] != 0) : true;
+
+    // Kick off the asynchronous H load (2 KB at n = 16) now; it is consumed only after the
+    // two line searches, so its latency is hidden behind them.
+    if (r == 0) {
+        if (!term) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(nn * sizeof(double)));
+            bulk_g2s(sH, A.H + p * nn, (uint32_t)(nn * sizeof(double)), bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    }
+    if (term) return;  // step! on a terminated optimizer is a no-op (:893)
+
+    double x = 0.0, g = 0.0, d = 0.0, dx = 0.0, dg = 0.0;
+    if (G.act) {
+        x = A.x[p * n + r];
+        g = A.g[p * n + r];
+        d = A.d[p * n + r];
+    }
+    double f0 = A.f[p];
+    double L = A.L[p];
+    long long iter = A.iter[p];
+    int type = DZO_STEP_NULL;
+    bool H_in_smem_is_current = true;  // sH holds the up-to-date matrix
+    bool H_dirty = false;              // sH differs from global
+    bool moved = false;
+    bool waited = false;
+
+    for (int s = 0; s < A.ksteps && !term; ++s) {
+        const double step_length = L;                                   // :918
+        const double grad_norm = sqrt(G.seq_sum(g * g));                // :921
+        double grad_step_length, grad_obj;
+        group_line_search<LPP, Obj>(G, x, g, f0, step_length / grad_norm, grad_step_length, grad_obj);  // :922-925
+        const double bfgs_norm = sqrt(G.seq_sum(d * d));                // :928
+        double bfgs_step_length, bfgs_obj;
+        group_line_search<LPP, Obj>(G, x, d, f0, step_length / bfgs_norm, bfgs_step_length, bfgs_obj);  // :929-932
+
+        if (bfgs_obj < f0 && !(bfgs_obj > grad_obj)) {                  // :934
+            f0 = bfgs_obj;                                              // :937
+            L = bfgs_step_length * bfgs_norm;                           // :938
+            type = DZO_STEP_BFGS;                                       // :939
+            iter += 1;                                                  // :940
+            moved = true;
+            dx = -x;                                                    // :943
+            dg = -g;                                                    // :944
+            const double alpha = -bfgs_step_length;
+            x = x + alpha * d;                                          // :945
+            g = Obj::grad(G, x);                                        // :948
+            dx = dx + x;                                                // :949
+            dg = dg + g;                                                // :950
+            // update_inverse_hessian!(H, -bfgs_step_length, d, dg, scratch)   :864-889
+            const double overlap = G.seq_sum(d * dg);                   // :873
+            const double sd = d * (1.0 / overlap);                      // :874
+            if (!waited) { mbar_wait(bar, 0); waited = true; }
+            double Hrow[LPP];
+#pragma unroll
+            for (int j = 0; j < LPP; ++j) Hrow[j] = (G.act && j < n) ? sH[r + j * n] : 0.0;
+            double* v0 = G.vbuf(0);
+            double* v1 = G.vbuf(1);
+            double* v2 = G.vbuf(2);
+            if (G.act) v0[r] = dg;
+            G.sync();
+            double t = 0.0;                                             // :875  scratch = H * delta_gradient
+#pragma unroll
+            for (int j = 0; j < LPP; ++j)
+                if (j < n) t += Hrow[j] * v0[j];
+            const double delta_norm = alpha * overlap + G.seq_sum(dg * t);  // :876 (seq_sum syncs the group)
+            if (G.act) { v0[r] = g; v1[r] = sd; v2[r] = t; }
+            G.sync();
+            double dnew = 0.0;
+#pragma unroll
+            for (int j = 0; j < LPP; ++j)
+                if (j < n) {
+                    const double sj = v1[j], tj = v2[j];
+                    Hrow[j] += (delta_norm * (sd * sj) - (t * sj + sd * tj));  // :882-884
+                    dnew += Hrow[j] * v0[j];                                  // :958-960  d = H * g
+                }
+            d = dnew;
+            if (G.act) {
+#pragma unroll
+                for (int j = 0; j < LPP; ++j)
+                    if (j < n) sH[r + j * n] = Hrow[j];
+            }
+            H_dirty = true;
+            G.sync();
+        } else if (grad_obj < f0) {                                     // :962
+            f0 = grad_obj;                                              // :965
+            L = grad_step_length * grad_norm;                           // :966
+            type = DZO_STEP_GRADIENT_DESCENT;                           // :967
+            iter += 1;                                                  // :968
+            moved = true;
+            dx = -x;                                                    // :971
+            dg = -g;                                                    // :972
+            const double alpha = -grad_step_length;
+            x = x + alpha * g;                                          // :973
+            g = Obj::grad(G, x);                                        // :976
+            dx = dx + x;                                                // :977
+            dg = dg + g;                                                // :978
+            if (!waited) { mbar_wait(bar, 0); waited = true; }          // the bulk load must land before we overwrite
+            if (G.act) {                                                // :981 identity_matrix!
+#pragma unroll
+                for (int j = 0; j < LPP; ++j)
+                    if (j < n) sH[r + j * n] = (j == r) ? 1.0 : 0.0;
+            }
+            H_dirty = true;
+            d = g;                                                      // :984-986
+            G.sync();
+        } else {
+            term = true;                                                // :989
+        }
+    }
+    (void)H_in_smem_is_current;
+
+    // ---- write back
+    if (moved && G.act) {
+        A.x[p * n + r] = x;
+        A.g[p * n + r] = g;
+        A.d[p * n + r] = d;
+        A.dx[p * n + r] = dx;
+        A.dg[p * n + r] = dg;
+    }
+    if (H_dirty) {
+        fence_proxy_async_smem();  // generic-proxy writes to sH -> visible to the bulk-copy engine
+        G.sync();
+        if (r == 0) {
+            bulk_s2g(A.H + p * nn, sH, (uint32_t)(nn * sizeof(double)));
+            bulk_commit();
+        }
+    }
+    if (r == 0) {
+        if (moved) {
+            A.f[p] = f0;
+            A.L[p] = L;
+            A.iter[p] = iter;
+            A.type[p] = type;
+        }
+        if (term) A.term[p] = 1;
+        if (A.probes) atomicAdd(A.probes, G.probes);
+        if (!waited) mbar_wait(bar, 0);  // never leave with an async copy still targeting our smem
+        if (H_dirty) bulk_wait_read0();
+    }
+}
+
+// ----------------------------------------------------------------------------- resume kernel
+// State-rebuilding constructor legacy/DZOptimization.jl:819-862: x, H, dx, dg, L, type, iter were
+// copied in by the host; recompute f (:828), g (:830-831), d = H*g (:833-836), clear the flag (:849).
+template <int LPP, class Obj>
+__global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_restore_kernel(BatchedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PPC = kBatchedThreads / LPP;
+    double* bc_all = reinterpret_cast<double*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int gi = threadIdx.x / LPP;
+    Group<LPP> G;
+    G.r = threadIdx.x % LPP;
+    G.n = A.n;
+    G.act = G.r < A.n;
+    G.mask = (LPP == 32) ? 0xffffffffu : (((1u << LPP) - 1u) << (lane - (lane % LPP)));
+    G.bc = bc_all + gi * (kBcBufs * LPP);
+    G.flip = 0;
+    G.probes = 0;
+    const long long p = (long long)blockIdx.x * PPC + gi;
+    if (p >= A.batch) return;
+    const int n = A.n;
+    const double x = G.act ? A.x[p * n + G.r] : 0.0;
+    const double f0 = Obj::eval(G, x);
+    const double g = Obj::grad(G, x);
+    double* v0 = G.vbuf(0);
+    if (G.act) v0[G.r] = g;
+    G.sync();
+    double d = 0.0;
+    const double* Hp = A.H + p * n * n;
+    if (G.act)
+        for (int j = 0; j < n; ++j) d += Hp[G.r + j * n] * v0[j];   // mul!(d, H, g), row sum j ascending
+    if (G.act) {
+        A.g[p * n + G.r] = g;
+        A.d[p * n + G.r] = d;
+    }
+    if (G.r == 0) {
+        A.f[p] = f0;
+        A.term[p] = 0;
+    }
+}
+
+// number of problems with has_terminated == false
+__global__ void count_active_kernel(const unsigned char* term, long long batch, unsigned long long* out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int v = (i < batch) ? (term[i] == 0) : 0;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)v);
+}
+
+template <int LPP>
+inline size_t batched_step_smem(int n) {
+    constexpr int PPC = kBatchedThreads / LPP;
+    return 16 + sizeof(double) * ((size_t)PPC * n * n + (size_t)PPC * kBcBufs * LPP);
+}
+template <int LPP>
+inline size_t batched_init_smem() {
+    constexpr int PPC = kBatchedThreads / LPP;
+    return sizeof(double) * ((size_t)PPC * kBcBufs * LPP);
+}
+
+}  // namespace dzo

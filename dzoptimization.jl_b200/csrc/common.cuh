@@ -1,0 +1,138 @@
+// common.cuh -- shared device/host helpers of libdzopt_b200 (sm_100a only).
+//
+// Arithmetic policy: the legacy Julia on this path contains no muladd and no
+// @simd reductions, so nothing may be contracted into FMA.  The whole library is compiled
+// with -fmad=false; double-precision '/' and sqrt() are IEEE-correct in CUDA regardless of
+// flags.  Never use rsqrt()/__drcp_* here.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/dzopt.h"
+
+#define DZO_DEVINL __device__ __forceinline__
+
+namespace dzo {
+
+// ----------------------------------------------------------------------------- control block
+// Per-problem scalars of the large-n path that kernels hand to one another on the device
+// (no host round trip inside step!).
+struct LargeCtrl {
+    double f;          // current_objective_value      legacy/DZOptimization.jl:740
+    double L;          // last_step_length             :744
+    long long iter;    // iteration_count              :737
+    int type;          // last_step_type               :745
+    int term;          // has_terminated               :738
+    // hand-off between the kernels of one step!
+    int kind;          // what THIS step did: DZO_STEP_NULL (nothing / terminated), _BFGS, _GRADIENT_DESCENT
+    int pad;
+    double step_length;// -alpha handed to update_inverse_hessian! (:954)
+    double overlap;    // :873
+    double delta_norm; // :876
+    // statistics
+    long long evals;   // objective evaluations so far
+};
+
+// ----------------------------------------------------------------------------- warp butterflies
+// Canonical tree (include/dzopt.h): lane bits are combined 16,8,4,2,1; every level
+// above the warp is combined in ASCENDING bit order.
+DZO_DEVINL double warp_butterfly_desc(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+DZO_DEVINL double warp_butterfly_asc(double v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Reduce K independent quantities over the canonical tree inside ONE CTA of 1024 threads.
+// Thread tid emulates the 4 virtual threads v = tid + 1024*q; p[k][q] is the partial of
+// quantity k on virtual thread v.  `sm` needs K*132 doubles.  Result (identical on every
+// thread) is written to out[k].  Contains 3 __syncthreads().
+template <int K>
+DZO_DEVINL void cta1024_tree_reduce(double (&p)[K][4], double* sm, double (&out)[K]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double s = warp_butterfly_desc(p[k][q]);           // bits 4,3,2,1,0
+            if (lane == 0) sm[k * 132 + q * 32 + warp] = s;
+        }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double r[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) r[q] = warp_butterfly_asc(sm[k * 132 + q * 32 + lane]); // bits 5..9
+            const double a = r[0] + r[1];                            // bit 10
+            const double b = r[2] + r[3];
+            if (lane == 0) sm[k * 132 + 128] = a + b;                // bit 11
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = sm[k * 132 + 128];
+    __syncthreads();  // sm may be reused immediately by the caller
+}
+
+// ----------------------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA 1-D)
+DZO_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+DZO_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+DZO_DEVINL void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+DZO_DEVINL void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DZO_DEVINL void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DZO_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+DZO_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global bulk copy (bulk-group completion)
+DZO_DEVINL void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+DZO_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DZO_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+DZO_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+DZO_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// streaming (evict-first) 128-bit global access for the n^2 sweeps: H has no reuse inside a sweep
+DZO_DEVINL double2 ldg_stream2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+DZO_DEVINL void stg_stream2(double* p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+DZO_DEVINL bool finite_(double v) { return isfinite(v); }
+
+}  // namespace dzo

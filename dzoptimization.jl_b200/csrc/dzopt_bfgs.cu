@@ -1,0 +1,757 @@
+// dzopt_bfgs.cu -- C ABI (include/dzopt.h) of the BFGSOptimizer path: handles, step!, field
+// reads, resume, kernel-level entry points, measurement hooks.  sm_100a only; -fmad=false.
+#include <dlfcn.h>
+
+#include <new>
+
+#include "batched_bfgs.cuh"
+#include "host_common.h"
+#include "large_bfgs.cuh"
+#include "small_ops.cuh"
+
+namespace dzo {
+thread_local char g_err[512] = "";
+Tuning g_tuning;
+
+int check_problem(int objective, int constraint, int64_t obj_param, int64_t n, int64_t batch) {
+    if (n <= 0 || batch <= 0) return fail(DZO_ERR_INVALID_ARGUMENT, "n and batch must be positive");
+    if (objective == DZO_OBJ_ROSENBROCK) {
+        if (n % 2) return fail(DZO_ERR_INVALID_ARGUMENT, "extended Rosenbrock needs even n");
+        if (constraint != DZO_CONSTRAINT_NONE) return fail(DZO_ERR_INVALID_ARGUMENT, "Rosenbrock takes DZO_CONSTRAINT_NONE");
+    } else if (objective == DZO_OBJ_RIESZ) {
+        if (obj_param <= 0 || obj_param > 16 || n % obj_param)
+            return fail(DZO_ERR_INVALID_ARGUMENT, "Riesz needs n = dim * N, 1 <= dim <= 16");
+        if (constraint != DZO_CONSTRAINT_NONE && constraint != DZO_CONSTRAINT_SPHERE)
+            return fail(DZO_ERR_INVALID_ARGUMENT, "unknown constraint id");
+    } else
+        return fail(DZO_ERR_INVALID_ARGUMENT, "unknown objective id");
+    return DZO_OK;
+}
+
+// ----------------------------------------------------------------------------- NCCL (dlopen'ed: only the
+// row-sharded mode needs it, and the process may already hold torch's copy of libnccl.so.2)
+struct NcclId128 { char b[128]; };  // ncclUniqueId (passed by value)
+struct NcclApi {
+    void* so = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId128, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+    if (g_nccl.so) return DZO_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* so = nullptr;
+    for (const char* nm : names) {
+        so = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (so) break;
+    }
+    if (!so) return fail(DZO_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(so, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(so, "ncclCommInitRank");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(so, "ncclAllGather");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(so, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(so, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+        return fail(DZO_ERR_NCCL, "libnccl lacks a required symbol");
+    g_nccl.so = so;
+    return DZO_OK;
+}
+#define DZO_NCCL(call)                                                                               \
+    do {                                                                                             \
+        int r__ = (call);                                                                            \
+        if (r__ != 0)                                                                                \
+            return ::dzo::fail(DZO_ERR_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call,            \
+                               g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error");   \
+    } while (0)
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+
+}  // namespace dzo
+
+using namespace dzo;
+
+// ============================================================================= handle
+struct dzo_bfgs {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int objective = 0, constraint = 0;
+    int64_t dim = 0, n = 0, batch = 0;
+    bool small = false;  // batched warp-resident path (n <= DZO_SMALL_N_MAX), SEQUENTIAL order
+    int lpp = 0;
+    // optimizer fields (device)
+    double *x = nullptr, *g = nullptr, *d = nullptr, *dx = nullptr, *dg = nullptr, *H = nullptr;
+    double *f = nullptr, *L = nullptr;
+    long long* iter = nullptr;
+    int* type = nullptr;
+    unsigned char* term = nullptr;
+    unsigned long long* counter = nullptr;
+    // large path
+    double *sd = nullptr, *t = nullptr, *partial = nullptr;
+    unsigned* tile_counters = nullptr;
+    LargeCtrl* ctrl = nullptr;
+    // row sharding
+    int rank = 0, nranks = 1;
+    int64_t row0 = 0, rows = 0;
+    void* comm = nullptr;
+};
+
+static void free_handle(dzo_bfgs* o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    if (o->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(o->comm);
+    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
+                    o->sd, o->t, o->partial, o->tile_counters, o->ctrl};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    delete o;
+}
+
+template <class T>
+static int dmalloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return fail(DZO_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    return DZO_OK;
+}
+
+static BatchedArgs batched_args(const dzo_bfgs* o, int ksteps) {
+    BatchedArgs A;
+    A.x = o->x; A.g = o->g; A.d = o->d; A.dx = o->dx; A.dg = o->dg; A.H = o->H; A.f = o->f; A.L = o->L;
+    A.iter = o->iter; A.type = o->type; A.term = o->term; A.probes = nullptr;
+    A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps;
+    return A;
+}
+
+static int pick_lpp(int64_t n) {
+    int l = 2;
+    while (l < n) l <<= 1;
+    return l;
+}
+
+// ---- batched launches, dispatched on lanes-per-problem
+template <int LPP>
+static int launch_batched_init(dzo_bfgs* o, double L0) {
+    constexpr int PPC = kBatchedThreads / LPP;
+    const unsigned grid = (unsigned)((o->batch + PPC - 1) / PPC);
+    bfgs_batched_init_kernel<LPP, RosenbrockSmall><<<grid, kBatchedThreads, batched_init_smem<LPP>(), o->stream>>>(batched_args(o, 0), L0);
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+template <int LPP>
+static int launch_batched_restore(dzo_bfgs* o) {
+    constexpr int PPC = kBatchedThreads / LPP;
+    const unsigned grid = (unsigned)((o->batch + PPC - 1) / PPC);
+    bfgs_batched_restore_kernel<LPP, RosenbrockSmall><<<grid, kBatchedThreads, batched_init_smem<LPP>(), o->stream>>>(batched_args(o, 0));
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+template <int LPP>
+static int launch_batched_step(dzo_bfgs* o, int k) {
+    constexpr int PPC = kBatchedThreads / LPP;
+    const unsigned grid = (unsigned)((o->batch + PPC - 1) / PPC);
+    const size_t smem = batched_step_smem<LPP>((int)o->n);
+    static bool attr_set[64] = {};
+    if (!attr_set[o->device & 63]) {
+        DZO_CUDA(cudaFuncSetAttribute(bfgs_batched_step_kernel<LPP, RosenbrockSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[o->device & 63] = true;
+    }
+    bfgs_batched_step_kernel<LPP, RosenbrockSmall><<<grid, kBatchedThreads, smem, o->stream>>>(batched_args(o, k));
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+#define DZO_LPP_DISPATCH(o, fn, ...)                                   \
+    switch ((o)->lpp) {                                                \
+        case 2: return fn<2>(__VA_ARGS__);                             \
+        case 4: return fn<4>(__VA_ARGS__);                             \
+        case 8: return fn<8>(__VA_ARGS__);                             \
+        case 16: return fn<16>(__VA_ARGS__);                           \
+        default: return fn<32>(__VA_ARGS__);                           \
+    }
+static int batched_init(dzo_bfgs* o, double L0) { DZO_LPP_DISPATCH(o, launch_batched_init, o, L0) }
+static int batched_restore(dzo_bfgs* o) { DZO_LPP_DISPATCH(o, launch_batched_restore, o) }
+static int batched_step(dzo_bfgs* o, int k) { DZO_LPP_DISPATCH(o, launch_batched_step, o, k) }
+
+// ---- large-path launches
+static LargeVecs large_vecs(const dzo_bfgs* o) {
+    LargeVecs v;
+    v.x = o->x; v.g = o->g; v.d = o->d; v.dx = o->dx; v.dg = o->dg; v.sd = o->sd; v.t = o->t;
+    v.ctrl = o->ctrl; v.n = o->n;
+    return v;
+}
+static SweepArgs sweep_args(const dzo_bfgs* o) {
+    SweepArgs a;
+    a.H = o->H; a.ld = o->rows; a.rows = o->rows; a.n = o->n; a.row0 = o->row0;
+    a.v = nullptr; a.s = o->sd; a.t = o->t; a.partial = o->partial; a.out = nullptr;
+    a.counters = o->tile_counters; a.ctrl = o->ctrl; a.need_kind = DZO_STEP_BFGS;
+    a.nchunks = (int)((o->n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
+    return a;
+}
+static dim3 sweep_grid(int64_t rows, int64_t n) {
+    return dim3((unsigned)((rows + kSweepRows - 1) / kSweepRows), (unsigned)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK), 1);
+}
+
+static int allgather_rows(dzo_bfgs* o, double* vec) {
+    if (o->nranks == 1) return DZO_OK;
+    DZO_NCCL(g_nccl.AllGather(vec + o->row0, vec, (size_t)o->rows, kNcclFloat64, o->comm, o->stream));
+    return DZO_OK;
+}
+
+// out = H * v on the local slab (+ allgather when sharded); predicate on ctrl->kind if need_kind >= 0
+static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind) {
+    SweepArgs a = sweep_args(o);
+    a.v = v; a.out = out;
+    if (need_kind < 0) a.ctrl = nullptr; else a.need_kind = need_kind;
+    gemv_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    return allgather_rows(o, out);
+}
+
+static int large_step_once(dzo_bfgs* o) {
+    const LargeVecs v = large_vecs(o);
+    vec_bfgs_search_kernel<<<1, 1024, 0, o->stream>>>(v);                       // :891-950, :873-874
+    DZO_CUDA(cudaGetLastError());
+    DZO_TRY(large_gemv(o, o->dg, o->t, DZO_STEP_BFGS));                         // :875
+    vec_delta_kernel<<<1, 1024, 0, o->stream>>>(v);                             // :876
+    DZO_CUDA(cudaGetLastError());
+    SweepArgs a = sweep_args(o);
+    a.v = o->g; a.out = o->d;
+    update_gemv_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);   // :878-886 + :958-960
+    DZO_CUDA(cudaGetLastError());
+    DZO_TRY(allgather_rows(o, o->d));
+    SweepArgs b = sweep_args(o);
+    b.need_kind = DZO_STEP_GRADIENT_DESCENT;
+    identity_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(b);      // :981
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+
+// ============================================================================= create / destroy
+static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t obj_param, int64_t n, int64_t batch,
+                         const double* x0, double L0, int device, int rank, int nranks, const void* nccl_id) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = nullptr;
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
+    if (objective != DZO_OBJ_ROSENBROCK)
+        return fail(DZO_ERR_UNSUPPORTED, "BFGSOptimizer device objectives: DZO_OBJ_ROSENBROCK (Riesz energy is served by dzo_gd_*)");
+    if (batch > 1 && n > DZO_SMALL_N_MAX)
+        return fail(DZO_ERR_UNSUPPORTED, "batched mode needs n <= %d; larger n runs one problem per handle", DZO_SMALL_N_MAX);
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(DZO_ERR_INVALID_ARGUMENT, "bad rank/nranks");
+    if (nranks > 1 && (n <= DZO_SMALL_N_MAX || n % (2 * nranks)))
+        return fail(DZO_ERR_INVALID_ARGUMENT, "row sharding needs n > %d and n divisible by 2*nranks", DZO_SMALL_N_MAX);
+    DZO_TRY(use_device(device));
+    dzo_bfgs* o = new (std::nothrow) dzo_bfgs();
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->device = device; o->objective = objective; o->constraint = constraint; o->dim = obj_param;
+    o->n = n; o->batch = batch; o->small = (n <= DZO_SMALL_N_MAX); o->lpp = pick_lpp(n);
+    o->rank = rank; o->nranks = nranks; o->rows = n / nranks; o->row0 = o->rows * rank;
+    int rc = DZO_OK;
+    auto bail = [&](int code) { free_handle(o); return code; };
+    if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "cudaStreamCreate failed"));
+    o->stream = o->own_stream;
+    const size_t nb = (size_t)n * (size_t)batch;
+    if ((rc = dmalloc(&o->x, nb)) || (rc = dmalloc(&o->g, nb)) || (rc = dmalloc(&o->d, nb)) || (rc = dmalloc(&o->dx, nb)) ||
+        (rc = dmalloc(&o->dg, nb)) || (rc = dmalloc(&o->counter, 1)))
+        return bail(rc);
+    if (o->small) {
+        if ((rc = dmalloc(&o->H, nb * (size_t)n)) || (rc = dmalloc(&o->f, (size_t)batch)) || (rc = dmalloc(&o->L, (size_t)batch)) ||
+            (rc = dmalloc(&o->iter, (size_t)batch)) || (rc = dmalloc(&o->type, (size_t)batch)) || (rc = dmalloc(&o->term, (size_t)batch)))
+            return bail(rc);
+    } else {
+        const size_t nchunks = (size_t)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
+        const size_t rblocks = (size_t)((o->rows + kSweepRows - 1) / kSweepRows);
+        if ((rc = dmalloc(&o->H, (size_t)o->rows * (size_t)n)) || (rc = dmalloc(&o->sd, (size_t)n)) || (rc = dmalloc(&o->t, (size_t)n)) ||
+            (rc = dmalloc(&o->partial, nchunks * (size_t)o->rows)) || (rc = dmalloc(&o->tile_counters, rblocks)) ||
+            (rc = dmalloc(&o->ctrl, 1)))
+            return bail(rc);
+        if (cudaMemsetAsync(o->tile_counters, 0, rblocks * sizeof(unsigned), o->stream) != cudaSuccess)
+            return bail(fail(DZO_ERR_CUDA, "memset failed"));
+    }
+    if (nranks > 1) {
+        if ((rc = load_nccl())) return bail(rc);
+        NcclId128 id;
+        memcpy(id.b, nccl_id, 128);
+        int r = g_nccl.CommInitRank(&o->comm, nranks, id, rank);
+        if (r != 0) return bail(fail(DZO_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+    }
+    // copy(initial_point)  legacy/DZOptimization.jl:769
+    if (cudaMemcpyAsync(o->x, x0, nb * sizeof(double), cudaMemcpyHostToDevice, o->stream) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "H2D copy of x0 failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (o->small) {
+        if ((rc = batched_init(o, L0))) return bail(rc);
+    } else {
+        vec_bfgs_init_kernel<<<1, 1024, 0, o->stream>>>(large_vecs(o), L0);
+        SweepArgs a = sweep_args(o);
+        a.ctrl = nullptr;
+        identity_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);   // :781-783
+    }
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "constructor kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
+    // @assert !isnan(initial_objective_value)   :773
+    {
+        bool any_nan = false;
+        if (o->small) {
+            double* hf = (double*)malloc((size_t)batch * sizeof(double));
+            if (!hf) return bail(fail(DZO_ERR_ALLOC, "out of memory"));
+            cudaMemcpy(hf, o->f, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost);
+            for (int64_t p = 0; p < batch; ++p) any_nan |= (hf[p] != hf[p]);
+            free(hf);
+        } else {
+            LargeCtrl c;
+            cudaMemcpy(&c, o->ctrl, sizeof c, cudaMemcpyDeviceToHost);
+            any_nan = (c.f != c.f);
+        }
+        if (any_nan) return bail(fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the initial point"));
+    }
+    *out = o;
+    return DZO_OK;
+}
+
+extern "C" {
+
+const char* dzo_last_error(void) { return g_err; }
+
+int dzo_bfgs_create(dzo_bfgs** out, int objective, int constraint, int64_t obj_param, int64_t n, int64_t batch,
+                    const double* x0, double initial_step_length, int device) {
+    return create_common(out, objective, constraint, obj_param, n, batch, x0, initial_step_length, device, 0, 1, nullptr);
+}
+
+int dzo_nccl_get_unique_id(void* out128) {
+    if (!out128) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(load_nccl());
+    DZO_NCCL(g_nccl.GetUniqueId(out128));
+    return DZO_OK;
+}
+
+int dzo_bfgs_create_sharded(dzo_bfgs** out, int objective, int constraint, int64_t obj_param, int64_t n,
+                            const double* x0, double initial_step_length, int device, int rank, int nranks,
+                            const void* nccl_unique_id) {
+    if (nranks > 1 && !nccl_unique_id) return fail(DZO_ERR_INVALID_ARGUMENT, "nccl_unique_id is null");
+    return create_common(out, objective, constraint, obj_param, n, 1, x0, initial_step_length, device, rank, nranks,
+                         nccl_unique_id);
+}
+
+void dzo_bfgs_destroy(dzo_bfgs* o) { free_handle(o); }
+
+int dzo_bfgs_set_stream(dzo_bfgs* o, void* cuda_stream) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    o->stream = cuda_stream ? (cudaStream_t)cuda_stream : o->own_stream;
+    return DZO_OK;
+}
+
+// ============================================================================= step!
+int dzo_bfgs_step_async(dzo_bfgs* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(use_device(o->device));
+    if (k == 0) return DZO_OK;
+    if (o->small) return batched_step(o, k);
+    for (int s = 0; s < k; ++s) DZO_TRY(large_step_once(o));
+    return DZO_OK;
+}
+int dzo_bfgs_sync(dzo_bfgs* o) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+int dzo_bfgs_step(dzo_bfgs* o, int k) {
+    DZO_TRY(dzo_bfgs_step_async(o, k));
+    return dzo_bfgs_sync(o);
+}
+
+// ============================================================================= field reads
+static int read_back(dzo_bfgs* o, void* dst, const void* src, size_t bytes) {
+    if (!o || !dst) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+static int read_ctrl(dzo_bfgs* o, LargeCtrl* c) { return read_back(o, c, o->ctrl, sizeof *c); }
+
+#define DZO_VEC_GETTER(name, field)                                                       \
+    int name(dzo_bfgs* o, double* out) {                                                  \
+        if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");                     \
+        return read_back(o, out, o->field, (size_t)o->n * (size_t)o->batch * 8);          \
+    }
+DZO_VEC_GETTER(dzo_bfgs_get_point, x)
+DZO_VEC_GETTER(dzo_bfgs_get_gradient, g)
+DZO_VEC_GETTER(dzo_bfgs_get_delta_point, dx)
+DZO_VEC_GETTER(dzo_bfgs_get_delta_gradient, dg)
+DZO_VEC_GETTER(dzo_bfgs_get_direction, d)
+#undef DZO_VEC_GETTER
+
+int dzo_bfgs_get_inverse_hessian(dzo_bfgs* o, int64_t problem, double* out) {
+    if (!o || problem < 0 || problem >= o->batch) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (o->small) return read_back(o, out, o->H + (size_t)problem * o->n * o->n, (size_t)o->n * o->n * 8);
+    return read_back(o, out, o->H, (size_t)o->rows * (size_t)o->n * 8);
+}
+int dzo_bfgs_get_objective(dzo_bfgs* o, double* out) {
+    if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small) return read_back(o, out, o->f, (size_t)o->batch * 8);
+    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.f; return DZO_OK;
+}
+int dzo_bfgs_get_step_length(dzo_bfgs* o, double* out) {
+    if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small) return read_back(o, out, o->L, (size_t)o->batch * 8);
+    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.L; return DZO_OK;
+}
+int dzo_bfgs_get_step_type(dzo_bfgs* o, int32_t* out) {
+    if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small) return read_back(o, out, o->type, (size_t)o->batch * 4);
+    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.type; return DZO_OK;
+}
+int dzo_bfgs_get_iteration_count(dzo_bfgs* o, int64_t* out) {
+    if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small) return read_back(o, out, o->iter, (size_t)o->batch * 8);
+    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.iter; return DZO_OK;
+}
+int dzo_bfgs_get_terminated(dzo_bfgs* o, uint8_t* out) {
+    if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small) return read_back(o, out, o->term, (size_t)o->batch);
+    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = (uint8_t)(c.term != 0); return DZO_OK;
+}
+int dzo_bfgs_count_active(dzo_bfgs* o, int64_t* out) {
+    if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!o->small) {
+        LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.term ? 0 : 1; return DZO_OK;
+    }
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaMemsetAsync(o->counter, 0, 8, o->stream));
+    count_active_kernel<<<(unsigned)((o->batch + 255) / 256), 256, 0, o->stream>>>(o->term, o->batch, o->counter);
+    DZO_CUDA(cudaGetLastError());
+    unsigned long long c = 0;
+    DZO_TRY(read_back(o, &c, o->counter, 8));
+    *out = (int64_t)c;
+    return DZO_OK;
+}
+int dzo_bfgs_info(dzo_bfgs* o, int64_t* n, int64_t* batch, int* order, int64_t* row_begin, int64_t* row_end) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    if (n) *n = o->n;
+    if (batch) *batch = o->batch;
+    if (order) *order = o->small ? DZO_ORDER_SEQUENTIAL : DZO_ORDER_TREE;
+    if (row_begin) *row_begin = o->small ? 0 : o->row0;
+    if (row_end) *row_end = o->small ? o->n : o->row0 + o->rows;
+    return DZO_OK;
+}
+
+// ============================================================================= resume
+int dzo_bfgs_set_state(dzo_bfgs* o, const double* point, const double* inverse_hessian, const double* delta_point,
+                       const double* delta_gradient, const double* last_step_length, const int32_t* last_step_type,
+                       const int64_t* iteration_count) {
+    if (!o || !point || !inverse_hessian || !delta_point || !delta_gradient || !last_step_length || !last_step_type ||
+        !iteration_count)
+        return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(use_device(o->device));
+    const size_t nb = (size_t)o->n * (size_t)o->batch * 8;
+    DZO_CUDA(cudaMemcpyAsync(o->x, point, nb, cudaMemcpyHostToDevice, o->stream));              // :825
+    DZO_CUDA(cudaMemcpyAsync(o->dx, delta_point, nb, cudaMemcpyHostToDevice, o->stream));       // :853
+    DZO_CUDA(cudaMemcpyAsync(o->dg, delta_gradient, nb, cudaMemcpyHostToDevice, o->stream));    // :854
+    if (o->small) {
+        DZO_CUDA(cudaMemcpyAsync(o->H, inverse_hessian, nb * (size_t)o->n, cudaMemcpyHostToDevice, o->stream));  // :832
+        DZO_CUDA(cudaMemcpyAsync(o->L, last_step_length, (size_t)o->batch * 8, cudaMemcpyHostToDevice, o->stream));
+        DZO_CUDA(cudaMemcpyAsync(o->type, last_step_type, (size_t)o->batch * 4, cudaMemcpyHostToDevice, o->stream));
+        DZO_CUDA(cudaMemcpyAsync(o->iter, iteration_count, (size_t)o->batch * 8, cudaMemcpyHostToDevice, o->stream));
+        DZO_TRY(batched_restore(o));
+        DZO_CUDA(cudaStreamSynchronize(o->stream));
+        double* hf = (double*)malloc((size_t)o->batch * 8);
+        if (!hf) return fail(DZO_ERR_ALLOC, "out of memory");
+        cudaMemcpy(hf, o->f, (size_t)o->batch * 8, cudaMemcpyDeviceToHost);
+        bool any_nan = false;
+        for (int64_t p = 0; p < o->batch; ++p) any_nan |= (hf[p] != hf[p]);
+        free(hf);
+        if (any_nan) return fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the restored point");   // :829
+        return DZO_OK;
+    }
+    // large: the caller passes the full n x n matrix; keep rows [row0, row0+rows) of every column
+    DZO_CUDA(cudaMemcpy2DAsync(o->H, (size_t)o->rows * 8, inverse_hessian + o->row0, (size_t)o->n * 8, (size_t)o->rows * 8,
+                               (size_t)o->n, cudaMemcpyHostToDevice, o->stream));
+    LargeCtrl c;
+    DZO_CUDA(cudaMemcpyAsync(&c, o->ctrl, sizeof c, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    c.L = last_step_length[0]; c.type = last_step_type[0]; c.iter = iteration_count[0];              // :848, :855-856
+    DZO_CUDA(cudaMemcpyAsync(o->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, o->stream));
+    vec_bfgs_restore_kernel<<<1, 1024, 0, o->stream>>>(large_vecs(o));
+    DZO_CUDA(cudaGetLastError());
+    DZO_TRY(large_gemv(o, o->g, o->d, -1));                                                          // :833-836
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    DZO_TRY(read_ctrl(o, &c));
+    if (c.f != c.f) return fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the restored point");
+    return DZO_OK;
+}
+
+// ============================================================================= kernel-level entry points
+static int h2d(DevBuf& b, const double* src, size_t count) {
+    DZO_TRY(b.alloc(count * 8));
+    if (src) DZO_CUDA(cudaMemcpy(b.p, src, count * 8, cudaMemcpyHostToDevice));
+    return DZO_OK;
+}
+static int d2h(double* dst, const DevBuf& b, size_t count) {
+    DZO_CUDA(cudaMemcpy(dst, b.p, count * 8, cudaMemcpyDeviceToHost));
+    return DZO_OK;
+}
+static int order_ok(int order, int64_t n) {
+    if (order == DZO_ORDER_SEQUENTIAL) {
+        if (n > DZO_SMALL_N_MAX) return fail(DZO_ERR_UNSUPPORTED, "SEQUENTIAL order on the device needs n <= %d", DZO_SMALL_N_MAX);
+        return DZO_OK;
+    }
+    if (order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    return DZO_OK;
+}
+
+int dzo_dev_dot(int order, int64_t n, const double* v, const double* w, double* out, int device) {
+    if (!v || !w || !out || n <= 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(order_ok(order, n));
+    DZO_TRY(use_device(device));
+    DevBuf dv, dw, dout;
+    DZO_TRY(h2d(dv, v, (size_t)n)); DZO_TRY(h2d(dw, w, (size_t)n)); DZO_TRY(h2d(dout, nullptr, 1));
+    if (order == DZO_ORDER_SEQUENTIAL) small_dot_kernel<<<1, 32>>>(dv.as<double>(), dw.as<double>(), (int)n, dout.as<double>());
+    else vec_dot_kernel<<<1, 1024>>>(dv.as<double>(), dw.as<double>(), n, dout.as<double>());
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    return d2h(out, dout, 1);
+}
+
+// scratch for a stand-alone TREE sweep on an n x n matrix
+struct SweepScratch {
+    DevBuf partial, counters, ctrl;
+    int init(int64_t n) {
+        const size_t nchunks = (size_t)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
+        const size_t rblocks = (size_t)((n + kSweepRows - 1) / kSweepRows);
+        DZO_TRY(partial.alloc(nchunks * (size_t)n * 8));
+        DZO_TRY(counters.alloc(rblocks * 4));
+        DZO_TRY(ctrl.alloc(sizeof(LargeCtrl)));
+        DZO_CUDA(cudaMemset(counters.p, 0, rblocks * 4));
+        DZO_CUDA(cudaMemset(ctrl.p, 0, sizeof(LargeCtrl)));
+        return DZO_OK;
+    }
+    SweepArgs args(double* H, int64_t n) const {
+        SweepArgs a;
+        a.H = H; a.ld = n; a.rows = n; a.n = n; a.row0 = 0; a.v = nullptr; a.s = nullptr; a.t = nullptr;
+        a.partial = partial.as<double>(); a.out = nullptr; a.counters = counters.as<unsigned>();
+        a.ctrl = nullptr; a.need_kind = DZO_STEP_BFGS;
+        a.nchunks = (int)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
+        return a;
+    }
+};
+
+int dzo_dev_gemv(int order, int64_t n, const double* H, const double* v, double* out, int device) {
+    if (!H || !v || !out || n <= 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(order_ok(order, n));
+    DZO_TRY(use_device(device));
+    DevBuf dH, dv, dout;
+    DZO_TRY(h2d(dH, H, (size_t)n * n)); DZO_TRY(h2d(dv, v, (size_t)n)); DZO_TRY(h2d(dout, nullptr, (size_t)n));
+    if (order == DZO_ORDER_SEQUENTIAL) {
+        small_gemv_kernel<<<1, 32>>>(dH.as<double>(), dv.as<double>(), (int)n, dout.as<double>());
+    } else {
+        SweepScratch sc;
+        DZO_TRY(sc.init(n));
+        SweepArgs a = sc.args(dH.as<double>(), n);
+        a.v = dv.as<double>(); a.out = dout.as<double>();
+        gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+        DZO_CUDA(cudaGetLastError());
+        DZO_CUDA(cudaDeviceSynchronize());
+    }
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    return d2h(out, dout, (size_t)n);
+}
+
+int dzo_dev_update_inverse_hessian(int order, int64_t n, double* H, double step_length, double* step_direction,
+                                   const double* delta_gradient, double* scratch, const double* next_gradient,
+                                   double* next_direction, int device) {
+    if (!H || !step_direction || !delta_gradient || !scratch || n <= 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(order_ok(order, n));
+    DZO_TRY(use_device(device));
+    const bool fused = next_gradient && next_direction;
+    DevBuf dH, dd, ddg, dt, dg, dnd, dsd;
+    DZO_TRY(h2d(dH, H, (size_t)n * n)); DZO_TRY(h2d(dd, step_direction, (size_t)n)); DZO_TRY(h2d(ddg, delta_gradient, (size_t)n));
+    DZO_TRY(h2d(dt, nullptr, (size_t)n)); DZO_TRY(h2d(dg, fused ? next_gradient : nullptr, (size_t)n));
+    DZO_TRY(h2d(dnd, nullptr, (size_t)n)); DZO_TRY(h2d(dsd, nullptr, (size_t)n));
+    if (order == DZO_ORDER_SEQUENTIAL) {
+        small_update_kernel<<<1, 32>>>(dH.as<double>(), step_length, dd.as<double>(), ddg.as<double>(), dt.as<double>(),
+                                       fused ? dg.as<double>() : nullptr, fused ? dnd.as<double>() : nullptr, (int)n);
+        DZO_CUDA(cudaGetLastError());
+        DZO_CUDA(cudaDeviceSynchronize());
+        DZO_TRY(d2h(step_direction, dd, (size_t)n));
+    } else {
+        SweepScratch sc;
+        DZO_TRY(sc.init(n));
+        LargeVecs v;
+        v.x = nullptr; v.g = dg.as<double>(); v.d = dd.as<double>(); v.dx = nullptr; v.dg = ddg.as<double>();
+        v.sd = dsd.as<double>(); v.t = dt.as<double>(); v.ctrl = sc.ctrl.as<LargeCtrl>(); v.n = n;
+        vec_overlap_scale_kernel<<<1, 1024>>>(v, step_length);                        // :873-874
+        SweepArgs a = sc.args(dH.as<double>(), n);
+        a.ctrl = sc.ctrl.as<LargeCtrl>();
+        a.v = ddg.as<double>(); a.out = dt.as<double>();
+        gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);                           // :875
+        vec_delta_kernel<<<1, 1024>>>(v);                                              // :876
+        a.v = fused ? dg.as<double>() : nullptr; a.out = fused ? dnd.as<double>() : nullptr;
+        a.s = dsd.as<double>(); a.t = dt.as<double>();
+        update_gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);                    // :878-886 (+ :958-960)
+        DZO_CUDA(cudaGetLastError());
+        DZO_CUDA(cudaDeviceSynchronize());
+        DZO_TRY(d2h(step_direction, dsd, (size_t)n));
+    }
+    DZO_TRY(d2h(H, dH, (size_t)n * n));
+    DZO_TRY(d2h(scratch, dt, (size_t)n));
+    if (fused) DZO_TRY(d2h(next_direction, dnd, (size_t)n));
+    return DZO_OK;
+}
+
+int dzo_dev_identity(int64_t n, double* H, int device) {
+    if (!H || n <= 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(use_device(device));
+    DevBuf dH;
+    DZO_TRY(h2d(dH, nullptr, (size_t)n * n));
+    SweepScratch sc;
+    DZO_TRY(sc.init(n));
+    SweepArgs a = sc.args(dH.as<double>(), n);
+    identity_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    return d2h(H, dH, (size_t)n * n);
+}
+
+int dzo_dev_line_search(int objective, int constraint, int64_t obj_param, int order, int64_t n, const double* x,
+                        const double* dir, double f0, double t1, double* t_best, double* f_best, int device);
+int dzo_dev_objective(int objective, int constraint, int64_t obj_param, int order, int64_t n, int64_t batch,
+                      const double* x, double* f, int device);
+int dzo_dev_gradient(int objective, int constraint, int64_t obj_param, int order, int64_t n, int64_t batch,
+                     const double* x, double* g, int device);
+
+}  // extern "C"
+
+// line search / objective / gradient: Rosenbrock handled here, Riesz in dzopt_gd.cu
+namespace dzo {
+int riesz_dev_objective(int constraint, int64_t dim, int order, int64_t n, int64_t batch, const double* x, double* f);
+int riesz_dev_gradient(int constraint, int64_t dim, int order, int64_t n, int64_t batch, const double* x, double* g);
+int riesz_dev_line_search(int constraint, int64_t dim, int order, int64_t n, const double* x, const double* dir, double f0,
+                          double t1, double* t_best, double* f_best);
+
+__global__ void __launch_bounds__(1024, 1) vec_line_search_kernel(const double* x, const double* dir, long long n, double f0,
+                                                                  double t1, double* out2) {
+    __shared__ double sm[132];
+    double tb, fb;
+    long long evals = 0;
+    cta_line_search_rosenbrock(x, dir, n, f0, t1, -1.0, 0, sm, tb, fb, evals);
+    if (threadIdx.x == 0) { out2[0] = tb; out2[1] = fb; }
+}
+}  // namespace dzo
+
+extern "C" {
+
+int dzo_dev_line_search(int objective, int constraint, int64_t obj_param, int order, int64_t n, const double* x,
+                        const double* dir, double f0, double t1, double* t_best, double* f_best, int device) {
+    if (!x || !dir || !t_best || !f_best) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, 1));
+    DZO_TRY(order_ok(order, n));
+    DZO_TRY(use_device(device));
+    if (objective == DZO_OBJ_RIESZ) return riesz_dev_line_search(constraint, obj_param, order, n, x, dir, f0, t1, t_best, f_best);
+    DevBuf dx, dd, dout;
+    DZO_TRY(h2d(dx, x, (size_t)n)); DZO_TRY(h2d(dd, dir, (size_t)n)); DZO_TRY(h2d(dout, nullptr, 2));
+    if (order == DZO_ORDER_SEQUENTIAL)
+        small_line_search_kernel<RosenbrockSmall><<<1, 32>>>(dx.as<double>(), dd.as<double>(), (int)n, f0, t1, dout.as<double>());
+    else
+        vec_line_search_kernel<<<1, 1024>>>(dx.as<double>(), dd.as<double>(), n, f0, t1, dout.as<double>());
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    double r[2];
+    DZO_TRY(d2h(r, dout, 2));
+    *t_best = r[0]; *f_best = r[1];
+    return DZO_OK;
+}
+
+int dzo_dev_objective(int objective, int constraint, int64_t obj_param, int order, int64_t n, int64_t batch,
+                      const double* x, double* f, int device) {
+    if (!x || !f) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
+    DZO_TRY(order_ok(order, n));
+    DZO_TRY(use_device(device));
+    if (objective == DZO_OBJ_RIESZ) return riesz_dev_objective(constraint, obj_param, order, n, batch, x, f);
+    DevBuf dx, df;
+    DZO_TRY(h2d(dx, x, (size_t)n * batch)); DZO_TRY(h2d(df, nullptr, (size_t)batch));
+    if (order == DZO_ORDER_SEQUENTIAL) small_objective_kernel<RosenbrockSmall><<<(unsigned)batch, 32>>>(dx.as<double>(), (int)n, df.as<double>());
+    else vec_rosenbrock_objective_kernel<<<(unsigned)batch, 1024>>>(dx.as<double>(), n, df.as<double>());
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    return d2h(f, df, (size_t)batch);
+}
+
+int dzo_dev_gradient(int objective, int constraint, int64_t obj_param, int order, int64_t n, int64_t batch,
+                     const double* x, double* g, int device) {
+    if (!x || !g) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
+    DZO_TRY(order_ok(order, n));
+    DZO_TRY(use_device(device));
+    if (objective == DZO_OBJ_RIESZ) return riesz_dev_gradient(constraint, obj_param, order, n, batch, x, g);
+    DevBuf dx, dg;
+    DZO_TRY(h2d(dx, x, (size_t)n * batch)); DZO_TRY(h2d(dg, nullptr, (size_t)n * batch));
+    if (order == DZO_ORDER_SEQUENTIAL) {
+        small_gradient_kernel<RosenbrockSmall><<<(unsigned)batch, 32>>>(dx.as<double>(), (int)n, dg.as<double>());
+    } else {
+        const long long pairs = (long long)n * batch / 2;
+        vec_rosenbrock_gradient_kernel<<<(unsigned)((pairs + 255) / 256), 256>>>(dx.as<double>(), pairs, dg.as<double>());
+    }
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    return d2h(g, dg, (size_t)n * batch);
+}
+
+// ============================================================================= measurement hooks
+int dzo_bench_kernel(int which, int64_t n, int reps, int variant, float* ms_per_launch, int device) {
+    if (!ms_per_launch || n <= 0 || reps <= 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    (void)variant;
+    DZO_TRY(use_device(device));
+    DevBuf dH, vs, vt, vg, vo;
+    DZO_TRY(h2d(dH, nullptr, (size_t)n * n));
+    DZO_TRY(h2d(vs, nullptr, (size_t)n)); DZO_TRY(h2d(vt, nullptr, (size_t)n)); DZO_TRY(h2d(vg, nullptr, (size_t)n));
+    DZO_TRY(h2d(vo, nullptr, (size_t)n));
+    SweepScratch sc;
+    DZO_TRY(sc.init(n));
+    SweepArgs a = sc.args(dH.as<double>(), n);
+    // H = I and tiny vectors: the sweeps are data-independent, values only need to stay finite
+    identity_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+    DZO_CUDA(cudaMemset(vs.p, 0, (size_t)n * 8)); DZO_CUDA(cudaMemset(vt.p, 0, (size_t)n * 8));
+    DZO_CUDA(cudaMemset(vg.p, 0, (size_t)n * 8));
+    LargeCtrl c;
+    memset(&c, 0, sizeof c);
+    c.kind = DZO_STEP_BFGS; c.delta_norm = 1.0;
+    DZO_CUDA(cudaMemcpy(sc.ctrl.p, &c, sizeof c, cudaMemcpyHostToDevice));
+    a.ctrl = sc.ctrl.as<LargeCtrl>();
+    a.v = vg.as<double>(); a.s = vs.as<double>(); a.t = vt.as<double>(); a.out = vo.as<double>();
+    cudaEvent_t e0, e1;
+    DZO_CUDA(cudaEventCreate(&e0)); DZO_CUDA(cudaEventCreate(&e1));
+    auto launch = [&]() {
+        if (which == DZO_BENCH_GEMV) gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+        else if (which == DZO_BENCH_UPDATE_GEMV) update_gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+        else identity_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+    };
+    for (int i = 0; i < 3; ++i) launch();
+    DZO_CUDA(cudaDeviceSynchronize());
+    DZO_CUDA(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) launch();
+    DZO_CUDA(cudaEventRecord(e1));
+    DZO_CUDA(cudaEventSynchronize(e1));
+    DZO_CUDA(cudaGetLastError());
+    float ms = 0;
+    DZO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_launch = ms / reps;
+    return DZO_OK;
+}
+
+int dzo_set_tuning(const char* key, int value) {
+    if (!key) return fail(DZO_ERR_INVALID_ARGUMENT, "null key");
+    if (!strcmp(key, "sweep_variant")) { g_tuning.sweep_variant = value; return DZO_OK; }
+    return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
+}
+
+}  // extern "C"

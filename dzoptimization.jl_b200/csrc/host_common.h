@@ -1,0 +1,73 @@
+// host_common.h -- host-side plumbing shared by the C-ABI translation units of libdzopt_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dzopt.h"
+
+namespace dzo {
+
+extern thread_local char g_err[512];
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DZO_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return ::dzo::fail(DZO_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,           \
+                               cudaGetErrorString(e__));                                            \
+    } while (0)
+
+#define DZO_TRY(call)                                                                               \
+    do {                                                                                            \
+        int rc__ = (call);                                                                          \
+        if (rc__ != DZO_OK) return rc__;                                                            \
+    } while (0)
+
+// There is no CPU fallback: every entry point that computes goes through this.
+inline int use_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(DZO_ERR_NO_DEVICE, "no CUDA device available (libdzopt_b200 has no CPU fallback): %s",
+                    cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(DZO_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, count);
+    DZO_CUDA(cudaSetDevice(device));
+    return DZO_OK;
+}
+
+int check_problem(int objective, int constraint, int64_t obj_param, int64_t n, int64_t batch);
+
+// process-wide tuning knobs (A/B measurements only; never change results)
+struct Tuning {
+    int sweep_variant = 0;    // 0 = LDG/STG streaming tiles, 1 = TMA-staged tiles
+    int batched_ksteps_max = 1 << 20;
+};
+extern Tuning g_tuning;
+
+// scoped device buffer for the kernel-level entry points
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        if (bytes == 0) bytes = 8;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { p = nullptr; return fail(DZO_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+        return DZO_OK;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace dzo

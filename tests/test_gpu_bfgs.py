@@ -1,0 +1,311 @@
+"""GPU parity tests of the BFGS step! path: CUDA (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): per-iteration iterates, objective values and step sizes within
+1e-12 relative for the first k iterations, converged points within 1e-9.  Because the CUDA
+kernels and the oracle share one summation order and never contract to FMA, the tests assert
+the stronger property: BITWISE equality of every field after every step!.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_bitwise
+
+pytestmark = pytest.mark.gpu
+
+SEQ, TREE = 0, 1
+ROSEN = 1
+
+
+def _x0(orc, count, seed):
+    return 4.0 * orc.pcg_fill(count, seed) - 2.0
+
+
+def _sym(orc, n, seed):
+    """random bitwise-symmetric matrix (the inverse Hessian is always bitwise symmetric)"""
+    a = orc.pcg_fill(n * n, seed).reshape(n, n)
+    return (a + a.T) + n * np.eye(n)
+
+
+# ----------------------------------------------------------------------------- kernel-level rows of SURVEY 8a
+@pytest.mark.parametrize("n", [2, 5, 16, 32])
+def test_dot_sequential(gpu, orc, n):
+    import dev
+    v, w = _x0(orc, n, 11), _x0(orc, n, 12)
+    assert dev.dot(v, w, SEQ) == orc.dot(v, w, orc.SEQ)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4096, 8191, 8192, 16384, 100003])
+def test_dot_tree(gpu, orc, n):
+    import dev
+    v, w = _x0(orc, n, 13), _x0(orc, n, 14)
+    assert dev.dot(v, w, TREE) == orc.dot(v, w, orc.TREE)
+
+
+@pytest.mark.parametrize("n", [2, 7, 16, 32])
+def test_gemv_sequential(gpu, orc, n):
+    import dev
+    H, v = _sym(orc, n, 21), _x0(orc, n, 22)
+    assert_bitwise(dev.gemv(H, v, SEQ), orc.gemv(H, v, orc.SEQ), "gemv seq")
+
+
+@pytest.mark.parametrize("n", [33, 64, 255, 256, 1000, 1024, 1025, 2050, 3073])
+def test_gemv_tree(gpu, orc, n):
+    import dev
+    a = orc.pcg_fill(n * n, 23).reshape(n, n) - 0.5      # NOT symmetric: pins the row/column convention
+    v = _x0(orc, n, 24)
+    assert_bitwise(dev.gemv(a, v, TREE), orc.gemv(a, v, orc.TREE), "gemv tree")
+
+
+@pytest.mark.parametrize("n", [2, 16, 32])
+def test_update_inverse_hessian_sequential(gpu, orc, n):
+    import dev
+    H, d, dg, g = _sym(orc, n, 31), _x0(orc, n, 32), _x0(orc, n, 33), _x0(orc, n, 34)
+    got = dev.update_inverse_hessian(H, -0.37, d, dg, g, SEQ)
+    ref = orc.update_inverse_hessian(H, -0.37, d, dg, g, orc.SEQ)
+    for a, b, what in zip(got, ref, ("H", "step_direction", "scratch", "next_direction")):
+        assert_bitwise(a, b, what)
+
+
+@pytest.mark.parametrize("n,fused", [(34, True), (256, True), (1000, False), (1026, True), (2051, True), (3072, True)])
+def test_update_inverse_hessian_tree(gpu, orc, n, fused):
+    import dev
+    H, d, dg, g = _sym(orc, n, 35), _x0(orc, n, 36), _x0(orc, n, 37), _x0(orc, n, 38)
+    got = dev.update_inverse_hessian(H, -0.37, d, dg, g if fused else None, TREE)
+    ref = orc.update_inverse_hessian(H, -0.37, d, dg, g if fused else None, orc.TREE)
+    for a, b, what in zip(got, ref, ("H", "step_direction", "scratch", "next_direction")):
+        if a is None and b is None:
+            continue
+        assert_bitwise(a, b, what)
+    # the update keeps H bitwise symmetric
+    assert_bitwise(got[0], got[0].T, "symmetry")
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 513, 2048])
+def test_identity(gpu, n):
+    import dev
+    assert_bitwise(dev.identity(n), np.eye(n), "identity")
+
+
+@pytest.mark.parametrize("n,order", [(2, SEQ), (16, SEQ), (32, SEQ), (34, TREE), (2048, TREE), (20000, TREE)])
+def test_rosenbrock_objective_gradient(gpu, orc, n, order):
+    import dev
+    x = _x0(orc, 5 * n, 41).reshape(5, n)
+    assert_bitwise(dev.objective(ROSEN, x, order), orc.objective(ROSEN, x, order), "objective")
+    assert_bitwise(dev.gradient(ROSEN, x, order), orc.gradient(ROSEN, x, order), "gradient")
+
+
+@pytest.mark.parametrize("n,order", [(2, SEQ), (16, SEQ), (64, TREE), (4096, TREE), (16384, TREE)])
+@pytest.mark.parametrize("t1", [1.0, 1e-3, 37.0, 1e-300, 1e300])
+def test_line_search(gpu, orc, n, order, t1):
+    import dev
+    x = _x0(orc, n, 51)
+    g = orc.gradient(ROSEN, x, order)[0]
+    f0 = orc.objective(ROSEN, x, order)[0]
+    got = dev.line_search(ROSEN, x, g, f0, t1, order)
+    ref = orc.line_search(ROSEN, x, g, f0, t1, order)
+    assert got == ref
+
+
+def test_line_search_degenerate(gpu, orc):
+    import dev
+    x = _x0(orc, 16, 52)
+    f0 = orc.objective(ROSEN, x, SEQ)[0]
+    z = np.zeros(16)
+    for order, xx in ((SEQ, x), (TREE, np.tile(x, 4))):
+        ff = orc.objective(ROSEN, xx, order)[0]
+        zz = np.zeros(xx.size)
+        assert dev.line_search(ROSEN, xx, zz, ff, 1.0, order) == (0.0, ff)            # zero direction :71-85
+        assert dev.line_search(ROSEN, xx, xx, ff, float("inf"), order) == (0.0, ff)   # t1 = L/0
+        assert dev.line_search(ROSEN, xx, xx, float("inf"), 1.0, order)[0] == 0.0     # non-finite f0 :64-66
+    assert f0 > 0 and z.sum() == 0
+
+
+# ----------------------------------------------------------------------------- step! traces
+FIELDS = ("point", "gradient", "delta_point", "delta_gradient", "direction", "objective", "step_length")
+
+
+def _compare_state(opt, ref, batched, tag):
+    get = {
+        "point": opt.current_point, "gradient": opt.current_gradient, "delta_point": opt.delta_point,
+        "delta_gradient": opt.delta_gradient, "direction": opt.next_step_direction,
+        "objective": opt.current_objective_value, "step_length": opt.last_step_length,
+    }
+    for name in FIELDS:
+        r = getattr(ref, name)
+        if not batched:
+            r = r[0]
+        assert_bitwise(np.asarray(get[name]), np.asarray(r), f"{tag}: {name}")
+    rt = ref.step_type if batched else ref.step_type[0]
+    ri = ref.iteration_count if batched else ref.iteration_count[0]
+    rz = ref.terminated if batched else ref.terminated[0]
+    assert np.array_equal(np.asarray(opt.last_step_type), np.asarray(rt)), f"{tag}: step type"
+    assert np.array_equal(np.asarray(opt.iteration_count), np.asarray(ri)), f"{tag}: iteration count"
+    assert np.array_equal(np.asarray(opt.has_converged), np.asarray(rz)), f"{tag}: has_converged"
+
+
+def test_readme_rosenbrock_n2(gpu, orc):
+    """config 1: README Rosenbrock n=2 from rand(2) (PCG seeds 0..999), step size 1.0, to has_converged."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = np.stack([orc.pcg_fill(2, s) for s in range(1000)])
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    ref = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ, nthreads=8)
+    _compare_state(opt, ref, True, "ctor")
+    for it in range(12):
+        dz.step_(opt); ref.step(1)
+        _compare_state(opt, ref, True, f"iter {it}")
+    for _ in range(40):
+        opt.step(25); ref.step(25)
+        if opt.count_active() == 0:
+            break
+    _compare_state(opt, ref, True, "converged")
+    assert opt.count_active() == 0 and ref.count_active() == 0
+    assert opt.has_converged.all()
+    assert np.abs(opt.current_point - 1.0).max() < 1e-6          # analytic minimum (1, 1)
+    for p in (0, 17, 999):
+        assert_bitwise(opt.inverse_hessian(p), ref.inverse_hessian(p), "H")
+
+
+@pytest.mark.parametrize("n,batch", [(4, 300), (16, 2000), (30, 70), (32, 129)])
+def test_batched_trace(gpu, orc, n, batch):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n * batch, 2024).reshape(batch, n)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    ref = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ, nthreads=8)
+    assert opt.summation_order == SEQ
+    for it in range(25):
+        dz.step_(opt); ref.step(1)
+        _compare_state(opt, ref, True, f"n={n} iter {it}")
+    opt.step(40); ref.step(40)                                   # k fused steps in ONE launch == 40 step! calls
+    _compare_state(opt, ref, True, f"n={n} after fused steps")
+    for p in (0, batch - 1):
+        assert_bitwise(opt.inverse_hessian(p), ref.inverse_hessian(p), "H")
+        assert_bitwise(opt.inverse_hessian(p), opt.inverse_hessian(p).T, "H symmetric")
+
+
+def test_batched_to_convergence(gpu, orc):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    n, batch = 16, 512
+    x0 = _x0(orc, n * batch, 7).reshape(batch, n)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    ref = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ, nthreads=8)
+    for _ in range(200):
+        opt.step(50); ref.step(50)
+        if opt.count_active() == 0:
+            break
+    assert opt.count_active() == 0 and ref.count_active() == 0
+    _compare_state(opt, ref, True, "converged")
+    # every problem sits at a stationary point; the global minimiser is (1,...,1), f = 0
+    at_global = np.abs(opt.current_point - 1.0).max(axis=1) < 1e-6
+    assert at_global.mean() > 0.5
+    assert (opt.current_objective_value[at_global] < 1e-10).all()
+
+
+@pytest.mark.parametrize("n", [34, 2048, 4098, 16384])
+def test_large_trace(gpu, orc, n):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n, 1)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0)
+    ref = orc.BFGS(ROSEN, x0[None, :], 1.0, order=orc.TREE, nthreads=8)
+    assert opt.summation_order == TREE
+    _compare_state(opt, ref, False, "ctor")
+    steps = 12 if n < 16384 else 6
+    types = []
+    for it in range(steps):
+        dz.step_(opt); ref.step(1)
+        _compare_state(opt, ref, False, f"n={n} iter {it}")
+        types.append(int(opt.last_step_type[()]))
+    assert dz.StepType.BFGSStep in types                         # the n^2 kernels really ran
+    if n <= 4098:
+        H = opt.inverse_hessian()
+        assert_bitwise(H, ref.inverse_hessian(0), "H")
+        assert_bitwise(H, H.T, "H symmetric")
+
+
+def test_large_to_convergence(gpu, orc):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    n = 64
+    x0 = _x0(orc, n, 5)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0)
+    ref = orc.BFGS(ROSEN, x0[None, :], 1.0, order=orc.TREE)
+    for _ in range(100):
+        opt.step(50); ref.step(50)
+        if opt.has_converged[()]:
+            break
+    assert bool(opt.has_converged[()]) and bool(ref.terminated[0])
+    _compare_state(opt, ref, False, "converged")
+    # converged point within 1e-9 of the oracle's (it is bitwise equal) and stationary
+    assert np.abs(opt.current_point - ref.point[0]).max() <= 1e-9
+    assert np.abs(opt.current_gradient).max() < 1e-5
+
+
+def test_set_state_resume(gpu, orc):
+    """save/load in the middle of optimization (README.md:11; legacy/DZOptimization.jl:819-862)."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    for n, batched, batch in ((16, True, 50), (2048, False, 1)):
+        x0 = _x0(orc, n * batch, 9).reshape(batch, n)
+        mk = lambda: dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0 if batched else x0[0], 1.0,
+                                      batched=batched)
+        a = mk()
+        a.step(7)
+        if batched:
+            H = np.stack([a.inverse_hessian(p) for p in range(batch)])
+        else:
+            H = a.inverse_hessian()
+        saved = (a.current_point, H, a.delta_point, a.delta_gradient, a.last_step_length, a.last_step_type,
+                 a.iteration_count)
+        b = mk()
+        b.set_state(*saved)
+        assert_bitwise(b.current_objective_value, a.current_objective_value, "f after resume")
+        assert_bitwise(b.current_gradient, a.current_gradient, "g after resume")
+        assert_bitwise(b.next_step_direction, a.next_step_direction, "d after resume")
+        a.step(5); b.step(5)
+        assert_bitwise(b.current_point, a.current_point, "resumed trajectory")
+        assert np.array_equal(b.iteration_count, a.iteration_count)
+
+
+def test_run_and_test_invariants_full_size(gpu, orc):
+    """run_and_test! (legacy/DZOptimization.jl:998-1049) on the device at a size the CPU oracle is not
+    asked to follow step by step: 200k problems x n=16.  Recomputed f / g equal the stored fields bitwise,
+    delta_point == x_{k+1} - x_k, terminated problems do not move."""
+    import dev
+    dz = gpu
+    EF = dz.ExampleFunctions
+    n, batch = 16, 200_000
+    x0 = _x0(orc, n * batch, 2024).reshape(batch, n)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    prev_x, prev_g = opt.current_point, opt.current_gradient
+    for it in range(3):
+        was_done = opt.has_converged
+        opt.step(1)
+        x, g = opt.current_point, opt.current_gradient
+        moved = opt.iteration_count > it
+        assert_bitwise(dev.objective(ROSEN, x, SEQ), opt.current_objective_value, "f(current_point)")   # :1019-1022
+        assert_bitwise(dev.gradient(ROSEN, x, SEQ), g, "g(current_point)")                              # :1025-1032
+        dx, dg = opt.delta_point, opt.delta_gradient
+        assert_bitwise(dx[moved], (-prev_x[moved]) + x[moved], "delta_point")                           # :1035-1039
+        assert_bitwise(dg[moved], (-prev_g[moved]) + g[moved], "delta_gradient")                        # :1042-1046
+        assert_bitwise(x[was_done], prev_x[was_done], "terminated problems stay put")
+        prev_x, prev_g = x, g
+    # spot-check 4096 problems of this big batch against the oracle
+    sel = np.arange(0, batch, batch // 4096)[:4096]
+    ref = orc.BFGS(ROSEN, x0[sel], 1.0, order=orc.SEQ, nthreads=8)
+    ref.step(3)
+    assert_bitwise(opt.current_point[sel], ref.point, "spot check")
+
+
+def test_errors(gpu):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    with pytest.raises(dz.DZOptError) as e:                      # @assert !isnan(f0)  :773
+        dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, np.array([np.nan, 1.0]), 1.0)
+    assert e.value.code == -3
+    with pytest.raises(dz.DZOptError):
+        dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, np.zeros(3), 1.0)   # odd n
+    with pytest.raises(TypeError):
+        dz.BFGSOptimizer(lambda x: 0.0, EF.rosenbrock_gradient_, np.zeros(2), 1.0)           # host closure
