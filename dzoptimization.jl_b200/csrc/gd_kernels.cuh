@@ -1,0 +1,527 @@
+// gd_kernels.cuh -- GradientDescentOptimizer step! (legacy/DZOptimization.jl:330-374, :393-449)
+// with device objectives, TREE summation order.
+//
+// (1) Riesz energy on the sphere (legacy/ExampleFunctions.jl:30-83; config 5: N = 4096 points,
+//     n = 12288): ONE cooperative persistent kernel (one 1024-thread CTA per SM) runs k whole
+//     step! calls -- the bracketing line search with its data-dependent number of O(N^2) energy
+//     evaluations, the point update, the O(N^2) gradient and the O(n) bookkeeping -- with grid-wide
+//     barriers between phases and no host round trip.  Pair work is cut into (32 rows x 128
+//     sources) warp items; the 128 trial points of a segment are staged once per item in a
+//     per-warp shared-memory buffer and broadcast to the 32 row lanes.
+//       energy   e_j   = sum over segments s (ascending, 128 sources each, only i < j) of the
+//                        sequential segment partial;  f = canonical tree over rows (row j -> virtual
+//                        thread j mod 4096)                                     [oracle riesz_energy_tree]
+//       gradient G_j   = sum over segments (ascending) of sequential partials skipping i == j,
+//                        then the tangent projection g_j -= (p_j . g_j) p_j      [oracle gradient_]
+// (2) extended Rosenbrock at any n > 32: one 1024-thread CTA does the whole step!.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "large_bfgs.cuh"
+
+namespace dzo {
+namespace cg = cooperative_groups;
+
+struct GdCtrl {
+    double f;        // current_objective_value   legacy/DZOptimization.jl:312
+    double df;       // delta_objective_value     :313
+    double L;        // last_step_length          :321
+    long long iter;  // iteration_count           :324
+    int term;        // has_terminated            :325
+    int pad;
+    long long evals;
+};
+
+struct RieszGdArgs {
+    double *x, *g, *d, *dx, *dg;  // dim x N column-major (point j contiguous)
+    double *segE;                 // [nseg][N]       energy segment partials
+    double *rowE;                 // [N]             row energies
+    double *segG;                 // [nseg][N][DIM]  gradient segment partials
+    const int2* e_items;          // (row block, segment) items of the strict lower triangle
+    int n_e_items;
+    GdCtrl* ctrl;
+    unsigned* counter;            // last-CTA-done counter (zero between uses)
+    double* fbox;                 // broadcast slot for the reduced energy
+    int N, sphere, max_increases, ksteps;
+    double initial_step_length;
+    int mode;                     // 0 = k step! calls, 1 = constructor, 2 = one energy evaluation of x,
+                                  // 3 = one gradient of x (kernel-level entries), 4 = one line search
+    double ls_f0, ls_t1, ls_sign; // mode 4 inputs; result in fbox[1], fbox[2]
+};
+
+constexpr int kRieszSegWarps = 32;   // warps per CTA, each with a private staging buffer
+
+template <int DIM>
+struct RieszDev {
+    // trial point of point j: w = x_j + alpha*d_j, then constraint_function! (normalise) [pmode 0];
+    // pmode 2: the stored point itself (already constrained).
+    static DZO_DEVINL void trial_point(const RieszGdArgs& a, const double* dir, int j, double alpha, int pmode,
+                                       double (&w)[DIM]) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) w[k] = a.x[(long long)j * DIM + k];
+        if (pmode == 2) return;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) w[k] = w[k] + alpha * dir[(long long)j * DIM + k];   // legacy/Kernels.jl:127-135
+        if (a.sphere) {                                                                    // [GLUE] SURVEY 8.0
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) s += w[k] * w[k];
+            const double inv = 1.0 / sqrt(s);
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) w[k] *= inv;
+        }
+    }
+
+    // ---- riesz_energy (legacy/ExampleFunctions.jl:30-45), phase 1: segment partials
+    static DZO_DEVINL void energy_segments(const RieszGdArgs& a, const double* dir, double alpha, int pmode, double* wsm) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
+        for (int idx = blockIdx.x + gridDim.x * warp; idx < a.n_e_items; idx += gridDim.x * kRieszSegWarps) {
+            const int2 it = a.e_items[idx];
+            const int i0 = it.y * DZO_RIESZ_SEG;
+            const int cnt = min(DZO_RIESZ_SEG, a.N - i0);
+            __syncwarp();
+            for (int q = lane; q < cnt; q += 32) {
+                double w[DIM];
+                trial_point(a, dir, i0 + q, alpha, pmode, w);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) buf[q * DIM + k] = w[k];
+            }
+            __syncwarp();
+            const int j = it.x * 32 + lane;
+            if (j < a.N) {
+                const int lim = min(cnt, j - i0);   // sources i < j inside this segment
+                if (lim > 0) {
+                    double wj[DIM];
+                    trial_point(a, dir, j, alpha, pmode, wj);
+                    double seg = 0.0;
+                    for (int i = 0; i < lim; ++i) {
+                        double dist_sq = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) {
+                            const double dist = buf[i * DIM + k] - wj[k];     // points[k,i] - points[k,j]  :37
+                            dist_sq += dist * dist;
+                        }
+                        seg += 1.0 / sqrt(dist_sq);                            // rsqrt(dist_sq)  :41
+                    }
+                    a.segE[(long long)it.y * a.N + j] = seg;
+                }
+            }
+        }
+    }
+
+    // phase 2: rows, then (last CTA to arrive) the canonical tree.  Returns after the grid barrier
+    // with the energy, identical on every thread of the grid.
+    static DZO_DEVINL double energy_finish(const RieszGdArgs& a, cg::grid_group& grid, double* sm) {
+        __shared__ int s_last;
+        for (int j = blockIdx.x * 1024 + threadIdx.x; j < a.N; j += gridDim.x * 1024) {
+            double ej = 0.0;
+            for (int s0 = 0; s0 < j; s0 += DZO_RIESZ_SEG) {
+                const double seg = __ldcg(&a.segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
+                ej = (s0 == 0) ? seg : ej + seg;
+            }
+            a.rowE[j] = ej;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double p[1][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double acc = 0.0;
+                for (int j = threadIdx.x + 1024 * q; j < a.N; j += DZO_TREE_WIDTH) acc += __ldcg(&a.rowE[j]);
+                p[0][q] = acc;
+            }
+            double out[1];
+            cta1024_tree_reduce<1>(p, sm, out);
+            if (threadIdx.x == 0) {
+                a.fbox[0] = out[0];
+                *a.counter = 0;
+                __threadfence();
+            }
+        }
+        grid.sync();
+        return __ldcg(&a.fbox[0]);
+    }
+
+    static DZO_DEVINL double energy(const RieszGdArgs& a, cg::grid_group& grid, const double* dir, double alpha, int pmode,
+                                    double* wsm, double* sm) {
+        energy_segments(a, dir, alpha, pmode, wsm);
+        grid.sync();
+        return energy_finish(a, grid, sm);
+    }
+
+    // ---- riesz_gradient! (:47-83) at the stored points + tangent projection (:361-374)
+    static DZO_DEVINL void gradient_segments(const RieszGdArgs& a, double* wsm) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
+        const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
+        const int nrb = (a.N + 31) / 32;
+        for (int idx = blockIdx.x + gridDim.x * warp; idx < nrb * nseg; idx += gridDim.x * kRieszSegWarps) {
+            const int rb = idx / nseg, s = idx - rb * nseg;
+            const int i0 = s * DZO_RIESZ_SEG;
+            const int cnt = min(DZO_RIESZ_SEG, a.N - i0);
+            __syncwarp();
+            for (int q = lane; q < cnt; q += 32)
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) buf[q * DIM + k] = a.x[(long long)(i0 + q) * DIM + k];
+            __syncwarp();
+            const int j = rb * 32 + lane;
+            if (j < a.N) {
+                double xj[DIM], part[DIM];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) { xj[k] = a.x[(long long)j * DIM + k]; part[k] = 0.0; }
+                for (int i = 0; i < cnt; ++i) {
+                    if (i0 + i == j) continue;                                 // :55, :69 (i != j)
+                    double dist_sq = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) {
+                        const double dist = buf[i * DIM + k] - xj[k];
+                        dist_sq += dist * dist;
+                    }
+                    const double inv_dist = 1.0 / sqrt(dist_sq);               // :61
+                    const double inv_dist_cubed = inv_dist / dist_sq;          // :62
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) {
+                        const double dist = buf[i * DIM + k] - xj[k];
+                        part[k] += dist * inv_dist_cubed;                      // :65
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) a.segG[((long long)s * a.N + j) * DIM + k] = part[k];
+            }
+        }
+    }
+    // rows: combine, project, write g (and dg = g_new - g_old when with_delta)
+    static DZO_DEVINL void gradient_rows(const RieszGdArgs& a, bool with_delta) {
+        const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
+        for (int j = blockIdx.x * 1024 + threadIdx.x; j < a.N; j += gridDim.x * 1024) {
+            double acc[DIM], xj[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                acc[k] = __ldcg(&a.segG[((long long)0 * a.N + j) * DIM + k]);
+                xj[k] = a.x[(long long)j * DIM + k];
+            }
+            for (int s = 1; s < nseg; ++s)
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) acc[k] += __ldcg(&a.segG[((long long)s * a.N + j) * DIM + k]);
+            if (a.sphere) {
+                double overlap = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) overlap += xj[k] * acc[k];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) acc[k] -= overlap * xj[k];
+            }
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const long long e = (long long)j * DIM + k;
+                if (with_delta) a.dg[e] = acc[k] - a.g[e];                     // :433-435
+                a.g[e] = acc[k];
+            }
+        }
+    }
+
+    // every CTA scans all points (N/1024 per thread): cheap, avoids a grid barrier
+    static DZO_DEVINL bool all_points(const RieszGdArgs& a, const double* dir, double alpha, double alpha_ref, int what) {
+        int bad = 0;
+        for (int j = threadIdx.x; j < a.N; j += 1024) {
+            if (what == 0) {            // step_is_zero: all(dir == 0)  :71-85
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) bad |= !(dir[(long long)j * DIM + k] == 0.0);
+            } else if (what == 1) {     // !point_changed: all(x == x + alpha*dir) before the constraint  :73-80
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) {
+                    const double xx = a.x[(long long)j * DIM + k];
+                    bad |= (xx != xx + alpha * dir[(long long)j * DIM + k]);
+                }
+            } else if (what == 2) {     // new_point == initial_point after the constraint  :119
+                double w[DIM];
+                trial_point(a, dir, j, alpha, 0, w);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) bad |= !(a.x[(long long)j * DIM + k] == w[k]);
+            } else {                    // new_point == reference_point  :150
+                double w[DIM], r[DIM];
+                trial_point(a, dir, j, alpha, 0, w);
+                trial_point(a, dir, j, alpha_ref, 0, r);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) bad |= !(w[k] == r[k]);
+            }
+        }
+        return __syncthreads_or(bad) == 0;
+    }
+
+    // QuadraticLineSearch (:191-216) over find_three_point_bracket (:49-172), first trial step t1
+    static DZO_DEVINL void line_search(const RieszGdArgs& a, cg::grid_group& grid, const double* dir, double f0, double t1,
+                                       double sign, double* wsm, double* sm, double& t_best, double& f_best,
+                                       long long& evals) {
+        double x1 = 0.0, f1 = f0, x2 = 0.0, f2 = f0;
+        do {
+            if (!isfinite(f0)) break;                                          // :64-66
+            if (!isfinite(t1) || t1 == 0.0) break;                             // [GLUE]
+            if (all_points(a, dir, 0.0, 0.0, 0)) break;                        // :71-85
+            double step = t1;
+            bool small = false;
+            bool unchanged = all_points(a, dir, sign * step, 0.0, 1);
+            int cap = DZO_LINESEARCH_CAP;
+            bool capped = false;
+            while (unchanged) {                                                // :91-101
+                step += step;
+                small = true;
+                unchanged = all_points(a, dir, sign * step, 0.0, 1);
+                if (--cap == 0) { capped = true; break; }
+            }
+            if (capped) break;
+            if (small && all_points(a, dir, sign * step, 0.0, 2)) break;       // :107-123
+            double fa = energy(a, grid, dir, sign * step, 0, wsm, sm);         // :126
+            ++evals;
+            if (fa <= f0) {                                                    // :130
+                int num_increases = 0;
+                cap = DZO_LINESEARCH_CAP;
+                for (;;) {                                                     // :143-156
+                    const double ds = step + step;
+                    num_increases += 1;
+                    const double fb = energy(a, grid, dir, sign * ds, 0, wsm, sm);
+                    ++evals;
+                    --cap;
+                    if (((a.max_increases > 0) && (num_increases >= a.max_increases)) || !isfinite(fb) || fb > fa ||
+                        all_points(a, dir, sign * ds, sign * step, 3) || cap == 0) {
+                        x1 = step; f1 = fa; x2 = ds; f2 = fb;
+                        break;
+                    }
+                    step = ds;
+                    fa = fb;
+                }
+            } else {                                                           // :157-171
+                cap = DZO_LINESEARCH_CAP;
+                for (;;) {
+                    const double hs = 0.5 * step;
+                    const double fb = energy(a, grid, dir, sign * hs, 0, wsm, sm);
+                    ++evals;
+                    --cap;
+                    if (fb <= f0 || cap == 0) {
+                        x1 = hs; f1 = fb; x2 = step; f2 = fa;
+                        break;
+                    }
+                    step = hs;
+                    fa = fb;
+                }
+            }
+        } while (0);
+        double xb = 0.0, fb = f0;                                              // :196-202
+        if (f1 < fb) { xb = x1; fb = f1; }
+        if (f2 < fb) { xb = x2; fb = f2; }
+        const double delta_1 = f0 - f1;                                        // :203-205
+        const double delta_2 = f2 - f1;
+        const double sum_deltas = delta_1 + delta_2;
+        if (delta_1 >= 0.0 && delta_2 >= 0.0 && sum_deltas > 0.0) {            // :206-214
+            const double twice_delta_1 = delta_1 + delta_1;
+            const double delta_ratio = (twice_delta_1 + sum_deltas) / (sum_deltas + sum_deltas);
+            const double xq = delta_ratio * x1;
+            const double fq = energy(a, grid, dir, sign * xq, 0, wsm, sm);
+            ++evals;
+            if (fq < fb) { xb = xq; fb = fq; }
+        }
+        t_best = xb;
+        f_best = fb;
+    }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);          // 132 doubles: tree reduction scratch
+    double* wsm = sm + 136;                                    // 32 warps x 128 x DIM staging
+    cg::grid_group grid = cg::this_grid();
+    using R = RieszDev<DIM>;
+    const long long n = (long long)a.N * DIM;
+    const long long gtid = (long long)blockIdx.x * 1024 + threadIdx.x, gsize = (long long)gridDim.x * 1024;
+    const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
+
+    if (a.mode == 2) {                                          // dzo_dev_objective: f(x) as given
+        const double f = R::energy(a, grid, a.x, 0.0, 2, wsm, sm);
+        if (leader) a.fbox[1] = f;
+        return;
+    }
+    if (a.mode == 3) {                                          // dzo_dev_gradient
+        R::gradient_segments(a, wsm);
+        grid.sync();
+        R::gradient_rows(a, false);
+        return;
+    }
+    if (a.mode == 4) {                                          // dzo_dev_line_search
+        double tb, fb;
+        long long ev = 0;
+        R::line_search(a, grid, a.d, a.ls_f0, a.ls_t1, a.ls_sign, wsm, sm, tb, fb, ev);
+        if (leader) { a.fbox[1] = tb; a.fbox[2] = fb; }
+        return;
+    }
+    if (a.mode == 1) {
+        // GradientDescentOptimizer(...)  legacy/DZOptimization.jl:330-374
+        if (a.sphere)
+            for (int j = (int)gtid; j < a.N; j += (int)gsize) {                // :340 constraint_function!(x)
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) s += a.x[(long long)j * DIM + k] * a.x[(long long)j * DIM + k];
+                const double inv = 1.0 / sqrt(s);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) a.x[(long long)j * DIM + k] *= inv;
+            }
+        for (long long e = gtid; e < n; e += gsize) { a.dx[e] = 0.0; a.dg[e] = 0.0; a.d[e] = 0.0; }
+        grid.sync();
+        const double f0 = R::energy(a, grid, a.x, 0.0, 2, wsm, sm);            // :343
+        R::gradient_segments(a, wsm);                                          // :347-348
+        grid.sync();
+        R::gradient_rows(a, false);
+        grid.sync();
+        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :352
+        if (isfinite(inv_gradient_norm)) {                                     // :354-357
+            const double alpha = -a.initial_step_length * inv_gradient_norm;
+            for (long long e = gtid; e < n; e += gsize) a.d[e] = a.g[e] * alpha;
+        }
+        if (leader) {
+            GdCtrl c;
+            c.f = f0; c.df = 0.0; c.L = 0.0; c.iter = 0; c.pad = 0; c.evals = 1;
+            c.term = (!isfinite(f0)) || (!isfinite(inv_gradient_norm));        // :364-366
+            *a.ctrl = c;
+        }
+        return;
+    }
+
+    // ---- k step! calls  (:393-449)
+    for (int s = 0; s < a.ksteps; ++s) {
+        grid.sync();                                   // ctrl, x, d, g of the previous step are complete
+        const int term = __ldcg(&a.ctrl->term);
+        if (term) break;                                                       // :402
+        const double f0 = __ldcg(&a.ctrl->f);
+        const long long iter = __ldcg(&a.ctrl->iter);
+        long long evals = 0;
+        double step_size, objective_value;
+        R::line_search(a, grid, a.d, f0, 1.0, 1.0, wsm, sm, step_size, objective_value, evals);   // :405-407
+        if (step_size == 0.0 || !(objective_value < f0)) {                     // :410-414
+            if (leader) a.ctrl->term = 1;
+            continue;                                   // next iteration's barrier publishes the flag
+        }
+        for (int j = (int)gtid; j < a.N; j += (int)gsize) {                    // :418-423
+            double w[DIM];
+            R::trial_point(a, a.d, j, step_size, 0, w);                        // x += step*d ; constraint!(x)
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const long long e = (long long)j * DIM + k;
+                a.dx[e] = w[k] - a.x[e];                                       // delta!(dx, x_new, x_old)
+            }
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) a.x[(long long)j * DIM + k] = w[k];
+        }
+        grid.sync();
+        R::gradient_segments(a, wsm);                                          // :434
+        grid.sync();
+        R::gradient_rows(a, true);                                             // :433-435
+        grid.sync();
+        const double step_length = sqrt(cta_tree_dot(a.dx, a.dx, n, sm));      // :424
+        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :438
+        const bool ok = isfinite(inv_gradient_norm);
+        if (ok) {
+            const double alpha = -step_length * inv_gradient_norm;             // :445-446
+            for (long long e = gtid; e < n; e += gsize) a.d[e] = alpha * a.g[e];
+        }
+        if (leader) {
+            a.ctrl->iter = iter + 1;                                           // :415
+            a.ctrl->L = step_length;                                           // :425
+            a.ctrl->df = objective_value - f0;                                 // :428-429
+            a.ctrl->f = objective_value;                                       // :430
+            a.ctrl->evals += evals;
+            if (!ok) a.ctrl->term = 1;                                         // :439-442
+        }
+    }
+}
+
+inline size_t riesz_gd_smem(int dim) { return sizeof(double) * (136 + (size_t)kRieszSegWarps * DZO_RIESZ_SEG * dim); }
+
+// ============================================================================= Rosenbrock GD, one CTA
+struct VecGdArgs {
+    double *x, *g, *d, *dx, *dg;
+    GdCtrl* ctrl;
+    long long n;
+    int max_increases, ksteps;
+    double initial_step_length;
+    int mode;  // 0 = steps, 1 = constructor
+};
+
+__global__ void __launch_bounds__(1024, 1) vec_gd_kernel(VecGdArgs a) {
+    __shared__ double sm[132];
+    const long long n = a.n, m = n >> 1;
+    if (a.mode == 1) {                                                         // :330-374
+        ProbeFlags fl;
+        const double f0 = cta_probe_rosenbrock<2>(a.x, a.x, m, 0.0, 0.0, sm, fl);   // :343
+        for (long long k = threadIdx.x; k < m; k += 1024) {
+            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+            reinterpret_cast<double2*>(a.g)[k] = RosenbrockVec::grad(xx.x, xx.y);    // :347-348
+            reinterpret_cast<double2*>(a.dx)[k] = make_double2(0.0, 0.0);
+            reinterpret_cast<double2*>(a.dg)[k] = make_double2(0.0, 0.0);
+            reinterpret_cast<double2*>(a.d)[k] = make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));  // :352
+        if (isfinite(inv_gradient_norm)) {
+            const double alpha = -a.initial_step_length * inv_gradient_norm;
+            for (long long e = threadIdx.x; e < n; e += 1024) a.d[e] = a.g[e] * alpha;
+        }
+        if (threadIdx.x == 0) {
+            GdCtrl c;
+            c.f = f0; c.df = 0.0; c.L = 0.0; c.iter = 0; c.pad = 0; c.evals = 1;
+            c.term = (!isfinite(f0)) || (!isfinite(inv_gradient_norm));
+            *a.ctrl = c;
+        }
+        return;
+    }
+    __shared__ GdCtrl sc;
+    if (threadIdx.x == 0) sc = *a.ctrl;
+    __syncthreads();
+    for (int s = 0; s < a.ksteps; ++s) {
+        if (sc.term) break;                                                    // :402
+        const double f0 = sc.f;
+        long long evals = 0;
+        double step_size, objective_value;
+        cta_line_search_rosenbrock(a.x, a.d, n, f0, 1.0, 1.0, a.max_increases, sm, step_size, objective_value, evals);
+        __syncthreads();
+        if (step_size == 0.0 || !(objective_value < f0)) {                     // :410-414
+            if (threadIdx.x == 0) sc.term = 1;
+            __syncthreads();
+            break;
+        }
+        for (long long k = threadIdx.x; k < m; k += 1024) {                    // each thread owns its pairs
+            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+            const double2 dd = reinterpret_cast<const double2*>(a.d)[k];
+            const double2 go = reinterpret_cast<const double2*>(a.g)[k];
+            double2 xn;
+            xn.x = xx.x + step_size * dd.x;                                    // :419
+            xn.y = xx.y + step_size * dd.y;
+            const double2 gn = RosenbrockVec::grad(xn.x, xn.y);                // :434
+            reinterpret_cast<double2*>(a.dx)[k] = make_double2(xn.x - xx.x, xn.y - xx.y);   // :423
+            reinterpret_cast<double2*>(a.dg)[k] = make_double2(gn.x - go.x, gn.y - go.y);   // :435
+            reinterpret_cast<double2*>(a.x)[k] = xn;
+            reinterpret_cast<double2*>(a.g)[k] = gn;
+        }
+        __syncthreads();
+        const double step_length = sqrt(cta_tree_dot(a.dx, a.dx, n, sm));      // :424
+        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :438
+        const bool ok = isfinite(inv_gradient_norm);
+        if (ok) {
+            const double alpha = -step_length * inv_gradient_norm;             // :445-446
+            for (long long e = threadIdx.x; e < n; e += 1024) a.d[e] = alpha * a.g[e];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sc.iter += 1; sc.L = step_length; sc.df = objective_value - f0; sc.f = objective_value;
+            sc.evals += evals;
+            if (!ok) sc.term = 1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *a.ctrl = sc;
+}
+
+}  // namespace dzo
