@@ -173,7 +173,7 @@ DZO_DEVINL void group_line_search(Group<LPP>& G, double x, double dir, double f0
 // ----------------------------------------------------------------------------- constructor kernel
 // BFGSOptimizer(f, g!, x0, L0)  legacy/DZOptimization.jl:762-810.  x already holds copy(x0).
 template <int LPP, class Obj>
-__global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_init_kernel(BatchedArgs A, double initial_step_length) {
+static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_init_kernel(BatchedArgs A, double initial_step_length) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PPC = kBatchedThreads / LPP;
     double* bc_all = reinterpret_cast<double*>(smem_raw);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_init_kernel(Batc
 
 // ----------------------------------------------------------------------------- step! kernel
 template <int LPP, class Obj>
-__global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kernel(BatchedArgs A) {
+static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kernel(BatchedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PPC = kBatchedThreads / LPP;
     const int n = A.n;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kernel(Batc
 // State-rebuilding constructor legacy/DZOptimization.jl:819-862: x, H, dx, dg, L, type, iter were
 // copied in by the host; recompute f (:828), g (:830-831), d = H*g (:833-836), clear the flag (:849).
 template <int LPP, class Obj>
-__global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_restore_kernel(BatchedArgs A) {
+static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_restore_kernel(BatchedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PPC = kBatchedThreads / LPP;
     double* bc_all = reinterpret_cast<double*>(smem_raw);
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_restore_kernel(B
 }
 
 // number of problems with has_terminated == false
-__global__ void count_active_kernel(const unsigned char* term, long long batch, unsigned long long* out) {
+static __global__ void count_active_kernel(const unsigned char* term, long long batch, unsigned long long* out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int v = (i < batch) ? (term[i] == 0) : 0;
     v = __reduce_add_sync(0xffffffffu, v);

@@ -1,29 +1,334 @@
-// dzopt_gd.cu -- placeholder translation unit (filled in by the GradientDescent / Riesz work)
+// dzopt_gd.cu -- C ABI of the GradientDescentOptimizer path (legacy/DZOptimization.jl:305-449) and the
+// Riesz-energy device objectives (legacy/ExampleFunctions.jl:30-83).  sm_100a only; -fmad=false.
+#include <new>
+#include <vector>
+
+#include "gd_kernels.cuh"
 #include "host_common.h"
+
 using namespace dzo;
-namespace dzo {
-int riesz_dev_objective(int, int64_t, int, int64_t, int64_t, const double*, double*) { return fail(DZO_ERR_UNSUPPORTED, "riesz: not built yet"); }
-int riesz_dev_gradient(int, int64_t, int, int64_t, int64_t, const double*, double*) { return fail(DZO_ERR_UNSUPPORTED, "riesz: not built yet"); }
-int riesz_dev_line_search(int, int64_t, int, int64_t, const double*, const double*, double, double, double*, double*) { return fail(DZO_ERR_UNSUPPORTED, "riesz: not built yet"); }
+
+// ============================================================================= handle
+struct dzo_gd {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int objective = 0, constraint = 0, max_increases = 0;
+    int64_t dim = 0, n = 0, batch = 0;
+    double *x = nullptr, *g = nullptr, *d = nullptr, *dx = nullptr, *dg = nullptr;
+    GdCtrl* ctrl = nullptr;
+    // Riesz cooperative kernel
+    double *segE = nullptr, *rowE = nullptr, *segG = nullptr, *fbox = nullptr;
+    int2* e_items = nullptr;
+    int n_e_items = 0;
+    unsigned* counter = nullptr;
+    int grid = 0;
+};
+
+static void free_gd(dzo_gd* o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    delete o;
 }
-struct dzo_gd { int dummy; };
-#define STUB return fail(DZO_ERR_UNSUPPORTED, "dzo_gd_*: not built yet")
+
+template <class T>
+static int dmalloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return fail(DZO_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    return DZO_OK;
+}
+
+// (row block of 32 rows, segment of 128 sources) items that contain at least one pair i < j,
+// heaviest first so the round-robin over warps stays balanced
+static std::vector<int2> energy_items(int N) {
+    std::vector<int2> full, diag;
+    const int nrb = (N + 31) / 32;
+    for (int rb = 0; rb < nrb; ++rb) {
+        const int jmax = std::min(N, rb * 32 + 32) - 1;
+        for (int s = 0; s * DZO_RIESZ_SEG < jmax; ++s) {
+            const bool whole = (s + 1) * DZO_RIESZ_SEG <= rb * 32;
+            (whole ? full : diag).push_back(make_int2(rb, s));
+        }
+    }
+    full.insert(full.end(), diag.begin(), diag.end());
+    return full;
+}
+
+static void* riesz_kernel_for(int dim) {
+    switch (dim) {
+        case 1: return (void*)riesz_gd_kernel<1>;
+        case 2: return (void*)riesz_gd_kernel<2>;
+        case 3: return (void*)riesz_gd_kernel<3>;
+        case 4: return (void*)riesz_gd_kernel<4>;
+        default: return nullptr;
+    }
+}
+
+// Everything the cooperative Riesz kernel needs besides the vectors
+struct RieszWork {
+    double *segE = nullptr, *rowE = nullptr, *segG = nullptr, *fbox = nullptr;
+    int2* e_items = nullptr;
+    int n_e_items = 0;
+    unsigned* counter = nullptr;
+    int grid = 0;
+    void* kernel = nullptr;
+    size_t smem = 0;
+    int init(int N, int dim, int device) {
+        kernel = riesz_kernel_for(dim);
+        if (!kernel) return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
+        const int nseg = (N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
+        DZO_TRY(dmalloc(&segE, (size_t)nseg * N));
+        DZO_TRY(dmalloc(&rowE, (size_t)N));
+        DZO_TRY(dmalloc(&segG, (size_t)nseg * N * dim));
+        DZO_TRY(dmalloc(&fbox, 4));
+        DZO_TRY(dmalloc(&counter, 1));
+        DZO_CUDA(cudaMemset(counter, 0, sizeof(unsigned)));
+        std::vector<int2> items = energy_items(N);
+        n_e_items = (int)items.size();
+        DZO_TRY(dmalloc(&e_items, items.size()));
+        if (!items.empty())
+            DZO_CUDA(cudaMemcpy(e_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        smem = riesz_gd_smem(dim);
+        DZO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaDeviceProp prop;
+        DZO_CUDA(cudaGetDeviceProperties(&prop, device));
+        int per_sm = 0;
+        DZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 1024, smem));
+        if (per_sm < 1) return fail(DZO_ERR_CUDA, "riesz_gd_kernel does not fit on an SM");
+        if (!prop.cooperativeLaunch) return fail(DZO_ERR_UNSUPPORTED, "device lacks cooperative launch");
+        grid = prop.multiProcessorCount;   // one persistent CTA per SM
+        return DZO_OK;
+    }
+    void release() {
+        void* ptrs[] = {segE, rowE, segG, fbox, e_items, counter};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+        segE = rowE = segG = fbox = nullptr; e_items = nullptr; counter = nullptr;
+    }
+    void fill(RieszGdArgs& a) const {
+        a.segE = segE; a.rowE = rowE; a.segG = segG; a.e_items = e_items; a.n_e_items = n_e_items;
+        a.counter = counter; a.fbox = fbox;
+    }
+    int launch(RieszGdArgs& a, cudaStream_t stream) const {
+        void* params[] = {&a};
+        DZO_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(1024), params, smem, stream));
+        return DZO_OK;
+    }
+};
+
+static RieszGdArgs riesz_args(const dzo_gd* o, int mode, int k) {
+    RieszGdArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg;
+    a.segE = o->segE; a.rowE = o->rowE; a.segG = o->segG; a.e_items = o->e_items; a.n_e_items = o->n_e_items;
+    a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox;
+    a.N = (int)(o->n / o->dim); a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.max_increases = o->max_increases;
+    a.ksteps = k; a.mode = mode;
+    return a;
+}
+
+static int gd_launch(dzo_gd* o, int mode, int k, double L0) {
+    if (o->objective == DZO_OBJ_RIESZ) {
+        RieszGdArgs a = riesz_args(o, mode, k);
+        a.initial_step_length = L0;
+        void* params[] = {&a};
+        DZO_CUDA(cudaLaunchCooperativeKernel(riesz_kernel_for((int)o->dim), dim3(o->grid), dim3(1024), params,
+                                             riesz_gd_smem((int)o->dim), o->stream));
+        return DZO_OK;
+    }
+    VecGdArgs a;
+    a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg; a.ctrl = o->ctrl; a.n = o->n;
+    a.max_increases = o->max_increases; a.ksteps = k; a.initial_step_length = L0; a.mode = mode;
+    vec_gd_kernel<<<1, 1024, 0, o->stream>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+
 extern "C" {
-int dzo_gd_create(dzo_gd**, int, int, int64_t, int64_t, int64_t, const double*, double, int, int) { STUB; }
-int dzo_gd_set_stream(dzo_gd*, void*) { STUB; }
-int dzo_gd_step(dzo_gd*, int) { STUB; }
-int dzo_gd_step_async(dzo_gd*, int) { STUB; }
-int dzo_gd_sync(dzo_gd*) { STUB; }
-int dzo_gd_get_point(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_delta_point(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_gradient(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_delta_gradient(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_direction(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_objective(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_delta_objective(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_step_length(dzo_gd*, double*) { STUB; }
-int dzo_gd_get_iteration_count(dzo_gd*, int64_t*) { STUB; }
-int dzo_gd_get_terminated(dzo_gd*, uint8_t*) { STUB; }
-int dzo_gd_info(dzo_gd*, int64_t*, int64_t*, int*) { STUB; }
-void dzo_gd_destroy(dzo_gd*) {}
+
+int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param, int64_t n, int64_t batch,
+                  const double* x0, double initial_step_length, int max_increases, int device) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = nullptr;
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
+    if (batch != 1) return fail(DZO_ERR_UNSUPPORTED, "GradientDescentOptimizer on the device runs one problem per handle");
+    if (objective == DZO_OBJ_RIESZ && (obj_param < 1 || obj_param > 4))
+        return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
+    if (n / (objective == DZO_OBJ_RIESZ ? obj_param : 1) > (1 << 30)) return fail(DZO_ERR_INVALID_ARGUMENT, "n too large");
+    DZO_TRY(use_device(device));
+    dzo_gd* o = new (std::nothrow) dzo_gd();
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->device = device; o->objective = objective; o->constraint = constraint; o->max_increases = max_increases;
+    o->dim = obj_param; o->n = n; o->batch = batch;
+    int rc = DZO_OK;
+    auto bail = [&](int code) { free_gd(o); return code; };
+    if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "cudaStreamCreate failed"));
+    o->stream = o->own_stream;
+    if ((rc = dmalloc(&o->x, (size_t)n)) || (rc = dmalloc(&o->g, (size_t)n)) || (rc = dmalloc(&o->d, (size_t)n)) ||
+        (rc = dmalloc(&o->dx, (size_t)n)) || (rc = dmalloc(&o->dg, (size_t)n)) || (rc = dmalloc(&o->ctrl, 1)))
+        return bail(rc);
+    if (objective == DZO_OBJ_RIESZ) {
+        RieszWork w;
+        if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
+        o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
+        o->n_e_items = w.n_e_items; o->counter = w.counter; o->grid = w.grid;
+    }
+    if (cudaMemcpyAsync(o->x, x0, (size_t)n * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)   // :339 collect
+        return bail(fail(DZO_ERR_CUDA, "H2D copy of x0 failed"));
+    if ((rc = gd_launch(o, 1, 0, initial_step_length))) return bail(rc);
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "constructor kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = o;
+    return DZO_OK;
 }
+
+void dzo_gd_destroy(dzo_gd* o) { free_gd(o); }
+
+int dzo_gd_set_stream(dzo_gd* o, void* cuda_stream) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    o->stream = cuda_stream ? (cudaStream_t)cuda_stream : o->own_stream;
+    return DZO_OK;
+}
+
+int dzo_gd_step_async(dzo_gd* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(use_device(o->device));
+    if (k == 0) return DZO_OK;
+    return gd_launch(o, 0, k, 0.0);
+}
+int dzo_gd_sync(dzo_gd* o) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+int dzo_gd_step(dzo_gd* o, int k) {
+    DZO_TRY(dzo_gd_step_async(o, k));
+    return dzo_gd_sync(o);
+}
+
+static int gd_read(dzo_gd* o, void* dst, const void* src, size_t bytes) {
+    if (!o || !dst) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+#define DZO_GD_VEC(name, field)                                                   \
+    int name(dzo_gd* o, double* out) {                                            \
+        if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");             \
+        return gd_read(o, out, o->field, (size_t)o->n * 8);                       \
+    }
+DZO_GD_VEC(dzo_gd_get_point, x)
+DZO_GD_VEC(dzo_gd_get_delta_point, dx)
+DZO_GD_VEC(dzo_gd_get_gradient, g)
+DZO_GD_VEC(dzo_gd_get_delta_gradient, dg)
+DZO_GD_VEC(dzo_gd_get_direction, d)
+#undef DZO_GD_VEC
+#define DZO_GD_SCALAR(name, type, expr)                                           \
+    int name(dzo_gd* o, type* out) {                                              \
+        if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");    \
+        GdCtrl c;                                                                 \
+        DZO_TRY(gd_read(o, &c, o->ctrl, sizeof c));                               \
+        *out = (type)(expr);                                                      \
+        return DZO_OK;                                                            \
+    }
+DZO_GD_SCALAR(dzo_gd_get_objective, double, c.f)
+DZO_GD_SCALAR(dzo_gd_get_delta_objective, double, c.df)
+DZO_GD_SCALAR(dzo_gd_get_step_length, double, c.L)
+DZO_GD_SCALAR(dzo_gd_get_iteration_count, int64_t, c.iter)
+DZO_GD_SCALAR(dzo_gd_get_terminated, uint8_t, c.term != 0)
+#undef DZO_GD_SCALAR
+
+int dzo_gd_info(dzo_gd* o, int64_t* n, int64_t* batch, int* order) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    if (n) *n = o->n;
+    if (batch) *batch = o->batch;
+    if (order) *order = DZO_ORDER_TREE;
+    return DZO_OK;
+}
+
+}  // extern "C"
+
+// ============================================================================= Riesz kernel-level entries
+namespace dzo {
+
+struct RieszScratch {
+    DevBuf x, g, d;
+    RieszWork w;
+    RieszGdArgs a;
+    ~RieszScratch() { w.release(); }
+    int init(int constraint, int64_t dim, int64_t n, const double* xh, const double* dh) {
+        int device = 0;
+        DZO_CUDA(cudaGetDevice(&device));
+        DZO_TRY(x.alloc((size_t)n * 8)); DZO_TRY(g.alloc((size_t)n * 8)); DZO_TRY(d.alloc((size_t)n * 8));
+        DZO_CUDA(cudaMemcpy(x.p, xh, (size_t)n * 8, cudaMemcpyHostToDevice));
+        if (dh) DZO_CUDA(cudaMemcpy(d.p, dh, (size_t)n * 8, cudaMemcpyHostToDevice));
+        DZO_TRY(w.init((int)(n / dim), (int)dim, device));
+        memset(&a, 0, sizeof a);
+        a.x = x.as<double>(); a.g = g.as<double>(); a.d = d.as<double>(); a.dx = nullptr; a.dg = nullptr;
+        w.fill(a);
+        a.N = (int)(n / dim); a.sphere = (constraint == DZO_CONSTRAINT_SPHERE);
+        return DZO_OK;
+    }
+};
+
+static int riesz_order_ok(int order, int64_t dim) {
+    if (order != DZO_ORDER_TREE) return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels compute in DZO_ORDER_TREE");
+    if (dim < 1 || dim > 4) return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
+    return DZO_OK;
+}
+
+int riesz_dev_objective(int constraint, int64_t dim, int order, int64_t n, int64_t batch, const double* x, double* f) {
+    DZO_TRY(riesz_order_ok(order, dim));
+    for (int64_t p = 0; p < batch; ++p) {
+        RieszScratch s;
+        DZO_TRY(s.init(constraint, dim, n, x + p * n, nullptr));
+        s.a.mode = 2;
+        DZO_TRY(s.w.launch(s.a, 0));
+        DZO_CUDA(cudaDeviceSynchronize());
+        double box[4];
+        DZO_CUDA(cudaMemcpy(box, s.w.fbox, sizeof box, cudaMemcpyDeviceToHost));
+        f[p] = box[1];
+    }
+    return DZO_OK;
+}
+
+int riesz_dev_gradient(int constraint, int64_t dim, int order, int64_t n, int64_t batch, const double* x, double* g) {
+    DZO_TRY(riesz_order_ok(order, dim));
+    for (int64_t p = 0; p < batch; ++p) {
+        RieszScratch s;
+        DZO_TRY(s.init(constraint, dim, n, x + p * n, nullptr));
+        s.a.mode = 3;
+        DZO_TRY(s.w.launch(s.a, 0));
+        DZO_CUDA(cudaDeviceSynchronize());
+        DZO_CUDA(cudaMemcpy(g + p * n, s.g.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    }
+    return DZO_OK;
+}
+
+// along x - t*dir (the BFGS functor sign), like dzo_cpu_line_search
+int riesz_dev_line_search(int constraint, int64_t dim, int order, int64_t n, const double* x, const double* dir, double f0,
+                          double t1, double* t_best, double* f_best) {
+    DZO_TRY(riesz_order_ok(order, dim));
+    RieszScratch s;
+    DZO_TRY(s.init(constraint, dim, n, x, dir));
+    s.a.mode = 4; s.a.ls_f0 = f0; s.a.ls_t1 = t1; s.a.ls_sign = -1.0; s.a.max_increases = 0;
+    DZO_TRY(s.w.launch(s.a, 0));
+    DZO_CUDA(cudaDeviceSynchronize());
+    double box[4];
+    DZO_CUDA(cudaMemcpy(box, s.w.fbox, sizeof box, cudaMemcpyDeviceToHost));
+    *t_best = box[1]; *f_best = box[2];
+    return DZO_OK;
+}
+
+}  // namespace dzo

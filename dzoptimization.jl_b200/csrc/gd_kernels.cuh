@@ -330,7 +330,7 @@ struct RieszDev {
 };
 
 template <int DIM>
-__global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a) {
+static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);          // 132 doubles: tree reduction scratch
     double* wsm = sm + 136;                                    // 32 warps x 128 x DIM staging
@@ -450,7 +450,7 @@ struct VecGdArgs {
     int mode;  // 0 = steps, 1 = constructor
 };
 
-__global__ void __launch_bounds__(1024, 1) vec_gd_kernel(VecGdArgs a) {
+static __global__ void __launch_bounds__(1024, 1) vec_gd_kernel(VecGdArgs a) {
     __shared__ double sm[132];
     const long long n = a.n, m = n >> 1;
     if (a.mode == 1) {                                                         // :330-374

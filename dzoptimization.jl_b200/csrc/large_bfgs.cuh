@@ -200,7 +200,7 @@ struct LargeVecs {
 };
 
 // Constructor, legacy/DZOptimization.jl:762-810 (x already holds copy(x0)).
-__global__ void __launch_bounds__(1024, 1) vec_bfgs_init_kernel(LargeVecs a, double initial_step_length) {
+static __global__ void __launch_bounds__(1024, 1) vec_bfgs_init_kernel(LargeVecs a, double initial_step_length) {
     __shared__ double sm[132];
     const long long n = a.n, m = n >> 1;
     ProbeFlags fl;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(1024, 1) vec_bfgs_init_kernel(LargeVecs a, dou
 }
 
 // set_state (:819-862): recompute f and g at the restored point; d = H*g follows as a GEMV.
-__global__ void __launch_bounds__(1024, 1) vec_bfgs_restore_kernel(LargeVecs a) {
+static __global__ void __launch_bounds__(1024, 1) vec_bfgs_restore_kernel(LargeVecs a) {
     __shared__ double sm[132];
     const long long n = a.n, m = n >> 1;
     ProbeFlags fl;
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(1024, 1) vec_bfgs_restore_kernel(LargeVecs a) 
 }
 
 // step! :891-960 up to (and including) the O(n) part of update_inverse_hessian! (:873-874).
-__global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVecs a) {
+static __global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVecs a) {
     __shared__ double sm[2 * 132];
     __shared__ LargeCtrl sc;
     const long long n = a.n, m = n >> 1;
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVecs a) {
 }
 
 // :876  delta_norm = step_length*overlap + dot(delta_gradient, scratch)
-__global__ void __launch_bounds__(1024, 1) vec_delta_kernel(LargeVecs a) {
+static __global__ void __launch_bounds__(1024, 1) vec_delta_kernel(LargeVecs a) {
     __shared__ double sm[132];
     if (a.ctrl->kind != DZO_STEP_BFGS) return;
     const double s = cta_tree_dot(a.dg, a.t, a.n, sm);
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(1024, 1) vec_delta_kernel(LargeVecs a) {
 }
 
 // overlap + in-place rescale for the kernel-level entry dzo_dev_update_inverse_hessian (:873-874)
-__global__ void __launch_bounds__(1024, 1) vec_overlap_scale_kernel(LargeVecs a, double step_length) {
+static __global__ void __launch_bounds__(1024, 1) vec_overlap_scale_kernel(LargeVecs a, double step_length) {
     __shared__ double sm[132];
     const double overlap = cta_tree_dot(a.d, a.dg, a.n, sm);
     const double inv_overlap = 1.0 / overlap;
@@ -363,21 +363,21 @@ __global__ void __launch_bounds__(1024, 1) vec_overlap_scale_kernel(LargeVecs a,
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) vec_dot_kernel(const double* v, const double* w, long long n, double* out) {
+static __global__ void __launch_bounds__(1024, 1) vec_dot_kernel(const double* v, const double* w, long long n, double* out) {
     __shared__ double sm[132];
     const double s = cta_tree_dot(v, w, n, sm);
     if (threadIdx.x == 0) *out = s;
 }
 
 // batch of extended-Rosenbrock objective / gradient evaluations in TREE order (dzo_dev_objective)
-__global__ void __launch_bounds__(1024, 1) vec_rosenbrock_objective_kernel(const double* x, long long n, double* f) {
+static __global__ void __launch_bounds__(1024, 1) vec_rosenbrock_objective_kernel(const double* x, long long n, double* f) {
     __shared__ double sm[132];
     ProbeFlags fl;
     const double* xp = x + (long long)blockIdx.x * n;
     const double v = cta_probe_rosenbrock<2>(xp, xp, n >> 1, 0.0, 0.0, sm, fl);
     if (threadIdx.x == 0) f[blockIdx.x] = v;
 }
-__global__ void vec_rosenbrock_gradient_kernel(const double* x, long long total_pairs, double* g) {
+static __global__ void vec_rosenbrock_gradient_kernel(const double* x, long long total_pairs, double* g) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= total_pairs) return;
     const double2 xx = reinterpret_cast<const double2*>(x)[k];
@@ -440,7 +440,7 @@ DZO_DEVINL void sweep_finish_rows(const SweepArgs& a, long long i0, double acc0,
 // mul!(out, H, v)  legacy/DZOptimization.jl:875, :958-960.  Thread-per-row walk over one
 // 1024-column chunk: a warp reads 512 contiguous bytes of every column (H is column-major),
 // and each thread's accumulator is exactly the sequential chunk partial of the oracle.
-__global__ void __launch_bounds__(kSweepThreads) gemv_kernel(SweepArgs a) {
+static __global__ void __launch_bounds__(kSweepThreads) gemv_kernel(SweepArgs a) {
     if (a.ctrl && a.ctrl->kind != a.need_kind) return;
     __shared__ double sv[DZO_GEMV_CHUNK];
     const long long c0 = (long long)blockIdx.y * DZO_GEMV_CHUNK;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kSweepThreads) gemv_kernel(SweepArgs a) {
 // update_inverse_hessian! rank-2 sweep (legacy/DZOptimization.jl:878-886, exact operation
 // order of :882-884) fused with next_step_direction = H' * gradient (:958-960): every element
 // of H is read once, updated, written once, and contributes to the new direction on the way.
-__global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(SweepArgs a) {
+static __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(SweepArgs a) {
     if (a.ctrl->kind != DZO_STEP_BFGS) return;
     __shared__ double ss[DZO_GEMV_CHUNK], st[DZO_GEMV_CHUNK], sg[DZO_GEMV_CHUNK];
     const double delta = a.ctrl->delta_norm;
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(SweepArgs a)
 
 // identity_matrix!  legacy/DZOptimization.jl:712-720 (after a gradient-descent step, :981).
 // Same tiling as the sweeps; pure streaming stores.
-__global__ void __launch_bounds__(kSweepThreads) identity_kernel(SweepArgs a) {
+static __global__ void __launch_bounds__(kSweepThreads) identity_kernel(SweepArgs a) {
     if (a.ctrl && a.ctrl->kind != a.need_kind) return;
     const long long c0 = (long long)blockIdx.y * DZO_GEMV_CHUNK;
     const int nc = (int)((a.n - c0 < DZO_GEMV_CHUNK) ? (a.n - c0) : DZO_GEMV_CHUNK);

@@ -23,7 +23,7 @@ DZO_DEVINL Group<32> make_warp_group(int n, double* bc) {
 }
 
 template <class Obj>
-__global__ void __launch_bounds__(32) small_objective_kernel(const double* x, int n, double* f) {
+static __global__ void __launch_bounds__(32) small_objective_kernel(const double* x, int n, double* f) {
     __shared__ double bc[kBcBufs * 32];
     Group<32> G = make_warp_group(n, bc);
     const long long p = blockIdx.x;
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(32) small_objective_kernel(const double* x, in
 }
 
 template <class Obj>
-__global__ void __launch_bounds__(32) small_gradient_kernel(const double* x, int n, double* g) {
+static __global__ void __launch_bounds__(32) small_gradient_kernel(const double* x, int n, double* g) {
     __shared__ double bc[kBcBufs * 32];
     Group<32> G = make_warp_group(n, bc);
     const long long p = blockIdx.x;
@@ -42,14 +42,14 @@ __global__ void __launch_bounds__(32) small_gradient_kernel(const double* x, int
     if (G.act) g[p * n + G.r] = v;
 }
 
-__global__ void __launch_bounds__(32) small_dot_kernel(const double* v, const double* w, int n, double* out) {
+static __global__ void __launch_bounds__(32) small_dot_kernel(const double* v, const double* w, int n, double* out) {
     __shared__ double bc[kBcBufs * 32];
     Group<32> G = make_warp_group(n, bc);
     const double s = G.seq_sum(G.act ? v[G.r] * w[G.r] : 0.0);
     if (G.r == 0) *out = s;
 }
 
-__global__ void __launch_bounds__(32) small_gemv_kernel(const double* H, const double* v, int n, double* out) {
+static __global__ void __launch_bounds__(32) small_gemv_kernel(const double* H, const double* v, int n, double* out) {
     const int r = threadIdx.x;
     if (r >= n) return;
     double acc = 0.0;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(32) small_gemv_kernel(const double* H, const d
 }
 
 // update_inverse_hessian!(H, step_length, step_direction, delta_gradient, scratch) + fused mul!
-__global__ void __launch_bounds__(32) small_update_kernel(double* H, double step_length, double* sd_io,
+static __global__ void __launch_bounds__(32) small_update_kernel(double* H, double step_length, double* sd_io,
                                                           const double* dg_in, double* scratch, const double* next_g,
                                                           double* next_d, int n) {
     __shared__ double bc[kBcBufs * 32];
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(32) small_update_kernel(double* H, double step
 }
 
 template <class Obj>
-__global__ void __launch_bounds__(32) small_line_search_kernel(const double* x, const double* dir, int n, double f0,
+static __global__ void __launch_bounds__(32) small_line_search_kernel(const double* x, const double* dir, int n, double f0,
                                                                double t1, double* out2) {
     __shared__ double bc[kBcBufs * 32];
     Group<32> G = make_warp_group(n, bc);

@@ -1,0 +1,88 @@
+"""CPU tests of the drop-in boundary: the C-ABI libraries load and export every symbol that
+include/dzopt.h declares (no compute calls: there is no GPU here), and the host-side mirror of the
+Julia API validates its arguments like the reference does."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dzopt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dzo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_both_families():
+    syms = declared_symbols()
+    assert "dzo_bfgs_step" in syms and "dzo_cpu_bfgs_step" in syms and "dzo_gd_step" in syms
+    assert len(syms) > 80
+
+
+def test_cuda_library_exports_every_declared_symbol(dz):
+    lib = C.CDLL(dz.lib_path)
+    missing = [s for s in declared_symbols() if not s.startswith("dzo_cpu_") and not hasattr(lib, s)]
+    assert not missing, f"libdzopt_b200.so lacks: {missing}"
+
+
+def test_oracle_library_exports_every_declared_symbol(orc):
+    lib = C.CDLL(orc.LIB_PATH)
+    missing = [s for s in declared_symbols() if s.startswith("dzo_cpu_") and not hasattr(lib, s)]
+    assert not missing, f"libdzo_oracle.so lacks: {missing}"
+
+
+def test_product_library_does_not_link_the_oracle(dz):
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    import subprocess
+    out = subprocess.run(["ldd", dz.lib_path], capture_output=True, text=True).stdout
+    assert "dzo_oracle" not in out
+    nm = subprocess.run(["nm", "-D", "--defined-only", dz.lib_path], capture_output=True, text=True).stdout
+    assert "dzo_cpu_" not in nm
+    pkg_dir = os.path.dirname(dz.lib_path)
+    for root, _, files in os.walk(os.path.dirname(pkg_dir)):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                text = open(os.path.join(root, f)).read()
+                assert "import oracle" not in text and "libdzo_oracle" not in text, f
+
+
+def test_no_gpu_means_loud_failure_not_fallback(dz):
+    """On this CPU-only box the constructor must raise DZO_ERR_NO_DEVICE (-6), never compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    EF = dz.ExampleFunctions
+    with pytest.raises(dz.DZOptError) as e:
+        dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, np.zeros(2), 1.0)
+    assert e.value.code == -6
+    with pytest.raises(dz.DZOptError) as e:
+        dz.GradientDescentOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, dz.QuadraticLineSearch(0),
+                                    np.zeros(64), 1.0)
+    assert e.value.code == -6
+
+
+def test_constructor_argument_validation(dz):
+    EF = dz.ExampleFunctions
+    with pytest.raises(TypeError):                                   # host closures cannot run in the CUDA step!
+        dz.BFGSOptimizer(lambda x: 0.0, EF.rosenbrock_gradient_, np.zeros(2), 1.0)
+    with pytest.raises(TypeError):                                   # objective / gradient of different functions
+        dz.BFGSOptimizer(EF.rosenbrock_function, EF.riesz_gradient_, np.zeros(2), 1.0)
+    with pytest.raises(TypeError):
+        dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, np.zeros(2))          # arity (:753-766)
+    with pytest.raises(TypeError):
+        dz.GradientDescentOptimizer(EF.riesz_energy, EF.riesz_gradient_, "not a line search", np.zeros((4, 3)), 1.0)
+    with pytest.raises(ValueError):
+        dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, np.zeros((3, 2)), 1.0)   # needs batched=True
+    assert dz.StepType.NullStep == 0 and dz.StepType.GradientDescentStep == 1 and dz.StepType.BFGSStep == 2
+    assert dz.QuadraticLineSearch().max_increases == 0
+
+
+def test_layout_matches_julia_column_major(dz):
+    a, n, batch, pshape, dim = dz._layout(np.zeros((5, 3)), dz.OBJ_RIESZ, False)   # Julia 3 x 5 Matrix
+    assert (n, batch, pshape, dim) == (15, 1, (5, 3), 3)
+    a, n, batch, pshape, dim = dz._layout(np.zeros((7, 16)), dz.OBJ_ROSENBROCK, True)
+    assert (n, batch, pshape, dim) == (16, 7, (16,), 0)
