@@ -1,0 +1,228 @@
+# DZOptimizationB200.jl -- the reference-side binding: DZOptimization.jl's optimizer API over
+# libdzopt_b200.so (C ABI: include/dzopt.h).  Julia host code `ccall`s the library; step! runs as
+# hand-written sm_100a CUDA kernels in Float64.
+#
+# Drop-in for the README loop (README.md:33-41 of the reference):
+#
+#     using DZOptimizationB200
+#     using DZOptimizationB200.ExampleFunctions: rosenbrock_function, rosenbrock_gradient!
+#     opt = BFGSOptimizer(rosenbrock_function, rosenbrock_gradient!, rand(2), 1.0)
+#     while !opt.has_converged[]
+#         step!(opt)
+#         println(opt.current_objective_value[], " ", opt.current_point)
+#     end
+#
+# NOTE: there is no Julia in the build/test environment of this repository, so this file is
+# reviewed against the header but has not been executed; tests/ drive the very same C symbols
+# through ctypes (dzoptimization.jl_b200/__init__.py is the executed twin of this file).
+#
+# Julia closures cannot run inside a CUDA kernel, so `f`, `g!` and `c!` must be the device
+# versions of legacy/ExampleFunctions.jl exported below; anything else raises ArgumentError.
+module DZOptimizationB200
+
+export BFGSOptimizer, GradientDescentOptimizer, QuadraticLineSearch, step!, StepType, NullStep,
+    GradientDescentStep, BFGSStep, NULL_CONSTRAINT, SPHERE_CONSTRAINT
+
+const libdzopt = get(ENV, "DZOPT_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libdzopt_b200.so"))
+
+# ------------------------------------------------------------------ device callbacks (ids of include/dzopt.h)
+struct DeviceFunction
+    objective::Cint      # DZO_OBJ_*
+    role::Symbol         # :objective | :gradient
+end
+struct DeviceConstraint
+    id::Cint             # DZO_CONSTRAINT_*
+end
+const NULL_CONSTRAINT = DeviceConstraint(0)      # x -> true        (legacy/DZOptimization.jl:384,759)
+const SPHERE_CONSTRAINT = DeviceConstraint(1)    # normalise columns + tangent-projected gradient
+
+module ExampleFunctions
+import ..DeviceFunction
+export rosenbrock_function, rosenbrock_gradient!, riesz_energy, riesz_gradient!
+const rosenbrock_function = DeviceFunction(1, :objective)     # legacy/ExampleFunctions.jl:10-15
+const rosenbrock_gradient! = DeviceFunction(1, :gradient)     # :17-24
+const riesz_energy = DeviceFunction(2, :objective)            # :30-45
+const riesz_gradient! = DeviceFunction(2, :gradient)          # :47-83
+end
+
+@enum StepType NullStep GradientDescentStep BFGSStep           # legacy/DZOptimization.jl:727-731
+
+struct QuadraticLineSearch                                      # :181-188
+    max_increases::Int
+end
+QuadraticLineSearch() = QuadraticLineSearch(0)
+
+struct DZOptError <: Exception
+    code::Cint
+    msg::String
+end
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:dzo_last_error, libdzopt), Cstring, ()))
+    # the reference raises AssertionError for these two (:771, :773)
+    (rc == -2 || rc == -3) && throw(AssertionError(msg))
+    throw(DZOptError(rc, msg))
+end
+
+function resolve(f, g!, c!)
+    (f isa DeviceFunction && f.role == :objective) ||
+        throw(ArgumentError("objective_function must be a device objective from DZOptimizationB200.ExampleFunctions"))
+    (g! isa DeviceFunction && g!.role == :gradient && g!.objective == f.objective) ||
+        throw(ArgumentError("gradient_function! must be the device gradient of the same example function"))
+    c! isa DeviceConstraint || throw(ArgumentError("constraint_function! must be NULL_CONSTRAINT or SPHERE_CONSTRAINT"))
+    return f.objective, c!.id
+end
+
+# ================================================================== BFGSOptimizer (legacy :733-751)
+mutable struct BFGSOptimizer{N}
+    handle::Ptr{Cvoid}
+    dims::NTuple{N,Int}
+    n::Int
+    function BFGSOptimizer(handle, dims::NTuple{N,Int}) where {N}
+        opt = new{N}(handle, dims, prod(dims))
+        finalizer(o -> ccall((:dzo_bfgs_destroy, libdzopt), Cvoid, (Ptr{Cvoid},), o.handle), opt)
+        return opt
+    end
+end
+
+# BFGSOptimizer(f, g!, x0, step)  :753-760    /    BFGSOptimizer(f, g!, c!, x0, step)  :762-810
+BFGSOptimizer(f, g!, x0::Array{Float64}, step::Float64; device::Integer=0) =
+    BFGSOptimizer(f, g!, NULL_CONSTRAINT, x0, step; device=device)
+function BFGSOptimizer(f, g!, c!, x0::Array{Float64,N}, step::Float64; device::Integer=0) where {N}
+    obj, cid = resolve(f, g!, c!)
+    dim = obj == 2 ? size(x0, 1) : 0
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dzo_bfgs_create, libdzopt), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Int64, Ptr{Float64}, Float64, Cint),
+        h, obj, cid, dim, length(x0), 1, x0, step, device))
+    return BFGSOptimizer(h[], size(x0))
+end
+
+# step!(opt)  :891-994 -- returns opt (:993)
+function step!(opt::BFGSOptimizer)
+    check(ccall((:dzo_bfgs_step, libdzopt), Cint, (Ptr{Cvoid}, Cint), opt.handle, 1))
+    return opt
+end
+
+vecfield(opt, sym) = (out = Array{Float64}(undef, opt.dims);
+    check(ccall((sym, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), opt.handle, out)); out)
+function scalarfield(opt, sym, ::Type{T}) where {T}
+    out = Array{T,0}(undef)                      # 0-dim Array, read with [] like the reference's fields
+    check(ccall((sym, libdzopt), Cint, (Ptr{Cvoid}, Ptr{T}), opt.handle, out))
+    return out
+end
+
+function Base.getproperty(opt::BFGSOptimizer, s::Symbol)
+    s === :current_point && return vecfield(opt, :dzo_bfgs_get_point)                     # :739
+    s === :current_gradient && return vecfield(opt, :dzo_bfgs_get_gradient)               # :741
+    s === :delta_point && return vecfield(opt, :dzo_bfgs_get_delta_point)                 # :742
+    s === :delta_gradient && return vecfield(opt, :dzo_bfgs_get_delta_gradient)           # :743
+    s === :next_step_direction && return vecfield(opt, :dzo_bfgs_get_direction)           # :747
+    s === :current_objective_value && return scalarfield(opt, :dzo_bfgs_get_objective, Float64)   # :740
+    s === :last_step_length && return scalarfield(opt, :dzo_bfgs_get_step_length, Float64)        # :744
+    s === :iteration_count && return scalarfield(opt, :dzo_bfgs_get_iteration_count, Int64)       # :737
+    if s === :last_step_type                                                                      # :745
+        t = scalarfield(opt, :dzo_bfgs_get_step_type, Int32)
+        return fill(StepType(t[]))
+    end
+    if s === :has_terminated || s === :has_converged                                # :738 / README.md:38
+        t = scalarfield(opt, :dzo_bfgs_get_terminated, UInt8)
+        return fill(t[] != 0)
+    end
+    if s === :approximate_inverse_hessian                                           # :746
+        n = getfield(opt, :n)
+        H = Matrix{Float64}(undef, n, n)
+        check(ccall((:dzo_bfgs_get_inverse_hessian, libdzopt), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}),
+            getfield(opt, :handle), 0, H))
+        return H
+    end
+    return getfield(opt, s)
+end
+
+# ================================================================== GradientDescentOptimizer (legacy :305-327)
+mutable struct GradientDescentOptimizer{N}
+    handle::Ptr{Cvoid}
+    dims::NTuple{N,Int}
+    n::Int
+    function GradientDescentOptimizer(handle, dims::NTuple{N,Int}) where {N}
+        opt = new{N}(handle, dims, prod(dims))
+        finalizer(o -> ccall((:dzo_gd_destroy, libdzopt), Cvoid, (Ptr{Cvoid},), o.handle), opt)
+        return opt
+    end
+end
+
+# GradientDescentOptimizer(f, g!, ls, x0, step) :377-390 / (c!, f, g!, ls, x0, step) :330-337
+GradientDescentOptimizer(f, g!, ls::QuadraticLineSearch, x0::Array{Float64}, step::Float64; device::Integer=0) =
+    GradientDescentOptimizer(NULL_CONSTRAINT, f, g!, ls, x0, step; device=device)
+function GradientDescentOptimizer(c!, f, g!, ls::QuadraticLineSearch, x0::Array{Float64,N}, step::Float64;
+    device::Integer=0) where {N}
+    obj, cid = resolve(f, g!, c!)
+    dim = obj == 2 ? size(x0, 1) : 0
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dzo_gd_create, libdzopt), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Int64, Ptr{Float64}, Float64, Cint, Cint),
+        h, obj, cid, dim, length(x0), 1, x0, step, ls.max_increases, device))
+    return GradientDescentOptimizer(h[], size(x0))
+end
+
+function step!(opt::GradientDescentOptimizer)                                       # :393-449
+    check(ccall((:dzo_gd_step, libdzopt), Cint, (Ptr{Cvoid}, Cint), opt.handle, 1))
+    return opt
+end
+
+function Base.getproperty(opt::GradientDescentOptimizer, s::Symbol)
+    s === :current_point && return vecfield(opt, :dzo_gd_get_point)                       # :308
+    s === :delta_point && return vecfield(opt, :dzo_gd_get_delta_point)                   # :309
+    s === :current_gradient && return vecfield(opt, :dzo_gd_get_gradient)                 # :316
+    s === :delta_gradient && return vecfield(opt, :dzo_gd_get_delta_gradient)             # :317
+    s === :next_step_direction && return vecfield(opt, :dzo_gd_get_direction)             # :320
+    s === :current_objective_value && return scalarfield(opt, :dzo_gd_get_objective, Float64)       # :312
+    s === :delta_objective_value && return scalarfield(opt, :dzo_gd_get_delta_objective, Float64)   # :313
+    s === :last_step_length && return scalarfield(opt, :dzo_gd_get_step_length, Float64)            # :321
+    s === :iteration_count && return scalarfield(opt, :dzo_gd_get_iteration_count, Int64)           # :324
+    if s === :has_terminated || s === :has_converged                                                # :325
+        t = scalarfield(opt, :dzo_gd_get_terminated, UInt8)
+        return fill(t[] != 0)
+    end
+    return getfield(opt, s)
+end
+
+# ================================================================== batched mode (README.md:12)
+# "run multiple optimizers in parallel": one handle holds `batch` independent optimizers whose
+# states live in adjacent device arrays; x0 is n x batch.  Scalar fields come back as Vectors.
+mutable struct BatchedBFGSOptimizer
+    handle::Ptr{Cvoid}
+    n::Int
+    batch::Int
+end
+function BatchedBFGSOptimizer(f, g!, x0::Matrix{Float64}, step::Float64; device::Integer=0)
+    obj, cid = resolve(f, g!, NULL_CONSTRAINT)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dzo_bfgs_create, libdzopt), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Int64, Ptr{Float64}, Float64, Cint),
+        h, obj, cid, 0, size(x0, 1), size(x0, 2), x0, step, device))
+    opt = BatchedBFGSOptimizer(h[], size(x0, 1), size(x0, 2))
+    finalizer(o -> ccall((:dzo_bfgs_destroy, libdzopt), Cvoid, (Ptr{Cvoid},), o.handle), opt)
+    return opt
+end
+function step!(opt::BatchedBFGSOptimizer, k::Integer=1)      # k consecutive step! calls in ONE kernel launch
+    check(ccall((:dzo_bfgs_step, libdzopt), Cint, (Ptr{Cvoid}, Cint), opt.handle, k))
+    return opt
+end
+function current_points(opt::BatchedBFGSOptimizer)
+    out = Matrix{Float64}(undef, opt.n, opt.batch)
+    check(ccall((:dzo_bfgs_get_point, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), opt.handle, out))
+    return out
+end
+function current_objective_values(opt::BatchedBFGSOptimizer)
+    out = Vector{Float64}(undef, opt.batch)
+    check(ccall((:dzo_bfgs_get_objective, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), opt.handle, out))
+    return out
+end
+function count_active(opt::BatchedBFGSOptimizer)
+    c = Ref{Int64}(0)
+    check(ccall((:dzo_bfgs_count_active, libdzopt), Cint, (Ptr{Cvoid}, Ref{Int64}), opt.handle, c))
+    return c[]
+end
+
+end # module

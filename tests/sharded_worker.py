@@ -1,0 +1,111 @@
+"""Row-sharded large-n BFGS (BASELINE configs[3]) -- one process per GPU.
+
+    torchrun --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 --master-port P tests/sharded_worker.py \
+        --size 4096 --steps 8 [--check] [--time]
+
+--check : every rank compares its replicated vectors and its row slab of the inverse Hessian with
+          the UNSHARDED CPU oracle (TREE order) bit for bit: results must not depend on the rank count.
+--time  : CUDA-event time per BFGS-type step!, max over ranks; prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--time", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import ctypes as C
+    import dzopt_b200 as dz
+    import oracle as orc
+    from conftest import assert_bitwise
+    EF = dz.ExampleFunctions
+
+    # the 128-byte ncclUniqueId travels over the host framework's own plumbing
+    idbuf = C.create_string_buffer(128)
+    if rank == 0:
+        rc = dz.lib().dzo_nccl_get_unique_id(idbuf)
+        assert rc == 0, dz.lib().dzo_last_error()
+    box = [bytes(idbuf.raw)]
+    dist.broadcast_object_list(box, src=0)
+
+    n = args.size
+    x0 = 4.0 * orc.pcg_fill(n, 2) - 2.0
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, device=local,
+                           shard=(rank, world, box[0]))
+    r0, r1 = opt.row_range
+    assert (r0, r1) == (rank * n // world, (rank + 1) * n // world)
+
+    if args.check:
+        ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0[None, :], 1.0, order=orc.TREE, nthreads=4)
+        types = []
+        for it in range(args.steps):
+            dz.step_(opt); ref.step(1)
+            assert_bitwise(opt.current_point, ref.point[0], f"rank {rank} iter {it} point")
+            assert_bitwise(opt.current_gradient, ref.gradient[0], f"rank {rank} iter {it} gradient")
+            assert_bitwise(opt.next_step_direction, ref.direction[0], f"rank {rank} iter {it} direction")
+            assert float(opt.current_objective_value[()]) == float(ref.objective[0])
+            assert float(opt.last_step_length[()]) == float(ref.step_length[0])
+            types.append(int(opt.last_step_type[()]))
+        assert dz.StepType.BFGSStep in types
+        assert_bitwise(opt.inverse_hessian(), ref.inverse_hessian(0)[r0:r1], f"rank {rank} H slab")
+        ok = torch.ones(1, device="cuda")
+        dist.all_reduce(ok)
+        if rank == 0:
+            print(f"sharded check ok: n={n} ranks={world} steps={args.steps} types={types}")
+
+    if args.time:
+        stream = torch.cuda.Stream()
+        torch.cuda.set_stream(stream)
+        opt.set_stream(stream.cuda_stream)
+        opt.step(3)
+        times, types = [], []
+        for _ in range(args.steps):
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            opt.step_async(1)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+            types.append(int(opt.last_step_type[()]))
+        bf = [t for t, ty in zip(times, types) if ty == dz.StepType.BFGSStep]
+        if rank == 0:
+            peak = 6456.8
+            try:
+                peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except Exception:
+                pass
+            ms = float(np.mean(bf)) if bf else float("nan")
+            gbs = 24.0 * n * n / world / (ms * 1e-3) / 1e9
+            print(json.dumps({"workload": f"row-sharded BFGS n={n}", "n_gpus": world, "bfgs_steps": len(bf),
+                              "ms_per_bfgs_step": ms, "steps_per_s": 1e3 / ms, "per_gpu_achieved_gbs": gbs,
+                              "frac_of_peak": gbs / peak, "rows_per_gpu": n // world}))
+    opt.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
