@@ -63,53 +63,67 @@ def x0_batch(orc, batch, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
-
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every
+    2 ms from a thread (nvidia-smi's fastest loop is too coarse for a 30 ms region)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop = index, [], False
+        self.nvml = None
+        self.max_mhz = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices; resolve through the PCI bus id of the torch device
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        h = hh
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml, self.h = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nvml = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                                  if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
+                                  else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.nvml:
+            self.t.join(timeout=1)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for nm, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = set()
+        for _, r in self.rows:
+            for b, nm in bits.items():
+                if r & b:
                     reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median([c for c, _ in self.rows])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
 # ----------------------------------------------------------------------------- CPU legs

@@ -5,6 +5,7 @@
 #include <new>
 
 #include "batched_bfgs.cuh"
+#include "batched_hybrid.cuh"
 #include "host_common.h"
 #include "large_bfgs.cuh"
 #include "small_ops.cuh"
@@ -174,7 +175,31 @@ static int launch_batched_step(dzo_bfgs* o, int k) {
     }
 static int batched_init(dzo_bfgs* o, double L0) { DZO_LPP_DISPATCH(o, launch_batched_init, o, L0) }
 static int batched_restore(dzo_bfgs* o) { DZO_LPP_DISPATCH(o, launch_batched_restore, o) }
-static int batched_step(dzo_bfgs* o, int k) { DZO_LPP_DISPATCH(o, launch_batched_step, o, k) }
+template <int N>
+static int launch_hybrid_step(dzo_bfgs* o, int k) {
+    const unsigned grid = (unsigned)((o->batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
+    const size_t smem = hybrid_smem<N>();
+    static bool attr_set[64] = {};
+    if (!attr_set[o->device & 63]) {
+        DZO_CUDA(cudaFuncSetAttribute(bfgs_batched_hybrid_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[o->device & 63] = true;
+    }
+    bfgs_batched_hybrid_kernel<N><<<grid, kHybridThreads, smem, o->stream>>>(batched_args(o, k));
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+static int batched_step(dzo_bfgs* o, int k) {
+    if (g_tuning.batched_variant == 0) {     // thread-per-problem line search + lanes-per-problem H update
+        switch (o->n) {
+            case 2: return launch_hybrid_step<2>(o, k);
+            case 4: return launch_hybrid_step<4>(o, k);
+            case 8: return launch_hybrid_step<8>(o, k);
+            case 16: return launch_hybrid_step<16>(o, k);
+            default: break;
+        }
+    }
+    DZO_LPP_DISPATCH(o, launch_batched_step, o, k)
+}
 
 // ---- large-path launches
 static LargeVecs large_vecs(const dzo_bfgs* o) {
@@ -751,6 +776,7 @@ int dzo_bench_kernel(int which, int64_t n, int reps, int variant, float* ms_per_
 int dzo_set_tuning(const char* key, int value) {
     if (!key) return fail(DZO_ERR_INVALID_ARGUMENT, "null key");
     if (!strcmp(key, "sweep_variant")) { g_tuning.sweep_variant = value; return DZO_OK; }
+    if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }
 

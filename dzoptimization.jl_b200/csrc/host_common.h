@@ -53,7 +53,7 @@ int check_problem(int objective, int constraint, int64_t obj_param, int64_t n, i
 // process-wide tuning knobs (A/B measurements only; never change results)
 struct Tuning {
     int sweep_variant = 0;    // 0 = LDG/STG streaming tiles, 1 = TMA-staged tiles
-    int batched_ksteps_max = 1 << 20;
+    int batched_variant = 0;  // 0 = hybrid kernel for n in {2,4,8,16}, 1 = lanes-per-problem kernel everywhere
 };
 extern Tuning g_tuning;
 
