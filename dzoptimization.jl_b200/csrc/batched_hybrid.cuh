@@ -12,11 +12,14 @@
 //            evaluation (so lanes in different stages of different searches share the expensive
 //            code), the BFGS / GD / terminate decision, x, g, dx, dg, overlap, d/overlap.
 //            Vectors live in a per-warp shared-memory tile [32 problems][17] (conflict-free).
-//   phase 2  N LANES PER PROBLEM, uniform control flow: lane r streams ROW r of the 2 KB inverse
-//            Hessian straight from HBM into registers (128 contiguous bytes per lane, the next
-//            round's rows prefetched while the current round computes), t = H*dg, delta, the
-//            rank-2 update fused with d = H'*g, rows streamed back.  A gradient-descent step
-//            writes the identity without reading H; a terminated problem moves no H bytes.
+//   phase 2  N LANES PER PROBLEM, uniform control flow: lane r recomputes element r of x, g, dx, dg
+//            (bit-identical elementwise formulas) and stores them coalesced, streams ROW r of the
+//            2 KB inverse Hessian from HBM into registers with coalesced loads (for a fixed column
+//            the N lanes read N consecutive doubles; the next round's rows are prefetched while the
+//            current round computes), t = H*dg, delta, the rank-2 update fused with d = H'*g, rows
+//            streamed back.  A gradient-descent step writes the identity without reading H; a
+//            terminated problem moves no H bytes.  (A first version let every lane read its row as
+//            128 contiguous bytes: ncu showed the L1TEX tag stage at 80 % -- 32 lines per request.)
 //
 // legacy/DZOptimization.jl:891-994 (step!), :864-889 (update_inverse_hessian!), :49-216 (line search).
 #pragma once
@@ -199,56 +202,43 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(
                     term = true;                                                          // :989
                 }
             }
-            if (kind != DZO_STEP_NULL) {
-                type = kind; iter += 1; moved = true;                                     // :939-940 / :967-968
-                const double* dir = (kind == DZO_STEP_BFGS) ? D : G;
-                double* gx = A.x + p * N;
-                double* gg = A.g + p * N;
-                double* gdx = A.dx + p * N;
-                double* gdg = A.dg + p * N;
+            if (kind != DZO_STEP_NULL) { type = kind; iter += 1; moved = true; }         // :939-940 / :967-968
+            if (kind == DZO_STEP_BFGS) {
+                // overlap = dot(step_direction, delta_gradient)  :873 -- thread-local and strictly sequential.
+                // The elementwise results (x, g, dx, dg, d/overlap) are recomputed bit-identically by the
+                // phase-2 lanes, which can store them coalesced.
 #pragma unroll
                 for (int k = 0; k < N / 2; ++k) {
                     const double xa = X[2 * k], xc = X[2 * k + 1];
                     const double ga = G[2 * k], gc = G[2 * k + 1];
-                    const double da = dir[2 * k], dc = dir[2 * k + 1];
-                    const double na = xa + alpha * da, nc = xc + alpha * dc;              // :945 / :973
+                    const double da = D[2 * k], dc = D[2 * k + 1];
+                    const double na = xa + alpha * da, nc = xc + alpha * dc;              // :945
                     const double t1_ = 1 - na;
                     const double t2_ = nc - na * na;
                     const double gna = -2 * t1_ - 400 * na * t2_;                         // :948 rosenbrock_gradient!
                     const double gnc = 200 * t2_;
-                    const double dxa = (-xa) + na, dxc = (-xc) + nc;                      // :943, :949
                     const double dga = (-ga) + gna, dgc = (-gc) + gnc;                    // :944, :950
-                    if (kind == DZO_STEP_BFGS) { overlap += da * dga; overlap += dc * dgc; }   // :873
-                    reinterpret_cast<double2*>(gx)[k] = make_double2(na, nc);
-                    reinterpret_cast<double2*>(gg)[k] = make_double2(gna, gnc);
-                    reinterpret_cast<double2*>(gdx)[k] = make_double2(dxa, dxc);
-                    reinterpret_cast<double2*>(gdg)[k] = make_double2(dga, dgc);
-                    X[2 * k] = dga; X[2 * k + 1] = dgc;      // tile X now carries delta_gradient
-                    G[2 * k] = gna; G[2 * k + 1] = gnc;      // tile G the new gradient
-                }
-                if (kind == DZO_STEP_BFGS) {
-                    const double inv_overlap = 1.0 / overlap;                             // :874
-#pragma unroll
-                    for (int i = 0; i < N; ++i) D[i] = D[i] * inv_overlap;                // tile D = step_direction / overlap
+                    overlap += da * dga;
+                    overlap += dc * dgc;
                 }
             }
         }
         __syncwarp();
 
         // ---------------------------------------------------------------- phase 2: N lanes per problem
+        // Lane r of problem q owns element r of every vector and row r of H.  Every global access below
+        // is coalesced: for a fixed instruction the N lanes of a problem touch N consecutive doubles.
         const int r = lane % N, sub = lane / N;
         const unsigned gmask = (N == 32) ? FULL : (((1u << N) - 1u) << (sub * N));   // lanes of my problem
         const double ao = alpha * overlap;                                            // first operand of :876
+        const double inv_overlap = 1.0 / overlap;                                     // :874 inv(overlap)
         auto load_rows = [&](int round, double (&row)[N], int& kq) {
             const int q = round * PPR + sub;
             kq = __shfl_sync(FULL, kind, q);
             if (kq == DZO_STEP_BFGS) {
-                const double* Hp = A.H + (p0 + q) * NN + r * N;      // row r == column r (H is bitwise symmetric)
+                const double* Hp = A.H + (p0 + q) * NN + r;          // H[r, j] at Hp[j*N] (column-major)
 #pragma unroll
-                for (int j = 0; j < N; j += 2) {
-                    const double2 v = __ldcs(reinterpret_cast<const double2*>(Hp + j));
-                    row[j] = v.x; row[j + 1] = v.y;
-                }
+                for (int j = 0; j < N; ++j) row[j] = __ldcs(Hp + j * N);
             }
         };
         double cur[N], nxt[N];
@@ -257,54 +247,75 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(
 #pragma unroll 1
         for (int round = 0; round < N; ++round) {
             const int q = round * PPR + sub;
+            const double alpha_q = __shfl_sync(FULL, alpha, q);
             const double ao_q = __shfl_sync(FULL, ao, q);
+            const double inv_overlap_q = __shfl_sync(FULL, inv_overlap, q);
             if (round + 1 < N) load_rows(round + 1, nxt, knxt);
-            double* Hp = A.H + (p0 + q) * NN + r * N;
-            if (kcur == DZO_STEP_BFGS) {
-                // update_inverse_hessian!  :875-886 fused with mul!(d, H, g)  :958-960
-                const double2* dg2 = reinterpret_cast<const double2*>(S.X[q]);
-                const double2* g2 = reinterpret_cast<const double2*>(S.G[q]);
-                const double2* sd2 = reinterpret_cast<const double2*>(S.D[q]);
-                const double2* t2 = reinterpret_cast<const double2*>(S.T[sub]);
-                const double2* p2 = reinterpret_cast<const double2*>(S.P[sub]);
-                double t = 0.0;
+            if (kcur != DZO_STEP_NULL) {
+                const long long e = (p0 + q) * N + r;
+                const double xo = S.X[q][r], go = S.G[q][r], dol = S.D[q][r];
+                const double dirv = (kcur == DZO_STEP_BFGS) ? dol : go;
+                const double xn = xo + alpha_q * dirv;                                    // :945 / :973
+                const double xp = __shfl_xor_sync(gmask, xn, 1);                          // the other element of my pair
+                const double xe = (r & 1) ? xp : xn, xod = (r & 1) ? xn : xp;
+                const double t1_ = 1 - xe;
+                const double t2_ = xod - xe * xe;
+                const double gn = (r & 1) ? (200 * t2_) : (-2 * t1_ - 400 * xe * t2_);    // :948 rosenbrock_gradient!
+                const double dgv = (-go) + gn;                                            // :944, :950
+                A.x[e] = xn;
+                A.g[e] = gn;
+                A.dx[e] = (-xo) + xn;                                                     // :943, :949
+                A.dg[e] = dgv;
+                double* Hp = A.H + (p0 + q) * NN + r;
+                if (kcur == DZO_STEP_BFGS) {
+                    // update_inverse_hessian!  :874-886 fused with mul!(d, H, g)  :958-960
+                    const double sd = dol * inv_overlap_q;                                // :874
+                    __syncwarp(gmask);              // every lane has read the old tile values
+                    S.X[q][r] = dgv;
+                    S.G[q][r] = gn;
+                    S.D[q][r] = sd;
+                    __syncwarp(gmask);
+                    const double2* dg2 = reinterpret_cast<const double2*>(S.X[q]);
+                    const double2* g2 = reinterpret_cast<const double2*>(S.G[q]);
+                    const double2* sd2 = reinterpret_cast<const double2*>(S.D[q]);
+                    const double2* t2 = reinterpret_cast<const double2*>(S.T[sub]);
+                    const double2* p2 = reinterpret_cast<const double2*>(S.P[sub]);
+                    double t = 0.0;
 #pragma unroll
-                for (int j = 0; j < N; j += 2) {                                          // :875
-                    const double2 v = dg2[j >> 1];
-                    t += cur[j] * v.x;
-                    t += cur[j + 1] * v.y;
+                    for (int j = 0; j < N; j += 2) {                                      // :875
+                        const double2 v = dg2[j >> 1];
+                        t += cur[j] * v.x;
+                        t += cur[j + 1] * v.y;
+                    }
+                    S.T[sub][r] = t;
+                    S.P[sub][r] = dgv * t;
+                    __syncwarp(gmask);
+                    double dot = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; j += 2) {                                      // Kernels.dot order
+                        const double2 v = p2[j >> 1];
+                        dot += v.x;
+                        dot += v.y;
+                    }
+                    const double delta_norm = ao_q + dot;                                 // :876
+                    double dnew = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; j += 2) {
+                        const double2 sj = sd2[j >> 1], tj = t2[j >> 1], gj = g2[j >> 1];
+                        cur[j] += (delta_norm * (sd * sj.x) - (t * sj.x + sd * tj.x));    // :882-884
+                        cur[j + 1] += (delta_norm * (sd * sj.y) - (t * sj.y + sd * tj.y));
+                        dnew += cur[j] * gj.x;                                            // :958-960
+                        dnew += cur[j + 1] * gj.y;
+                    }
+#pragma unroll
+                    for (int j = 0; j < N; ++j) __stcs(Hp + j * N, cur[j]);
+                    A.d[e] = dnew;
+                    __syncwarp(gmask);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) __stcs(Hp + j * N, (j == r) ? 1.0 : 0.0);  // :981 identity_matrix!
+                    A.d[e] = gn;                                                          // :984-986
                 }
-                S.T[sub][r] = t;
-                S.P[sub][r] = S.X[q][r] * t;
-                const double sd = S.D[q][r];
-                __syncwarp(gmask);
-                double dot = 0.0;
-#pragma unroll
-                for (int j = 0; j < N; j += 2) {                                          // Kernels.dot order
-                    const double2 v = p2[j >> 1];
-                    dot += v.x;
-                    dot += v.y;
-                }
-                const double delta_norm = ao_q + dot;                                     // :876
-                double dnew = 0.0;
-#pragma unroll
-                for (int j = 0; j < N; j += 2) {
-                    const double2 sj = sd2[j >> 1], tj = t2[j >> 1], gj = g2[j >> 1];
-                    cur[j] += (delta_norm * (sd * sj.x) - (t * sj.x + sd * tj.x));        // :882-884
-                    cur[j + 1] += (delta_norm * (sd * sj.y) - (t * sj.y + sd * tj.y));
-                    dnew += cur[j] * gj.x;                                                // :958-960
-                    dnew += cur[j + 1] * gj.y;
-                }
-#pragma unroll
-                for (int j = 0; j < N; j += 2)
-                    __stcs(reinterpret_cast<double2*>(Hp + j), make_double2(cur[j], cur[j + 1]));
-                A.d[(p0 + q) * N + r] = dnew;
-                __syncwarp(gmask);
-            } else if (kcur == DZO_STEP_GRADIENT_DESCENT) {
-#pragma unroll
-                for (int j = 0; j < N; j += 2)                                            // :981 identity_matrix!
-                    __stcs(reinterpret_cast<double2*>(Hp + j), make_double2(j == r ? 1.0 : 0.0, j + 1 == r ? 1.0 : 0.0));
-                A.d[(p0 + q) * N + r] = S.G[q][r];                                        // :984-986
             }
 #pragma unroll
             for (int j = 0; j < N; ++j) cur[j] = nxt[j];
