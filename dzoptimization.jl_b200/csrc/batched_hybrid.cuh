@@ -43,6 +43,9 @@ struct HybridSmem {
 
 enum : int { HS_INIT = 0, HS_EXPAND = 1, HS_SHRINK = 2, HS_QUAD = 3, HS_DONE = 4 };
 
+constexpr int kHybridPrefetchRounds = 4;   // phase-2 rounds whose H tiles are pulled into L2 ahead of use
+DZO_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int N>
 __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(BatchedArgs A) {
     static_assert(N == 2 || N == 4 || N == 8 || N == 16, "hybrid mapping: n in {2,4,8,16}");
@@ -79,6 +82,24 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(
         double* X = S.X[lane];
         double* G = S.G[lane];
         double* D = S.D[lane];
+        // Pull the inverse Hessians of the first phase-2 rounds into L2 now: they arrive while phase 1
+        // computes.  One 128-byte line per lane and request; tiles of terminated problems are skipped.
+        constexpr int LINES_PER_ROUND = PPR * NN * 8 / 128 > 0 ? PPR * NN * 8 / 128 : 1;   // 32 at n = 16
+        const unsigned live = __ballot_sync(FULL, !term);
+        auto prefetch_round = [&](int round) {
+            if (round >= N) return;
+            for (int l = lane; l < LINES_PER_ROUND; l += 32) {
+                const int q = round * PPR + (l * 128) / (NN * 8 > 128 ? NN * 8 : 128) % PPR;
+                const char* base = reinterpret_cast<const char*>(A.H + (p0 + round * PPR) * NN);
+                if (NN * 8 >= 128) {
+                    if ((live >> q) & 1u) prefetch_l2(base + l * 128);
+                } else {
+                    prefetch_l2(base + l * 128);
+                }
+            }
+        };
+#pragma unroll
+        for (int rr = 0; rr < kHybridPrefetchRounds; ++rr) prefetch_round(rr);
 
         // ---------------------------------------------------------------- phase 1: one thread per problem
         int kind = DZO_STEP_NULL;
@@ -251,6 +272,7 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(
             const double ao_q = __shfl_sync(FULL, ao, q);
             const double inv_overlap_q = __shfl_sync(FULL, inv_overlap, q);
             if (round + 1 < N) load_rows(round + 1, nxt, knxt);
+            prefetch_round(round + kHybridPrefetchRounds);
             if (kcur != DZO_STEP_NULL) {
                 const long long e = (p0 + q) * N + r;
                 const double xo = S.X[q][r], go = S.G[q][r], dol = S.D[q][r];
