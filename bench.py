@@ -181,6 +181,9 @@ def run_gpu(args):
 
     import dzopt_b200 as dz
     EF = dz.ExampleFunctions
+    for kv in args.tune:
+        k, v = kv.split("=")
+        dz.set_tuning(k, int(v))
     orc = oracle_mod()  # input generator (PCG) and, on rank 0, the cpu_baseline leg
     peak, peak_src = load_peaks()
     K, W = args.steps, args.warmup
@@ -343,6 +346,7 @@ def main():
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=50_000)
+    ap.add_argument("--tune", action="append", default=[], help="key=value passed to dzo_set_tuning (A/B runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -25,6 +25,7 @@ struct BatchedArgs {
     int n;
     long long batch;
     int ksteps;
+    int prefetch_rounds;  // hybrid kernel: phase-2 rounds whose H tiles are pulled into L2 ahead of use
 };
 
 constexpr int kBatchedThreads = 256;

@@ -43,7 +43,6 @@ struct HybridSmem {
 
 enum : int { HS_INIT = 0, HS_EXPAND = 1, HS_SHRINK = 2, HS_QUAD = 3, HS_DONE = 4 };
 
-constexpr int kHybridPrefetchRounds = 4;   // phase-2 rounds whose H tiles are pulled into L2 ahead of use
 DZO_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int N>
@@ -98,8 +97,7 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(
                 }
             }
         };
-#pragma unroll
-        for (int rr = 0; rr < kHybridPrefetchRounds; ++rr) prefetch_round(rr);
+        for (int rr = 0; rr < A.prefetch_rounds; ++rr) prefetch_round(rr);
 
         // ---------------------------------------------------------------- phase 1: one thread per problem
         int kind = DZO_STEP_NULL;
@@ -272,7 +270,7 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(
             const double ao_q = __shfl_sync(FULL, ao, q);
             const double inv_overlap_q = __shfl_sync(FULL, inv_overlap, q);
             if (round + 1 < N) load_rows(round + 1, nxt, knxt);
-            prefetch_round(round + kHybridPrefetchRounds);
+            prefetch_round(round + A.prefetch_rounds);
             if (kcur != DZO_STEP_NULL) {
                 const long long e = (p0 + q) * N + r;
                 const double xo = S.X[q][r], go = S.G[q][r], dol = S.D[q][r];

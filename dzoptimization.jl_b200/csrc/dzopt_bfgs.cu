@@ -124,7 +124,7 @@ static BatchedArgs batched_args(const dzo_bfgs* o, int ksteps) {
     BatchedArgs A;
     A.x = o->x; A.g = o->g; A.d = o->d; A.dx = o->dx; A.dg = o->dg; A.H = o->H; A.f = o->f; A.L = o->L;
     A.iter = o->iter; A.type = o->type; A.term = o->term; A.probes = nullptr;
-    A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps;
+    A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps; A.prefetch_rounds = g_tuning.batched_prefetch;
     return A;
 }
 
@@ -777,6 +777,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!key) return fail(DZO_ERR_INVALID_ARGUMENT, "null key");
     if (!strcmp(key, "sweep_variant")) { g_tuning.sweep_variant = value; return DZO_OK; }
     if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
+    if (!strcmp(key, "batched_prefetch")) { g_tuning.batched_prefetch = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }
 
