@@ -6,6 +6,7 @@
 
 #include "batched_bfgs.cuh"
 #include "batched_hybrid.cuh"
+#include "cluster_search.cuh"
 #include "host_common.h"
 #include "large_bfgs.cuh"
 #include "small_ops.cuh"
@@ -238,10 +239,13 @@ static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind) 
 
 static int large_step_once(dzo_bfgs* o) {
     const LargeVecs v = large_vecs(o);
-    vec_bfgs_search_kernel<<<1, 1024, 0, o->stream>>>(v);                       // :891-950, :873-874
+    const bool cluster = (g_tuning.search_variant == 0);   // 8-CTA cluster with DSMEM reductions vs one CTA
+    if (cluster) cluster_bfgs_search_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);   // :891-950, :873-874
+    else vec_bfgs_search_kernel<<<1, 1024, 0, o->stream>>>(v);
     DZO_CUDA(cudaGetLastError());
     DZO_TRY(large_gemv(o, o->dg, o->t, DZO_STEP_BFGS));                         // :875
-    vec_delta_kernel<<<1, 1024, 0, o->stream>>>(v);                             // :876
+    if (cluster) cluster_delta_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);         // :876
+    else vec_delta_kernel<<<1, 1024, 0, o->stream>>>(v);
     DZO_CUDA(cudaGetLastError());
     SweepArgs a = sweep_args(o);
     a.v = o->g; a.out = o->d;
@@ -777,6 +781,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!key) return fail(DZO_ERR_INVALID_ARGUMENT, "null key");
     if (!strcmp(key, "sweep_variant")) { g_tuning.sweep_variant = value; return DZO_OK; }
     if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
+    if (!strcmp(key, "search_variant")) { g_tuning.search_variant = value; return DZO_OK; }
     if (!strcmp(key, "batched_prefetch")) { g_tuning.batched_prefetch = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }
