@@ -168,14 +168,44 @@ def _layout(initial_point, objective, batched):
 
 class _Optimizer:
     _prefix = ""
+    _cache = None
+
+    def reuse_host_buffers(self, enable: bool = True):
+        """Like the Julia wrapper's cached host Arrays: every field read fills (and returns) ONE
+        page-locked host buffer per field instead of a fresh pageable array, so the device->host
+        copy is a straight DMA.  The returned arrays are overwritten by the next read of that field."""
+        self._release_cache()
+        self._cache = {} if enable else None
+        return self
+
+    def _release_cache(self):
+        for _, ptr in (self._cache or {}).values():
+            try:
+                lib().dzo_host_free(ptr)
+            except Exception:
+                pass
+        self._cache = None
+
+    def _out(self, getter, shape, dtype):
+        if self._cache is None:
+            return np.empty(shape, dtype=dtype)
+        hit = self._cache.get(getter)
+        if hit is None:
+            nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+            ptr = C.c_void_p()
+            _check(lib().dzo_host_alloc(C.byref(ptr), max(nbytes, 8)))
+            raw = (C.c_char * max(nbytes, 8)).from_address(ptr.value)
+            hit = (np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape), ptr)
+            self._cache[getter] = hit
+        return hit[0]
 
     def _vec(self, getter):
-        out = np.empty((self._batch,) + self._pshape if self._batched else self._pshape, dtype=np.float64)
+        out = self._out(getter, (self._batch,) + self._pshape if self._batched else self._pshape, np.float64)
         _check(getattr(lib(), f"dzo_{self._prefix}_{getter}")(self._h, _dp(out)))
         return out
 
     def _scalar(self, getter, dtype=np.float64, ptr=_capi.c_double_p):
-        out = np.empty(self._batch, dtype=dtype)
+        out = self._out(getter, self._batch, dtype)
         _check(getattr(lib(), f"dzo_{self._prefix}_{getter}")(self._h, out.ctypes.data_as(ptr)))
         # reference scalars are 0-dim Arrays read with `[]`; numpy 0-dim arrays read with `[()]`
         return out if self._batched else out.reshape(())
@@ -199,7 +229,7 @@ class _Optimizer:
     def iteration_count(self): return self._scalar("get_iteration_count", np.int64, _capi.c_i64_p)
     @property
     def has_terminated(self):
-        return self._scalar("get_terminated", np.uint8, _capi.c_u8_p).astype(bool)
+        return self._scalar("get_terminated", np.uint8, _capi.c_u8_p).view(np.bool_)
     #: README.md:38 spelling of has_terminated
     has_converged = has_terminated
 
@@ -221,6 +251,7 @@ class _Optimizer:
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
+            self._release_cache()
             getattr(lib(), f"dzo_{self._prefix}_destroy")(h)
 
     def __del__(self):

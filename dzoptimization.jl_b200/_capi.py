@@ -87,6 +87,10 @@ def bind(lib, cpu: bool):
         sig("identity", [I64, c_double_p, I])
         sig("bench_kernel", [I, I64, I, I, c_float_p, I])
         sig("set_tuning", [C.c_char_p, I])
+        sig("host_register", [C.c_void_p, C.c_uint64])
+        sig("host_unregister", [C.c_void_p])
+        sig("host_alloc", [C.POINTER(C.c_void_p), C.c_uint64])
+        sig("host_free", [C.c_void_p])
     return lib
 
 

@@ -99,25 +99,64 @@ struct dzo_bfgs {
     void* comm = nullptr;
 };
 
+// Device memory of a handle comes from the device's stream-ordered pool (cudaMallocAsync) with an
+// unbounded release threshold: constructing optimizer after optimizer in one process reuses the
+// pages instead of paying cudaMalloc / cudaFree of gigabytes each time.
 static void free_handle(dzo_bfgs* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(o->comm);
     void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
                     o->sd, o->t, o->partial, o->tile_counters, o->ctrl};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
-    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    if (o->own_stream) {
+        cudaStreamSynchronize(o->stream);
+        for (void* p : ptrs)
+            if (p) cudaFreeAsync(p, o->own_stream);
+        cudaStreamSynchronize(o->own_stream);
+        cudaStreamDestroy(o->own_stream);
+    }
     delete o;
 }
 
+static void init_pool(int device) {
+    static bool done[64] = {};
+    if (done[device & 63]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+    done[device & 63] = true;
+}
+
 template <class T>
-static int dmalloc(T** p, size_t count) {
-    cudaError_t e = cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
+static int dmalloc_on(cudaStream_t stream, T** p, size_t count) {
+    cudaError_t e = cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), stream);
     if (e != cudaSuccess) {
         *p = nullptr;
-        return fail(DZO_ERR_ALLOC, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        cudaGetLastError();
+        return fail(DZO_ERR_ALLOC, "cudaMallocAsync of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
     }
+    return DZO_OK;
+}
+#define dmalloc(p, count) dmalloc_on(o->own_stream, p, count)
+
+// any(isnan(f)) on the device: 4 bytes come back instead of the whole objective vector
+static __global__ void any_nan_kernel(const double* f, long long count, int* flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool bad = (i < count) && (f[i] != f[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+static int any_nan(dzo_bfgs* o, const double* f, long long count, bool* out) {
+    int* flag = reinterpret_cast<int*>(o->counter);
+    DZO_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), o->stream));
+    any_nan_kernel<<<(unsigned)((count + 255) / 256), 256, 0, o->stream>>>(f, count, flag);
+    DZO_CUDA(cudaGetLastError());
+    int h = 0;
+    DZO_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    *out = (h != 0);
     return DZO_OK;
 }
 
@@ -283,6 +322,7 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "cudaStreamCreate failed"));
     o->stream = o->own_stream;
+    init_pool(device);
     const size_t nb = (size_t)n * (size_t)batch;
     if ((rc = dmalloc(&o->x, nb)) || (rc = dmalloc(&o->g, nb)) || (rc = dmalloc(&o->d, nb)) || (rc = dmalloc(&o->dx, nb)) ||
         (rc = dmalloc(&o->dg, nb)) || (rc = dmalloc(&o->counter, 1)))
@@ -323,19 +363,15 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
         return bail(fail(DZO_ERR_CUDA, "constructor kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
     // @assert !isnan(initial_objective_value)   :773
     {
-        bool any_nan = false;
+        bool bad = false;
         if (o->small) {
-            double* hf = (double*)malloc((size_t)batch * sizeof(double));
-            if (!hf) return bail(fail(DZO_ERR_ALLOC, "out of memory"));
-            cudaMemcpy(hf, o->f, (size_t)batch * sizeof(double), cudaMemcpyDeviceToHost);
-            for (int64_t p = 0; p < batch; ++p) any_nan |= (hf[p] != hf[p]);
-            free(hf);
+            if ((rc = any_nan(o, o->f, batch, &bad))) return bail(rc);
         } else {
             LargeCtrl c;
             cudaMemcpy(&c, o->ctrl, sizeof c, cudaMemcpyDeviceToHost);
-            any_nan = (c.f != c.f);
+            bad = (c.f != c.f);
         }
-        if (any_nan) return bail(fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the initial point"));
+        if (bad) return bail(fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the initial point"));
     }
     *out = o;
     return DZO_OK;
@@ -489,14 +525,9 @@ int dzo_bfgs_set_state(dzo_bfgs* o, const double* point, const double* inverse_h
         DZO_CUDA(cudaMemcpyAsync(o->type, last_step_type, (size_t)o->batch * 4, cudaMemcpyHostToDevice, o->stream));
         DZO_CUDA(cudaMemcpyAsync(o->iter, iteration_count, (size_t)o->batch * 8, cudaMemcpyHostToDevice, o->stream));
         DZO_TRY(batched_restore(o));
-        DZO_CUDA(cudaStreamSynchronize(o->stream));
-        double* hf = (double*)malloc((size_t)o->batch * 8);
-        if (!hf) return fail(DZO_ERR_ALLOC, "out of memory");
-        cudaMemcpy(hf, o->f, (size_t)o->batch * 8, cudaMemcpyDeviceToHost);
-        bool any_nan = false;
-        for (int64_t p = 0; p < o->batch; ++p) any_nan |= (hf[p] != hf[p]);
-        free(hf);
-        if (any_nan) return fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the restored point");   // :829
+        bool bad = false;
+        DZO_TRY(any_nan(o, o->f, o->batch, &bad));
+        if (bad) return fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the restored point");   // :829
         return DZO_OK;
     }
     // large: the caller passes the full n x n matrix; keep rows [row0, row0+rows) of every column
@@ -774,6 +805,42 @@ int dzo_bench_kernel(int which, int64_t n, int reps, int variant, float* ms_per_
     DZO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ms_per_launch = ms / reps;
+    return DZO_OK;
+}
+
+int dzo_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(DZO_ERR_NO_DEVICE, "no CUDA device available");
+    }
+    DZO_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return DZO_OK;
+}
+int dzo_host_unregister(void* ptr) {
+    if (!ptr) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_CUDA(cudaHostUnregister(ptr));
+    return DZO_OK;
+}
+
+int dzo_host_alloc(void** out, uint64_t bytes) {
+    if (!out || bytes == 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(DZO_ERR_NO_DEVICE, "no CUDA device available");
+    }
+    if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(DZO_ERR_ALLOC, "cudaHostAlloc of %llu bytes failed", (unsigned long long)bytes);
+    }
+    return DZO_OK;
+}
+int dzo_host_free(void* ptr) {
+    if (!ptr) return DZO_OK;
+    DZO_CUDA(cudaFreeHost(ptr));
     return DZO_OK;
 }
 
