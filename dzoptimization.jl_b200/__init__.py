@@ -323,6 +323,13 @@ class BFGSOptimizer(_Optimizer):
         _check(lib().dzo_bfgs_info(self._h, None, None, C.byref(o), None, None))
         return o.value
 
+    def step_log(self):
+        """(calls, kinds) -- kinds[c % 64] is the StepType of step! call c (large-n handles)."""
+        calls = C.c_int64()
+        kinds = np.zeros(64, dtype=np.uint8)
+        _check(lib().dzo_bfgs_get_step_log(self._h, C.byref(calls), kinds.ctypes.data_as(_capi.c_u8_p)))
+        return calls.value, kinds
+
     def count_active(self) -> int:
         c = C.c_int64()
         _check(lib().dzo_bfgs_count_active(self._h, C.byref(c)))

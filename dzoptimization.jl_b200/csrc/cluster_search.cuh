@@ -251,6 +251,8 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
             a.ctrl->term = 1;
             a.ctrl->kind = DZO_STEP_NULL;
             a.ctrl->evals = sc.evals + evals;
+            a.ctrl->kind_log[sc.calls & 63] = DZO_STEP_NULL;
+            a.ctrl->calls = sc.calls + 1;
         }
         return;
     }
@@ -294,6 +296,8 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
         c.f = fnew; c.L = Lnew; c.type = kind; c.iter = sc.iter + 1;
         c.kind = kind; c.step_length = alpha; c.overlap = overlap; c.delta_norm = 0.0;
         c.evals = sc.evals + evals;
+        c.kind_log[sc.calls & 63] = (unsigned char)kind;
+        c.calls = sc.calls + 1;
         *a.ctrl = c;
     }
 }

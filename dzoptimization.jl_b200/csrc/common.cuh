@@ -32,6 +32,9 @@ struct LargeCtrl {
     double delta_norm; // :876
     // statistics
     long long evals;   // objective evaluations so far
+    long long calls;   // step! calls so far on a non-terminated optimizer
+    unsigned char kind_log[64];  // kind of call c at kind_log[c % 64] (lets a host time back-to-back steps
+                                 // without a sync per step and still know which ones were BFGS-type)
 };
 
 // ----------------------------------------------------------------------------- warp butterflies

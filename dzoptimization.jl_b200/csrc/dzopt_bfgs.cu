@@ -288,13 +288,10 @@ static int large_step_once(dzo_bfgs* o) {
     DZO_CUDA(cudaGetLastError());
     SweepArgs a = sweep_args(o);
     a.v = o->g; a.out = o->d;
+    a.need_kind = DZO_STEP_GRADIENT_DESCENT + 100;   // this launch also serves identity_matrix! (:981) after a GD step
     update_gemv_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);   // :878-886 + :958-960
     DZO_CUDA(cudaGetLastError());
     DZO_TRY(allgather_rows(o, o->d));
-    SweepArgs b = sweep_args(o);
-    b.need_kind = DZO_STEP_GRADIENT_DESCENT;
-    identity_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(b);      // :981
-    DZO_CUDA(cudaGetLastError());
     return DZO_OK;
 }
 
@@ -495,6 +492,14 @@ int dzo_bfgs_count_active(dzo_bfgs* o, int64_t* out) {
     unsigned long long c = 0;
     DZO_TRY(read_back(o, &c, o->counter, 8));
     *out = (int64_t)c;
+    return DZO_OK;
+}
+int dzo_bfgs_get_step_log(dzo_bfgs* o, int64_t* calls, uint8_t* kinds64) {
+    if (!o || !calls || !kinds64) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small) return fail(DZO_ERR_UNSUPPORTED, "step log exists for large-n handles only");
+    LargeCtrl c; DZO_TRY(read_ctrl(o, &c));
+    *calls = c.calls;
+    memcpy(kinds64, c.kind_log, 64);
     return DZO_OK;
 }
 int dzo_bfgs_info(dzo_bfgs* o, int64_t* n, int64_t* batch, int* order, int64_t* row_begin, int64_t* row_end) {

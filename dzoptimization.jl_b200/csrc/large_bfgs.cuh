@@ -218,6 +218,8 @@ static __global__ void __launch_bounds__(1024, 1) vec_bfgs_init_kernel(LargeVecs
         c.f = f0; c.L = initial_step_length; c.iter = 0; c.type = DZO_STEP_NULL; c.term = 0;
         c.kind = DZO_STEP_NULL; c.pad = 0; c.step_length = 0.0; c.overlap = 0.0; c.delta_norm = 0.0;
         c.evals = 1;
+        c.calls = 0;
+        for (int i = 0; i < 64; ++i) c.kind_log[i] = 0;
         *a.ctrl = c;
     }
 }
@@ -289,6 +291,8 @@ static __global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVe
             a.ctrl->term = 1;
             a.ctrl->kind = DZO_STEP_NULL;
             a.ctrl->evals = sc.evals + evals;
+            a.ctrl->kind_log[sc.calls & 63] = DZO_STEP_NULL;
+            a.ctrl->calls = sc.calls + 1;
         }
         return;
     }
@@ -338,6 +342,8 @@ static __global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVe
         c.f = fnew; c.L = Lnew; c.type = kind; c.iter = sc.iter + 1;  // :937-940 / :965-968
         c.kind = kind; c.step_length = alpha; c.overlap = overlap; c.delta_norm = 0.0;
         c.evals = sc.evals + evals;
+        c.kind_log[sc.calls & 63] = (unsigned char)kind;
+        c.calls = sc.calls + 1;
         *a.ctrl = c;
     }
 }
@@ -483,7 +489,13 @@ static __global__ void __launch_bounds__(kSweepThreads) gemv_kernel(SweepArgs a)
 // update_inverse_hessian! rank-2 sweep (legacy/DZOptimization.jl:878-886, exact operation
 // order of :882-884) fused with next_step_direction = H' * gradient (:958-960): every element
 // of H is read once, updated, written once, and contributes to the new direction on the way.
+DZO_DEVINL void identity_tile(const SweepArgs& a);
+
 static __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(SweepArgs a) {
+    if (a.need_kind == DZO_STEP_GRADIENT_DESCENT + 100 && a.ctrl->kind == DZO_STEP_GRADIENT_DESCENT) {
+        identity_tile(a);   // :981 -- step! resets H after a gradient-descent step; same launch, same tiling
+        return;
+    }
     if (a.ctrl->kind != DZO_STEP_BFGS) return;
     __shared__ double ss[DZO_GEMV_CHUNK], st[DZO_GEMV_CHUNK], sg[DZO_GEMV_CHUNK];
     const double delta = a.ctrl->delta_norm;
@@ -547,14 +559,13 @@ static __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(Sweep
 
 // identity_matrix!  legacy/DZOptimization.jl:712-720 (after a gradient-descent step, :981).
 // Same tiling as the sweeps; pure streaming stores.
-static __global__ void __launch_bounds__(kSweepThreads) identity_kernel(SweepArgs a) {
-    if (a.ctrl && a.ctrl->kind != a.need_kind) return;
+DZO_DEVINL void identity_tile(const SweepArgs& a) {
     const long long c0 = (long long)blockIdx.y * DZO_GEMV_CHUNK;
     const int nc = (int)((a.n - c0 < DZO_GEMV_CHUNK) ? (a.n - c0) : DZO_GEMV_CHUNK);
     const long long i0 = (long long)blockIdx.x * kSweepRows + 2 * threadIdx.x;
     const bool one = i0 < a.rows, two = i0 + 1 < a.rows;
     double* base = a.H + i0 + c0 * a.ld;
-    const long long gi = a.row0 + i0;  // global row of acc0
+    const long long gi = a.row0 + i0;  // global row of the first of my two rows
     if (two && ((a.ld & 1) == 0)) {
 #pragma unroll 8
         for (int j = 0; j < nc; ++j) {
@@ -569,6 +580,10 @@ static __global__ void __launch_bounds__(kSweepThreads) identity_kernel(SweepArg
             if (two) base[(long long)j * a.ld + 1] = (gj == gi + 1) ? 1.0 : 0.0;
         }
     }
+}
+static __global__ void __launch_bounds__(kSweepThreads) identity_kernel(SweepArgs a) {
+    if (a.ctrl && a.ctrl->kind != a.need_kind) return;
+    identity_tile(a);
 }
 
 }  // namespace dzo
