@@ -272,6 +272,10 @@ def run_gpu(args):
     if rank == 0 and not args.skip_large:
         large = bench_large(dz, orc, torch, stream, peak, local_rank)
 
+    riesz = None
+    if rank == 0 and not args.skip_large:
+        riesz = bench_riesz(dz, orc, torch, stream, local_rank)
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_leg(orc, K, W, args.cpu_sample)
@@ -299,6 +303,8 @@ def run_gpu(args):
             line["cpu_baseline"] = cpu
         if large:
             line["large_n"] = large
+        if riesz:
+            line["riesz_gd"] = riesz
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
@@ -339,6 +345,34 @@ def bench_large(dz, orc, torch, stream, peak, device):
         if rc == 0:
             g = nbytes * n * n / (ms.value * 1e-3) / 1e9
             out[name] = {"ms": ms.value, "achieved_gbs": g, "frac_of_peak": g / peak}
+    return out
+
+
+def bench_riesz(dz, orc, torch, stream, device):
+    """BASELINE configs[4]: GradientDescentOptimizer on Riesz-energy points on the sphere, N=4096 (n=12288).
+    FP64-pipe bound (one sqrt + one or two divisions per pair), not an HBM roofline: reported as GD steps/s
+    and pair terms/s.  Inputs per SURVEY 8d: PCG seed 3 uniform in [-1,1)^3, normalised; initial step 1e-3."""
+    EF = dz.ExampleFunctions
+    N = 4096
+    p = 2.0 * orc.pcg_fill(3 * N, 3).reshape(N, 3) - 1.0
+    p = p / np.sqrt((p * p).sum(axis=1, keepdims=True))
+    opt = dz.GradientDescentOptimizer(dz.SPHERE_CONSTRAINT, EF.riesz_energy, EF.riesz_gradient_,
+                                      dz.QuadraticLineSearch(0), p, 1e-3, device=device)
+    opt.set_stream(stream.cuda_stream)
+    opt.step(3)
+    k = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    it0 = int(opt.iteration_count[()])
+    e0.record(stream)
+    opt.step_async(k)            # k step! calls inside ONE cooperative launch
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    done = int(opt.iteration_count[()]) - it0
+    f = float(opt.current_objective_value[()])
+    opt.close()
+    out = {"N": N, "n": 3 * N, "gd_steps": done, "ms_per_gd_step": ms / max(done, 1), "gd_steps_per_s": 1e3 * done / ms,
+           "objective": f}
     return out
 
 

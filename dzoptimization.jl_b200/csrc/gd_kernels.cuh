@@ -95,6 +95,8 @@ struct RieszDev {
                     double wj[DIM];
                     trial_point(a, dir, j, alpha, pmode, wj);
                     double seg = 0.0;
+                    // the sqrt / division of different sources are independent (ILP); only the adds are ordered
+#pragma unroll 4
                     for (int i = 0; i < lim; ++i) {
                         double dist_sq = 0.0;
 #pragma unroll
@@ -174,6 +176,7 @@ struct RieszDev {
                 double xj[DIM], part[DIM];
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) { xj[k] = a.x[(long long)j * DIM + k]; part[k] = 0.0; }
+#pragma unroll 4
                 for (int i = 0; i < cnt; ++i) {
                     if (i0 + i == j) continue;                                 // :55, :69 (i != j)
                     double dist_sq = 0.0;
