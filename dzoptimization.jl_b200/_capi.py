@@ -71,6 +71,8 @@ def bind(lib, cpu: bool):
 
     if cpu:
         sig("pcg_fill", [c_double_p, I64, C.c_uint64])
+        sig("gemv_rows", [I, I64, I64, I64, c_double_p, c_double_p, c_double_p])
+        sig("update_rows", [I64, I64, I64, c_double_p, D, c_double_p, c_double_p])
     else:
         # CUDA-only entry points (dzo_dev_* are spelled dzo_dev_ in the header; the kernel-level
         # names above are looked up through the alias table below)

@@ -839,3 +839,29 @@ int dzo_cpu_update_inverse_hessian(int order, int64_t n, double* H, double step_
                             next_gradient, next_direction, nthreads < 1 ? 1 : nthreads);
     return DZO_OK;
 }
+
+/* ======================================================================= row-slab twins (sharded-mode model) */
+int dzo_cpu_gemv_rows(int order, int64_t n, int64_t row_begin, int64_t row_end, const double* Hslab,
+                      const double* v, double* out) {
+    if (!Hslab || !v || !out || n <= 0 || row_begin < 0 || row_end > n || row_begin >= row_end)
+        return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    const int64_t rows = row_end - row_begin;
+    /* gemv_rows_ indexes the slab by local row: pass r0 = 0 and a leading dimension of `rows` */
+    gemv_rows_(order, n, 0, rows, Hslab, rows, v, out, 1);
+    return DZO_OK;
+}
+int dzo_cpu_update_rows(int64_t n, int64_t row_begin, int64_t row_end, double* Hslab, double delta_norm,
+                        const double* sd, const double* scratch) {
+    if (!Hslab || !sd || !scratch || n <= 0 || row_begin < 0 || row_end > n || row_begin >= row_end)
+        return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    const int64_t rows = row_end - row_begin;
+    for (int64_t j = 0; j < n; ++j) {                          /* legacy/DZOptimization.jl:878-886 */
+        const double sj = sd[j], tj = scratch[j];
+        double* col = Hslab + j * rows;
+        for (int64_t i = 0; i < rows; ++i) {
+            const int64_t gi = row_begin + i;
+            col[i] += (delta_norm * (sd[gi] * sj) - (scratch[gi] * sj + sd[gi] * tj));
+        }
+    }
+    return DZO_OK;
+}
