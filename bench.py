@@ -51,6 +51,15 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def oracle_mod():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
@@ -270,11 +279,12 @@ def run_gpu(args):
     # ---- large-n step! (configs[2]) and its two n^2 kernels, rank 0 only at N=1
     large = None
     if rank == 0 and not args.skip_large:
-        large = bench_large(dz, orc, torch, stream, peak, local_rank)
+        large = bench_large(dz, orc, torch, stream, peak, local_rank, cpu=(world == 1 and not args.skip_cpu))
 
     riesz = None
     if rank == 0 and not args.skip_large:
-        riesz = bench_riesz(dz, orc, torch, stream, local_rank)
+        riesz = bench_riesz(dz, orc, torch, stream, local_rank, cpu=(world == 1 and not args.skip_cpu))
+    readme = bench_readme(dz, orc) if (rank == 0 and world == 1 and not args.skip_cpu) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -295,9 +305,11 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "BFGSOptimizer(host x0) + W+K x [step!; has_converged[]; current_objective_value[]] via the C ABI"},
             "gpu_launches": K,
-            "roofline": {"bound": "hbm", "kernel": "bfgs_batched_step_kernel<16>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_problem_step": BYTES_PER_PROBLEM_STEP},
+            "roofline": {"bound": "hbm", "kernel": "bfgs_batched_hybrid_kernel<16>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("bfgs_batched_hybrid_kernel<16>"),
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)",
+                         "algorithmic_bytes_per_launch": BYTES_PER_PROBLEM_STEP * BATCH,
+                         "peak_source": peak_src, "bytes_per_problem_step": BYTES_PER_PROBLEM_STEP},
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -305,12 +317,14 @@ def run_gpu(args):
             line["large_n"] = large
         if riesz:
             line["riesz_gd"] = riesz
+        if readme:
+            line["readme_rosenbrock_n2"] = readme
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
 
 
-def bench_large(dz, orc, torch, stream, peak, device):
+def bench_large(dz, orc, torch, stream, peak, device, cpu=True):
     import ctypes as C
     EF = dz.ExampleFunctions
     n = LARGE_N
@@ -339,6 +353,18 @@ def bench_large(dz, orc, torch, stream, peak, device):
         gbs = 24.0 * n * n / (ms * 1e-3) / 1e9
         out.update({"ms_per_bfgs_step": ms, "steps_per_s": 1e3 / ms, "achieved_gbs": gbs, "frac_of_peak": gbs / peak,
                     "algorithmic_bytes_per_step": 24 * n * n})
+    if cpu:
+        # the same step! on the host: oracle, TREE order, every host thread over rows (bit-identical to 1 thread)
+        threads = os.cpu_count() or 1
+        ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0[None, :], 1.0, order=orc.TREE, nthreads=threads)
+        ref.step(3)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter(); ref.step(1); ts.append((time.perf_counter() - t0, int(ref.step_type[0])))
+        bfc = [t for t, ty in ts if ty == 2]
+        if bfc:
+            out["cpu_baseline"] = {"ms_per_bfgs_step": 1e3 * float(np.mean(bfc)), "cores": threads, "kind": "port",
+                                   "sample": f"{len(bfc)} BFGS-type step! calls of the same n=16384 problem, oracle with OpenMP over rows"}
     ms = C.c_float()
     for which, name, nbytes in ((1, "gemv_kernel", 8), (2, "update_gemv_kernel", 16), (3, "identity_kernel", 8)):
         rc = dz.lib().dzo_bench_kernel(which, n, 10, 0, C.byref(ms), device)
@@ -348,7 +374,7 @@ def bench_large(dz, orc, torch, stream, peak, device):
     return out
 
 
-def bench_riesz(dz, orc, torch, stream, device):
+def bench_riesz(dz, orc, torch, stream, device, cpu=True):
     """BASELINE configs[4]: GradientDescentOptimizer on Riesz-energy points on the sphere, N=4096 (n=12288).
     FP64-pipe bound (one sqrt + one or two divisions per pair), not an HBM roofline: reported as GD steps/s
     and pair terms/s.  Inputs per SURVEY 8d: PCG seed 3 uniform in [-1,1)^3, normalised; initial step 1e-3."""
@@ -373,7 +399,36 @@ def bench_riesz(dz, orc, torch, stream, device):
     opt.close()
     out = {"N": N, "n": 3 * N, "gd_steps": done, "ms_per_gd_step": ms / max(done, 1), "gd_steps_per_s": 1e3 * done / ms,
            "objective": f}
+    if cpu:
+        ref = orc.GD(orc.OBJ_RIESZ, p.reshape(1, -1), 1e-3, order=orc.TREE, constraint=orc.CONSTRAINT_SPHERE, dim=3)
+        ref.step(3)
+        t0 = time.perf_counter(); ref.step(3); dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"ms_per_gd_step": 1e3 * dt / 3, "cores": 1, "kind": "port",
+                               "sample": "3 GD step! calls of the same N=4096 problem, oracle single thread (the reference is single-threaded)"}
     return out
+
+
+def bench_readme(dz, orc):
+    """BASELINE configs[0]: README Rosenbrock n=2 from rand(2), step 1.0, run to has_converged -- the
+    reference's own CPU-runnable case (README.md:49-66 reports 2.8 us min / 5.6 us median per optimisation
+    on an unspecified CPU).  Oracle: 1000 PCG seeds, one thread; GPU: the same 1000 problems as one batch."""
+    x0 = np.stack([orc.pcg_fill(2, s) for s in range(1000)])
+    t0 = time.perf_counter()
+    ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0, 1.0, order=orc.SEQ, nthreads=1)
+    while ref.count_active():
+        ref.step(16)
+    cpu_us = 1e6 * (time.perf_counter() - t0) / 1000
+    EF = dz.ExampleFunctions
+    t0 = time.perf_counter()
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    while opt.count_active():
+        opt.step(16)
+    gpu_us = 1e6 * (time.perf_counter() - t0) / 1000
+    same = bool(np.array_equal(opt.current_point, ref.point))
+    opt.close()
+    return {"problems": 1000, "cpu_us_per_optimisation": cpu_us, "cpu_cores": 1, "cpu_kind": "port",
+            "gpu_us_per_optimisation_batched": gpu_us, "bitwise_equal_to_oracle": same,
+            "reference_published_us": {"min": 2.8, "median": 5.563, "hardware": "unspecified (README.md:62-63)"}}
 
 
 def main():
