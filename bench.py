@@ -285,6 +285,7 @@ def run_gpu(args):
     if rank == 0 and not args.skip_large:
         riesz = bench_riesz(dz, orc, torch, stream, local_rank, cpu=(world == 1 and not args.skip_cpu))
     readme = bench_readme(dz, orc) if (rank == 0 and world == 1 and not args.skip_cpu) else None
+    pairwise = bench_pairwise(dz, orc, torch, cpu=(world == 1 and not args.skip_cpu)) if (rank == 0 and not args.skip_large) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -319,6 +320,8 @@ def run_gpu(args):
             line["riesz_gd"] = riesz
         if readme:
             line["readme_rosenbrock_n2"] = readme
+        if pairwise:
+            line["pairwise_radial"] = pairwise
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
@@ -405,6 +408,37 @@ def bench_riesz(dz, orc, torch, stream, device, cpu=True):
         t0 = time.perf_counter(); ref.step(3); dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"ms_per_gd_step": 1e3 * dt / 3, "cores": 1, "kind": "port",
                                "sample": "3 GD step! calls of the same N=4096 problem, oracle single thread (the reference is single-threaded)"}
+    return out
+
+
+def bench_pairwise(dz, orc, torch, cpu=True):
+    """the live package's accelerated pairwise radial kernels (Lennard-Jones), device arrays
+    in / out as in the reference API.  FP64-pipe bound; reported as pair terms/s (n^2 per launch)."""
+    EF = dz.ExampleFunctions
+    n = 16384
+    L = 1.2 * n ** (1.0 / 3.0)
+    p = orc.pcg_fill(3 * n, 21).reshape(3, n) * L
+    t = [torch.from_numpy(a.copy()).cuda() for a in p]
+    g = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3)]
+    out = {"n": n, "potential": "lennard_jones"}
+    for name, order in (("sequential", 0), ("tree", 1)):
+        for _ in range(3):
+            dz.accelerated_pairwise_radial_gradient_(*g, EF.lj_first_derivative, *t, order=order)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            dz.accelerated_pairwise_radial_gradient_(*g, EF.lj_first_derivative, *t, order=order)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out["gradient_" + name] = {"ms": ms, "pair_terms_per_s": n * n / (ms * 1e-3)}
+    if cpu:
+        t0 = time.perf_counter()
+        orc.pairwise_gradient(p[0], p[1], p[2], orc.SEQ)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"ms": 1e3 * dt, "pair_terms_per_s": n * n / dt, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "one gradient of the same n=16384 cloud, oracle with OpenMP over particles"}
     return out
 
 

@@ -31,6 +31,7 @@ import numpy as np
 from . import _capi
 
 __all__ = [
+    "accelerated_pairwise_radial_energy", "accelerated_pairwise_radial_gradient_", "accelerated_pairwise_radial_hvp_",
     "BFGSOptimizer", "GradientDescentOptimizer", "QuadraticLineSearch", "step_",
     "ExampleFunctions", "NULL_CONSTRAINT", "SPHERE_CONSTRAINT", "StepType",
     "DZOptError", "lib", "lib_path",
@@ -115,6 +116,94 @@ ExampleFunctions = SimpleNamespace(
     #: legacy/ExampleFunctions.jl:47-83
     riesz_gradient_=_DeviceFunction("riesz_gradient!", OBJ_RIESZ, "gradient"),
 )
+
+
+class _RadialFunction:
+    def __init__(self, name, potential, derivative):
+        self.name, self.potential, self.derivative = name, potential, derivative
+
+    def __repr__(self):
+        return f"<device radial function {self.name}>"
+
+
+POT_LENNARD_JONES = 1
+#: src/ExampleFunctions.jl:16-72 of the live package
+ExampleFunctions.lj_energy = _RadialFunction("lj_energy", POT_LENNARD_JONES, 0)
+ExampleFunctions.lj_first_derivative = _RadialFunction("lj_first_derivative", POT_LENNARD_JONES, 1)
+ExampleFunctions.lj_second_derivative = _RadialFunction("lj_second_derivative", POT_LENNARD_JONES, 2)
+
+
+def _radial(fn, derivative):
+    if not isinstance(fn, _RadialFunction) or fn.derivative != derivative:
+        want = ("lj_energy", "lj_first_derivative", "lj_second_derivative")[derivative]
+        raise TypeError(f"expected the device radial function ExampleFunctions.{want}")
+    return fn.potential
+
+
+def _is_cuda_tensor(a):
+    return hasattr(a, "is_cuda") and a.is_cuda
+
+
+def _axes_check(arrays):
+    n = arrays[0].shape[0]
+    for a in arrays:
+        if tuple(a.shape) != (n,):                       # @assert (Base.OneTo(n),) == axes(.)  src/...:160-162
+            raise AssertionError("all particle arrays must be vectors of one length")
+    return n
+
+
+def accelerated_pairwise_radial_energy(energy_function, x, y, z, order=ORDER_SEQUENTIAL, workgroupsize=256):
+    """src/ExampleFunctions.jl:152-173.  numpy arrays (host) or CUDA torch tensors (device, asynchronous
+    launch on the current torch stream; the scalar read at the end synchronises like the reference's sum)."""
+    pot = _radial(energy_function, 0)
+    if _is_cuda_tensor(x):
+        import torch
+        n = _axes_check([x, y, z])
+        pe = torch.empty_like(x); out = torch.empty(1, dtype=torch.float64, device=x.device)
+        _check(lib().dzo_pairwise_energy_device(torch.cuda.current_stream().cuda_stream, pot, order, n, x.data_ptr(),
+                                                y.data_ptr(), z.data_ptr(), pe.data_ptr(), out.data_ptr(), None))
+        return float(out.item())
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    n = _axes_check([x, y, z])
+    e = C.c_double()
+    _check(lib().dzo_pairwise_energy(pot, order, n, _dp(x), _dp(y), _dp(z), None, C.byref(e), 0))
+    return e.value
+
+
+def accelerated_pairwise_radial_gradient_(gx, gy, gz, energy_first_derivative, x, y, z, order=ORDER_SEQUENTIAL,
+                                          workgroupsize=256):
+    """src/ExampleFunctions.jl:265-294; writes gx, gy, gz in place and returns None (asynchronously for
+    CUDA tensors, like the reference launcher)."""
+    pot = _radial(energy_first_derivative, 1)
+    if _is_cuda_tensor(x):
+        import torch
+        n = _axes_check([gx, gy, gz, x, y, z])
+        _check(lib().dzo_pairwise_gradient_device(torch.cuda.current_stream().cuda_stream, pot, order, n, x.data_ptr(),
+                                                  y.data_ptr(), z.data_ptr(), gx.data_ptr(), gy.data_ptr(), gz.data_ptr(), None))
+        return None
+    n = _axes_check([gx, gy, gz, x, y, z])
+    x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+    _check(lib().dzo_pairwise_gradient(pot, order, n, _dp(x), _dp(y), _dp(z), _dp(gx), _dp(gy), _dp(gz), 0))
+    return None
+
+
+def accelerated_pairwise_radial_hvp_(px, py, pz, energy_first_derivative, energy_second_derivative, x, y, z, u, v, w,
+                                     order=ORDER_SEQUENTIAL, workgroupsize=256):
+    """src/ExampleFunctions.jl:427-468"""
+    pot = _radial(energy_first_derivative, 1)
+    if _radial(energy_second_derivative, 2) != pot:
+        raise TypeError("first and second derivative belong to different potentials")
+    if _is_cuda_tensor(x):
+        import torch
+        n = _axes_check([px, py, pz, x, y, z, u, v, w])
+        _check(lib().dzo_pairwise_hvp_device(torch.cuda.current_stream().cuda_stream, pot, order, n, x.data_ptr(),
+                                             y.data_ptr(), z.data_ptr(), u.data_ptr(), v.data_ptr(), w.data_ptr(),
+                                             px.data_ptr(), py.data_ptr(), pz.data_ptr(), None))
+        return None
+    n = _axes_check([px, py, pz, x, y, z, u, v, w])
+    x, y, z, u, v, w = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, u, v, w))
+    _check(lib().dzo_pairwise_hvp(pot, order, n, _dp(x), _dp(y), _dp(z), _dp(u), _dp(v), _dp(w), _dp(px), _dp(py), _dp(pz), 0))
+    return None
 
 
 class StepType:

@@ -69,6 +69,10 @@ def bind(lib, cpu: bool):
                                    c_double_p, c_double_p, I])
     sig("line_search", [I, I, I64, I, I64, c_double_p, c_double_p, D, D, c_double_p, c_double_p] + dev)
 
+    P = c_double_p
+    sig("pairwise_energy", [I, I, I64, P, P, P, P, P] + dev)
+    sig("pairwise_gradient", [I, I, I64, P, P, P, P, P, P] + dev)
+    sig("pairwise_hvp", [I, I, I64, P, P, P, P, P, P, P, P, P] + dev)
     if cpu:
         sig("pcg_fill", [c_double_p, I64, C.c_uint64])
         sig("gemv_rows", [I, I64, I64, I64, c_double_p, c_double_p, c_double_p])
@@ -90,6 +94,11 @@ def bind(lib, cpu: bool):
         sig("identity", [I64, c_double_p, I])
         sig("bench_kernel", [I, I64, I, I, c_float_p, I])
         sig("set_tuning", [C.c_char_p, I])
+        V = C.c_void_p
+        sig("pairwise_workspace_bytes", [I64], C.c_uint64)
+        sig("pairwise_energy_device", [V, I, I, I64, V, V, V, V, V, V])
+        sig("pairwise_gradient_device", [V, I, I, I64, V, V, V, V, V, V, V])
+        sig("pairwise_hvp_device", [V, I, I, I64, V, V, V, V, V, V, V, V, V, V])
         sig("host_register", [C.c_void_p, C.c_uint64])
         sig("host_unregister", [C.c_void_p])
         sig("host_alloc", [C.POINTER(C.c_void_p), C.c_uint64])
@@ -102,7 +111,7 @@ class _DevAlias:
     under the same short names the oracle uses (``dzo_cpu_<name>``) so bind() is uniform."""
 
     _DEV = {"objective", "gradient", "dot", "gemv", "update_inverse_hessian", "line_search",
-            "identity"}
+            "identity", "pairwise_energy", "pairwise_gradient", "pairwise_hvp"}
 
     def __init__(self, lib):
         object.__setattr__(self, "_lib", lib)

@@ -865,3 +865,109 @@ int dzo_cpu_update_rows(int64_t n, int64_t row_begin, int64_t row_end, double* H
     }
     return DZO_OK;
 }
+
+/* ======================================================================= pairwise radial kernels
+ * src/ExampleFunctions.jl (the LIVE package).  muladd == fma (explicit); nothing else contracts. */
+static inline double lj_energy(double r2) {            /* :16-27 */
+    const double inv_r2 = 1.0 / r2;
+    const double inv_r4 = inv_r2 * inv_r2;
+    const double inv_r6 = inv_r4 * inv_r2;
+    return 4.0 * fma(inv_r6, inv_r6, -inv_r6);
+}
+static inline double lj_first_derivative(double r2) {  /* :30-47 */
+    const double inv_r2 = 1.0 / r2;
+    const double inv_r4 = inv_r2 * inv_r2;
+    const double inv_r6 = inv_r4 * inv_r2;
+    const double inv_r8 = inv_r4 * inv_r4;
+    return -12.0 * fma(inv_r8, inv_r6 + inv_r6, -inv_r8);
+}
+static inline double lj_second_derivative(double r2) { /* :50-72 */
+    const double inv_r2 = 1.0 / r2;
+    const double inv_r4 = inv_r2 * inv_r2;
+    const double inv_r8 = inv_r4 * inv_r4;
+    const double inv_r10 = inv_r8 * inv_r2;
+    return 48.0 * fma(3.5, inv_r8 * inv_r8, -inv_r10);
+}
+static int pairwise_args_ok(int potential, int order, int64_t n) {
+    if (potential != DZO_POT_LENNARD_JONES) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown radial potential id");
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    if (n <= 0) return fail(DZO_ERR_INVALID_ARGUMENT, "n must be positive");
+    return DZO_OK;
+}
+/* One work-item of the three kernels (:131-147, :239-260, :389-421).  `what`: 0 energy, 1 gradient,
+ * 2 hvp.  The j loop is one segment (SEQUENTIAL) or segments of DZO_RIESZ_SEG (TREE). */
+static void pairwise_item(int what, int order, int64_t n, int64_t i, const double* x, const double* y, const double* z,
+                          const double* u, const double* v, const double* w, double out[3]) {
+    const int64_t seg = (order == DZO_ORDER_SEQUENTIAL) ? n : DZO_RIESZ_SEG;
+    const double xi = x[i], yi = y[i], zi = z[i];
+    const double ui = u ? u[i] : 0.0, vi = v ? v[i] : 0.0, wi = w ? w[i] : 0.0;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t s0 = 0; s0 < n; s0 += seg) {
+        const int64_t s1 = (s0 + seg < n) ? s0 + seg : n;
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int64_t j = s0; j < s1; ++j) {
+            const double dx = xi - x[j], dy = yi - y[j], dz = zi - z[j];
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            if (what == 0) {
+                ax += (i == j) ? 0.0 : lj_energy(r2);                       /* :145 */
+            } else if (what == 1) {
+                const double f = (i == j) ? 0.0 : lj_first_derivative(r2);  /* :253 */
+                ax += f * dx; ay += f * dy; az += f * dz;                   /* :254-256 */
+            } else {
+                const double du = ui - u[j], dv = vi - v[j], dw = wi - w[j];
+                const double f = (i == j) ? 0.0 : lj_first_derivative(r2);  /* :409 */
+                const double s = (i == j) ? 0.0 : lj_second_derivative(r2); /* :410 */
+                const double overlap = dx * du + dy * dv + dz * dw;         /* :411 */
+                const double os = overlap * s;
+                const double g = os + os;                                   /* :413 twice(overlap * s) */
+                ax += f * du + g * dx; ay += f * dv + g * dy; az += f * dw + g * dz;   /* :416-418 */
+            }
+        }
+        if (s0 == 0) { acc[0] = ax; acc[1] = ay; acc[2] = az; }
+        else { acc[0] += ax; acc[1] += ay; acc[2] += az; }
+    }
+    if (what == 0) out[0] = 0.5 * acc[0];                                   /* :148 */
+    else { out[0] = acc[0] + acc[0]; out[1] = acc[1] + acc[1]; out[2] = acc[2] + acc[2]; }   /* :258-260, :419-421 */
+}
+int dzo_cpu_pairwise_energy(int potential, int order, int64_t n, const double* x, const double* y, const double* z,
+                            double* point_energies, double* energy) {
+    int rc = pairwise_args_ok(potential, order, n);
+    if (rc) return rc;
+    if (!x || !y || !z || !energy) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    double part[DZO_TREE_WIDTH];
+    for (int k = 0; k < DZO_TREE_WIDTH; ++k) part[k] = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+        double o[3];
+        pairwise_item(0, order, n, i, x, y, z, NULL, NULL, NULL, o);
+        if (point_energies) point_energies[i] = o[0];
+        part[i & (DZO_TREE_WIDTH - 1)] += o[0];                            /* [GLUE] sum(point_energies) :172 */
+    }
+    *energy = tree_combine(part);
+    return DZO_OK;
+}
+int dzo_cpu_pairwise_gradient(int potential, int order, int64_t n, const double* x, const double* y, const double* z,
+                              double* gx, double* gy, double* gz) {
+    int rc = pairwise_args_ok(potential, order, n);
+    if (rc) return rc;
+    if (!x || !y || !z || !gx || !gy || !gz) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double o[3];
+        pairwise_item(1, order, n, i, x, y, z, NULL, NULL, NULL, o);
+        gx[i] = o[0]; gy[i] = o[1]; gz[i] = o[2];
+    }
+    return DZO_OK;
+}
+int dzo_cpu_pairwise_hvp(int potential, int order, int64_t n, const double* x, const double* y, const double* z,
+                         const double* u, const double* v, const double* w, double* px, double* py, double* pz) {
+    int rc = pairwise_args_ok(potential, order, n);
+    if (rc) return rc;
+    if (!x || !y || !z || !u || !v || !w || !px || !py || !pz) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double o[3];
+        pairwise_item(2, order, n, i, x, y, z, u, v, w, o);
+        px[i] = o[0]; py[i] = o[1]; pz[i] = o[2];
+    }
+    return DZO_OK;
+}

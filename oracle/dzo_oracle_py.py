@@ -427,3 +427,101 @@ class GradientDescentOptimizer:
         for i in range(n):
             d[i] = a * g[i]
         return self
+
+
+# ------------------------------------------------------------------ live src/ExampleFunctions.jl (pairwise radial)
+def _fma(a, b, c):
+    """muladd(a, b, c) as ONE rounding (exact rational arithmetic, then round to nearest even)."""
+    from fractions import Fraction
+    if not (math.isfinite(a) and math.isfinite(b) and math.isfinite(c)):
+        return a * b + c
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def lj_energy(r2):  # :16-27
+    inv_r2 = 1.0 / r2
+    inv_r4 = inv_r2 * inv_r2
+    inv_r6 = inv_r4 * inv_r2
+    return 4.0 * _fma(inv_r6, inv_r6, -inv_r6)
+
+
+def lj_first_derivative(r2):  # :30-47
+    inv_r2 = 1.0 / r2
+    inv_r4 = inv_r2 * inv_r2
+    inv_r6 = inv_r4 * inv_r2
+    inv_r8 = inv_r4 * inv_r4
+    return -12.0 * _fma(inv_r8, inv_r6 + inv_r6, -inv_r8)
+
+
+def lj_second_derivative(r2):  # :50-72
+    inv_r2 = 1.0 / r2
+    inv_r4 = inv_r2 * inv_r2
+    inv_r8 = inv_r4 * inv_r4
+    inv_r10 = inv_r8 * inv_r2
+    return 48.0 * _fma(3.5, inv_r8 * inv_r8, -inv_r10)
+
+
+def _segments(n, tree):
+    seg = RIESZ_SEG if tree else n
+    return [(s0, min(s0 + seg, n)) for s0 in range(0, n, seg)]
+
+
+def pairwise_point_energies(x, y, z, tree=False):  # kernel :117-149
+    n = len(x)
+    out = []
+    for i in range(n):
+        acc = None
+        for s0, s1 in _segments(n, tree):
+            e = 0.0
+            for j in range(s0, s1):
+                dx, dy, dz = x[i] - x[j], y[i] - y[j], z[i] - z[j]
+                r2 = dx * dx + dy * dy + dz * dz
+                e += 0.0 if i == j else lj_energy(r2)
+            acc = e if acc is None else acc + e
+        out.append(0.5 * acc)
+    return out
+
+
+def pairwise_energy(x, y, z, tree=False):  # :152-173, sum through the canonical tree [GLUE]
+    return ksum(pairwise_point_energies(x, y, z, tree), True)
+
+
+def pairwise_gradient(x, y, z, tree=False):  # kernel :224-262
+    n = len(x)
+    g = ([], [], [])
+    for i in range(n):
+        acc = None
+        for s0, s1 in _segments(n, tree):
+            ax = ay = az = 0.0
+            for j in range(s0, s1):
+                dx, dy, dz = x[i] - x[j], y[i] - y[j], z[i] - z[j]
+                r2 = dx * dx + dy * dy + dz * dz
+                f = 0.0 if i == j else lj_first_derivative(r2)
+                ax += f * dx; ay += f * dy; az += f * dz
+            acc = (ax, ay, az) if acc is None else (acc[0] + ax, acc[1] + ay, acc[2] + az)
+        for k in range(3):
+            g[k].append(acc[k] + acc[k])
+    return g
+
+
+def pairwise_hvp(x, y, z, u, v, w, tree=False):  # kernel :367-424
+    n = len(x)
+    p = ([], [], [])
+    for i in range(n):
+        acc = None
+        for s0, s1 in _segments(n, tree):
+            ax = ay = az = 0.0
+            for j in range(s0, s1):
+                dx, dy, dz = x[i] - x[j], y[i] - y[j], z[i] - z[j]
+                du, dv, dw = u[i] - u[j], v[i] - v[j], w[i] - w[j]
+                r2 = dx * dx + dy * dy + dz * dz
+                f = 0.0 if i == j else lj_first_derivative(r2)
+                s = 0.0 if i == j else lj_second_derivative(r2)
+                overlap = dx * du + dy * dv + dz * dw
+                os_ = overlap * s
+                gg = os_ + os_
+                ax += f * du + gg * dx; ay += f * dv + gg * dy; az += f * dw + gg * dz
+            acc = (ax, ay, az) if acc is None else (acc[0] + ax, acc[1] + ay, acc[2] + az)
+        for k in range(3):
+            p[k].append(acc[k] + acc[k])
+    return p

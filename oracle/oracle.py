@@ -209,3 +209,37 @@ def line_search(obj, x, direction, f0, t1, order=SEQ, constraint=CONSTRAINT_NONE
     _check(lib().dzo_cpu_line_search(obj, constraint, dim, order, x.size, _dp(x), _dp(d), float(f0),
                                      float(t1), C.byref(tb), C.byref(fb)))
     return tb.value, fb.value
+
+
+# ---------------------------------------------------------------------------------------------
+# pairwise radial kernels of the live package (src/ExampleFunctions.jl:117-468), Lennard-Jones
+POT_LJ = 1
+
+
+def _v(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def pairwise_energy(x, y, z, order=SEQ):
+    """(point_energies, energy) -- :117-173"""
+    x, y, z = _v(x), _v(y), _v(z)
+    pe = np.empty(x.size); e = C.c_double()
+    _check(lib().dzo_cpu_pairwise_energy(POT_LJ, order, x.size, _dp(x), _dp(y), _dp(z), _dp(pe), C.byref(e)))
+    return pe, e.value
+
+
+def pairwise_gradient(x, y, z, order=SEQ):
+    """(gx, gy, gz) -- :224-294"""
+    x, y, z = _v(x), _v(y), _v(z)
+    g = [np.empty(x.size) for _ in range(3)]
+    _check(lib().dzo_cpu_pairwise_gradient(POT_LJ, order, x.size, _dp(x), _dp(y), _dp(z), _dp(g[0]), _dp(g[1]), _dp(g[2])))
+    return g
+
+
+def pairwise_hvp(x, y, z, u, v, w, order=SEQ):
+    """(px, py, pz) -- :367-468"""
+    x, y, z, u, v, w = map(_v, (x, y, z, u, v, w))
+    p = [np.empty(x.size) for _ in range(3)]
+    _check(lib().dzo_cpu_pairwise_hvp(POT_LJ, order, x.size, _dp(x), _dp(y), _dp(z), _dp(u), _dp(v), _dp(w),
+                                      _dp(p[0]), _dp(p[1]), _dp(p[2])))
+    return p
