@@ -285,6 +285,7 @@ def run_gpu(args):
     if rank == 0 and not args.skip_large:
         riesz = bench_riesz(dz, orc, torch, stream, local_rank, cpu=(world == 1 and not args.skip_cpu))
     readme = bench_readme(dz, orc) if (rank == 0 and world == 1 and not args.skip_cpu) else None
+    lbfgs = bench_lbfgs(dz, orc, torch, stream, cpu=(world == 1 and not args.skip_cpu)) if (rank == 0 and not args.skip_large) else None
     pairwise = bench_pairwise(dz, orc, torch, cpu=(world == 1 and not args.skip_cpu)) if (rank == 0 and not args.skip_large) else None
 
     cpu = None
@@ -322,6 +323,8 @@ def run_gpu(args):
             line["readme_rosenbrock_n2"] = readme
         if pairwise:
             line["pairwise_radial"] = pairwise
+        if lbfgs:
+            line["live_lbfgs"] = lbfgs
         print(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
@@ -439,6 +442,33 @@ def bench_pairwise(dz, orc, torch, cpu=True):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"ms": 1e3 * dt, "pair_terms_per_s": n * n / dt, "cores": os.cpu_count(), "kind": "port",
                                "sample": "one gradient of the same n=16384 cloud, oracle with OpenMP over particles"}
+    return out
+
+
+def bench_lbfgs(dz, orc, torch, stream, cpu=True):
+    """the live package's LBFGSOptimizer (the package's own answer for large n) on
+    extended Rosenbrock n = 2^20, history 10: k step! calls in ONE cluster-kernel launch."""
+    EF = dz.ExampleFunctions
+    n, m, k = 1 << 20, 10, 50
+    x0 = 4.0 * orc.pcg_fill(n, 9) - 2.0
+    opt = dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, m)
+    opt.set_stream(stream.cuda_stream)
+    opt.step(5)
+    it0 = int(opt.iteration_count[()])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); opt.step_async(k); e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    done = int(opt.iteration_count[()]) - it0
+    out = {"n": n, "history_length": m, "steps": done, "ms_per_step": ms / max(done, 1), "steps_per_s": 1e3 * done / ms,
+           "objective": float(opt.current_objective_value[()])}
+    opt.close()
+    if cpu:
+        ref = orc.LBFGS(orc.OBJ_ROSENBROCK, x0, 1.0, m, orc.TREE)
+        ref.step(5)
+        t0 = time.perf_counter(); ref.step(5); dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"ms_per_step": 1e3 * dt / 5, "cores": 1, "kind": "port",
+                               "sample": "5 step! calls of the same problem, oracle single thread"}
     return out
 
 

@@ -31,6 +31,7 @@ import numpy as np
 from . import _capi
 
 __all__ = [
+    "LBFGSOptimizer",
     "accelerated_pairwise_radial_energy", "accelerated_pairwise_radial_gradient_", "accelerated_pairwise_radial_hvp_",
     "BFGSOptimizer", "GradientDescentOptimizer", "QuadraticLineSearch", "step_",
     "ExampleFunctions", "NULL_CONSTRAINT", "SPHERE_CONSTRAINT", "StepType",
@@ -470,6 +471,85 @@ class GradientDescentOptimizer(_Optimizer):
 
     @property
     def delta_objective_value(self): return self._scalar("get_delta_objective")
+
+
+class LBFGSOptimizer:
+    """struct LBFGSOptimizer of the LIVE package, src/DZOptimization.jl:321-344.
+
+    ``LBFGSOptimizer(c_, f, g_, x0, initial_step_length, history_length)`` (:400-427); ``c_`` is ``None``
+    (Julia ``nothing``) or NULL_CONSTRAINT.  Fields as in the reference: ``is_stuck`` (the live spelling of
+    has_terminated), ``iteration_count``, ``current_point``, ``delta_point``, ``current_objective_value``,
+    ``delta_objective_value``, ``current_gradient``, ``delta_gradient``, ``step_direction``, ``rho_history``."""
+
+    def __init__(self, constraint_function_, objective_function, gradient_function_, initial_point,
+                 initial_step_length, history_length, device=0):
+        c = NULL_CONSTRAINT if constraint_function_ is None else constraint_function_
+        obj, cid = _resolve(objective_function, gradient_function_, c)
+        a = np.ascontiguousarray(initial_point, dtype=np.float64)
+        if a.ndim != 1:
+            raise ValueError("initial point must be a vector")
+        if not initial_step_length > 0:
+            raise AssertionError("initial_step_length > 0")              # @assert :375
+        self._n = a.size
+        self._h = None
+        h = C.c_void_p()
+        _check(lib().dzo_lbfgs_create(C.byref(h), obj, cid, 0, self._n, _dp(a), float(initial_step_length),
+                                      int(history_length), int(device)))
+        self._h = h
+        self.history_length = int(history_length)
+
+    def _vec(self, name):
+        out = np.empty(self._n)
+        _check(getattr(lib(), "dzo_lbfgs_" + name)(self._h, _dp(out)))
+        return out
+
+    def _sc(self, name, ctype, dtype):
+        v = ctype()
+        _check(getattr(lib(), "dzo_lbfgs_" + name)(self._h, C.byref(v)))
+        return np.array(v.value, dtype=dtype)
+
+    current_point = property(lambda s: s._vec("get_point"))
+    delta_point = property(lambda s: s._vec("get_delta_point"))
+    current_gradient = property(lambda s: s._vec("get_gradient"))
+    delta_gradient = property(lambda s: s._vec("get_delta_gradient"))
+    step_direction = property(lambda s: s._vec("get_direction"))
+    current_objective_value = property(lambda s: s._sc("get_objective", C.c_double, np.float64))
+    delta_objective_value = property(lambda s: s._sc("get_delta_objective", C.c_double, np.float64))
+    iteration_count = property(lambda s: s._sc("get_iteration_count", C.c_int64, np.int64))
+    is_stuck = property(lambda s: s._sc("get_stuck", C.c_uint8, np.bool_))
+    has_converged = is_stuck
+
+    @property
+    def rho_history(self):
+        cnt = C.c_int64(); rho = np.zeros(64)
+        _check(lib().dzo_lbfgs_get_rho_history(self._h, C.byref(cnt), _dp(rho)))
+        return rho[:cnt.value].copy()
+
+    def set_stream(self, cuda_stream):
+        _check(lib().dzo_lbfgs_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def step(self, k: int = 1):
+        _check(lib().dzo_lbfgs_step(self._h, int(k)))
+        return self
+
+    def step_async(self, k: int = 1):
+        _check(lib().dzo_lbfgs_step_async(self._h, int(k)))
+        return self
+
+    def sync(self):
+        _check(lib().dzo_lbfgs_sync(self._h))
+        return self
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().dzo_lbfgs_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def step_(opt):

@@ -60,6 +60,17 @@ def bind(lib, cpu: bool):
     sig("gd_get_terminated", [H, c_u8_p])
     sig("gd_destroy", [H], None)
 
+    tail_lb = [I, I] if cpu else [I, I]               # (history_length, order) | (history_length, device)
+    sig("lbfgs_create", [HP, I, I, I64, I64, c_double_p, D] + tail_lb)
+    sig("lbfgs_step", [H, I])
+    for g in ("get_point", "get_delta_point", "get_gradient", "get_delta_gradient", "get_direction",
+              "get_objective", "get_delta_objective"):
+        sig("lbfgs_" + g, [H, c_double_p])
+    sig("lbfgs_get_iteration_count", [H, c_i64_p])
+    sig("lbfgs_get_stuck", [H, c_u8_p])
+    sig("lbfgs_get_rho_history", [H, c_i64_p, c_double_p])
+    sig("lbfgs_destroy", [H], None)
+
     dev = [] if cpu else [I]
     sig("objective", [I, I, I64, I, I64, I64, c_double_p, c_double_p] + dev)
     sig("gradient", [I, I, I64, I, I64, I64, c_double_p, c_double_p] + dev)
@@ -87,6 +98,9 @@ def bind(lib, cpu: bool):
         sig("bfgs_sync", [H])
         sig("bfgs_info", [H, c_i64_p, c_i64_p, c_int_p, c_i64_p, c_i64_p])
         sig("bfgs_get_step_log", [H, c_i64_p, c_u8_p])
+        sig("lbfgs_set_stream", [H, C.c_void_p])
+        sig("lbfgs_step_async", [H, I])
+        sig("lbfgs_sync", [H])
         sig("gd_set_stream", [H, C.c_void_p])
         sig("gd_step_async", [H, I])
         sig("gd_sync", [H])

@@ -1,0 +1,142 @@
+// dzopt_lbfgs.cu -- C ABI of the live package's LBFGSOptimizer (src/DZOptimization.jl:321-509).
+#include <new>
+
+#include "host_common.h"
+#include "lbfgs_kernels.cuh"
+
+using namespace dzo;
+
+struct dzo_lbfgs {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int64_t n = 0;
+    int m = 0;
+    double *x = nullptr, *dx = nullptr, *g = nullptr, *dg = nullptr, *d = nullptr, *S = nullptr, *Y = nullptr;
+    LbfgsCtrl* ctrl = nullptr;
+};
+
+static void free_lbfgs(dzo_lbfgs* o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->d, o->S, o->Y, o->ctrl};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    delete o;
+}
+
+static int lbfgs_launch(dzo_lbfgs* o, int mode, int k, double L0) {
+    LbfgsArgs a;
+    a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.d = o->d; a.S = o->S; a.Y = o->Y; a.ctrl = o->ctrl;
+    a.n = o->n; a.m = o->m; a.ksteps = k; a.initial_step_length = L0; a.mode = mode;
+    cluster_lbfgs_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+
+extern "C" {
+
+int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj_param, int64_t n, const double* x0,
+                     double initial_step_length, int history_length, int device) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = nullptr;
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, 1));
+    if (objective != DZO_OBJ_ROSENBROCK) return fail(DZO_ERR_UNSUPPORTED, "LBFGSOptimizer device objective: DZO_OBJ_ROSENBROCK");
+    if (history_length < 1 || history_length > DZO_LBFGS_MAX_HISTORY)
+        return fail(DZO_ERR_INVALID_ARGUMENT, "history_length must be in [1, %d]", DZO_LBFGS_MAX_HISTORY);
+    if (!(initial_step_length > 0.0)) return fail(DZO_ERR_INVALID_ARGUMENT, "initial_step_length must be positive");   // :375
+    DZO_TRY(use_device(device));
+    dzo_lbfgs* o = new (std::nothrow) dzo_lbfgs();
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->device = device; o->n = n; o->m = history_length;
+    auto bail = [&](int code) { free_lbfgs(o); return code; };
+    if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "cudaStreamCreate failed"));
+    o->stream = o->own_stream;
+    const size_t vb = (size_t)n * 8;
+    double** vecs[] = {&o->x, &o->dx, &o->g, &o->dg, &o->d};
+    for (double** v : vecs)
+        if (cudaMalloc((void**)v, vb) != cudaSuccess) return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+    if (cudaMalloc((void**)&o->S, vb * history_length) != cudaSuccess || cudaMalloc((void**)&o->Y, vb * history_length) != cudaSuccess ||
+        cudaMalloc((void**)&o->ctrl, sizeof(LbfgsCtrl)) != cudaSuccess)
+        return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+    if (cudaMemcpyAsync(o->x, x0, vb, cudaMemcpyHostToDevice, o->stream) != cudaSuccess ||
+        cudaMemsetAsync(o->S, 0, vb * history_length, o->stream) != cudaSuccess ||
+        cudaMemsetAsync(o->Y, 0, vb * history_length, o->stream) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "initial copies failed"));
+    int rc = lbfgs_launch(o, 1, 0, initial_step_length);
+    if (rc) return bail(rc);
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "constructor kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = o;
+    return DZO_OK;
+}
+
+void dzo_lbfgs_destroy(dzo_lbfgs* o) { free_lbfgs(o); }
+
+int dzo_lbfgs_set_stream(dzo_lbfgs* o, void* cuda_stream) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    o->stream = cuda_stream ? (cudaStream_t)cuda_stream : o->own_stream;
+    return DZO_OK;
+}
+int dzo_lbfgs_step_async(dzo_lbfgs* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(use_device(o->device));
+    if (k == 0) return DZO_OK;
+    return lbfgs_launch(o, 0, k, 0.0);
+}
+int dzo_lbfgs_sync(dzo_lbfgs* o) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+int dzo_lbfgs_step(dzo_lbfgs* o, int k) {
+    DZO_TRY(dzo_lbfgs_step_async(o, k));
+    return dzo_lbfgs_sync(o);
+}
+
+static int lb_read(dzo_lbfgs* o, void* dst, const void* src, size_t bytes) {
+    if (!o || !dst) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+#define DZO_LB_VEC(name, field)                                                   \
+    int name(dzo_lbfgs* o, double* out) {                                         \
+        if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");             \
+        return lb_read(o, out, o->field, (size_t)o->n * 8);                       \
+    }
+DZO_LB_VEC(dzo_lbfgs_get_point, x)
+DZO_LB_VEC(dzo_lbfgs_get_delta_point, dx)
+DZO_LB_VEC(dzo_lbfgs_get_gradient, g)
+DZO_LB_VEC(dzo_lbfgs_get_delta_gradient, dg)
+DZO_LB_VEC(dzo_lbfgs_get_direction, d)
+#undef DZO_LB_VEC
+#define DZO_LB_SCALAR(name, type, expr)                                           \
+    int name(dzo_lbfgs* o, type* out) {                                           \
+        if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");    \
+        LbfgsCtrl c;                                                              \
+        DZO_TRY(lb_read(o, &c, o->ctrl, sizeof c));                               \
+        *out = (type)(expr);                                                      \
+        return DZO_OK;                                                            \
+    }
+DZO_LB_SCALAR(dzo_lbfgs_get_objective, double, c.f)
+DZO_LB_SCALAR(dzo_lbfgs_get_delta_objective, double, c.df)
+DZO_LB_SCALAR(dzo_lbfgs_get_iteration_count, int64_t, c.iter)
+DZO_LB_SCALAR(dzo_lbfgs_get_stuck, uint8_t, c.stuck != 0)
+#undef DZO_LB_SCALAR
+
+int dzo_lbfgs_get_rho_history(dzo_lbfgs* o, int64_t* count, double* rho) {
+    if (!o || !count || !rho) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    LbfgsCtrl c;
+    DZO_TRY(lb_read(o, &c, o->ctrl, sizeof c));
+    *count = c.count;
+    for (int i = 0; i < DZO_LBFGS_MAX_HISTORY; ++i) rho[i] = (i < c.count) ? c.rho[(c.head + i) % o->m] : 0.0;   // newest first
+    return DZO_OK;
+}
+
+}  // extern "C"

@@ -971,3 +971,155 @@ int dzo_cpu_pairwise_hvp(int potential, int order, int64_t n, const double* x, c
     }
     return DZO_OK;
 }
+
+/* ======================================================================= live LBFGSOptimizer
+ * src/DZOptimization.jl:107-154 (take_backtracking_step!), :321-509.  History index 0 = newest
+ * (the reference pushfirst!s).  dot / norm: BLAS in the reference -> dot_ / sqrt(norm2_) here. */
+struct dzo_cpu_lbfgs {
+    problem_t P;
+    int m, count;
+    double *x, *dx, *g, *dg, *d;
+    double *S, *Y;                 /* m x n each, logical slot i at S + i*n (shifted on push) */
+    double rho[DZO_LBFGS_MAX_HISTORY], alpha[DZO_LBFGS_MAX_HISTORY];
+    double f, df;
+    int64_t iter;
+    int stuck;
+};
+
+static int julia_isequal(double a, double b) { /* isequal: NaN == NaN, -0.0 != 0.0 */
+    if (a == b) return signbit(a) == signbit(b);
+    return (a != a) && (b != b);
+}
+
+int dzo_cpu_lbfgs_create(dzo_cpu_lbfgs** out, int objective, int constraint, int64_t obj_param, int64_t n,
+                         const double* x0, double initial_step_length, int history_length, int order) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = NULL;
+    int rc = check_problem(objective, constraint, obj_param, n, 1);
+    if (rc) return rc;
+    if (history_length < 1 || history_length > DZO_LBFGS_MAX_HISTORY) return fail(DZO_ERR_INVALID_ARGUMENT, "history_length must be in [1, 64]");
+    if (!(initial_step_length > 0.0)) return fail(DZO_ERR_INVALID_ARGUMENT, "initial_step_length must be positive"); /* :375 */
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    dzo_cpu_lbfgs* o = (dzo_cpu_lbfgs*)calloc(1, sizeof *o);
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->P.objective = objective; o->P.constraint = constraint; o->P.order = order; o->P.n = n;
+    o->P.dim = obj_param > 0 ? obj_param : 1;
+    o->m = history_length;
+    o->x = (double*)malloc((size_t)n * 8); o->dx = (double*)calloc((size_t)n, 8);       /* :364-367 */
+    o->g = (double*)malloc((size_t)n * 8); o->dg = (double*)calloc((size_t)n, 8);       /* :369-372 */
+    o->d = (double*)calloc((size_t)n, 8);
+    o->S = (double*)calloc((size_t)n * (size_t)(history_length > 0 ? history_length : 1), 8);
+    o->Y = (double*)calloc((size_t)n * (size_t)(history_length > 0 ? history_length : 1), 8);
+    if (!o->x || !o->dx || !o->g || !o->dg || !o->d || !o->S || !o->Y) { dzo_cpu_lbfgs_destroy(o); return fail(DZO_ERR_ALLOC, "out of memory"); }
+    memcpy(o->x, x0, (size_t)n * 8);
+    if (!constraint_(&o->P, o->x)) { dzo_cpu_lbfgs_destroy(o); return fail(DZO_ERR_CONSTRAINT_FAILED, "constraint_function! failed on the initial point"); } /* :413-415 */
+    o->f = objective_(&o->P, o->x);                                                     /* :417 */
+    gradient_(&o->P, o->g, o->x);                                                       /* :419-422 */
+    const double gnorm = sqrt(norm2_(order, o->g, n));                                  /* :376 */
+    o->stuck = (gnorm == 0.0);                                                          /* :377 */
+    if (!o->stuck) {                                                                    /* :380-383 */
+        const double c = -initial_step_length / gnorm;
+        for (int64_t i = 0; i < n; ++i) o->d[i] = o->g[i] * c;
+    }
+    *out = o;
+    return DZO_OK;
+}
+
+/* compute_lbfgs_step_direction!  :430-451 */
+static void lbfgs_direction(dzo_cpu_lbfgs* o) {
+    const int64_t n = o->P.n;
+    const int order = o->P.order;
+    memcpy(o->d, o->g, (size_t)n * 8);
+    for (int i = 0; i < o->count; ++i) {
+        o->alpha[i] = dot_(order, o->S + (size_t)i * n, o->d, n) / o->rho[i];           /* :439 */
+        const double a = -o->alpha[i];
+        const double* y = o->Y + (size_t)i * n;
+        for (int64_t k = 0; k < n; ++k) o->d[k] += a * y[k];                            /* :440 axpy! */
+    }
+    if (o->count > 0) {
+        const double c = -o->rho[0] / dot_(order, o->Y, o->Y, n);                       /* :443 */
+        for (int64_t k = 0; k < n; ++k) o->d[k] *= c;
+    }
+    for (int i = o->count - 1; i >= 0; --i) {
+        const double beta = dot_(order, o->Y + (size_t)i * n, o->d, n) / o->rho[i];     /* :446 */
+        const double a = -(o->alpha[i] + beta);
+        const double* s = o->S + (size_t)i * n;
+        for (int64_t k = 0; k < n; ++k) o->d[k] += a * s[k];                            /* :447 */
+    }
+}
+
+static void lbfgs_step_one(dzo_cpu_lbfgs* o) {
+    if (o->stuck) return;                                                               /* :456-458 */
+    const int64_t n = o->P.n;
+    const int order = o->P.order;
+    if (o->iter > 0) lbfgs_direction(o);                                                /* :463-471 */
+    /* take_backtracking_step!(opt, 1, step_direction)  :107-154 */
+    double step = 1.0;
+    memcpy(o->dx, o->x, (size_t)n * 8);                                                 /* :118 */
+    for (;;) {
+        int same = 1;
+        for (int64_t k = 0; k < n; ++k) {
+            o->x[k] += step * o->d[k];                                                  /* :124 axpy! */
+            same &= julia_isequal(o->x[k], o->dx[k]);
+        }
+        if (same) { o->stuck = 1; return; }                                             /* :128-131 */
+        if (constraint_(&o->P, o->x)) {                                                 /* :134-135 */
+            const double next = objective_(&o->P, o->x);                                /* :138 */
+            if (next < o->f) {                                                          /* :139 */
+                o->df = next - o->f;                                                    /* :142-143 */
+                o->f = next;
+                for (int64_t k = 0; k < n; ++k) o->dx[k] = 1.0 * o->x[k] + (-1.0) * o->dx[k];   /* :145 axpby! */
+                break;
+            }
+        }
+        memcpy(o->x, o->dx, (size_t)n * 8);                                             /* :151 */
+        step *= 0.5;                                                                    /* :152 */
+    }
+    memcpy(o->dg, o->g, (size_t)n * 8);                                                 /* :478 */
+    gradient_(&o->P, o->g, o->x);                                                       /* :479 */
+    for (int64_t k = 0; k < n; ++k) o->dg[k] = 1.0 * o->g[k] + (-1.0) * o->dg[k];       /* :480 */
+    if (o->m > 0) {                                                                     /* :482-505 pushfirst! */
+        const int keep = (o->count < o->m) ? o->count : o->m - 1;
+        memmove(o->S + n, o->S, (size_t)keep * n * 8);
+        memmove(o->Y + n, o->Y, (size_t)keep * n * 8);
+        memmove(o->rho + 1, o->rho, (size_t)keep * 8);
+        memcpy(o->S, o->dx, (size_t)n * 8);
+        memcpy(o->Y, o->dg, (size_t)n * 8);
+        o->rho[0] = dot_(order, o->dx, o->dg, n);                                       /* :505 */
+        o->count = keep + 1;
+    }
+    o->iter += 1;                                                                       /* :507 */
+}
+
+int dzo_cpu_lbfgs_step(dzo_cpu_lbfgs* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    for (int s = 0; s < k; ++s) lbfgs_step_one(o);
+    return DZO_OK;
+}
+#define LGET(name, field)                                                               \
+    int name(dzo_cpu_lbfgs* o, double* out) {                                           \
+        if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");          \
+        memcpy(out, o->field, (size_t)o->P.n * 8);                                      \
+        return DZO_OK;                                                                  \
+    }
+LGET(dzo_cpu_lbfgs_get_point, x)
+LGET(dzo_cpu_lbfgs_get_delta_point, dx)
+LGET(dzo_cpu_lbfgs_get_gradient, g)
+LGET(dzo_cpu_lbfgs_get_delta_gradient, dg)
+LGET(dzo_cpu_lbfgs_get_direction, d)
+#undef LGET
+int dzo_cpu_lbfgs_get_objective(dzo_cpu_lbfgs* o, double* out) { if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer"); *out = o->f; return DZO_OK; }
+int dzo_cpu_lbfgs_get_delta_objective(dzo_cpu_lbfgs* o, double* out) { if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer"); *out = o->df; return DZO_OK; }
+int dzo_cpu_lbfgs_get_iteration_count(dzo_cpu_lbfgs* o, int64_t* out) { if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer"); *out = o->iter; return DZO_OK; }
+int dzo_cpu_lbfgs_get_stuck(dzo_cpu_lbfgs* o, uint8_t* out) { if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer"); *out = (uint8_t)o->stuck; return DZO_OK; }
+int dzo_cpu_lbfgs_get_rho_history(dzo_cpu_lbfgs* o, int64_t* count, double* rho) {
+    if (!o || !count || !rho) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *count = o->count;
+    for (int i = 0; i < DZO_LBFGS_MAX_HISTORY; ++i) rho[i] = (i < o->count) ? o->rho[i] : 0.0;
+    return DZO_OK;
+}
+void dzo_cpu_lbfgs_destroy(dzo_cpu_lbfgs* o) {
+    if (!o) return;
+    free(o->x); free(o->dx); free(o->g); free(o->dg); free(o->d); free(o->S); free(o->Y);
+    free(o);
+}

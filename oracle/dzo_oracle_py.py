@@ -525,3 +525,90 @@ def pairwise_hvp(x, y, z, u, v, w, tree=False):  # kernel :367-424
         for k in range(3):
             p[k].append(acc[k] + acc[k])
     return p
+
+
+# ------------------------------------------------------------------ live src/DZOptimization.jl: L-BFGS
+def _isequal(a, b):  # Julia isequal on floats
+    if a == b:
+        return math.copysign(1.0, a) == math.copysign(1.0, b)
+    return math.isnan(a) and math.isnan(b)
+
+
+class LiveLBFGSOptimizer:
+    """src/DZOptimization.jl:321-509 with take_backtracking_step! (:107-154); history index 0 = newest."""
+
+    def __init__(self, fn, x0, initial_step_length, history_length, tree=True):  # :347-427
+        self.fn, self.tree, self.m = fn, tree, history_length
+        self.current_point = list(x0)
+        assert fn.constraint(self.current_point)
+        self.current_objective_value = fn.f(self.current_point)
+        n = len(x0)
+        self.current_gradient = [0.0] * n
+        fn.g(self.current_gradient, self.current_point)
+        self.delta_point = [0.0] * n
+        self.delta_gradient = [0.0] * n
+        self.delta_objective_value = 0.0
+        assert initial_step_length > 0.0
+        gnorm = math.sqrt(norm2(self.current_gradient, tree))
+        self.is_stuck = gnorm == 0.0
+        if self.is_stuck:
+            self.step_direction = [0.0] * n
+        else:
+            c = -initial_step_length / gnorm
+            self.step_direction = [gi * c for gi in self.current_gradient]
+        self.iteration_count = 0
+        self.s, self.y, self.alpha, self.rho = [], [], [], []
+
+    def _direction(self):  # :430-451
+        d = list(self.current_gradient)
+        k = len(self.s)
+        for i in range(k):
+            self.alpha[i] = dot(self.s[i], d, self.tree) / self.rho[i]
+            a = -self.alpha[i]
+            d = [di + a * yi for di, yi in zip(d, self.y[i])]
+        if k:
+            c = -self.rho[0] / dot(self.y[0], self.y[0], self.tree)
+            d = [di * c for di in d]
+        for i in reversed(range(k)):
+            beta = dot(self.y[i], d, self.tree) / self.rho[i]
+            a = -(self.alpha[i] + beta)
+            d = [di + a * si for di, si in zip(d, self.s[i])]
+        self.step_direction = d
+
+    def step(self):  # :454-509
+        if self.is_stuck:
+            return self
+        if self.iteration_count > 0:
+            self._direction()
+        # take_backtracking_step!  :107-154
+        x, d = self.current_point, self.step_direction
+        self.delta_point = list(x)
+        step = 1.0
+        while True:
+            for k in range(len(x)):
+                x[k] += step * d[k]
+            if all(_isequal(a, b) for a, b in zip(x, self.delta_point)):
+                self.is_stuck = True
+                return self
+            if self.fn.constraint(x):
+                nxt = self.fn.f(x)
+                if nxt < self.current_objective_value:
+                    self.delta_objective_value = nxt - self.current_objective_value
+                    self.current_objective_value = nxt
+                    self.delta_point = [1.0 * a + (-1.0) * b for a, b in zip(x, self.delta_point)]
+                    break
+            x[:] = self.delta_point
+            step *= 0.5
+        self.delta_gradient = list(self.current_gradient)
+        self.fn.g(self.current_gradient, x)
+        self.delta_gradient = [1.0 * a + (-1.0) * b for a, b in zip(self.current_gradient, self.delta_gradient)]
+        if len(self.s) >= self.m:
+            self.s.pop(); self.y.pop()
+        self.s.insert(0, list(self.delta_point)); self.y.insert(0, list(self.delta_gradient))
+        if len(self.alpha) < self.m:
+            self.alpha.append(0.0)
+        if len(self.rho) >= self.m:
+            self.rho.pop()
+        self.rho.insert(0, dot(self.delta_point, self.delta_gradient, self.tree))
+        self.iteration_count += 1
+        return self

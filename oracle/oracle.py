@@ -243,3 +243,57 @@ def pairwise_hvp(x, y, z, u, v, w, order=SEQ):
     _check(lib().dzo_cpu_pairwise_hvp(POT_LJ, order, x.size, _dp(x), _dp(y), _dp(z), _dp(u), _dp(v), _dp(w),
                                       _dp(p[0]), _dp(p[1]), _dp(p[2])))
     return p
+
+
+class LBFGS:
+    """live LBFGSOptimizer (src/DZOptimization.jl:321-509), one problem; x0: (n,)"""
+
+    def __init__(self, objective, x0, step, history_length, order=TREE):
+        a = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+        self.n = a.size
+        self._h = None
+        h = C.c_void_p()
+        _check(lib().dzo_cpu_lbfgs_create(C.byref(h), objective, CONSTRAINT_NONE, 0, self.n, _dp(a), float(step),
+                                          int(history_length), order))
+        self._h = h
+
+    def _vec(self, name):
+        out = np.empty(self.n)
+        _check(getattr(lib(), "dzo_cpu_lbfgs_" + name)(self._h, _dp(out)))
+        return out
+
+    def _sc(self, name, ctype=C.c_double):
+        v = ctype()
+        _check(getattr(lib(), "dzo_cpu_lbfgs_" + name)(self._h, C.byref(v)))
+        return v.value
+
+    point = property(lambda s: s._vec("get_point"))
+    delta_point = property(lambda s: s._vec("get_delta_point"))
+    gradient = property(lambda s: s._vec("get_gradient"))
+    delta_gradient = property(lambda s: s._vec("get_delta_gradient"))
+    direction = property(lambda s: s._vec("get_direction"))
+    objective = property(lambda s: s._sc("get_objective"))
+    delta_objective = property(lambda s: s._sc("get_delta_objective"))
+    iteration_count = property(lambda s: s._sc("get_iteration_count", C.c_int64))
+    stuck = property(lambda s: bool(s._sc("get_stuck", C.c_uint8)))
+
+    @property
+    def rho_history(self):
+        cnt = C.c_int64(); rho = np.zeros(64)
+        _check(lib().dzo_cpu_lbfgs_get_rho_history(self._h, C.byref(cnt), _dp(rho)))
+        return rho[:cnt.value].copy()
+
+    def step(self, k=1):
+        _check(lib().dzo_cpu_lbfgs_step(self._h, int(k)))
+        return self
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().dzo_cpu_lbfgs_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,89 @@
+"""Live LBFGSOptimizer (src/DZOptimization.jl:321-509) + take_backtracking_step! (:107-154):
+oracle vs the independent Python restatement (CPU) and CUDA vs oracle (GPU), all bitwise."""
+import numpy as np
+import pytest
+
+from conftest import assert_bitwise
+
+ROSEN = 1
+
+
+def _x0(orc, n, seed):
+    return 4.0 * orc.pcg_fill(n, seed) - 2.0
+
+
+@pytest.mark.parametrize("n,m,tree", [(2, 3, False), (10, 4, True), (64, 5, True), (30, 1, True)])
+def test_c_oracle_equals_python_restatement(orc, n, m, tree):
+    import dzo_oracle_py as P
+    x0 = _x0(orc, n, 3)
+    py = P.LiveLBFGSOptimizer(P.Rosenbrock(tree), list(x0), 0.5, m, tree)
+    c = orc.LBFGS(ROSEN, x0, 0.5, m, orc.TREE if tree else orc.SEQ)
+    for it in range(40):
+        py.step(); c.step(1)
+        assert_bitwise(c.point, np.array(py.current_point), f"iter {it} point")
+        assert_bitwise(c.direction, np.array(py.step_direction), f"iter {it} direction")
+        assert_bitwise(c.delta_point, np.array(py.delta_point), f"iter {it} delta_point")
+        assert_bitwise(c.delta_gradient, np.array(py.delta_gradient), f"iter {it} delta_gradient")
+        assert c.objective == py.current_objective_value and c.delta_objective == py.delta_objective_value
+        assert c.iteration_count == py.iteration_count and c.stuck == py.is_stuck
+        assert_bitwise(c.rho_history, np.array(py.rho), "rho history")
+
+
+def test_lbfgs_converges_to_the_rosenbrock_minimum(orc):
+    x0 = _x0(orc, 8, 4)
+    c = orc.LBFGS(ROSEN, x0, 1.0, 6, orc.SEQ)
+    for _ in range(400):
+        c.step(50)
+        if c.stuck:
+            break
+    assert c.stuck                                     # the live spelling of has_terminated
+    assert np.abs(c.point - 1.0).max() < 1e-6 and c.objective < 1e-12
+    # at the minimum the gradient is zero: constructor reports is_stuck at once  (:377)
+    z = orc.LBFGS(ROSEN, np.ones(4), 1.0, 3)
+    assert z.stuck and z.iteration_count == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(2, 2), (34, 5), (2048, 8), (16384, 10), (20000, 3)])
+def test_gpu_lbfgs_trace(gpu, orc, n, m):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n, 5)
+    opt = dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, m)
+    ref = orc.LBFGS(ROSEN, x0, 1.0, m, orc.TREE)
+
+    def compare(tag):
+        assert_bitwise(opt.current_point, ref.point, f"{tag}: point")
+        assert_bitwise(opt.delta_point, ref.delta_point, f"{tag}: delta_point")
+        assert_bitwise(opt.current_gradient, ref.gradient, f"{tag}: gradient")
+        assert_bitwise(opt.delta_gradient, ref.delta_gradient, f"{tag}: delta_gradient")
+        assert_bitwise(opt.step_direction, ref.direction, f"{tag}: direction")
+        assert float(opt.current_objective_value[()]) == ref.objective
+        assert float(opt.delta_objective_value[()]) == ref.delta_objective
+        assert int(opt.iteration_count[()]) == ref.iteration_count and bool(opt.is_stuck[()]) == ref.stuck
+        assert_bitwise(opt.rho_history, ref.rho_history, f"{tag}: rho")
+
+    compare("ctor")
+    for it in range(20):
+        dz.step_(opt); ref.step(1)
+        compare(f"n={n} iter {it}")
+    opt.step(25); ref.step(25)            # 25 step! calls in one cluster-kernel launch
+    compare("fused")
+
+
+@pytest.mark.gpu
+def test_gpu_lbfgs_to_convergence(gpu, orc):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, 64, 6)
+    opt = dz.LBFGSOptimizer(dz.NULL_CONSTRAINT, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, 8)
+    ref = orc.LBFGS(ROSEN, x0, 1.0, 8, orc.TREE)
+    for _ in range(200):
+        opt.step(100); ref.step(100)
+        if opt.is_stuck[()]:
+            break
+    assert bool(opt.is_stuck[()]) and ref.stuck
+    assert_bitwise(opt.current_point, ref.point, "converged point")
+    assert np.abs(opt.current_gradient).max() < 1e-5
+    with pytest.raises(AssertionError):
+        dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 0.0, 8)     # @assert step > 0
