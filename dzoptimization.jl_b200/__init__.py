@@ -413,6 +413,13 @@ class BFGSOptimizer(_Optimizer):
         _check(lib().dzo_bfgs_info(self._h, None, None, C.byref(o), None, None))
         return o.value
 
+    @property
+    def gather_mode(self):
+        """0 = not sharded, 1 = fused peer-memory gathers, 2 = ncclAllGather"""
+        m = C.c_int()
+        _check(lib().dzo_bfgs_gather_mode(self._h, C.byref(m)))
+        return m.value
+
     def step_log(self):
         """(calls, kinds) -- kinds[c % 64] is the StepType of step! call c (large-n handles)."""
         calls = C.c_int64()

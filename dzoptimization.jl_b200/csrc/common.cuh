@@ -138,4 +138,33 @@ DZO_DEVINL void stg_stream2(double* p, double2 v) {
 
 DZO_DEVINL bool finite_(double v) { return isfinite(v); }
 
+// ----------------------------------------------------------------------------- peer memory (row-sharded mode)
+// One process per GPU; every rank maps the result vectors and the flag words of all its peers
+// (CUDA IPC over NVLink / NVSwitch).  A producer kernel stores its rows of the result straight into
+// every peer's copy and then raises flag[producer rank] = sequence number in every peer; a consumer
+// kernel spins on its LOCAL flag words.  This replaces "kernel -> ncclAllGather -> kernel".
+constexpr int kMaxPeers = 8;
+struct PeerSet {
+    int nranks;                               // 1 = not sharded (or NCCL fallback): no peer traffic
+    int rank;
+    double* out[kMaxPeers];                   // out[p] = rank p's copy of the vector being produced
+    unsigned long long* flags[kMaxPeers];     // flags[p] = rank p's flag array (kMaxPeers words)
+    unsigned* done;                           // local: row blocks finished in this launch
+};
+DZO_DEVINL void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+DZO_DEVINL unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// consumer side: wait until every rank's slab of sequence `seq` has landed in local memory
+DZO_DEVINL void peer_wait(const unsigned long long* local_flags, int nranks, unsigned long long seq) {
+    if (nranks > 1 && threadIdx.x < nranks) {
+        while (ld_acquire_sys(local_flags + threadIdx.x) < seq) { __nanosleep(64); }
+    }
+    __syncthreads();
+}
+
 }  // namespace dzo

@@ -97,6 +97,15 @@ struct dzo_bfgs {
     int rank = 0, nranks = 1;
     int64_t row0 = 0, rows = 0;
     void* comm = nullptr;
+    // fused gathers over peer memory (CUDA IPC): every rank's t, d and flag words mapped here
+    bool pooled = true;                 // device memory from the stream-ordered pool (false: cudaMalloc, IPC-able)
+    bool fused = false;
+    unsigned long long *flags_t = nullptr, *flags_d = nullptr;   // local, kMaxPeers words each
+    unsigned* done = nullptr;
+    char* arena = nullptr;              // sharded: ONE cudaMalloc block [t | d | flags_t | flags_d] exported through IPC
+    char* peer_arena[kMaxPeers] = {};   // mapped base pointers of the peers' blocks
+    double *peer_t[kMaxPeers] = {}, *peer_d[kMaxPeers] = {};
+    unsigned long long *peer_flags_t[kMaxPeers] = {}, *peer_flags_d[kMaxPeers] = {};
 };
 
 // Device memory of a handle comes from the device's stream-ordered pool (cudaMallocAsync) with an
@@ -106,15 +115,21 @@ static void free_handle(dzo_bfgs* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(o->comm);
+    if (o->arena) { o->t = nullptr; o->d = nullptr; o->flags_t = nullptr; o->flags_d = nullptr; }   // live inside the arena
     void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
-                    o->sd, o->t, o->partial, o->tile_counters, o->ctrl};
+                    o->sd, o->t, o->partial, o->tile_counters, o->ctrl, o->flags_t, o->flags_d, o->done, o->arena};
     if (o->own_stream) {
         cudaStreamSynchronize(o->stream);
-        for (void* p : ptrs)
-            if (p) cudaFreeAsync(p, o->own_stream);
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p != o->rank && o->peer_arena[p]) cudaIpcCloseMemHandle(o->peer_arena[p]);
+        for (void* p : ptrs) {
+            if (!p) continue;
+            if (o->pooled) cudaFreeAsync(p, o->own_stream); else cudaFree(p);
+        }
         cudaStreamSynchronize(o->own_stream);
         cudaStreamDestroy(o->own_stream);
     }
+    cudaGetLastError();
     delete o;
 }
 
@@ -131,8 +146,9 @@ static void init_pool(int device) {
 }
 
 template <class T>
-static int dmalloc_on(cudaStream_t stream, T** p, size_t count) {
-    cudaError_t e = cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), stream);
+static int dmalloc_on(cudaStream_t stream, T** p, size_t count, bool pooled = true) {
+    cudaError_t e = pooled ? cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), stream)
+                           : cudaMalloc((void**)p, (count ? count : 1) * sizeof(T));
     if (e != cudaSuccess) {
         *p = nullptr;
         cudaGetLastError();
@@ -140,7 +156,7 @@ static int dmalloc_on(cudaStream_t stream, T** p, size_t count) {
     }
     return DZO_OK;
 }
-#define dmalloc(p, count) dmalloc_on(o->own_stream, p, count)
+#define dmalloc(p, count) dmalloc_on(o->own_stream, p, count, o->pooled)
 
 // any(isnan(f)) on the device: 4 bytes come back instead of the whole objective vector
 static __global__ void any_nan_kernel(const double* f, long long count, int* flag) {
@@ -246,7 +262,20 @@ static LargeVecs large_vecs(const dzo_bfgs* o) {
     LargeVecs v;
     v.x = o->x; v.g = o->g; v.d = o->d; v.dx = o->dx; v.dg = o->dg; v.sd = o->sd; v.t = o->t;
     v.ctrl = o->ctrl; v.n = o->n;
+    v.flags_t = o->flags_t; v.flags_d = o->flags_d; v.nranks = o->fused ? o->nranks : 1;
     return v;
+}
+static PeerSet peer_set(const dzo_bfgs* o, bool for_t) {
+    PeerSet ps;
+    memset(&ps, 0, sizeof ps);
+    ps.nranks = o->fused ? o->nranks : 1;
+    ps.rank = o->rank;
+    ps.done = o->done;
+    for (int p = 0; p < kMaxPeers; ++p) {
+        ps.out[p] = for_t ? o->peer_t[p] : o->peer_d[p];
+        ps.flags[p] = for_t ? o->peer_flags_t[p] : o->peer_flags_d[p];
+    }
+    return ps;
 }
 static SweepArgs sweep_args(const dzo_bfgs* o) {
     SweepArgs a;
@@ -254,6 +283,8 @@ static SweepArgs sweep_args(const dzo_bfgs* o) {
     a.v = nullptr; a.s = o->sd; a.t = o->t; a.partial = o->partial; a.out = nullptr;
     a.counters = o->tile_counters; a.ctrl = o->ctrl; a.need_kind = DZO_STEP_BFGS;
     a.nchunks = (int)((o->n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
+    memset(&a.peers, 0, sizeof a.peers);
+    a.peers.nranks = 1;
     return a;
 }
 static dim3 sweep_grid(int64_t rows, int64_t n) {
@@ -267,31 +298,109 @@ static int allgather_rows(dzo_bfgs* o, double* vec) {
 }
 
 // out = H * v on the local slab (+ allgather when sharded); predicate on ctrl->kind if need_kind >= 0
-static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind) {
+static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind, bool fused_t = false) {
     SweepArgs a = sweep_args(o);
     a.v = v; a.out = out;
     if (need_kind < 0) a.ctrl = nullptr; else a.need_kind = need_kind;
+    if (fused_t) a.peers = peer_set(o, true);      // rows go straight into every peer's t; no collective call
     gemv_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);
     DZO_CUDA(cudaGetLastError());
-    return allgather_rows(o, out);
+    return fused_t ? DZO_OK : allgather_rows(o, out);
 }
 
 static int large_step_once(dzo_bfgs* o) {
     const LargeVecs v = large_vecs(o);
-    const bool cluster = (g_tuning.search_variant == 0);   // 8-CTA cluster with DSMEM reductions vs one CTA
+    const bool cluster = (g_tuning.search_variant == 0) || o->fused;   // 8-CTA cluster with DSMEM reductions vs one CTA
+                                                                        // (the peer-flag waits live in the cluster kernels)
     if (cluster) cluster_bfgs_search_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);   // :891-950, :873-874
     else vec_bfgs_search_kernel<<<1, 1024, 0, o->stream>>>(v);
     DZO_CUDA(cudaGetLastError());
-    DZO_TRY(large_gemv(o, o->dg, o->t, DZO_STEP_BFGS));                         // :875
+    DZO_TRY(large_gemv(o, o->dg, o->t, DZO_STEP_BFGS, o->fused));               // :875
     if (cluster) cluster_delta_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);         // :876
     else vec_delta_kernel<<<1, 1024, 0, o->stream>>>(v);
     DZO_CUDA(cudaGetLastError());
     SweepArgs a = sweep_args(o);
     a.v = o->g; a.out = o->d;
     a.need_kind = DZO_STEP_GRADIENT_DESCENT + 100;   // this launch also serves identity_matrix! (:981) after a GD step
+    if (o->fused) a.peers = peer_set(o, false);
     update_gemv_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);   // :878-886 + :958-960
     DZO_CUDA(cudaGetLastError());
-    DZO_TRY(allgather_rows(o, o->d));
+    if (!o->fused) DZO_TRY(allgather_rows(o, o->d));
+    return DZO_OK;
+}
+
+// Map every peer's t, d and flag words into this process (CUDA IPC; NVLink peer access).  The 4 x 64-byte
+// handles of all ranks travel over the NCCL communicator that was just created -- the only collective the
+// fused mode ever issues.  Falls back to NCCL all-gathers (o->fused = false) if any rank cannot map.
+struct IpcBundle { cudaIpcMemHandle_t arena; unsigned long long offset; int ok; int pad; };
+// cudaIpcGetMemHandle exports the whole underlying allocation: find its base so peers can add the offset
+static bool allocation_base(const void* p, unsigned long long* offset) {
+    typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+    static GetRange fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) != cudaSuccess || !sym) {
+            cudaGetLastError();
+            return false;
+        }
+        fn = (GetRange)sym;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return false;
+    *offset = (unsigned long long)(uintptr_t)p - base;
+    return true;
+}
+static int exchange_peer_memory(dzo_bfgs* o) {
+    o->fused = false;
+    IpcBundle mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = (g_tuning.sharded_variant == 0) && o->arena && allocation_base(o->arena, &mine.offset) &&
+              cudaIpcGetMemHandle(&mine.arena, o->arena) == cudaSuccess;
+    cudaGetLastError();
+    IpcBundle* dev = nullptr;
+    DZO_CUDA(cudaMalloc((void**)&dev, sizeof(IpcBundle) * o->nranks));
+    DZO_CUDA(cudaMemcpyAsync(dev + o->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, o->stream));
+    int r = g_nccl.AllGather(dev + o->rank, dev, sizeof(IpcBundle), /*ncclInt8*/ 0, o->comm, o->stream);
+    if (r != 0) { cudaFree(dev); return fail(DZO_ERR_NCCL, "ncclAllGather of IPC handles failed"); }
+    IpcBundle all[kMaxPeers];
+    DZO_CUDA(cudaMemcpyAsync(all, dev, sizeof(IpcBundle) * o->nranks, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    cudaFree(dev);
+    bool ok = true;
+    for (int p = 0; p < o->nranks; ++p) ok = ok && all[p].ok;
+    const size_t nb = (size_t)o->n;
+    for (int p = 0; p < o->nranks && ok; ++p) {
+        char* base = nullptr;
+        if (p == o->rank) {
+            base = o->arena;
+        } else {
+            void* mapped = nullptr;
+            ok = cudaIpcOpenMemHandle(&mapped, all[p].arena, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            if (!ok) { cudaGetLastError(); break; }
+            o->peer_arena[p] = static_cast<char*>(mapped);
+            base = o->peer_arena[p] + all[p].offset;
+        }
+        o->peer_t[p] = reinterpret_cast<double*>(base);
+        o->peer_d[p] = o->peer_t[p] + nb;
+        o->peer_flags_t[p] = reinterpret_cast<unsigned long long*>(o->peer_d[p] + nb);
+        o->peer_flags_d[p] = o->peer_flags_t[p] + kMaxPeers;
+    }
+    // every rank must agree on the mode: one more tiny gather of the outcome
+    int* flag = nullptr;
+    DZO_CUDA(cudaMalloc((void**)&flag, sizeof(int) * o->nranks));
+    int okint = ok ? 1 : 0;
+    DZO_CUDA(cudaMemcpyAsync(flag + o->rank, &okint, sizeof(int), cudaMemcpyHostToDevice, o->stream));
+    r = g_nccl.AllGather(flag + o->rank, flag, sizeof(int), /*ncclInt8*/ 0, o->comm, o->stream);
+    int res[kMaxPeers];
+    if (r == 0) cudaMemcpyAsync(res, flag, sizeof(int) * o->nranks, cudaMemcpyDeviceToHost, o->stream);
+    cudaStreamSynchronize(o->stream);
+    cudaFree(flag);
+    if (r != 0) return fail(DZO_ERR_NCCL, "ncclAllGather failed");
+    bool all_ok = true;
+    for (int p = 0; p < o->nranks; ++p) all_ok = all_ok && res[p];
+    o->fused = all_ok;
     return DZO_OK;
 }
 
@@ -314,6 +423,8 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     o->device = device; o->objective = objective; o->constraint = constraint; o->dim = obj_param;
     o->n = n; o->batch = batch; o->small = (n <= DZO_SMALL_N_MAX); o->lpp = pick_lpp(n);
     o->rank = rank; o->nranks = nranks; o->rows = n / nranks; o->row0 = o->rows * rank;
+    o->pooled = (nranks == 1);        // sharded handles use cudaMalloc: CUDA IPC cannot export pool memory
+    if (nranks > kMaxPeers) { delete o; return fail(DZO_ERR_INVALID_ARGUMENT, "at most %d ranks", kMaxPeers); }
     int rc = DZO_OK;
     auto bail = [&](int code) { free_handle(o); return code; };
     if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -321,8 +432,17 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     o->stream = o->own_stream;
     init_pool(device);
     const size_t nb = (size_t)n * (size_t)batch;
-    if ((rc = dmalloc(&o->x, nb)) || (rc = dmalloc(&o->g, nb)) || (rc = dmalloc(&o->d, nb)) || (rc = dmalloc(&o->dx, nb)) ||
-        (rc = dmalloc(&o->dg, nb)) || (rc = dmalloc(&o->counter, 1)))
+    const bool use_arena = (nranks > 1);
+    if (use_arena) {
+        const size_t bytes = 2 * nb * sizeof(double) + 2 * kMaxPeers * sizeof(unsigned long long);
+        if ((rc = dmalloc(&o->arena, bytes))) return bail(rc);
+        o->t = reinterpret_cast<double*>(o->arena);
+        o->d = o->t + nb;
+        o->flags_t = reinterpret_cast<unsigned long long*>(o->d + nb);
+        o->flags_d = o->flags_t + kMaxPeers;
+    }
+    if ((rc = dmalloc(&o->x, nb)) || (rc = dmalloc(&o->g, nb)) || (!use_arena && (rc = dmalloc(&o->d, nb))) ||
+        (rc = dmalloc(&o->dx, nb)) || (rc = dmalloc(&o->dg, nb)) || (rc = dmalloc(&o->counter, 1)))
         return bail(rc);
     if (o->small) {
         if ((rc = dmalloc(&o->H, nb * (size_t)n)) || (rc = dmalloc(&o->f, (size_t)batch)) || (rc = dmalloc(&o->L, (size_t)batch)) ||
@@ -331,11 +451,16 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     } else {
         const size_t nchunks = (size_t)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
         const size_t rblocks = (size_t)((o->rows + kSweepRows - 1) / kSweepRows);
-        if ((rc = dmalloc(&o->H, (size_t)o->rows * (size_t)n)) || (rc = dmalloc(&o->sd, (size_t)n)) || (rc = dmalloc(&o->t, (size_t)n)) ||
+        if ((rc = dmalloc(&o->H, (size_t)o->rows * (size_t)n)) || (rc = dmalloc(&o->sd, (size_t)n)) ||
+            (!use_arena && (rc = dmalloc(&o->t, (size_t)n))) ||
             (rc = dmalloc(&o->partial, nchunks * (size_t)o->rows)) || (rc = dmalloc(&o->tile_counters, rblocks)) ||
-            (rc = dmalloc(&o->ctrl, 1)))
+            (rc = dmalloc(&o->ctrl, 1)) || (!use_arena && (rc = dmalloc(&o->flags_t, (size_t)kMaxPeers))) ||
+            (!use_arena && (rc = dmalloc(&o->flags_d, (size_t)kMaxPeers))) || (rc = dmalloc(&o->done, 1)))
             return bail(rc);
-        if (cudaMemsetAsync(o->tile_counters, 0, rblocks * sizeof(unsigned), o->stream) != cudaSuccess)
+        if (cudaMemsetAsync(o->tile_counters, 0, rblocks * sizeof(unsigned), o->stream) != cudaSuccess ||
+            cudaMemsetAsync(o->flags_t, 0, kMaxPeers * 8, o->stream) != cudaSuccess ||
+            cudaMemsetAsync(o->flags_d, 0, kMaxPeers * 8, o->stream) != cudaSuccess ||
+            cudaMemsetAsync(o->done, 0, sizeof(unsigned), o->stream) != cudaSuccess)
             return bail(fail(DZO_ERR_CUDA, "memset failed"));
     }
     if (nranks > 1) {
@@ -344,6 +469,7 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
         memcpy(id.b, nccl_id, 128);
         int r = g_nccl.CommInitRank(&o->comm, nranks, id, rank);
         if (r != 0) return bail(fail(DZO_ERR_NCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+        if ((rc = exchange_peer_memory(o))) return bail(rc);
     }
     // copy(initial_point)  legacy/DZOptimization.jl:769
     if (cudaMemcpyAsync(o->x, x0, nb * sizeof(double), cudaMemcpyHostToDevice, o->stream) != cudaSuccess)
@@ -502,6 +628,11 @@ int dzo_bfgs_get_step_log(dzo_bfgs* o, int64_t* calls, uint8_t* kinds64) {
     memcpy(kinds64, c.kind_log, 64);
     return DZO_OK;
 }
+int dzo_bfgs_gather_mode(dzo_bfgs* o, int* mode) {
+    if (!o || !mode) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *mode = (o->nranks <= 1) ? 0 : (o->fused ? 1 : 2);
+    return DZO_OK;
+}
 int dzo_bfgs_info(dzo_bfgs* o, int64_t* n, int64_t* batch, int* order, int64_t* row_begin, int64_t* row_end) {
     if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
     if (n) *n = o->n;
@@ -603,6 +734,8 @@ struct SweepScratch {
         a.partial = partial.as<double>(); a.out = nullptr; a.counters = counters.as<unsigned>();
         a.ctrl = nullptr; a.need_kind = DZO_STEP_BFGS;
         a.nchunks = (int)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
+        memset(&a.peers, 0, sizeof a.peers);
+        a.peers.nranks = 1;
         return a;
     }
 };
@@ -854,6 +987,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "sweep_variant")) { g_tuning.sweep_variant = value; return DZO_OK; }
     if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
     if (!strcmp(key, "search_variant")) { g_tuning.search_variant = value; return DZO_OK; }
+    if (!strcmp(key, "sharded_variant")) { g_tuning.sharded_variant = value; return DZO_OK; }
     if (!strcmp(key, "batched_prefetch")) { g_tuning.batched_prefetch = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }

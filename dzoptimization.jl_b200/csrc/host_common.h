@@ -54,6 +54,7 @@ int check_problem(int objective, int constraint, int64_t obj_param, int64_t n, i
 struct Tuning {
     int sweep_variant = 0;    // 0 = LDG/STG streaming tiles, 1 = TMA-staged tiles
     int batched_prefetch = 2;  // hybrid kernel: L2 prefetch distance in phase-2 rounds (measured: 0:0.70 1:0.75 2:0.89 3:0.89 4:0.88 6:0.83 of HBM peak)
+    int sharded_variant = 0;  // row-sharded gathers: 0 = fused into the producing kernels over peer memory, 1 = ncclAllGather
     int search_variant = 0;   // large-n O(n) stage: 0 = 8-CTA cluster + DSMEM reductions, 1 = single 1024-thread CTA
     int batched_variant = 0;  // 0 = hybrid kernel for n in {2,4,8,16}, 1 = lanes-per-problem kernel everywhere
 };

@@ -197,6 +197,10 @@ struct LargeVecs {
     double *t;                    // _scratch_space = H * delta_gradient (:875)
     LargeCtrl* ctrl;
     long long n;
+    // row-sharded mode with fused peer-memory gathers: LOCAL flag words raised by the producers
+    const unsigned long long* flags_t;   // t = H*dg slabs of step `calls`
+    const unsigned long long* flags_d;   // d = H'*g slabs of step `calls`
+    int nranks;
 };
 
 // Constructor, legacy/DZOptimization.jl:762-810 (x already holds copy(x0)).
@@ -408,7 +412,34 @@ struct SweepArgs {
     const LargeCtrl* ctrl;  // device-side predicate (may be null = always run)
     int need_kind;
     int nchunks;
+    PeerSet peers;          // fused all-gather over peer memory (nranks == 1: plain local store)
 };
+
+// store one finished row: locally and, when sharded with the fused gather, into every peer's copy
+DZO_DEVINL void sweep_store_row(const SweepArgs& a, long long gi, double r) {
+    a.out[gi] = r;
+    if (a.peers.nranks > 1) {
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < a.peers.nranks && p != a.peers.rank) a.peers.out[p][gi] = r;
+    }
+}
+// called by the CTA that finished a row block, after its stores: the LAST row block of the launch raises
+// flag[rank] = seq in every peer (release at system scope; the fences make every CTA's row stores visible first)
+DZO_DEVINL void sweep_signal_peers(const SweepArgs& a) {
+    if (a.peers.nranks <= 1) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(a.peers.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *a.peers.done = 0;
+            __threadfence_system();
+            const unsigned long long seq = (unsigned long long)a.ctrl->calls;
+            for (int p = 0; p < a.peers.nranks; ++p) st_release_sys(a.peers.flags[p] + a.peers.rank, seq);
+        }
+    }
+}
 
 // Chunk partials -> out, ascending chunk order starting from partial 0 (oracle gemv_rows_).
 // Executed by the LAST tile of a row block to finish (threadfence + counter), so the result
@@ -416,8 +447,9 @@ struct SweepArgs {
 DZO_DEVINL void sweep_finish_rows(const SweepArgs& a, long long i0, double acc0, double acc1, bool two, bool one) {
     const int c = blockIdx.y;
     if (a.nchunks == 1) {
-        if (one) a.out[a.row0 + i0] = acc0;
-        if (two) a.out[a.row0 + i0 + 1] = acc1;
+        if (one) sweep_store_row(a, a.row0 + i0, acc0);
+        if (two) sweep_store_row(a, a.row0 + i0 + 1, acc1);
+        sweep_signal_peers(a);
         return;
     }
     if (one) a.partial[(long long)c * a.rows + i0] = acc0;
@@ -438,9 +470,10 @@ DZO_DEVINL void sweep_finish_rows(const SweepArgs& a, long long i0, double acc0,
         const volatile double* pp = a.partial + i;
         double r = pp[0];
         for (int cc = 1; cc < a.nchunks; ++cc) r += pp[(long long)cc * a.rows];
-        a.out[a.row0 + i] = r;
+        sweep_store_row(a, a.row0 + i, r);
     }
     if (threadIdx.x == 0) a.counters[blockIdx.x] = 0;  // ready for the next launch
+    sweep_signal_peers(a);
 }
 
 // mul!(out, H, v)  legacy/DZOptimization.jl:875, :958-960.  Thread-per-row walk over one

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="use ncclAllGather instead of the fused peer-memory gathers")
     args = ap.parse_args()
 
     import torch
@@ -40,6 +41,8 @@ def main():
     import oracle as orc
     from conftest import assert_bitwise
     EF = dz.ExampleFunctions
+    if args.nccl:
+        dz.set_tuning("sharded_variant", 1)
 
     # the 128-byte ncclUniqueId travels over the host framework's own plumbing
     idbuf = C.create_string_buffer(128)
@@ -53,6 +56,7 @@ def main():
     x0 = 4.0 * orc.pcg_fill(n, 2) - 2.0
     opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, device=local,
                            shard=(rank, world, box[0]))
+    mode = {0: "single", 1: "fused-peer-memory", 2: "nccl-allgather"}[opt.gather_mode]
     r0, r1 = opt.row_range
     assert (r0, r1) == (rank * n // world, (rank + 1) * n // world)
 
@@ -72,25 +76,26 @@ def main():
         ok = torch.ones(1, device="cuda")
         dist.all_reduce(ok)
         if rank == 0:
-            print(f"sharded check ok: n={n} ranks={world} steps={args.steps} types={types}")
+            print(f"sharded check ok: n={n} ranks={world} steps={args.steps} types={types} gather={mode}")
 
     if args.time:
         stream = torch.cuda.Stream()
         torch.cuda.set_stream(stream)
         opt.set_stream(stream.cuda_stream)
         opt.step(3)
-        times, types = [], []
-        for _ in range(args.steps):
-            dist.barrier(); torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+        dist.barrier(); torch.cuda.synchronize()
+        calls0, _ = opt.step_log()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        evs[0].record(stream)
+        for i in range(args.steps):          # back to back: no host sync between step! calls
             opt.step_async(1)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            times.append(float(t.item()))
-            types.append(int(opt.last_step_type[()]))
+            evs[i + 1].record(stream)
+        torch.cuda.synchronize()
+        tt = torch.tensor([evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        times = tt.tolist()
+        _, kinds = opt.step_log()
+        types = [int(kinds[(calls0 + i) % 64]) for i in range(args.steps)]
         bf = [t for t, ty in zip(times, types) if ty == dz.StepType.BFGSStep]
         if rank == 0:
             peak = 6456.8
@@ -102,7 +107,7 @@ def main():
             gbs = 24.0 * n * n / world / (ms * 1e-3) / 1e9
             print(json.dumps({"workload": f"row-sharded BFGS n={n}", "n_gpus": world, "bfgs_steps": len(bf),
                               "ms_per_bfgs_step": ms, "steps_per_s": 1e3 / ms, "per_gpu_achieved_gbs": gbs,
-                              "frac_of_peak": gbs / peak, "rows_per_gpu": n // world}))
+                              "frac_of_peak": gbs / peak, "rows_per_gpu": n // world, "gather": mode}))
     opt.close()
     dist.destroy_process_group()
 
