@@ -309,3 +309,48 @@ def test_errors(gpu):
         dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, np.zeros(3), 1.0)   # odd n
     with pytest.raises(TypeError):
         dz.BFGSOptimizer(lambda x: 0.0, EF.rosenbrock_gradient_, np.zeros(2), 1.0)           # host closure
+
+
+# ----------------------------------------------------------------------------- degenerate starts (state, never an error)
+@pytest.mark.parametrize("n,batched", [(16, True), (2048, False)])
+def test_degenerate_starts(gpu, orc, n, batched):
+    dz = gpu
+    EF = dz.ExampleFunctions
+
+    def both(x0, step):
+        a = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0 if batched else x0[0], step, batched=batched)
+        b = orc.BFGS(ROSEN, x0, step, order=orc.SEQ if batched else orc.TREE)
+        return a, b
+
+    # already at the minimiser: gradient 0 -> L/||g|| = Inf -> no probe -> has_converged after one step!, nothing moves
+    a, b = both(np.ones((1, n)), 1.0)
+    a.step(2); b.step(2)
+    _compare_state(a, b, batched, "at minimum")
+    assert np.asarray(a.has_converged).all() and int(np.asarray(a.iteration_count).max()) == 0
+    # zero initial step length: t1 = 0 -> [GLUE] no probe -> terminates
+    a, b = both(np.zeros((1, n)), 0.0)
+    a.step(1); b.step(1)
+    _compare_state(a, b, batched, "zero step length")
+    assert np.asarray(a.has_converged).all()
+    # enormous start: objective overflows to +Inf (not NaN) -> constructor accepts (:773), step! terminates (:64-66)
+    a, b = both(np.full((1, n), 1e200), 1.0)
+    a.step(1); b.step(1)
+    _compare_state(a, b, batched, "infinite objective")
+    assert np.isinf(np.asarray(a.current_objective_value)).all() and np.asarray(a.has_converged).all()
+    # tiny step length: the bracket has to double many times before the point moves (:91-101)
+    x0 = _x0(orc, n, 3).reshape(1, n)
+    a, b = both(x0, 1e-300)
+    for it in range(3):
+        a.step(1); b.step(1)
+        _compare_state(a, b, batched, f"tiny step iter {it}")
+
+
+def test_batch_sizes_not_multiple_of_the_warp(gpu, orc):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    for n, batch in ((16, 1), (16, 33), (8, 31), (2, 65), (4, 7)):
+        x0 = _x0(orc, n * batch, 77).reshape(batch, n)
+        a = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+        b = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ)
+        a.step(6); b.step(6)
+        _compare_state(a, b, True, f"n={n} batch={batch}")
