@@ -20,8 +20,9 @@
 # versions of legacy/ExampleFunctions.jl exported below; anything else raises ArgumentError.
 module DZOptimizationB200
 
-export BFGSOptimizer, GradientDescentOptimizer, QuadraticLineSearch, step!, StepType, NullStep,
-    GradientDescentStep, BFGSStep, NULL_CONSTRAINT, SPHERE_CONSTRAINT
+export BFGSOptimizer, GradientDescentOptimizer, LBFGSOptimizer, QuadraticLineSearch, step!, StepType, NullStep,
+    GradientDescentStep, BFGSStep, NULL_CONSTRAINT, SPHERE_CONSTRAINT,
+    accelerated_pairwise_radial_energy, accelerated_pairwise_radial_gradient!, accelerated_pairwise_radial_hvp!
 
 const libdzopt = get(ENV, "DZOPT_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libdzopt_b200.so"))
 
@@ -36,13 +37,22 @@ end
 const NULL_CONSTRAINT = DeviceConstraint(0)      # x -> true        (legacy/DZOptimization.jl:384,759)
 const SPHERE_CONSTRAINT = DeviceConstraint(1)    # normalise columns + tangent-projected gradient
 
+struct RadialFunction
+    potential::Cint      # DZO_POT_*
+    derivative::Int      # 0 energy, 1 first, 2 second derivative
+end
+
 module ExampleFunctions
-import ..DeviceFunction
-export rosenbrock_function, rosenbrock_gradient!, riesz_energy, riesz_gradient!
+import ..DeviceFunction, ..RadialFunction
+export rosenbrock_function, rosenbrock_gradient!, riesz_energy, riesz_gradient!,
+    lj_energy, lj_first_derivative, lj_second_derivative
 const rosenbrock_function = DeviceFunction(1, :objective)     # legacy/ExampleFunctions.jl:10-15
 const rosenbrock_gradient! = DeviceFunction(1, :gradient)     # :17-24
 const riesz_energy = DeviceFunction(2, :objective)            # :30-45
 const riesz_gradient! = DeviceFunction(2, :gradient)          # :47-83
+const lj_energy = RadialFunction(1, 0)                        # src/ExampleFunctions.jl:16-27
+const lj_first_derivative = RadialFunction(1, 1)              # :30-47
+const lj_second_derivative = RadialFunction(1, 2)             # :50-72
 end
 
 @enum StepType NullStep GradientDescentStep BFGSStep           # legacy/DZOptimization.jl:727-731
@@ -223,6 +233,77 @@ function count_active(opt::BatchedBFGSOptimizer)
     c = Ref{Int64}(0)
     check(ccall((:dzo_bfgs_count_active, libdzopt), Cint, (Ptr{Cvoid}, Ref{Int64}), opt.handle, c))
     return c[]
+end
+
+# ================================================================== LBFGSOptimizer (live src/DZOptimization.jl:321-509)
+mutable struct LBFGSOptimizer
+    handle::Ptr{Cvoid}
+    n::Int
+    history_length::Int
+end
+# LBFGSOptimizer(c!, f, g!, x0, initial_step_length, history_length)  :400-427 ; c! may be `nothing`
+function LBFGSOptimizer(c!, f, g!, x0::Vector{Float64}, step::Float64, history_length::Int; device::Integer=0)
+    obj, cid = resolve(f, g!, c! === nothing ? NULL_CONSTRAINT : c!)
+    @assert step > 0                                                                 # :375
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dzo_lbfgs_create, libdzopt), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Ptr{Float64}, Float64, Cint, Cint),
+        h, obj, cid, 0, length(x0), x0, step, history_length, device))
+    opt = LBFGSOptimizer(h[], length(x0), history_length)
+    finalizer(o -> ccall((:dzo_lbfgs_destroy, libdzopt), Cvoid, (Ptr{Cvoid},), o.handle), opt)
+    return opt
+end
+function step!(opt::LBFGSOptimizer)                                                 # :454-509
+    check(ccall((:dzo_lbfgs_step, libdzopt), Cint, (Ptr{Cvoid}, Cint), getfield(opt, :handle), 1))
+    return opt
+end
+function Base.getproperty(opt::LBFGSOptimizer, s::Symbol)
+    h, n = getfield(opt, :handle), getfield(opt, :n)
+    vec(sym) = (out = Vector{Float64}(undef, n); check(ccall((sym, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, out)); out)
+    sc(sym, T) = (out = Array{T,0}(undef); check(ccall((sym, libdzopt), Cint, (Ptr{Cvoid}, Ptr{T}), h, out)); out)
+    s === :current_point && return vec(:dzo_lbfgs_get_point)                        # :330
+    s === :delta_point && return vec(:dzo_lbfgs_get_delta_point)                    # :331
+    s === :current_gradient && return vec(:dzo_lbfgs_get_gradient)                  # :334
+    s === :delta_gradient && return vec(:dzo_lbfgs_get_delta_gradient)              # :335
+    s === :step_direction && return vec(:dzo_lbfgs_get_direction)                   # :337
+    s === :current_objective_value && return sc(:dzo_lbfgs_get_objective, Float64)  # :332
+    s === :delta_objective_value && return sc(:dzo_lbfgs_get_delta_objective, Float64)  # :333
+    s === :iteration_count && return sc(:dzo_lbfgs_get_iteration_count, Int64)      # :328
+    if s === :is_stuck || s === :has_converged                                      # :327
+        t = sc(:dzo_lbfgs_get_stuck, UInt8)
+        return fill(t[] != 0)
+    end
+    return getfield(opt, s)
+end
+
+# ================================================================== pairwise radial kernels (live src/ExampleFunctions.jl)
+# Host Vectors here; a CUDA.jl user passes `pointer(cu_x)` to the dzo_pairwise_*_device entry points instead and
+# gets the reference's asynchronous launch semantics (src/ExampleFunctions.jl:171, :292, :463-466).
+function accelerated_pairwise_radial_energy(f::RadialFunction, x::Vector{Float64}, y::Vector{Float64},
+    z::Vector{Float64}; order::Integer=0, workgroupsize::Int=256)                   # :152-173
+    @assert f.derivative == 0 && axes(x) == axes(y) == axes(z)
+    e = Ref{Float64}(0.0)
+    check(ccall((:dzo_dev_pairwise_energy, libdzopt), Cint,
+        (Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Cint),
+        f.potential, order, length(x), x, y, z, C_NULL, e, 0))
+    return e[]
+end
+function accelerated_pairwise_radial_gradient!(gx, gy, gz, f::RadialFunction, x::Vector{Float64},
+    y::Vector{Float64}, z::Vector{Float64}; order::Integer=0, workgroupsize::Int=256)   # :265-294
+    @assert f.derivative == 1 && axes(gx) == axes(gy) == axes(gz) == axes(x) == axes(y) == axes(z)
+    check(ccall((:dzo_dev_pairwise_gradient, libdzopt), Cint,
+        (Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+        f.potential, order, length(x), x, y, z, gx, gy, gz, 0))
+    return nothing
+end
+function accelerated_pairwise_radial_hvp!(px, py, pz, f1::RadialFunction, f2::RadialFunction, x, y, z, u, v, w;
+    order::Integer=0, workgroupsize::Int=256)                                       # :427-468
+    @assert f1.derivative == 1 && f2.derivative == 2 && f1.potential == f2.potential
+    check(ccall((:dzo_dev_pairwise_hvp, libdzopt), Cint,
+        (Cint, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+            Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+        f1.potential, order, length(x), x, y, z, u, v, w, px, py, pz, 0))
+    return nothing
 end
 
 end # module
