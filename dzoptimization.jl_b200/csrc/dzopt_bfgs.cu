@@ -287,8 +287,35 @@ static SweepArgs sweep_args(const dzo_bfgs* o) {
     a.peers.nranks = 1;
     return a;
 }
+// threads per sweep CTA (each thread owns 2 rows): the largest size that still gives >= 4 tiles per SM
+static int sweep_threads(int64_t rows, int64_t n) {
+    if (g_tuning.sweep_threads > 0) return g_tuning.sweep_threads;
+    const int64_t nchunks = (n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK;
+    int t = kSweepThreads;
+    while (t > 32 && ((rows + 2 * t - 1) / (2 * t)) * nchunks < 4 * 148) t >>= 1;
+    return t;
+}
 static dim3 sweep_grid(int64_t rows, int64_t n) {
-    return dim3((unsigned)((rows + kSweepRows - 1) / kSweepRows), (unsigned)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK), 1);
+    const int64_t r = 2 * sweep_threads(rows, n);
+    return dim3((unsigned)((rows + r - 1) / r), (unsigned)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK), 1);
+}
+static void launch_gemv(dim3 grid, int threads, cudaStream_t st, const SweepArgs& a) {
+    switch (g_tuning.sweep_unroll) {
+        case 4: gemv_kernel<4><<<grid, threads, 0, st>>>(a); break;
+        case 16: gemv_kernel<16><<<grid, threads, 0, st>>>(a); break;
+        case 24: gemv_kernel<24><<<grid, threads, 0, st>>>(a); break;
+        case 32: gemv_kernel<32><<<grid, threads, 0, st>>>(a); break;
+        default: gemv_kernel<8><<<grid, threads, 0, st>>>(a); break;
+    }
+}
+static void launch_update(dim3 grid, int threads, cudaStream_t st, const SweepArgs& a) {
+    switch (g_tuning.sweep_unroll) {
+        case 4: update_gemv_kernel<4><<<grid, threads, 0, st>>>(a); break;
+        case 16: update_gemv_kernel<16><<<grid, threads, 0, st>>>(a); break;
+        case 24: update_gemv_kernel<24><<<grid, threads, 0, st>>>(a); break;
+        case 32: update_gemv_kernel<32><<<grid, threads, 0, st>>>(a); break;
+        default: update_gemv_kernel<8><<<grid, threads, 0, st>>>(a); break;
+    }
 }
 
 static int allgather_rows(dzo_bfgs* o, double* vec) {
@@ -303,7 +330,7 @@ static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind, 
     a.v = v; a.out = out;
     if (need_kind < 0) a.ctrl = nullptr; else a.need_kind = need_kind;
     if (fused_t) a.peers = peer_set(o, true);      // rows go straight into every peer's t; no collective call
-    gemv_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);
+    launch_gemv(sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), o->stream, a);
     DZO_CUDA(cudaGetLastError());
     return fused_t ? DZO_OK : allgather_rows(o, out);
 }
@@ -323,7 +350,7 @@ static int large_step_once(dzo_bfgs* o) {
     a.v = o->g; a.out = o->d;
     a.need_kind = DZO_STEP_GRADIENT_DESCENT + 100;   // this launch also serves identity_matrix! (:981) after a GD step
     if (o->fused) a.peers = peer_set(o, false);
-    update_gemv_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);   // :878-886 + :958-960
+    launch_update(sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), o->stream, a);   // :878-886 + :958-960
     DZO_CUDA(cudaGetLastError());
     if (!o->fused) DZO_TRY(allgather_rows(o, o->d));
     return DZO_OK;
@@ -450,7 +477,7 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
             return bail(rc);
     } else {
         const size_t nchunks = (size_t)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
-        const size_t rblocks = (size_t)((o->rows + kSweepRows - 1) / kSweepRows);
+        const size_t rblocks = (size_t)((o->rows + kSweepMinRows - 1) / kSweepMinRows);
         if ((rc = dmalloc(&o->H, (size_t)o->rows * (size_t)n)) || (rc = dmalloc(&o->sd, (size_t)n)) ||
             (!use_arena && (rc = dmalloc(&o->t, (size_t)n))) ||
             (rc = dmalloc(&o->partial, nchunks * (size_t)o->rows)) || (rc = dmalloc(&o->tile_counters, rblocks)) ||
@@ -480,7 +507,7 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
         vec_bfgs_init_kernel<<<1, 1024, 0, o->stream>>>(large_vecs(o), L0);
         SweepArgs a = sweep_args(o);
         a.ctrl = nullptr;
-        identity_kernel<<<sweep_grid(o->rows, o->n), kSweepThreads, 0, o->stream>>>(a);   // :781-783
+        identity_kernel<<<sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), 0, o->stream>>>(a);   // :781-783
     }
     if (cudaStreamSynchronize(o->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "constructor kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -720,7 +747,7 @@ struct SweepScratch {
     DevBuf partial, counters, ctrl;
     int init(int64_t n) {
         const size_t nchunks = (size_t)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
-        const size_t rblocks = (size_t)((n + kSweepRows - 1) / kSweepRows);
+        const size_t rblocks = (size_t)((n + kSweepMinRows - 1) / kSweepMinRows);
         DZO_TRY(partial.alloc(nchunks * (size_t)n * 8));
         DZO_TRY(counters.alloc(rblocks * 4));
         DZO_TRY(ctrl.alloc(sizeof(LargeCtrl)));
@@ -753,7 +780,7 @@ int dzo_dev_gemv(int order, int64_t n, const double* H, const double* v, double*
         DZO_TRY(sc.init(n));
         SweepArgs a = sc.args(dH.as<double>(), n);
         a.v = dv.as<double>(); a.out = dout.as<double>();
-        gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+        launch_gemv(sweep_grid(n, n), sweep_threads(n, n), nullptr, a);
         DZO_CUDA(cudaGetLastError());
         DZO_CUDA(cudaDeviceSynchronize());
     }
@@ -789,11 +816,11 @@ int dzo_dev_update_inverse_hessian(int order, int64_t n, double* H, double step_
         SweepArgs a = sc.args(dH.as<double>(), n);
         a.ctrl = sc.ctrl.as<LargeCtrl>();
         a.v = ddg.as<double>(); a.out = dt.as<double>();
-        gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);                           // :875
+        launch_gemv(sweep_grid(n, n), sweep_threads(n, n), nullptr, a);                // :875
         vec_delta_kernel<<<1, 1024>>>(v);                                              // :876
         a.v = fused ? dg.as<double>() : nullptr; a.out = fused ? dnd.as<double>() : nullptr;
         a.s = dsd.as<double>(); a.t = dt.as<double>();
-        update_gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);                    // :878-886 (+ :958-960)
+        launch_update(sweep_grid(n, n), sweep_threads(n, n), nullptr, a);             // :878-886 (+ :958-960)
         DZO_CUDA(cudaGetLastError());
         DZO_CUDA(cudaDeviceSynchronize());
         DZO_TRY(d2h(step_direction, dsd, (size_t)n));
@@ -812,7 +839,7 @@ int dzo_dev_identity(int64_t n, double* H, int device) {
     SweepScratch sc;
     DZO_TRY(sc.init(n));
     SweepArgs a = sc.args(dH.as<double>(), n);
-    identity_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+    identity_kernel<<<sweep_grid(n, n), sweep_threads(n, n)>>>(a);
     DZO_CUDA(cudaGetLastError());
     DZO_CUDA(cudaDeviceSynchronize());
     return d2h(H, dH, (size_t)n * n);
@@ -916,7 +943,7 @@ int dzo_bench_kernel(int which, int64_t n, int reps, int variant, float* ms_per_
     DZO_TRY(sc.init(n));
     SweepArgs a = sc.args(dH.as<double>(), n);
     // H = I and tiny vectors: the sweeps are data-independent, values only need to stay finite
-    identity_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+    identity_kernel<<<sweep_grid(n, n), sweep_threads(n, n)>>>(a);
     DZO_CUDA(cudaMemset(vs.p, 0, (size_t)n * 8)); DZO_CUDA(cudaMemset(vt.p, 0, (size_t)n * 8));
     DZO_CUDA(cudaMemset(vg.p, 0, (size_t)n * 8));
     LargeCtrl c;
@@ -928,9 +955,9 @@ int dzo_bench_kernel(int which, int64_t n, int reps, int variant, float* ms_per_
     cudaEvent_t e0, e1;
     DZO_CUDA(cudaEventCreate(&e0)); DZO_CUDA(cudaEventCreate(&e1));
     auto launch = [&]() {
-        if (which == DZO_BENCH_GEMV) gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
-        else if (which == DZO_BENCH_UPDATE_GEMV) update_gemv_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
-        else identity_kernel<<<sweep_grid(n, n), kSweepThreads>>>(a);
+        if (which == DZO_BENCH_GEMV) launch_gemv(sweep_grid(n, n), sweep_threads(n, n), nullptr, a);
+        else if (which == DZO_BENCH_UPDATE_GEMV) launch_update(sweep_grid(n, n), sweep_threads(n, n), nullptr, a);
+        else identity_kernel<<<sweep_grid(n, n), sweep_threads(n, n)>>>(a);
     };
     for (int i = 0; i < 3; ++i) launch();
     DZO_CUDA(cudaDeviceSynchronize());
@@ -988,6 +1015,11 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
     if (!strcmp(key, "search_variant")) { g_tuning.search_variant = value; return DZO_OK; }
     if (!strcmp(key, "sharded_variant")) { g_tuning.sharded_variant = value; return DZO_OK; }
+    if (!strcmp(key, "sweep_unroll")) { g_tuning.sweep_unroll = value; return DZO_OK; }
+    if (!strcmp(key, "sweep_threads")) {
+        if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256) return fail(DZO_ERR_INVALID_ARGUMENT, "sweep_threads: 0, 32, 64, 128 or 256");
+        g_tuning.sweep_threads = value; return DZO_OK;
+    }
     if (!strcmp(key, "batched_prefetch")) { g_tuning.batched_prefetch = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }

@@ -395,9 +395,13 @@ static __global__ void vec_rosenbrock_gradient_kernel(const double* x, long long
 }
 
 // ============================================================================= n^2 sweeps
-constexpr int kSweepThreads = 128;                 // each thread owns two adjacent rows
-constexpr int kSweepRows = 2 * kSweepThreads;      // rows per tile
-constexpr int kSweepUnroll = 8;                    // columns in flight per thread
+// A sweep CTA has blockDim.x in {32, 64, 128, 256} threads, each owning two adjacent rows: the host picks
+// the size so that even a thin row slab (row-sharded mode) yields enough tiles to fill the GPU.
+constexpr int kSweepMaxThreads = 256;
+constexpr int kSweepMinRows = 64;                  // rows per tile of the smallest CTA (counter arrays are sized for it)
+constexpr int kSweepThreads = 128;                 // default (n x n on one GPU)
+constexpr int kSweepRows = 2 * kSweepThreads;
+constexpr int kSweepUnroll = 8;                    // columns in flight per thread (default; tunable 4 / 8 / 16)
 
 struct SweepArgs {
     double* H;              // rows x n slab, column-major, leading dimension ld
@@ -479,26 +483,27 @@ DZO_DEVINL void sweep_finish_rows(const SweepArgs& a, long long i0, double acc0,
 // mul!(out, H, v)  legacy/DZOptimization.jl:875, :958-960.  Thread-per-row walk over one
 // 1024-column chunk: a warp reads 512 contiguous bytes of every column (H is column-major),
 // and each thread's accumulator is exactly the sequential chunk partial of the oracle.
-static __global__ void __launch_bounds__(kSweepThreads) gemv_kernel(SweepArgs a) {
+template <int U>
+static __global__ void __launch_bounds__(kSweepMaxThreads) gemv_kernel(SweepArgs a) {
     if (a.ctrl && a.ctrl->kind != a.need_kind) return;
     __shared__ double sv[DZO_GEMV_CHUNK];
     const long long c0 = (long long)blockIdx.y * DZO_GEMV_CHUNK;
     const int nc = (int)((a.n - c0 < DZO_GEMV_CHUNK) ? (a.n - c0) : DZO_GEMV_CHUNK);
-    for (int j = threadIdx.x; j < nc; j += kSweepThreads) sv[j] = a.v[c0 + j];
+    for (int j = threadIdx.x; j < nc; j += blockDim.x) sv[j] = a.v[c0 + j];
     __syncthreads();
-    const long long i0 = (long long)blockIdx.x * kSweepRows + 2 * threadIdx.x;
+    const long long i0 = (long long)blockIdx.x * (2 * blockDim.x) + 2 * threadIdx.x;
     const bool one = i0 < a.rows, two = i0 + 1 < a.rows;
     double acc0 = 0.0, acc1 = 0.0;
     const double* base = a.H + i0 + c0 * a.ld;
     if (two && ((a.ld & 1) == 0)) {
         int j = 0;
-        for (; j + kSweepUnroll <= nc; j += kSweepUnroll) {
-            double2 h[kSweepUnroll];
+        for (; j + U <= nc; j += U) {
+            double2 h[U];
 #pragma unroll
-            for (int u = 0; u < kSweepUnroll; ++u)
+            for (int u = 0; u < U; ++u)
                 h[u] = __ldcs(reinterpret_cast<const double2*>(base + (long long)(j + u) * a.ld));
 #pragma unroll
-            for (int u = 0; u < kSweepUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const double vj = sv[j + u];
                 acc0 += h[u].x * vj;
                 acc1 += h[u].y * vj;
@@ -524,7 +529,8 @@ static __global__ void __launch_bounds__(kSweepThreads) gemv_kernel(SweepArgs a)
 // of H is read once, updated, written once, and contributes to the new direction on the way.
 DZO_DEVINL void identity_tile(const SweepArgs& a);
 
-static __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(SweepArgs a) {
+template <int U>
+static __global__ void __launch_bounds__(kSweepMaxThreads) update_gemv_kernel(SweepArgs a) {
     if (a.need_kind == DZO_STEP_GRADIENT_DESCENT + 100 && a.ctrl->kind == DZO_STEP_GRADIENT_DESCENT) {
         identity_tile(a);   // :981 -- step! resets H after a gradient-descent step; same launch, same tiling
         return;
@@ -534,13 +540,13 @@ static __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(Sweep
     const double delta = a.ctrl->delta_norm;
     const long long c0 = (long long)blockIdx.y * DZO_GEMV_CHUNK;
     const int nc = (int)((a.n - c0 < DZO_GEMV_CHUNK) ? (a.n - c0) : DZO_GEMV_CHUNK);
-    for (int j = threadIdx.x; j < nc; j += kSweepThreads) {
+    for (int j = threadIdx.x; j < nc; j += blockDim.x) {
         ss[j] = a.s[c0 + j];
         st[j] = a.t[c0 + j];
         sg[j] = a.v ? a.v[c0 + j] : 0.0;
     }
     __syncthreads();
-    const long long i0 = (long long)blockIdx.x * kSweepRows + 2 * threadIdx.x;
+    const long long i0 = (long long)blockIdx.x * (2 * blockDim.x) + 2 * threadIdx.x;
     const bool one = i0 < a.rows, two = i0 + 1 < a.rows;
     double acc0 = 0.0, acc1 = 0.0;
     double* base = a.H + i0 + c0 * a.ld;
@@ -548,13 +554,13 @@ static __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(Sweep
     const double si1 = two ? a.s[a.row0 + i0 + 1] : 0.0, ti1 = two ? a.t[a.row0 + i0 + 1] : 0.0;
     if (two && ((a.ld & 1) == 0)) {
         int j = 0;
-        for (; j + kSweepUnroll <= nc; j += kSweepUnroll) {
-            double2 h[kSweepUnroll];
+        for (; j + U <= nc; j += U) {
+            double2 h[U];
 #pragma unroll
-            for (int u = 0; u < kSweepUnroll; ++u)
+            for (int u = 0; u < U; ++u)
                 h[u] = __ldcs(reinterpret_cast<const double2*>(base + (long long)(j + u) * a.ld));
 #pragma unroll
-            for (int u = 0; u < kSweepUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const double sj = ss[j + u], tj = st[j + u], gj = sg[j + u];
                 h[u].x = h[u].x + (delta * (si0 * sj) - (ti0 * sj + si0 * tj));   // :882-884
                 h[u].y = h[u].y + (delta * (si1 * sj) - (ti1 * sj + si1 * tj));
@@ -595,7 +601,7 @@ static __global__ void __launch_bounds__(kSweepThreads) update_gemv_kernel(Sweep
 DZO_DEVINL void identity_tile(const SweepArgs& a) {
     const long long c0 = (long long)blockIdx.y * DZO_GEMV_CHUNK;
     const int nc = (int)((a.n - c0 < DZO_GEMV_CHUNK) ? (a.n - c0) : DZO_GEMV_CHUNK);
-    const long long i0 = (long long)blockIdx.x * kSweepRows + 2 * threadIdx.x;
+    const long long i0 = (long long)blockIdx.x * (2 * blockDim.x) + 2 * threadIdx.x;
     const bool one = i0 < a.rows, two = i0 + 1 < a.rows;
     double* base = a.H + i0 + c0 * a.ld;
     const long long gi = a.row0 + i0;  // global row of the first of my two rows
@@ -614,7 +620,7 @@ DZO_DEVINL void identity_tile(const SweepArgs& a) {
         }
     }
 }
-static __global__ void __launch_bounds__(kSweepThreads) identity_kernel(SweepArgs a) {
+static __global__ void __launch_bounds__(kSweepMaxThreads) identity_kernel(SweepArgs a) {
     if (a.ctrl && a.ctrl->kind != a.need_kind) return;
     identity_tile(a);
 }

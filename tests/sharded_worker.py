@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--tune", action="append", default=[], help="key=value for dzo_set_tuning")
     ap.add_argument("--nccl", action="store_true", help="use ncclAllGather instead of the fused peer-memory gathers")
     args = ap.parse_args()
 
@@ -43,6 +44,9 @@ def main():
     EF = dz.ExampleFunctions
     if args.nccl:
         dz.set_tuning("sharded_variant", 1)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        dz.set_tuning(k, int(v))
 
     # the 128-byte ncclUniqueId travels over the host framework's own plumbing
     idbuf = C.create_string_buffer(128)
@@ -107,7 +111,7 @@ def main():
             gbs = 24.0 * n * n / world / (ms * 1e-3) / 1e9
             print(json.dumps({"workload": f"row-sharded BFGS n={n}", "n_gpus": world, "bfgs_steps": len(bf),
                               "ms_per_bfgs_step": ms, "steps_per_s": 1e3 / ms, "per_gpu_achieved_gbs": gbs,
-                              "frac_of_peak": gbs / peak, "rows_per_gpu": n // world, "gather": mode}))
+                              "frac_of_peak": gbs / peak, "rows_per_gpu": n // world, "gather": mode, "tune": args.tune}))
     opt.close()
     dist.destroy_process_group()
 
