@@ -253,6 +253,14 @@ def run_gpu(args):
     opt.close()
 
     # ---- end to end through the public API with host buffers
+    # untimed warm-up pass of the same code path: fills the device memory pool and the recycled page-locked
+    # field buffers (page-locking costs 10-40 ms on this virtualised host), like the W warm-up steps do for kernels
+    w_opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
+                             device=local_rank)
+    w_opt.reuse_host_buffers(True)
+    w_opt.step(1)
+    _ = w_opt.has_converged, w_opt.current_objective_value
+    w_opt.close()
     barrier()
     barrier()
     t1 = time.perf_counter()

@@ -256,6 +256,31 @@ def _layout(initial_point, objective, batched):
     return a, n, batch, pshape, dim
 
 
+# Page-locking host memory costs milliseconds (tens of them on a virtualised host), so page-locked field
+# buffers are recycled process-wide instead of being freed with the optimizer that used them.
+_PINNED_FREE = {}
+
+
+def _pinned_take(nbytes):
+    free = _PINNED_FREE.get(nbytes)
+    if free:
+        return free.pop()
+    ptr = C.c_void_p()
+    _check(lib().dzo_host_alloc(C.byref(ptr), nbytes))
+    return ptr
+
+
+def _pinned_give(nbytes, ptr):
+    _PINNED_FREE.setdefault(nbytes, []).append(ptr)
+
+
+def release_pinned_buffers():
+    """cudaFreeHost every recycled page-locked buffer (optional; they are reused otherwise)."""
+    for free in _PINNED_FREE.values():
+        while free:
+            lib().dzo_host_free(free.pop())
+
+
 class _Optimizer:
     _prefix = ""
     _cache = None
@@ -269,11 +294,8 @@ class _Optimizer:
         return self
 
     def _release_cache(self):
-        for _, ptr in (self._cache or {}).values():
-            try:
-                lib().dzo_host_free(ptr)
-            except Exception:
-                pass
+        for arr, ptr in (self._cache or {}).values():
+            _pinned_give(max(arr.nbytes, 8), ptr)
         self._cache = None
 
     def _out(self, getter, shape, dtype):
@@ -282,8 +304,7 @@ class _Optimizer:
         hit = self._cache.get(getter)
         if hit is None:
             nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
-            ptr = C.c_void_p()
-            _check(lib().dzo_host_alloc(C.byref(ptr), max(nbytes, 8)))
+            ptr = _pinned_take(max(nbytes, 8))
             raw = (C.c_char * max(nbytes, 8)).from_address(ptr.value)
             hit = (np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape), ptr)
             self._cache[getter] = hit
