@@ -354,3 +354,34 @@ def test_batch_sizes_not_multiple_of_the_warp(gpu, orc):
         b = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ)
         a.step(6); b.step(6)
         _compare_state(a, b, True, f"n={n} batch={batch}")
+
+
+def test_tuning_variants_do_not_change_any_bit(gpu, orc):
+    """the A/B knobs (columns in flight, CTA size of the sweeps, line-search kernel, prefetch distance,
+    batched kernel generation) only change scheduling: every variant reproduces the oracle bit for bit."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    n = 2100
+    x0 = _x0(orc, n, 19)
+    ref = orc.BFGS(ROSEN, x0[None, :], 1.0, order=orc.TREE)
+    ref.step(6)
+    for key, values in (("sweep_unroll", (4, 8, 24, 32, 16)), ("sweep_threads", (32, 64, 256, 0)), ("search_variant", (1, 0))):
+        for v in values:
+            dz.set_tuning(key, v)
+            a = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0)
+            a.step(6)
+            assert_bitwise(a.current_point, ref.point[0], f"{key}={v}: point")
+            assert_bitwise(a.next_step_direction, ref.direction[0], f"{key}={v}: direction")
+            assert_bitwise(a.inverse_hessian(), ref.inverse_hessian(0), f"{key}={v}: H")
+            a.close()
+    xb = _x0(orc, 16 * 100, 20).reshape(100, 16)
+    rb = orc.BFGS(ROSEN, xb, 1.0)
+    rb.step(8)
+    for key, values in (("batched_prefetch", (0, 1, 5, 2)), ("batched_variant", (1, 0))):
+        for v in values:
+            dz.set_tuning(key, v)
+            b = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, xb, 1.0, batched=True)
+            b.step(8)
+            assert_bitwise(b.current_point, rb.point, f"{key}={v}: batched point")
+            assert_bitwise(b.inverse_hessian(99), rb.inverse_hessian(99), f"{key}={v}: batched H")
+            b.close()
