@@ -252,6 +252,24 @@ def run_gpu(args):
     active_frac = problem_steps / (K * BATCH)
     opt.close()
 
+    # ---- k step! calls fused into ONE launch ("report also with k fused steps per launch")
+    fused = None
+    if rank == 0 and not args.skip_large:
+        kf = 50
+        f_opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
+                                 device=local_rank)
+        f_opt.set_stream(stream.cuda_stream)
+        f_opt.step(W)
+        f_it0, f_done0 = f_opt.iteration_count.copy(), f_opt.has_converged.copy()
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fe0.record(stream); f_opt.step_async(kf); fe1.record(stream)
+        torch.cuda.synchronize()
+        f_ms = fe0.elapsed_time(fe1)
+        f_steps = float((f_opt.iteration_count - f_it0).sum() + (f_opt.has_converged & ~f_done0).sum())
+        fused = {"k": kf, "launches": 1, "ms": f_ms, "problem_steps": f_steps, "problem_steps_per_s": f_steps / (f_ms * 1e-3),
+                 "still_active_after": int(f_opt.count_active())}
+        f_opt.close()
+
     # ---- end to end through the public API with host buffers
     # untimed warm-up pass of the same code path: fills the device memory pool and the recycled page-locked
     # field buffers (page-locking costs 10-40 ms on this virtualised host), like the W warm-up steps do for kernels
@@ -323,6 +341,8 @@ def run_gpu(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if fused:
+            line["fused_k_steps"] = fused
         if large:
             line["large_n"] = large
         if riesz:

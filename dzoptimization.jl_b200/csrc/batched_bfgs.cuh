@@ -267,7 +267,6 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kern
     double L = A.L[p];
     long long iter = A.iter[p];
     int type = DZO_STEP_NULL;
-    bool H_in_smem_is_current = true;  // sH holds the up-to-date matrix
     bool H_dirty = false;              // sH differs from global
     bool moved = false;
     bool waited = false;
@@ -355,7 +354,6 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kern
             term = true;                                                // :989
         }
     }
-    (void)H_in_smem_is_current;
 
     // ---- write back
     if (moved && G.act) {

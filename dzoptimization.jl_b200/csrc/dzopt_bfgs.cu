@@ -1011,7 +1011,6 @@ int dzo_host_free(void* ptr) {
 
 int dzo_set_tuning(const char* key, int value) {
     if (!key) return fail(DZO_ERR_INVALID_ARGUMENT, "null key");
-    if (!strcmp(key, "sweep_variant")) { g_tuning.sweep_variant = value; return DZO_OK; }
     if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
     if (!strcmp(key, "search_variant")) { g_tuning.search_variant = value; return DZO_OK; }
     if (!strcmp(key, "sharded_variant")) { g_tuning.sharded_variant = value; return DZO_OK; }
