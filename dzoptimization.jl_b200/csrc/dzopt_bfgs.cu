@@ -72,6 +72,13 @@ constexpr int kNcclFloat64 = 8;  // ncclDouble
 
 }  // namespace dzo
 
+namespace dzo {   // BFGS x Riesz hook, dzopt_gd.cu
+int riesz_bfgs_attach(int64_t n, int64_t dim, int constraint, int device, void** out);
+void riesz_bfgs_detach(void* p);
+int riesz_bfgs_launch(void* p, int mode, cudaStream_t stream, double* x, double* g, double* d, double* dx, double* dg,
+                      double* sd, LargeCtrl* ctrl, double initial_step_length);
+}
+
 using namespace dzo;
 
 // ============================================================================= handle
@@ -102,6 +109,7 @@ struct dzo_bfgs {
     bool fused = false;
     unsigned long long *flags_t = nullptr, *flags_d = nullptr;   // local, kMaxPeers words each
     unsigned* done = nullptr;
+    void* riesz = nullptr;              // Riesz objective: the cooperative search-stage kernel's workspace
     char* arena = nullptr;              // sharded: ONE cudaMalloc block [t | d | flags_t | flags_d] exported through IPC
     char* peer_arena[kMaxPeers] = {};   // mapped base pointers of the peers' blocks
     double *peer_t[kMaxPeers] = {}, *peer_d[kMaxPeers] = {};
@@ -115,6 +123,7 @@ static void free_handle(dzo_bfgs* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(o->comm);
+    if (o->riesz) riesz_bfgs_detach(o->riesz);
     if (o->arena) { o->t = nullptr; o->d = nullptr; o->flags_t = nullptr; o->flags_d = nullptr; }   // live inside the arena
     void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
                     o->sd, o->t, o->partial, o->tile_counters, o->ctrl, o->flags_t, o->flags_d, o->done, o->arena};
@@ -337,9 +346,13 @@ static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind, 
 
 static int large_step_once(dzo_bfgs* o) {
     const LargeVecs v = large_vecs(o);
+    if (o->riesz) {
+        DZO_TRY(riesz_bfgs_launch(o->riesz, 5, o->stream, o->x, o->g, o->d, o->dx, o->dg, o->sd, o->ctrl, 0.0));
+    }
     const bool cluster = (g_tuning.search_variant == 0) || o->fused;   // 8-CTA cluster with DSMEM reductions vs one CTA
                                                                         // (the peer-flag waits live in the cluster kernels)
-    if (cluster) cluster_bfgs_search_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);   // :891-950, :873-874
+    if (o->riesz) { /* search stage already enqueued above (cooperative Riesz kernel) */ }
+    else if (cluster) cluster_bfgs_search_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);   // :891-950, :873-874
     else vec_bfgs_search_kernel<<<1, 1024, 0, o->stream>>>(v);
     DZO_CUDA(cudaGetLastError());
     DZO_TRY(large_gemv(o, o->dg, o->t, DZO_STEP_BFGS, o->fused));               // :875
@@ -437,8 +450,8 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     *out = nullptr;
     DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
-    if (objective != DZO_OBJ_ROSENBROCK)
-        return fail(DZO_ERR_UNSUPPORTED, "BFGSOptimizer device objectives: DZO_OBJ_ROSENBROCK (Riesz energy is served by dzo_gd_*)");
+    if (objective == DZO_OBJ_RIESZ && (n <= DZO_SMALL_N_MAX || batch != 1 || nranks != 1))
+        return fail(DZO_ERR_UNSUPPORTED, "BFGSOptimizer with the Riesz objective: one problem per handle, n > %d, one GPU", DZO_SMALL_N_MAX);
     if (batch > 1 && n > DZO_SMALL_N_MAX)
         return fail(DZO_ERR_UNSUPPORTED, "batched mode needs n <= %d; larger n runs one problem per handle", DZO_SMALL_N_MAX);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(DZO_ERR_INVALID_ARGUMENT, "bad rank/nranks");
@@ -504,7 +517,11 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     if (o->small) {
         if ((rc = batched_init(o, L0))) return bail(rc);
     } else {
-        vec_bfgs_init_kernel<<<1, 1024, 0, o->stream>>>(large_vecs(o), L0);
+        if (objective == DZO_OBJ_RIESZ) {
+            if ((rc = riesz_bfgs_attach(n, obj_param, constraint, device, &o->riesz))) return bail(rc);
+            if ((rc = riesz_bfgs_launch(o->riesz, 6, o->stream, o->x, o->g, o->d, o->dx, o->dg, o->sd, o->ctrl, L0))) return bail(rc);
+        } else
+            vec_bfgs_init_kernel<<<1, 1024, 0, o->stream>>>(large_vecs(o), L0);
         SweepArgs a = sweep_args(o);
         a.ctrl = nullptr;
         identity_kernel<<<sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), 0, o->stream>>>(a);   // :781-783
@@ -678,6 +695,7 @@ int dzo_bfgs_set_state(dzo_bfgs* o, const double* point, const double* inverse_h
         !iteration_count)
         return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     DZO_TRY(use_device(o->device));
+    if (o->riesz) return fail(DZO_ERR_UNSUPPORTED, "set_state is not available for the Riesz objective yet");
     const size_t nb = (size_t)o->n * (size_t)o->batch * 8;
     DZO_CUDA(cudaMemcpyAsync(o->x, point, nb, cudaMemcpyHostToDevice, o->stream));              // :825
     DZO_CUDA(cudaMemcpyAsync(o->dx, delta_point, nb, cudaMemcpyHostToDevice, o->stream));       // :853

@@ -259,6 +259,45 @@ int dzo_gd_info(dzo_gd* o, int64_t* n, int64_t* batch, int* order) {
 
 }  // extern "C"
 
+// ============================================================================= BFGS x Riesz hook (used by dzopt_bfgs.cu)
+namespace dzo {
+
+struct RieszBfgs {
+    RieszWork w;
+    int N = 0, dim = 0, sphere = 0;
+};
+
+int riesz_bfgs_attach(int64_t n, int64_t dim, int constraint, int device, void** out) {
+    *out = nullptr;
+    if (dim < 1 || dim > 4) return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
+    RieszBfgs* r = new (std::nothrow) RieszBfgs();
+    if (!r) return fail(DZO_ERR_ALLOC, "out of memory");
+    r->N = (int)(n / dim); r->dim = (int)dim; r->sphere = (constraint == DZO_CONSTRAINT_SPHERE);
+    int rc = r->w.init(r->N, r->dim, device);
+    if (rc) { r->w.release(); delete r; return rc; }
+    *out = r;
+    return DZO_OK;
+}
+void riesz_bfgs_detach(void* p) {
+    RieszBfgs* r = static_cast<RieszBfgs*>(p);
+    if (!r) return;
+    r->w.release();
+    delete r;
+}
+// mode 6 = constructor, 5 = search stage of one step!
+int riesz_bfgs_launch(void* p, int mode, cudaStream_t stream, double* x, double* g, double* d, double* dx, double* dg,
+                      double* sd, LargeCtrl* ctrl, double initial_step_length) {
+    RieszBfgs* r = static_cast<RieszBfgs*>(p);
+    RieszGdArgs a;
+    memset(&a, 0, sizeof a);
+    a.x = x; a.g = g; a.d = d; a.dx = dx; a.dg = dg; a.sd = sd; a.bctrl = ctrl;
+    r->w.fill(a);
+    a.N = r->N; a.sphere = r->sphere; a.max_increases = 0; a.mode = mode; a.initial_step_length = initial_step_length;
+    return r->w.launch(a, stream);
+}
+
+}  // namespace dzo
+
 // ============================================================================= Riesz kernel-level entries
 namespace dzo {
 

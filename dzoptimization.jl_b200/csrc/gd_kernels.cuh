@@ -44,9 +44,13 @@ struct RieszGdArgs {
     double* fbox;                 // broadcast slot for the reduced energy
     int N, sphere, max_increases, ksteps;
     double initial_step_length;
-    int mode;                     // 0 = k step! calls, 1 = constructor, 2 = one energy evaluation of x,
-                                  // 3 = one gradient of x (kernel-level entries), 4 = one line search
+    int mode;                     // 0 = k GD step! calls, 1 = GD constructor, 2 = one energy evaluation of x,
+                                  // 3 = one gradient of x (kernel-level entries), 4 = one line search,
+                                  // 5 = the O(n)/O(N^2) stage of a BFGS step! (search, decision, bookkeeping),
+                                  // 6 = BFGSOptimizer constructor
     double ls_f0, ls_t1, ls_sign; // mode 4 inputs; result in fbox[1], fbox[2]
+    LargeCtrl* bctrl;             // modes 5, 6: the BFGS control block shared with the n^2 sweep kernels
+    double* sd;                   // mode 5: step_direction / overlap  (legacy/DZOptimization.jl:874)
 };
 
 constexpr int kRieszSegWarps = 32;   // warps per CTA, each with a private staging buffer
@@ -359,6 +363,104 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         long long ev = 0;
         R::line_search(a, grid, a.d, a.ls_f0, a.ls_t1, a.ls_sign, wsm, sm, tb, fb, ev);
         if (leader) { a.fbox[1] = tb; a.fbox[2] = fb; }
+        return;
+    }
+    if (a.mode == 6) {
+        // BFGSOptimizer(f, g!, c!, x0, L0)  legacy/DZOptimization.jl:762-810 with the Riesz objective
+        if (a.sphere)
+            for (int j = (int)gtid; j < a.N; j += (int)gsize) {                // :770 constraint_function!(x)
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) s += a.x[(long long)j * DIM + k] * a.x[(long long)j * DIM + k];
+                const double inv = 1.0 / sqrt(s);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) a.x[(long long)j * DIM + k] *= inv;
+            }
+        for (long long e = gtid; e < n; e += gsize) { a.dx[e] = 0.0; a.dg[e] = 0.0; }   // :777-778
+        grid.sync();
+        const double f0 = R::energy(a, grid, a.x, 0.0, 2, wsm, sm);            // :772
+        R::gradient_segments(a, wsm);                                          // :775-776
+        grid.sync();
+        R::gradient_rows(a, false);
+        grid.sync();
+        for (long long e = gtid; e < n; e += gsize) a.d[e] = a.g[e];           // :784 next_step_direction = copy(gradient)
+        if (leader) {
+            LargeCtrl c;
+            c.f = f0; c.L = a.initial_step_length; c.iter = 0; c.type = DZO_STEP_NULL; c.term = 0;
+            c.kind = DZO_STEP_NULL; c.pad = 0; c.step_length = 0.0; c.overlap = 0.0; c.delta_norm = 0.0;
+            c.evals = 1; c.calls = 0;
+            for (int i = 0; i < 64; ++i) c.kind_log[i] = 0;
+            *a.bctrl = c;
+        }
+        return;
+    }
+    if (a.mode == 5) {
+        // step!(::BFGSOptimizer) :891-950 and :873-874 with the Riesz objective: the cooperative grid plays the
+        // role cluster_bfgs_search_kernel plays for Rosenbrock; the n^2 sweeps that follow are the same kernels.
+        const int term = __ldcg(&a.bctrl->term);
+        if (term) {                                                            // :893
+            if (leader) a.bctrl->kind = DZO_STEP_NULL;
+            return;
+        }
+        const double f0 = __ldcg(&a.bctrl->f);
+        const double step_length = __ldcg(&a.bctrl->L);                        // :918
+        const long long iter0 = __ldcg(&a.bctrl->iter), calls0 = __ldcg(&a.bctrl->calls), evals0 = __ldcg(&a.bctrl->evals);
+        long long evals = 0;
+        grid.sync();                       // every CTA holds the control block before the leader may rewrite it
+        const double grad_norm = sqrt(cta_tree_dot(a.g, a.g, n, sm));          // :921
+        const double bfgs_norm = sqrt(cta_tree_dot(a.d, a.d, n, sm));          // :928
+        double grad_step_length, grad_obj, bfgs_step_length, bfgs_obj;
+        R::line_search(a, grid, a.g, f0, step_length / grad_norm, -1.0, wsm, sm, grad_step_length, grad_obj, evals);  // :922-925
+        R::line_search(a, grid, a.d, f0, step_length / bfgs_norm, -1.0, wsm, sm, bfgs_step_length, bfgs_obj, evals);  // :929-932
+        int kind;
+        double alpha, fnew, Lnew;
+        if (bfgs_obj < f0 && !(bfgs_obj > grad_obj)) {                         // :934
+            kind = DZO_STEP_BFGS; alpha = -bfgs_step_length; fnew = bfgs_obj; Lnew = bfgs_step_length * bfgs_norm;
+        } else if (grad_obj < f0) {                                            // :962
+            kind = DZO_STEP_GRADIENT_DESCENT; alpha = -grad_step_length; fnew = grad_obj; Lnew = grad_step_length * grad_norm;
+        } else {
+            if (leader) {                                                      // :989
+                a.bctrl->term = 1;
+                a.bctrl->kind = DZO_STEP_NULL;
+                a.bctrl->evals = evals0 + evals;
+                a.bctrl->kind_log[calls0 & 63] = DZO_STEP_NULL;
+                a.bctrl->calls = calls0 + 1;
+            }
+            return;
+        }
+        const double* dir = (kind == DZO_STEP_BFGS) ? a.d : a.g;
+        for (int j = (int)gtid; j < a.N; j += (int)gsize) {                    // :943-947 / :971-975
+            double w[DIM];
+            R::trial_point(a, dir, j, alpha, 0, w);                            // x += alpha*dir ; constraint!(x)
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const long long e = (long long)j * DIM + k;
+                a.dx[e] = w[k] - a.x[e];                                       // (-x_old) + x_new  :943, :949
+            }
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) a.x[(long long)j * DIM + k] = w[k];
+        }
+        grid.sync();                                   // every CTA is done reading the old gradient as `dir`
+        R::gradient_segments(a, wsm);                                          // :948
+        grid.sync();
+        R::gradient_rows(a, true);                                             // dg = (-g_old) + g_new  :944, :950
+        grid.sync();
+        double overlap = 0.0;
+        if (kind == DZO_STEP_BFGS) {
+            overlap = cta_tree_dot(a.d, a.dg, n, sm);                          // :873
+            const double inv_overlap = 1.0 / overlap;                          // :874
+            for (long long e = gtid; e < n; e += gsize) a.sd[e] = a.d[e] * inv_overlap;
+        } else {
+            for (long long e = gtid; e < n; e += gsize) a.d[e] = a.g[e];       // :984-986
+        }
+        if (leader) {
+            LargeCtrl* c = a.bctrl;
+            c->f = fnew; c->L = Lnew; c->type = kind; c->iter = iter0 + 1;     // :937-940 / :965-968
+            c->kind = kind; c->step_length = alpha; c->overlap = overlap; c->delta_norm = 0.0;
+            c->evals = evals0 + evals;
+            c->kind_log[calls0 & 63] = (unsigned char)kind;
+            c->calls = calls0 + 1;
+        }
         return;
     }
     if (a.mode == 1) {
