@@ -109,6 +109,9 @@ struct dzo_bfgs {
     bool fused = false;
     unsigned long long *flags_t = nullptr, *flags_d = nullptr;   // local, kMaxPeers words each
     unsigned* done = nullptr;
+    cudaGraphExec_t step_graph = nullptr;   // one large-n step! (4 launches) captured once, replayed per step
+    cudaStream_t graph_stream = nullptr;
+    int graph_tuning_epoch = -1;
     void* riesz = nullptr;              // Riesz objective: the cooperative search-stage kernel's workspace
     char* arena = nullptr;              // sharded: ONE cudaMalloc block [t | d | flags_t | flags_d] exported through IPC
     char* peer_arena[kMaxPeers] = {};   // mapped base pointers of the peers' blocks
@@ -124,6 +127,7 @@ static void free_handle(dzo_bfgs* o) {
     cudaSetDevice(o->device);
     if (o->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(o->comm);
     if (o->riesz) riesz_bfgs_detach(o->riesz);
+    if (o->step_graph) cudaGraphExecDestroy(o->step_graph);
     if (o->arena) { o->t = nullptr; o->d = nullptr; o->flags_t = nullptr; o->flags_d = nullptr; }   // live inside the arena
     void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
                     o->sd, o->t, o->partial, o->tile_counters, o->ctrl, o->flags_t, o->flags_d, o->done, o->arena};
@@ -579,12 +583,44 @@ int dzo_bfgs_set_stream(dzo_bfgs* o, void* cuda_stream) {
 }
 
 // ============================================================================= step!
+// One large-n step! is a fixed sequence of four launches whose behaviour is decided on the device, so it is
+// captured into a CUDA graph once and replayed: the launches reach the GPU front end as one unit.
+static int large_step_graph(dzo_bfgs* o) {
+    const bool eligible = g_tuning.use_graph && !o->riesz && (o->nranks == 1 || o->fused);
+    if (!eligible) return large_step_once(o);
+    if (!o->step_graph || o->graph_stream != o->stream || o->graph_tuning_epoch != g_tuning.epoch) {
+        if (o->step_graph) { cudaGraphExecDestroy(o->step_graph); o->step_graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        DZO_CUDA(cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = large_step_once(o);
+        const cudaError_t e = cudaStreamEndCapture(o->stream, &graph);
+        if (rc != DZO_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            g_tuning.use_graph = 0;                       // capture unavailable: plain launches from now on
+            return large_step_once(o);
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&o->step_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) {
+            o->step_graph = nullptr;
+            cudaGetLastError();
+            g_tuning.use_graph = 0;
+            return large_step_once(o);
+        }
+        o->graph_stream = o->stream;
+        o->graph_tuning_epoch = g_tuning.epoch;
+    }
+    DZO_CUDA(cudaGraphLaunch(o->step_graph, o->stream));
+    return DZO_OK;
+}
+
 int dzo_bfgs_step_async(dzo_bfgs* o, int k) {
     if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
     DZO_TRY(use_device(o->device));
     if (k == 0) return DZO_OK;
     if (o->small) return batched_step(o, k);
-    for (int s = 0; s < k; ++s) DZO_TRY(large_step_once(o));
+    for (int s = 0; s < k; ++s) DZO_TRY(large_step_graph(o));
     return DZO_OK;
 }
 int dzo_bfgs_sync(dzo_bfgs* o) {
@@ -1029,6 +1065,8 @@ int dzo_host_free(void* ptr) {
 
 int dzo_set_tuning(const char* key, int value) {
     if (!key) return fail(DZO_ERR_INVALID_ARGUMENT, "null key");
+    g_tuning.epoch += 1;                                  // captured step graphs are rebuilt
+    if (!strcmp(key, "use_graph")) { g_tuning.use_graph = value; return DZO_OK; }
     if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
     if (!strcmp(key, "search_variant")) { g_tuning.search_variant = value; return DZO_OK; }
     if (!strcmp(key, "sharded_variant")) { g_tuning.sharded_variant = value; return DZO_OK; }

@@ -53,6 +53,8 @@ int check_problem(int objective, int constraint, int64_t obj_param, int64_t n, i
 // process-wide tuning knobs (A/B measurements only; never change results)
 struct Tuning {
     int batched_prefetch = 2;  // hybrid kernel: L2 prefetch distance in phase-2 rounds (measured: 0:0.70 1:0.75 2:0.89 3:0.89 4:0.88 6:0.83 of HBM peak)
+    int use_graph = 1;        // large-n step!: replay a captured CUDA graph of its four launches
+    int epoch = 0;            // bumped by every dzo_set_tuning call
     int sweep_unroll = 16;    // columns in flight per thread in the n^2 sweeps; measured on one box at n=16384:
                               // update kernel 0.79 (U=8), 0.96 (U=16), 0.84 (U=24), 0.87 (U=32) of HBM peak
     int sweep_threads = 0;    // threads per sweep CTA (0 = pick from the slab shape)
