@@ -7,6 +7,7 @@
 #include "batched_bfgs.cuh"
 #include "batched_hybrid.cuh"
 #include "cluster_search.cuh"
+#include "gd_batched.cuh"
 #include "host_common.h"
 #include "large_bfgs.cuh"
 #include "small_ops.cuh"
@@ -242,8 +243,25 @@ static int launch_batched_step(dzo_bfgs* o, int k) {
         case 16: return fn<16>(__VA_ARGS__);                           \
         default: return fn<32>(__VA_ARGS__);                           \
     }
-static int batched_init(dzo_bfgs* o, double L0) { DZO_LPP_DISPATCH(o, launch_batched_init, o, L0) }
-static int batched_restore(dzo_bfgs* o) { DZO_LPP_DISPATCH(o, launch_batched_restore, o) }
+// objectives the warp-resident kernels do not cover (Riesz): generic one-thread-per-problem kernel
+static int generic_launch(dzo_bfgs* o, int mode, int k, double L0) {
+    BfgsGenericArgs a;
+    a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg; a.H = o->H; a.f = o->f; a.L = o->L;
+    a.iter = o->iter; a.type = o->type; a.term = o->term; a.n = (int)o->n; a.dim = (int)o->dim;
+    a.objective = o->objective; a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.ksteps = k; a.batch = o->batch;
+    a.initial_step_length = L0; a.mode = mode;
+    bfgs_generic_kernel<<<(unsigned)((o->batch + 63) / 64), 64, 0, o->stream>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+static int batched_init(dzo_bfgs* o, double L0) {
+    if (o->objective != DZO_OBJ_ROSENBROCK) return generic_launch(o, 1, 0, L0);
+    DZO_LPP_DISPATCH(o, launch_batched_init, o, L0)
+}
+static int batched_restore(dzo_bfgs* o) {
+    if (o->objective != DZO_OBJ_ROSENBROCK) return generic_launch(o, 2, 0, 0.0);
+    DZO_LPP_DISPATCH(o, launch_batched_restore, o)
+}
 template <int N>
 static int launch_hybrid_step(dzo_bfgs* o, int k) {
     const unsigned grid = (unsigned)((o->batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
@@ -258,6 +276,7 @@ static int launch_hybrid_step(dzo_bfgs* o, int k) {
     return DZO_OK;
 }
 static int batched_step(dzo_bfgs* o, int k) {
+    if (o->objective != DZO_OBJ_ROSENBROCK) return generic_launch(o, 0, k, 0.0);
     if (g_tuning.batched_variant == 0) {     // thread-per-problem line search + lanes-per-problem H update
         switch (o->n) {
             case 2: return launch_hybrid_step<2>(o, k);
@@ -454,8 +473,8 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     *out = nullptr;
     DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
-    if (objective == DZO_OBJ_RIESZ && (n <= DZO_SMALL_N_MAX || batch != 1 || nranks != 1))
-        return fail(DZO_ERR_UNSUPPORTED, "BFGSOptimizer with the Riesz objective: one problem per handle, n > %d, one GPU", DZO_SMALL_N_MAX);
+    if (objective == DZO_OBJ_RIESZ && (obj_param > 4 || nranks != 1))
+        return fail(DZO_ERR_UNSUPPORTED, "BFGSOptimizer with the Riesz objective: dim <= 4, one GPU");
     if (batch > 1 && n > DZO_SMALL_N_MAX)
         return fail(DZO_ERR_UNSUPPORTED, "batched mode needs n <= %d; larger n runs one problem per handle", DZO_SMALL_N_MAX);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(DZO_ERR_INVALID_ARGUMENT, "bad rank/nranks");
@@ -731,7 +750,7 @@ int dzo_bfgs_set_state(dzo_bfgs* o, const double* point, const double* inverse_h
         !iteration_count)
         return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     DZO_TRY(use_device(o->device));
-    if (o->riesz) return fail(DZO_ERR_UNSUPPORTED, "set_state is not available for the Riesz objective yet");
+    if (o->riesz) return fail(DZO_ERR_UNSUPPORTED, "set_state is not available for the large-n Riesz objective yet");
     const size_t nb = (size_t)o->n * (size_t)o->batch * 8;
     DZO_CUDA(cudaMemcpyAsync(o->x, point, nb, cudaMemcpyHostToDevice, o->stream));              // :825
     DZO_CUDA(cudaMemcpyAsync(o->dx, delta_point, nb, cudaMemcpyHostToDevice, o->stream));       // :853

@@ -3,6 +3,7 @@
 #include <new>
 #include <vector>
 
+#include "gd_batched.cuh"
 #include "gd_kernels.cuh"
 #include "host_common.h"
 
@@ -16,6 +17,11 @@ struct dzo_gd {
     int64_t dim = 0, n = 0, batch = 0;
     double *x = nullptr, *g = nullptr, *d = nullptr, *dx = nullptr, *dg = nullptr;
     GdCtrl* ctrl = nullptr;
+    // batched small-n path (n <= DZO_SMALL_N_MAX): one thread per problem, SEQUENTIAL order
+    bool small = false;
+    double *f = nullptr, *df = nullptr, *L = nullptr;
+    long long* iter = nullptr;
+    unsigned char* term = nullptr;
     // Riesz cooperative kernel
     double *segE = nullptr, *rowE = nullptr, *segG = nullptr, *fbox = nullptr;
     int2* e_items = nullptr;
@@ -27,7 +33,8 @@ struct dzo_gd {
 static void free_gd(dzo_gd* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter};
+    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter,
+                    o->f, o->df, o->L, o->iter, o->term};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
@@ -134,6 +141,16 @@ static RieszGdArgs riesz_args(const dzo_gd* o, int mode, int k) {
 }
 
 static int gd_launch(dzo_gd* o, int mode, int k, double L0) {
+    if (o->small) {
+        GdBatchedArgs a;
+        a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.d = o->d; a.f = o->f; a.df = o->df; a.L = o->L;
+        a.iter = o->iter; a.term = o->term; a.n = (int)o->n; a.dim = (int)o->dim; a.objective = o->objective;
+        a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.max_increases = o->max_increases; a.ksteps = k;
+        a.batch = o->batch; a.initial_step_length = L0; a.mode = mode;
+        gd_batched_kernel<<<(unsigned)((o->batch + 127) / 128), 128, 0, o->stream>>>(a);
+        DZO_CUDA(cudaGetLastError());
+        return DZO_OK;
+    }
     if (o->objective == DZO_OBJ_RIESZ) {
         RieszGdArgs a = riesz_args(o, mode, k);
         a.initial_step_length = L0;
@@ -157,7 +174,8 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
     if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     *out = nullptr;
     DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
-    if (batch != 1) return fail(DZO_ERR_UNSUPPORTED, "GradientDescentOptimizer on the device runs one problem per handle");
+    if (batch != 1 && n > DZO_SMALL_N_MAX)
+        return fail(DZO_ERR_UNSUPPORTED, "batched GradientDescentOptimizer needs n <= %d; larger n runs one problem per handle", DZO_SMALL_N_MAX);
     if (objective == DZO_OBJ_RIESZ && (obj_param < 1 || obj_param > 4))
         return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
     if (n / (objective == DZO_OBJ_RIESZ ? obj_param : 1) > (1 << 30)) return fail(DZO_ERR_INVALID_ARGUMENT, "n too large");
@@ -166,21 +184,27 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
     if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
     o->device = device; o->objective = objective; o->constraint = constraint; o->max_increases = max_increases;
     o->dim = obj_param; o->n = n; o->batch = batch;
+    o->small = (n <= DZO_SMALL_N_MAX);
     int rc = DZO_OK;
     auto bail = [&](int code) { free_gd(o); return code; };
     if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "cudaStreamCreate failed"));
     o->stream = o->own_stream;
-    if ((rc = dmalloc(&o->x, (size_t)n)) || (rc = dmalloc(&o->g, (size_t)n)) || (rc = dmalloc(&o->d, (size_t)n)) ||
-        (rc = dmalloc(&o->dx, (size_t)n)) || (rc = dmalloc(&o->dg, (size_t)n)) || (rc = dmalloc(&o->ctrl, 1)))
+    const size_t nb = (size_t)n * (size_t)batch;
+    if ((rc = dmalloc(&o->x, nb)) || (rc = dmalloc(&o->g, nb)) || (rc = dmalloc(&o->d, nb)) ||
+        (rc = dmalloc(&o->dx, nb)) || (rc = dmalloc(&o->dg, nb)) || (rc = dmalloc(&o->ctrl, 1)))
         return bail(rc);
-    if (objective == DZO_OBJ_RIESZ) {
+    if (o->small) {
+        if ((rc = dmalloc(&o->f, (size_t)batch)) || (rc = dmalloc(&o->df, (size_t)batch)) || (rc = dmalloc(&o->L, (size_t)batch)) ||
+            (rc = dmalloc(&o->iter, (size_t)batch)) || (rc = dmalloc(&o->term, (size_t)batch)))
+            return bail(rc);
+    } else if (objective == DZO_OBJ_RIESZ) {
         RieszWork w;
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
         o->n_e_items = w.n_e_items; o->counter = w.counter; o->grid = w.grid;
     }
-    if (cudaMemcpyAsync(o->x, x0, (size_t)n * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)   // :339 collect
+    if (cudaMemcpyAsync(o->x, x0, nb * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)   // :339 collect
         return bail(fail(DZO_ERR_CUDA, "H2D copy of x0 failed"));
     if ((rc = gd_launch(o, 1, 0, initial_step_length))) return bail(rc);
     if (cudaStreamSynchronize(o->stream) != cudaSuccess)
@@ -226,7 +250,7 @@ static int gd_read(dzo_gd* o, void* dst, const void* src, size_t bytes) {
 #define DZO_GD_VEC(name, field)                                                   \
     int name(dzo_gd* o, double* out) {                                            \
         if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");             \
-        return gd_read(o, out, o->field, (size_t)o->n * 8);                       \
+        return gd_read(o, out, o->field, (size_t)o->n * (size_t)o->batch * 8);    \
     }
 DZO_GD_VEC(dzo_gd_get_point, x)
 DZO_GD_VEC(dzo_gd_get_delta_point, dx)
@@ -234,26 +258,27 @@ DZO_GD_VEC(dzo_gd_get_gradient, g)
 DZO_GD_VEC(dzo_gd_get_delta_gradient, dg)
 DZO_GD_VEC(dzo_gd_get_direction, d)
 #undef DZO_GD_VEC
-#define DZO_GD_SCALAR(name, type, expr)                                           \
+#define DZO_GD_SCALAR(name, type, expr, field)                                    \
     int name(dzo_gd* o, type* out) {                                              \
         if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");    \
+        if (o->small) return gd_read(o, out, o->field, (size_t)o->batch * sizeof(type));   \
         GdCtrl c;                                                                 \
         DZO_TRY(gd_read(o, &c, o->ctrl, sizeof c));                               \
         *out = (type)(expr);                                                      \
         return DZO_OK;                                                            \
     }
-DZO_GD_SCALAR(dzo_gd_get_objective, double, c.f)
-DZO_GD_SCALAR(dzo_gd_get_delta_objective, double, c.df)
-DZO_GD_SCALAR(dzo_gd_get_step_length, double, c.L)
-DZO_GD_SCALAR(dzo_gd_get_iteration_count, int64_t, c.iter)
-DZO_GD_SCALAR(dzo_gd_get_terminated, uint8_t, c.term != 0)
+DZO_GD_SCALAR(dzo_gd_get_objective, double, c.f, f)
+DZO_GD_SCALAR(dzo_gd_get_delta_objective, double, c.df, df)
+DZO_GD_SCALAR(dzo_gd_get_step_length, double, c.L, L)
+DZO_GD_SCALAR(dzo_gd_get_iteration_count, int64_t, c.iter, iter)
+DZO_GD_SCALAR(dzo_gd_get_terminated, uint8_t, c.term != 0, term)
 #undef DZO_GD_SCALAR
 
 int dzo_gd_info(dzo_gd* o, int64_t* n, int64_t* batch, int* order) {
     if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
     if (n) *n = o->n;
     if (batch) *batch = o->batch;
-    if (order) *order = DZO_ORDER_TREE;
+    if (order) *order = o->small ? DZO_ORDER_SEQUENTIAL : DZO_ORDER_TREE;
     return DZO_OK;
 }
 
