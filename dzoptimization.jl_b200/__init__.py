@@ -31,7 +31,7 @@ import numpy as np
 from . import _capi
 
 __all__ = [
-    "LBFGSOptimizer",
+    "LBFGSOptimizer", "AdGDOptimizer",
     "accelerated_pairwise_radial_energy", "accelerated_pairwise_radial_gradient_", "accelerated_pairwise_radial_hvp_",
     "BFGSOptimizer", "GradientDescentOptimizer", "QuadraticLineSearch", "step_",
     "ExampleFunctions", "NULL_CONSTRAINT", "SPHERE_CONSTRAINT", "StepType",
@@ -572,6 +572,63 @@ class LBFGSOptimizer:
         h, self._h = getattr(self, "_h", None), None
         if h:
             lib().dzo_lbfgs_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class AdGDOptimizer:
+    """struct AdGDOptimizer of the LIVE package, src/DZOptimization.jl:179-198;
+    ``AdGDOptimizer(c_, f, g_, x0, initial_step_length)`` (:252-271)."""
+
+    def __init__(self, constraint_function_, objective_function, gradient_function_, initial_point,
+                 initial_step_length, device=0):
+        c = NULL_CONSTRAINT if constraint_function_ is None else constraint_function_
+        obj, cid = _resolve(objective_function, gradient_function_, c)
+        a = np.ascontiguousarray(initial_point, dtype=np.float64)
+        if a.ndim != 1:
+            raise ValueError("initial point must be a vector")
+        if not initial_step_length > 0:
+            raise AssertionError("initial_step_length > 0")              # @assert :232
+        self._n = a.size
+        self._h = None
+        h = C.c_void_p()
+        _check(lib().dzo_adgd_create(C.byref(h), obj, cid, 0, self._n, _dp(a), float(initial_step_length), int(device)))
+        self._h = h
+
+    def _vec(self, name):
+        out = np.empty(self._n)
+        _check(getattr(lib(), "dzo_adgd_" + name)(self._h, _dp(out)))
+        return out
+
+    def _scalars(self):
+        out = np.empty(6)
+        _check(lib().dzo_adgd_get_scalars(self._h, _dp(out)))
+        return out
+
+    current_point = property(lambda s: s._vec("get_point"))
+    delta_point = property(lambda s: s._vec("get_delta_point"))
+    current_gradient = property(lambda s: s._vec("get_gradient"))
+    delta_gradient = property(lambda s: s._vec("get_delta_gradient"))
+    current_objective_value = property(lambda s: np.array(s._scalars()[0]))
+    delta_objective_value = property(lambda s: np.array(s._scalars()[1]))
+    current_step_size = property(lambda s: np.array(s._scalars()[2]))
+    previous_step_size = property(lambda s: np.array(s._scalars()[3]))
+    iteration_count = property(lambda s: np.array(int(s._scalars()[4])))
+    is_stuck = property(lambda s: np.array(bool(s._scalars()[5])))
+    has_converged = is_stuck
+
+    def step(self, k: int = 1):
+        _check(lib().dzo_adgd_step(self._h, int(k)))
+        return self
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().dzo_adgd_destroy(h)
 
     def __del__(self):
         try:

@@ -71,6 +71,12 @@ def bind(lib, cpu: bool):
     sig("lbfgs_get_rho_history", [H, c_i64_p, c_double_p])
     sig("lbfgs_destroy", [H], None)
 
+    sig("adgd_create", [HP, I, I, I64, I64, c_double_p, D, I])      # last: order (oracle) | device (CUDA)
+    sig("adgd_step", [H, I])
+    for g in ("get_point", "get_delta_point", "get_gradient", "get_delta_gradient", "get_scalars"):
+        sig("adgd_" + g, [H, c_double_p])
+    sig("adgd_destroy", [H], None)
+
     dev = [] if cpu else [I]
     sig("objective", [I, I, I64, I, I64, I64, c_double_p, c_double_p] + dev)
     sig("gradient", [I, I, I64, I, I64, I64, c_double_p, c_double_p] + dev)

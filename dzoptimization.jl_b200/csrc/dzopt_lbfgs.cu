@@ -140,3 +140,82 @@ int dzo_lbfgs_get_rho_history(dzo_lbfgs* o, int64_t* count, double* rho) {
 }
 
 }  // extern "C"
+
+// ============================================================================= AdGDOptimizer (src/DZOptimization.jl:179-312)
+struct dzo_adgd {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t n = 0;
+    double *x = nullptr, *dx = nullptr, *g = nullptr, *dg = nullptr;
+    AdgdCtrl* ctrl = nullptr;
+};
+static void free_adgd(dzo_adgd* o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->ctrl};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (o->stream) cudaStreamDestroy(o->stream);
+    delete o;
+}
+static int adgd_launch(dzo_adgd* o, int mode, int k, double L0) {
+    AdgdArgs a;
+    a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.ctrl = o->ctrl; a.n = o->n; a.ksteps = k; a.mode = mode;
+    a.initial_step_length = L0;
+    cluster_adgd_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+extern "C" {
+int dzo_adgd_create(dzo_adgd** out, int objective, int constraint, int64_t obj_param, int64_t n, const double* x0,
+                    double initial_step_length, int device) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = nullptr;
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, 1));
+    if (objective != DZO_OBJ_ROSENBROCK) return fail(DZO_ERR_UNSUPPORTED, "AdGDOptimizer device objective: DZO_OBJ_ROSENBROCK");
+    if (!(initial_step_length > 0.0)) return fail(DZO_ERR_INVALID_ARGUMENT, "initial_step_length must be positive");   // :232
+    DZO_TRY(use_device(device));
+    dzo_adgd* o = new (std::nothrow) dzo_adgd();
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->device = device; o->n = n;
+    auto bail = [&](int code) { free_adgd(o); return code; };
+    if (cudaStreamCreateWithFlags(&o->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(DZO_ERR_CUDA, "cudaStreamCreate failed"));
+    double** vecs[] = {&o->x, &o->dx, &o->g, &o->dg};
+    for (double** v : vecs)
+        if (cudaMalloc((void**)v, (size_t)n * 8) != cudaSuccess) return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+    if (cudaMalloc((void**)&o->ctrl, sizeof(AdgdCtrl)) != cudaSuccess) return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+    if (cudaMemcpyAsync(o->x, x0, (size_t)n * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "H2D copy failed"));
+    int rc = adgd_launch(o, 1, 0, initial_step_length);
+    if (rc) return bail(rc);
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess) return bail(fail(DZO_ERR_CUDA, "constructor kernel failed"));
+    *out = o;
+    return DZO_OK;
+}
+void dzo_adgd_destroy(dzo_adgd* o) { free_adgd(o); }
+int dzo_adgd_step(dzo_adgd* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(use_device(o->device));
+    if (k > 0) DZO_TRY(adgd_launch(o, 0, k, 0.0));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+static int ad_read(dzo_adgd* o, void* dst, const void* src, size_t bytes) {
+    if (!o || !dst) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+int dzo_adgd_get_point(dzo_adgd* o, double* out) { return o ? ad_read(o, out, o->x, (size_t)o->n * 8) : fail(DZO_ERR_INVALID_ARGUMENT, "null handle"); }
+int dzo_adgd_get_delta_point(dzo_adgd* o, double* out) { return o ? ad_read(o, out, o->dx, (size_t)o->n * 8) : fail(DZO_ERR_INVALID_ARGUMENT, "null handle"); }
+int dzo_adgd_get_gradient(dzo_adgd* o, double* out) { return o ? ad_read(o, out, o->g, (size_t)o->n * 8) : fail(DZO_ERR_INVALID_ARGUMENT, "null handle"); }
+int dzo_adgd_get_delta_gradient(dzo_adgd* o, double* out) { return o ? ad_read(o, out, o->dg, (size_t)o->n * 8) : fail(DZO_ERR_INVALID_ARGUMENT, "null handle"); }
+int dzo_adgd_get_scalars(dzo_adgd* o, double* s) {
+    if (!o || !s) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    AdgdCtrl c;
+    DZO_TRY(ad_read(o, &c, o->ctrl, sizeof c));
+    s[0] = c.f; s[1] = c.df; s[2] = c.cur; s[3] = c.prev; s[4] = (double)c.iter; s[5] = (double)c.stuck;
+    return DZO_OK;
+}
+}  // extern "C"

@@ -186,4 +186,115 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
     if (leader) *a.ctrl = sc;
 }
 
+// ============================================================================= live AdGDOptimizer (:179-312)
+struct AdgdCtrl {
+    double f, df, cur, prev;
+    long long iter;
+    int stuck, pad;
+};
+struct AdgdArgs {
+    double *x, *dx, *g, *dg;
+    AdgdCtrl* ctrl;
+    long long n;
+    int ksteps, mode;              // mode 0 = steps, 1 = constructor
+    double initial_step_length;
+};
+DZO_DEVINL double julia_min(double a, double b) {   // Base.min(::Float64, ::Float64)
+    if (a != a) return a;
+    if (b != b) return b;
+    if (a == b) return signbit(a) ? a : b;
+    return a < b ? a : b;
+}
+
+static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
+    cluster_adgd_kernel(AdgdArgs a) {
+    __shared__ ClusterRed R;
+    __shared__ AdgdCtrl sc;
+    cg::cluster_group cluster = cg::this_cluster();
+    const long long n = a.n, m2 = n >> 1;
+    const long long v = (long long)cluster.block_rank() * kClusterThreads + threadIdx.x;
+    const bool leader = (cluster.block_rank() == 0 && threadIdx.x == 0);
+    if (threadIdx.x == 0) { if (a.mode == 0) sc = *a.ctrl; R.parity = 0; }
+    __syncthreads();
+    cluster.sync();
+    if (a.mode == 1) {                                                                          // :201-271
+        bool ch, sm_;
+        const double f0 = cluster_probe<2>(cluster, R, a.x, a.x, m2, 0.0, 0.0, ch, sm_);        // :260
+        for (long long k = v; k < m2; k += DZO_TREE_WIDTH) {
+            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+            reinterpret_cast<double2*>(a.g)[k] = RosenbrockVec::grad(xx.x, xx.y);               // :265
+            reinterpret_cast<double2*>(a.dx)[k] = make_double2(0.0, 0.0);
+            reinterpret_cast<double2*>(a.dg)[k] = make_double2(0.0, 0.0);
+        }
+        const double gnorm = sqrt(cluster_dot(cluster, R, a.g, a.g, n));                        // :233
+        if (leader) {
+            AdgdCtrl t;
+            t.f = f0; t.df = 0.0; t.iter = 0; t.pad = 0;
+            t.stuck = (gnorm == 0.0);                                                           // :234
+            t.cur = t.prev = t.stuck ? 0.0 : a.initial_step_length / gnorm;                     // :235-236
+            *a.ctrl = t;
+        }
+        return;
+    }
+    const double inv_sqrt_two = sqrt(0.5);
+    for (int step_i = 0; step_i < a.ksteps; ++step_i) {
+        if (sc.stuck) break;                                                                    // :276-278
+        const double previous = sc.prev, current = sc.cur;
+        double next = current;
+        if (sc.iter > 0) {                                                                      // :288-297
+            const double theta = current / previous;
+            next *= sqrt(1.0 + theta);
+            const double dgn = sqrt(cluster_dot(cluster, R, a.dg, a.dg, n));
+            if (dgn != 0.0) {
+                const double inv_L = sqrt(cluster_dot(cluster, R, a.dx, a.dx, n)) / dgn;
+                next = julia_min(next, inv_sqrt_two * inv_L);
+            }
+        }
+        // take_backtracking_step!(opt, -next, current_gradient)  :301, :107-154
+        double step = -next, nxt = 0.0;
+        bool accepted = false;
+        for (;;) {
+            double acc = 0.0;
+            unsigned fl = 0;
+            for (long long k = v; k < m2; k += DZO_TREE_WIDTH) {
+                const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+                const double2 gg = reinterpret_cast<const double2*>(a.g)[k];
+                const double w0 = xx.x + step * gg.x, w1 = xx.y + step * gg.y;
+                if (!julia_isequal(w0, xx.x) || !julia_isequal(w1, xx.y)) fl |= 1u;
+                acc += RosenbrockVec::term(w0, w1);
+            }
+            double pr[1] = {acc};
+            cluster_tree_reduce<1>(cluster, R, pr, fl);
+            if (!(fl & 1u)) break;
+            nxt = pr[0];
+            if (nxt < sc.f) { accepted = true; break; }
+            step *= 0.5;
+        }
+        if (!accepted) {
+            DZO_OWN_ELEMENTS(e, n, v) a.dx[e] = a.x[e];
+            if (threadIdx.x == 0) { sc.stuck = 1; sc.prev = current; sc.cur = next; }
+            __syncthreads();
+            break;
+        }
+        for (long long k = v; k < m2; k += DZO_TREE_WIDTH) {
+            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+            const double2 go = reinterpret_cast<const double2*>(a.g)[k];
+            double2 xn, dxv, dgv;
+            xn.x = xx.x + step * go.x; xn.y = xx.y + step * go.y;
+            dxv.x = 1.0 * xn.x + (-1.0) * xx.x; dxv.y = 1.0 * xn.y + (-1.0) * xx.y;
+            const double2 gn = RosenbrockVec::grad(xn.x, xn.y);
+            dgv.x = 1.0 * gn.x + (-1.0) * go.x; dgv.y = 1.0 * gn.y + (-1.0) * go.y;
+            reinterpret_cast<double2*>(a.x)[k] = xn;
+            reinterpret_cast<double2*>(a.dx)[k] = dxv;
+            reinterpret_cast<double2*>(a.g)[k] = gn;
+            reinterpret_cast<double2*>(a.dg)[k] = dgv;
+        }
+        if (threadIdx.x == 0) {
+            sc.df = nxt - sc.f; sc.f = nxt; sc.prev = current; sc.cur = next; sc.iter += 1;     // :298-299, :310
+        }
+        __syncthreads();
+    }
+    if (leader) *a.ctrl = sc;
+}
+
 }  // namespace dzo

@@ -1123,3 +1123,115 @@ void dzo_cpu_lbfgs_destroy(dzo_cpu_lbfgs* o) {
     free(o->x); free(o->dx); free(o->g); free(o->dg); free(o->d); free(o->S); free(o->Y);
     free(o);
 }
+
+/* ======================================================================= live AdGDOptimizer
+ * src/DZOptimization.jl:179-312 */
+struct dzo_cpu_adgd {
+    problem_t P;
+    double *x, *dx, *g, *dg;
+    double f, df, cur, prev;
+    int64_t iter;
+    int stuck;
+};
+static double julia_min(double a, double b) { /* Base.min for Float64: NaN-propagating, min(-0.0, 0.0) = -0.0 */
+    if (a != a) return a;
+    if (b != b) return b;
+    if (a == b) return signbit(a) ? a : b;
+    return a < b ? a : b;
+}
+int dzo_cpu_adgd_create(dzo_cpu_adgd** out, int objective, int constraint, int64_t obj_param, int64_t n,
+                        const double* x0, double initial_step_length, int order) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = NULL;
+    int rc = check_problem(objective, constraint, obj_param, n, 1);
+    if (rc) return rc;
+    if (!(initial_step_length > 0.0)) return fail(DZO_ERR_INVALID_ARGUMENT, "initial_step_length must be positive"); /* :232 */
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    dzo_cpu_adgd* o = (dzo_cpu_adgd*)calloc(1, sizeof *o);
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->P.objective = objective; o->P.constraint = constraint; o->P.order = order; o->P.n = n;
+    o->P.dim = obj_param > 0 ? obj_param : 1;
+    o->x = (double*)malloc((size_t)n * 8); o->dx = (double*)calloc((size_t)n, 8);
+    o->g = (double*)malloc((size_t)n * 8); o->dg = (double*)calloc((size_t)n, 8);
+    if (!o->x || !o->dx || !o->g || !o->dg) { dzo_cpu_adgd_destroy(o); return fail(DZO_ERR_ALLOC, "out of memory"); }
+    memcpy(o->x, x0, (size_t)n * 8);
+    if (!constraint_(&o->P, o->x)) { dzo_cpu_adgd_destroy(o); return fail(DZO_ERR_CONSTRAINT_FAILED, "constraint_function! failed on the initial point"); }
+    o->f = objective_(&o->P, o->x);                                                     /* :260 */
+    gradient_(&o->P, o->g, o->x);                                                       /* :265 */
+    const double gnorm = sqrt(norm2_(order, o->g, n));                                  /* :233 */
+    o->stuck = (gnorm == 0.0);                                                          /* :234 */
+    o->cur = o->prev = o->stuck ? 0.0 : initial_step_length / gnorm;                    /* :235-236 */
+    *out = o;
+    return DZO_OK;
+}
+static void adgd_step_one(dzo_cpu_adgd* o) {
+    if (o->stuck) return;                                                               /* :276-278 */
+    const int64_t n = o->P.n;
+    const int order = o->P.order;
+    const double inv_sqrt_two = sqrt(0.5);
+    const double previous = o->prev, current = o->cur;
+    double next = current;
+    if (o->iter > 0) {                                                                  /* :288-297 */
+        const double theta = current / previous;
+        next *= sqrt(1.0 + theta);
+        const double dgn = sqrt(norm2_(order, o->dg, n));
+        if (dgn != 0.0) {
+            const double inv_L = sqrt(norm2_(order, o->dx, n)) / dgn;
+            next = julia_min(next, inv_sqrt_two * inv_L);
+        }
+    }
+    o->prev = current;                                                                  /* :298-299 */
+    o->cur = next;
+    /* take_backtracking_step!(opt, -next_step_size, opt.current_gradient)  :301, :107-154 */
+    double step = -next;
+    memcpy(o->dx, o->x, (size_t)n * 8);
+    for (;;) {
+        int same = 1;
+        for (int64_t k = 0; k < n; ++k) {
+            o->x[k] += step * o->g[k];
+            same &= julia_isequal(o->x[k], o->dx[k]);
+        }
+        if (same) { o->stuck = 1; return; }
+        if (constraint_(&o->P, o->x)) {
+            const double nxt = objective_(&o->P, o->x);
+            if (nxt < o->f) {
+                o->df = nxt - o->f;
+                o->f = nxt;
+                for (int64_t k = 0; k < n; ++k) o->dx[k] = 1.0 * o->x[k] + (-1.0) * o->dx[k];
+                break;
+            }
+        }
+        memcpy(o->x, o->dx, (size_t)n * 8);
+        step *= 0.5;
+    }
+    memcpy(o->dg, o->g, (size_t)n * 8);                                                 /* :306 */
+    gradient_(&o->P, o->g, o->x);                                                       /* :307 */
+    for (int64_t k = 0; k < n; ++k) o->dg[k] = 1.0 * o->g[k] + (-1.0) * o->dg[k];       /* :308 */
+    o->iter += 1;                                                                       /* :310 */
+}
+int dzo_cpu_adgd_step(dzo_cpu_adgd* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    for (int s = 0; s < k; ++s) adgd_step_one(o);
+    return DZO_OK;
+}
+#define AGET(name, field)                                                               \
+    int name(dzo_cpu_adgd* o, double* out) {                                            \
+        if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");          \
+        memcpy(out, o->field, (size_t)o->P.n * 8);                                      \
+        return DZO_OK;                                                                  \
+    }
+AGET(dzo_cpu_adgd_get_point, x)
+AGET(dzo_cpu_adgd_get_delta_point, dx)
+AGET(dzo_cpu_adgd_get_gradient, g)
+AGET(dzo_cpu_adgd_get_delta_gradient, dg)
+#undef AGET
+int dzo_cpu_adgd_get_scalars(dzo_cpu_adgd* o, double* s) {
+    if (!o || !s) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    s[0] = o->f; s[1] = o->df; s[2] = o->cur; s[3] = o->prev; s[4] = (double)o->iter; s[5] = (double)o->stuck;
+    return DZO_OK;
+}
+void dzo_cpu_adgd_destroy(dzo_cpu_adgd* o) {
+    if (!o) return;
+    free(o->x); free(o->dx); free(o->g); free(o->dg);
+    free(o);
+}

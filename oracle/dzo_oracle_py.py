@@ -612,3 +612,72 @@ class LiveLBFGSOptimizer:
         self.rho.insert(0, dot(self.delta_point, self.delta_gradient, self.tree))
         self.iteration_count += 1
         return self
+
+
+def _julia_min(a, b):
+    if math.isnan(a):
+        return a
+    if math.isnan(b):
+        return b
+    if a == b:
+        return a if math.copysign(1.0, a) < 0 else b
+    return a if a < b else b
+
+
+class LiveAdGDOptimizer:
+    """src/DZOptimization.jl:179-312 (Algorithm 1 of MM24 + backtracking safeguard)."""
+
+    def __init__(self, fn, x0, initial_step_length, tree=True):  # :201-271
+        self.fn, self.tree = fn, tree
+        self.current_point = list(x0)
+        assert fn.constraint(self.current_point)
+        self.current_objective_value = fn.f(self.current_point)
+        n = len(x0)
+        self.current_gradient = [0.0] * n
+        fn.g(self.current_gradient, self.current_point)
+        self.delta_point = [0.0] * n
+        self.delta_gradient = [0.0] * n
+        self.delta_objective_value = 0.0
+        assert initial_step_length > 0.0
+        gnorm = math.sqrt(norm2(self.current_gradient, tree))
+        self.is_stuck = gnorm == 0.0
+        s0 = 0.0 if self.is_stuck else initial_step_length / gnorm
+        self.current_step_size = self.previous_step_size = s0
+        self.iteration_count = 0
+
+    def step(self):  # :274-312
+        if self.is_stuck:
+            return self
+        previous, current = self.previous_step_size, self.current_step_size
+        nxt = current
+        if self.iteration_count > 0:
+            theta = current / previous
+            nxt *= math.sqrt(1.0 + theta)
+            dgn = math.sqrt(norm2(self.delta_gradient, self.tree))
+            if dgn != 0.0:
+                inv_L = math.sqrt(norm2(self.delta_point, self.tree)) / dgn
+                nxt = _julia_min(nxt, math.sqrt(0.5) * inv_L)
+        self.previous_step_size, self.current_step_size = current, nxt
+        x, g = self.current_point, self.current_gradient
+        self.delta_point = list(x)
+        step = -nxt
+        while True:  # take_backtracking_step!  :107-154
+            for k in range(len(x)):
+                x[k] += step * g[k]
+            if all(_isequal(a, b) for a, b in zip(x, self.delta_point)):
+                self.is_stuck = True
+                return self
+            if self.fn.constraint(x):
+                val = self.fn.f(x)
+                if val < self.current_objective_value:
+                    self.delta_objective_value = val - self.current_objective_value
+                    self.current_objective_value = val
+                    self.delta_point = [1.0 * a + (-1.0) * b for a, b in zip(x, self.delta_point)]
+                    break
+            x[:] = self.delta_point
+            step *= 0.5
+        self.delta_gradient = list(g)
+        self.fn.g(g, x)
+        self.delta_gradient = [1.0 * a + (-1.0) * b for a, b in zip(g, self.delta_gradient)]
+        self.iteration_count += 1
+        return self

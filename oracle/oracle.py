@@ -297,3 +297,47 @@ class LBFGS:
             self.close()
         except Exception:
             pass
+
+
+class AdGD:
+    """live AdGDOptimizer (src/DZOptimization.jl:179-312), one problem"""
+
+    def __init__(self, objective, x0, step, order=TREE):
+        a = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+        self.n = a.size
+        self._h = None
+        h = C.c_void_p()
+        _check(lib().dzo_cpu_adgd_create(C.byref(h), objective, CONSTRAINT_NONE, 0, self.n, _dp(a), float(step), order))
+        self._h = h
+
+    def _vec(self, name):
+        out = np.empty(self.n)
+        _check(getattr(lib(), "dzo_cpu_adgd_" + name)(self._h, _dp(out)))
+        return out
+
+    point = property(lambda s: s._vec("get_point"))
+    delta_point = property(lambda s: s._vec("get_delta_point"))
+    gradient = property(lambda s: s._vec("get_gradient"))
+    delta_gradient = property(lambda s: s._vec("get_delta_gradient"))
+
+    @property
+    def scalars(self):
+        """(f, df, current_step_size, previous_step_size, iteration_count, is_stuck)"""
+        out = np.empty(6)
+        _check(lib().dzo_cpu_adgd_get_scalars(self._h, _dp(out)))
+        return out
+
+    def step(self, k=1):
+        _check(lib().dzo_cpu_adgd_step(self._h, int(k)))
+        return self
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().dzo_cpu_adgd_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

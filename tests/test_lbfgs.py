@@ -87,3 +87,45 @@ def test_gpu_lbfgs_to_convergence(gpu, orc):
     assert np.abs(opt.current_gradient).max() < 1e-5
     with pytest.raises(AssertionError):
         dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 0.0, 8)     # @assert step > 0
+
+
+# ----------------------------------------------------------------------------- live AdGDOptimizer (:179-312)
+@pytest.mark.parametrize("n,tree", [(2, False), (10, True), (64, True)])
+def test_adgd_c_oracle_equals_python_restatement(orc, n, tree):
+    import dzo_oracle_py as P
+    x0 = _x0(orc, n, 7) * 0.5
+    py = P.LiveAdGDOptimizer(P.Rosenbrock(tree), list(x0), 1e-3, tree)
+    c = orc.AdGD(ROSEN, x0, 1e-3, orc.TREE if tree else orc.SEQ)
+    for it in range(60):
+        py.step(); c.step(1)
+        assert_bitwise(c.point, np.array(py.current_point), f"iter {it} point")
+        assert_bitwise(c.delta_gradient, np.array(py.delta_gradient), f"iter {it} delta_gradient")
+        s = c.scalars
+        assert s[0] == py.current_objective_value and s[1] == py.delta_objective_value
+        assert s[2] == py.current_step_size and s[3] == py.previous_step_size
+        assert int(s[4]) == py.iteration_count and bool(s[5]) == py.is_stuck
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 34, 4096, 20000])
+def test_gpu_adgd_trace(gpu, orc, n):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n, 8) * 0.5
+    opt = dz.AdGDOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1e-3)
+    ref = orc.AdGD(ROSEN, x0, 1e-3, orc.TREE)
+
+    def compare(tag):
+        assert_bitwise(opt.current_point, ref.point, f"{tag}: point")
+        assert_bitwise(opt.delta_point, ref.delta_point, f"{tag}: delta_point")
+        assert_bitwise(opt.current_gradient, ref.gradient, f"{tag}: gradient")
+        assert_bitwise(opt.delta_gradient, ref.delta_gradient, f"{tag}: delta_gradient")
+        assert_bitwise(opt._scalars(), ref.scalars, f"{tag}: scalars (f, df, step sizes, iteration, stuck)")
+
+    compare("ctor")
+    for it in range(30):
+        dz.step_(opt); ref.step(1)
+        compare(f"n={n} iter {it}")
+    opt.step(200); ref.step(200)
+    compare("fused")
+    assert float(opt.current_objective_value[()]) < orc.objective(ROSEN, x0, orc.TREE)[0]
