@@ -86,3 +86,45 @@ def test_layout_matches_julia_column_major(dz):
     assert (n, batch, pshape, dim) == (15, 1, (5, 3), 3)
     a, n, batch, pshape, dim = dz._layout(np.zeros((7, 16)), dz.OBJ_ROSENBROCK, True)
     assert (n, batch, pshape, dim) == (16, 7, (16,), 0)
+
+
+def test_error_paths_need_no_gpu(dz):
+    """argument validation happens before any CUDA call: null handles / pointers and bad shapes give
+    DZO_ERR_INVALID_ARGUMENT (-1) with a message, on any machine"""
+    lib = dz.lib()
+    assert lib.dzo_bfgs_step(None, 1) == -1 and b"bad arguments" in lib.dzo_last_error()
+    assert lib.dzo_gd_step(None, 1) == -1
+    assert lib.dzo_lbfgs_step(None, 1) == -1
+    assert lib.dzo_adgd_step(None, 1) == -1
+    out = np.zeros(4)
+    dp = out.ctypes.data_as(dz._capi.c_double_p)
+    assert lib.dzo_bfgs_get_point(None, dp) == -1
+    h = C.c_void_p()
+    assert lib.dzo_bfgs_create(C.byref(h), 1, 0, 0, 3, 1, dp, 1.0, 0) == -1          # odd n for Rosenbrock
+    assert b"even n" in lib.dzo_last_error()
+    assert lib.dzo_bfgs_create(C.byref(h), 7, 0, 0, 4, 1, dp, 1.0, 0) == -1          # unknown objective id
+    assert lib.dzo_bfgs_create(C.byref(h), 2, 0, 5, 4, 1, dp, 1.0, 0) == -1          # Riesz: n not a multiple of dim
+    assert lib.dzo_lbfgs_create(C.byref(h), 1, 0, 0, 4, dp, 1.0, 0, 0) == -1         # history_length < 1
+    assert lib.dzo_set_tuning(b"no_such_knob", 1) == -1
+    assert lib.dzo_dot(0, 0, dp, dp, dp, 0) == -1                                     # n <= 0
+    e = C.c_double()
+    assert lib.dzo_pairwise_energy(9, 0, 4, dp, dp, dp, None, C.byref(e), 0) == -1    # unknown potential
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs without a GPU and prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
