@@ -215,7 +215,7 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
     cluster.sync();          // every CTA has read ctrl (the leader rewrites it at the end) and initialised R
     // row-sharded mode: the direction slabs of the previous BFGS-type step are stored into this GPU's
     // memory by the peers' update kernels; wait for all of them (flag = that step's sequence number)
-    if (a.nranks > 1 && sc.kind == DZO_STEP_BFGS) peer_wait(a.flags_d, a.nranks, (unsigned long long)sc.calls);
+    if (a.nranks > 1 && sc.kind == DZO_STEP_BFGS) peer_wait(a.flags_d, a.nranks, (unsigned long long)sc.calls, &a.ctrl->pad);
     if (sc.term) {                                                        // :893
         if (leader) a.ctrl->kind = DZO_STEP_NULL;
         return;
@@ -301,6 +301,7 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
         c.evals = sc.evals + evals;
         c.kind_log[sc.calls & 63] = (unsigned char)kind;
         c.calls = sc.calls + 1;
+        c.pad = *reinterpret_cast<volatile int*>(&a.ctrl->pad);           // keep a peer-timeout mark set during this kernel
         *a.ctrl = c;
     }
 }
@@ -314,7 +315,7 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
     if (threadIdx.x == 0) R.parity = 0;
     __syncthreads();
     cluster.sync();
-    if (a.nranks > 1) peer_wait(a.flags_t, a.nranks, (unsigned long long)a.ctrl->calls);   // all slabs of t have landed
+    if (a.nranks > 1) peer_wait(a.flags_t, a.nranks, (unsigned long long)a.ctrl->calls, &a.ctrl->pad);   // all slabs of t have landed
     const long long v = (long long)cluster.block_rank() * kClusterThreads + threadIdx.x;
     double acc = 0.0;
     for (long long k = v; 2 * k < a.n; k += DZO_TREE_WIDTH) {

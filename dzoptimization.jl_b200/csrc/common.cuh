@@ -26,7 +26,7 @@ struct LargeCtrl {
     int term;          // has_terminated               :738
     // hand-off between the kernels of one step!
     int kind;          // what THIS step did: DZO_STEP_NULL (nothing / terminated), _BFGS, _GRADIENT_DESCENT
-    int pad;
+    int pad;           // row-sharded mode: set to 1 when a wait for a peer's slab timed out
     double step_length;// -alpha handed to update_inverse_hessian! (:954)
     double overlap;    // :873
     double delta_norm; // :876
@@ -159,10 +159,22 @@ DZO_DEVINL unsigned long long ld_acquire_sys(const unsigned long long* p) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// consumer side: wait until every rank's slab of sequence `seq` has landed in local memory
-DZO_DEVINL void peer_wait(const unsigned long long* local_flags, int nranks, unsigned long long seq) {
+// consumer side: wait until every rank's slab of sequence `seq` has landed in local memory.  A peer that
+// stops stepping (host error, killed process) must not hang this GPU for ever: after kPeerTimeoutNs the
+// wait gives up and records the fact in *timeout_flag, which the host turns into DZO_ERR_NCCL at the next sync.
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+DZO_DEVINL unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+DZO_DEVINL void peer_wait(const unsigned long long* local_flags, int nranks, unsigned long long seq, int* timeout_flag) {
     if (nranks > 1 && threadIdx.x < nranks) {
-        while (ld_acquire_sys(local_flags + threadIdx.x) < seq) { __nanosleep(64); }
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(local_flags + threadIdx.x) < seq) {
+            __nanosleep(64);
+            if (global_timer_ns() - t0 > kPeerTimeoutNs) { atomicExch(timeout_flag, 1); break; }
+        }
     }
     __syncthreads();
 }

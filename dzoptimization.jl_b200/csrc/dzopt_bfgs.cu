@@ -646,6 +646,11 @@ int dzo_bfgs_sync(dzo_bfgs* o) {
     if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
     DZO_TRY(use_device(o->device));
     DZO_CUDA(cudaStreamSynchronize(o->stream));
+    if (o->fused) {                       // did a wait for a peer's slab give up?
+        LargeCtrl c;
+        DZO_CUDA(cudaMemcpy(&c, o->ctrl, sizeof c, cudaMemcpyDeviceToHost));
+        if (c.pad) return fail(DZO_ERR_NCCL, "row-sharded step!: timed out waiting for a peer GPU's rows (is every rank stepping?)");
+    }
     return DZO_OK;
 }
 int dzo_bfgs_step(dzo_bfgs* o, int k) {
