@@ -121,7 +121,7 @@ class Riesz:
                 s = 0.0
                 for k in range(d):
                     s += x[j * d + k] * x[j * d + k]
-                inv = 1.0 / math.sqrt(s)
+                inv = _div(1.0, math.sqrt(s))
                 for k in range(d):
                     x[j * d + k] *= inv
         return True
@@ -141,7 +141,7 @@ class Riesz:
             result = 0.0
             for j in range(1, npts):
                 for i in range(j):
-                    result += 1.0 / math.sqrt(self._rsqrt_dist(p, i, j))
+                    result += _div(1.0, math.sqrt(self._rsqrt_dist(p, i, j)))
             return result
         rows = []
         for j in range(npts):
@@ -149,7 +149,7 @@ class Riesz:
             for s0 in range(0, j, RIESZ_SEG):
                 seg = 0.0
                 for i in range(s0, min(s0 + RIESZ_SEG, j)):
-                    seg += 1.0 / math.sqrt(self._rsqrt_dist(p, i, j))
+                    seg += _div(1.0, math.sqrt(self._rsqrt_dist(p, i, j)))
                 ej = seg if s0 == 0 else ej + seg
             rows.append(ej)
         return ksum(rows, True)
@@ -166,8 +166,8 @@ class Riesz:
                     if i == j:
                         continue
                     dist_sq = self._rsqrt_dist(p, i, j)
-                    inv_dist = 1.0 / math.sqrt(dist_sq)
-                    inv_dist_cubed = inv_dist / dist_sq
+                    inv_dist = _div(1.0, math.sqrt(dist_sq))
+                    inv_dist_cubed = _div(inv_dist, dist_sq)
                     for k in range(d):
                         part[k] += (p[i * d + k] - p[j * d + k]) * inv_dist_cubed
                 acc = part if s0 == 0 else [a + b for a, b in zip(acc, part)]
