@@ -385,3 +385,47 @@ def test_tuning_variants_do_not_change_any_bit(gpu, orc):
             assert_bitwise(b.current_point, rb.point, f"{key}={v}: batched point")
             assert_bitwise(b.inverse_hessian(99), rb.inverse_hessian(99), f"{key}={v}: batched H")
             b.close()
+
+
+@pytest.mark.parametrize("L0", [1.0, 1e-12, 1e6, 1e-300])
+@pytest.mark.parametrize("n", [2, 8, 16, 12])
+def test_batched_awkward_inputs(gpu, orc, n, L0):
+    """coordinates drawn from a mix of special values (±0, ±1, 1e-8, 1e6, 1e-160, 1e150) and random ones:
+    exercises every branch of the per-thread line-search state machine (tiny steps that do not move the
+    point, overflowing objectives, zero gradients) against the oracle, bit for bit."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    batch = 1500
+    u = orc.pcg_fill(n * batch, 4242 + n)
+    pick = (orc.pcg_fill(n * batch, 777 + n) * 14).astype(int)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 1e-8, -1e-8, 1e6, -1e6, 1e-160, 1e150])
+    x0 = np.where(pick < 10, special[np.minimum(pick, 9)], 6.0 * u - 3.0).reshape(batch, n)
+    x0[0] = 1.0                                   # exactly at the minimiser
+    x0[1] = 0.0
+    keep = ~np.isnan(orc.objective(ROSEN, x0, SEQ))      # the constructor asserts !isnan(f0)  (:773)
+    x0 = np.ascontiguousarray(x0[keep])
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, L0, batched=True)
+    ref = orc.BFGS(ROSEN, x0, L0, order=orc.SEQ, nthreads=8)
+    _compare_state(opt, ref, True, "ctor")
+    for it in range(10):
+        dz.step_(opt); ref.step(1)
+        _compare_state(opt, ref, True, f"n={n} L0={L0} iter {it}")
+    opt.step(30); ref.step(30)
+    _compare_state(opt, ref, True, "fused")
+
+
+@pytest.mark.parametrize("L0", [1.0, 1e-12, 1e6, 1e-300])
+def test_large_awkward_inputs(gpu, orc, L0):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    n = 2050
+    u = orc.pcg_fill(n, 99)
+    pick = (orc.pcg_fill(n, 98) * 40).astype(int)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 1e-8, -1e-8, 1e3, -1e3, 1e-160, 1e-300])
+    x0 = np.where(pick < 10, special[np.minimum(pick, 9)], 4.0 * u - 2.0)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, L0)
+    ref = orc.BFGS(ROSEN, x0[None, :], L0, order=orc.TREE)
+    _compare_state(opt, ref, False, "ctor")
+    for it in range(10):
+        dz.step_(opt); ref.step(1)
+        _compare_state(opt, ref, False, f"L0={L0} iter {it}")
