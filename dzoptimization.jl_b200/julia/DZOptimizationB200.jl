@@ -20,7 +20,7 @@
 # versions of legacy/ExampleFunctions.jl exported below; anything else raises ArgumentError.
 module DZOptimizationB200
 
-export BFGSOptimizer, GradientDescentOptimizer, LBFGSOptimizer, QuadraticLineSearch, step!, StepType, NullStep,
+export BFGSOptimizer, GradientDescentOptimizer, LBFGSOptimizer, AdGDOptimizer, QuadraticLineSearch, step!, StepType, NullStep,
     GradientDescentStep, BFGSStep, NULL_CONSTRAINT, SPHERE_CONSTRAINT,
     accelerated_pairwise_radial_energy, accelerated_pairwise_radial_gradient!, accelerated_pairwise_radial_hvp!
 
@@ -273,6 +273,44 @@ function Base.getproperty(opt::LBFGSOptimizer, s::Symbol)
         t = sc(:dzo_lbfgs_get_stuck, UInt8)
         return fill(t[] != 0)
     end
+    return getfield(opt, s)
+end
+
+# ================================================================== AdGDOptimizer (live src/DZOptimization.jl:179-312)
+mutable struct AdGDOptimizer
+    handle::Ptr{Cvoid}
+    n::Int
+end
+function AdGDOptimizer(c!, f, g!, x0::Vector{Float64}, step::Float64; device::Integer=0)      # :252-271
+    obj, cid = resolve(f, g!, c! === nothing ? NULL_CONSTRAINT : c!)
+    @assert step > 0                                                                 # :232
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dzo_adgd_create, libdzopt), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Ptr{Float64}, Float64, Cint),
+        h, obj, cid, 0, length(x0), x0, step, device))
+    opt = AdGDOptimizer(h[], length(x0))
+    finalizer(o -> ccall((:dzo_adgd_destroy, libdzopt), Cvoid, (Ptr{Cvoid},), getfield(o, :handle)), opt)
+    return opt
+end
+function step!(opt::AdGDOptimizer)                                                  # :274-312
+    check(ccall((:dzo_adgd_step, libdzopt), Cint, (Ptr{Cvoid}, Cint), getfield(opt, :handle), 1))
+    return opt
+end
+function Base.getproperty(opt::AdGDOptimizer, s::Symbol)
+    h, n = getfield(opt, :handle), getfield(opt, :n)
+    vec(sym) = (out = Vector{Float64}(undef, n); check(ccall((sym, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, out)); out)
+    s === :current_point && return vec(:dzo_adgd_get_point)                         # :188
+    s === :delta_point && return vec(:dzo_adgd_get_delta_point)                     # :189
+    s === :current_gradient && return vec(:dzo_adgd_get_gradient)                   # :192
+    s === :delta_gradient && return vec(:dzo_adgd_get_delta_gradient)               # :193
+    sc = Vector{Float64}(undef, 6)
+    check(ccall((:dzo_adgd_get_scalars, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, sc))
+    s === :current_objective_value && return fill(sc[1])                            # :190
+    s === :delta_objective_value && return fill(sc[2])                              # :191
+    s === :current_step_size && return fill(sc[3])                                  # :195
+    s === :previous_step_size && return fill(sc[4])                                 # :196
+    s === :iteration_count && return fill(Int(sc[5]))                               # :186
+    (s === :is_stuck || s === :has_converged) && return fill(sc[6] != 0)            # :185
     return getfield(opt, s)
 end
 
