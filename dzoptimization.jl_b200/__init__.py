@@ -31,7 +31,8 @@ import numpy as np
 from . import _capi
 
 __all__ = [
-    "LBFGSOptimizer", "AdGDOptimizer",
+    "LBFGSOptimizer", "AdGDOptimizer", "LegacyLBFGSOptimizer",
+    "L2RegularizationWrapper", "L2GradientWrapper", "UniformBoxConstraint", "UniformBoxGradientWrapper",
     "accelerated_pairwise_radial_energy", "accelerated_pairwise_radial_gradient_", "accelerated_pairwise_radial_hvp_",
     "BFGSOptimizer", "GradientDescentOptimizer", "QuadraticLineSearch", "step_",
     "ExampleFunctions", "NULL_CONSTRAINT", "SPHERE_CONSTRAINT", "StepType",
@@ -629,6 +630,158 @@ class AdGDOptimizer:
         h, self._h = getattr(self, "_h", None), None
         if h:
             lib().dzo_adgd_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------
+# legacy decorators (legacy/DZOptimization.jl:222-296) and the legacy L-BFGS (:458-695)
+DECOR_L2, DECOR_BOX = 1, 2
+
+
+class L2RegularizationWrapper:
+    """legacy/DZOptimization.jl:228-234: ``f(x) + lambda * norm2(x)`` around a device objective."""
+
+    def __init__(self, objective_function, lambda_):
+        self.objective_function, self.lambda_ = objective_function, float(lambda_)
+
+
+class L2GradientWrapper:
+    """legacy/DZOptimization.jl:237-251: ``g += (lambda + lambda) * x`` after a device gradient."""
+
+    def __init__(self, gradient_function_, lambda_):
+        self.gradient_function_, self.lambda_ = gradient_function_, float(lambda_)
+
+
+class UniformBoxConstraint:
+    """legacy/DZOptimization.jl:257-272: clamp every coordinate to [lower_bound, upper_bound]; returns true."""
+
+    def __init__(self, lower_bound, upper_bound):
+        self.lower_bound, self.upper_bound = float(lower_bound), float(upper_bound)
+
+
+class UniformBoxGradientWrapper:
+    """legacy/DZOptimization.jl:275-296: zero the gradient entries that point out of the box at an active bound."""
+
+    def __init__(self, gradient_function_, lower_bound, upper_bound):
+        self.gradient_function_ = gradient_function_
+        self.lower_bound, self.upper_bound = float(lower_bound), float(upper_bound)
+
+
+def _resolve_decorated(constraint_function_, objective_function, gradient_function_):
+    """Peel the legacy wrappers off the three callables; the device applies them in the fixed order
+    gradient! = Box(L2(g!)) (include/dzopt.h).  Inconsistent wrappers raise TypeError."""
+    lam_f = lam_g = None
+    box_c = box_g = None
+    if isinstance(objective_function, L2RegularizationWrapper):
+        lam_f, objective_function = objective_function.lambda_, objective_function.objective_function
+    if isinstance(gradient_function_, UniformBoxGradientWrapper):
+        box_g = (gradient_function_.lower_bound, gradient_function_.upper_bound)
+        gradient_function_ = gradient_function_.gradient_function_
+    if isinstance(gradient_function_, L2GradientWrapper):
+        lam_g, gradient_function_ = gradient_function_.lambda_, gradient_function_.gradient_function_
+    if isinstance(gradient_function_, UniformBoxGradientWrapper):
+        raise TypeError("device composition order is UniformBoxGradientWrapper(L2GradientWrapper(g!, lambda), lo, hi)")
+    if isinstance(constraint_function_, UniformBoxConstraint):
+        box_c = (constraint_function_.lower_bound, constraint_function_.upper_bound)
+        constraint_function_ = NULL_CONSTRAINT
+    if constraint_function_ is None:
+        constraint_function_ = NULL_CONSTRAINT
+    if lam_f != lam_g:
+        raise TypeError("L2RegularizationWrapper and L2GradientWrapper must be used together with one lambda")
+    if box_c != box_g:
+        raise TypeError("UniformBoxConstraint and UniformBoxGradientWrapper must be used together with the same bounds")
+    obj, cid = _resolve(objective_function, gradient_function_, constraint_function_)
+    return obj, cid, lam_f, box_c
+
+
+class LegacyLBFGSOptimizer:
+    """struct LBFGSOptimizer of the LEGACY file, legacy/DZOptimization.jl:458-486.
+
+    ``LegacyLBFGSOptimizer(c_, f, g_, linesearch, x0, initial_step_length, history_length)`` (:489-548) or the
+    6-argument form without a constraint (:551-562).  ``linesearch`` is a :class:`QuadraticLineSearch`;
+    ``f`` / ``g_`` / ``c_`` may carry the L2 / uniform-box wrappers.  (The live package's optimizer of the
+    same Julia name is :class:`LBFGSOptimizer`.)"""
+
+    def __init__(self, *args, device=0):
+        if len(args) == 7:
+            c, f, g, ls, x0, L0, m = args
+        elif len(args) == 6:
+            f, g, ls, x0, L0, m = args
+            c = NULL_CONSTRAINT
+        else:
+            raise TypeError("LegacyLBFGSOptimizer([c!,] f, g!, linesearch, x0, initial_step_length, history_length)")
+        if not isinstance(ls, QuadraticLineSearch):
+            raise TypeError("line_search_function! must be a QuadraticLineSearch")
+        obj, cid, lam, box = _resolve_decorated(c, f, g)
+        a = np.ascontiguousarray(x0, dtype=np.float64)
+        if a.ndim != 1:
+            raise ValueError("initial point must be a vector")
+        if not int(m) > 0:
+            raise AssertionError("history_length > 0")                   # @assert :528
+        self._n, self.history_length = a.size, int(m)
+        self._h = None
+        h = C.c_void_p()
+        decor = (DECOR_L2 if lam is not None else 0) | (DECOR_BOX if box is not None else 0)
+        lo, hi = box if box is not None else (0.0, 0.0)
+        _check(lib().dzo_legacy_lbfgs_create(C.byref(h), obj, cid, 0, self._n, _dp(a), float(L0), int(m), ls.max_increases,
+                                             decor, float(lam if lam is not None else 0.0), lo, hi, int(device)))
+        self._h = h
+
+    def _vec(self, name):
+        out = np.empty(self._n)
+        _check(getattr(lib(), "dzo_legacy_lbfgs_" + name)(self._h, _dp(out)))
+        return out
+
+    def _scalars(self):
+        out = np.empty(6)
+        _check(lib().dzo_legacy_lbfgs_get_scalars(self._h, _dp(out)))
+        return out
+
+    current_point = property(lambda s: s._vec("get_point"))
+    delta_point = property(lambda s: s._vec("get_delta_point"))
+    current_gradient = property(lambda s: s._vec("get_gradient"))
+    delta_gradient = property(lambda s: s._vec("get_delta_gradient"))
+    next_step_direction = property(lambda s: s._vec("get_direction"))
+    current_objective_value = property(lambda s: np.array(s._scalars()[0]))
+    delta_objective_value = property(lambda s: np.array(s._scalars()[1]))
+    last_step_length = property(lambda s: np.array(s._scalars()[2]))
+    iteration_count = property(lambda s: np.array(int(s._scalars()[3])))
+    has_terminated = property(lambda s: np.array(bool(s._scalars()[4])))
+    has_converged = has_terminated
+    _history_count = property(lambda s: np.array(int(s._scalars()[5])))
+
+    def _history(self):
+        rho, alpha = np.zeros(self.history_length), np.zeros(self.history_length)
+        _check(lib().dzo_legacy_lbfgs_get_history(self._h, _dp(rho), _dp(alpha)))
+        return rho, alpha
+
+    _rho = property(lambda s: s._history()[0])
+    _alpha = property(lambda s: s._history()[1])
+
+    def set_stream(self, cuda_stream):
+        _check(lib().dzo_legacy_lbfgs_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def step(self, k: int = 1):
+        _check(lib().dzo_legacy_lbfgs_step(self._h, int(k)))
+        return self
+
+    def step_async(self, k: int = 1):
+        _check(lib().dzo_legacy_lbfgs_step_async(self._h, int(k)))
+        return self
+
+    def sync(self):
+        _check(lib().dzo_legacy_lbfgs_sync(self._h))
+        return self
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().dzo_legacy_lbfgs_destroy(h)
 
     def __del__(self):
         try:

@@ -77,6 +77,14 @@ def bind(lib, cpu: bool):
         sig("adgd_" + g, [H, c_double_p])
     sig("adgd_destroy", [H], None)
 
+    # last: order (oracle) | device (CUDA)
+    sig("legacy_lbfgs_create", [HP, I, I, I64, I64, c_double_p, D, I, I, I, D, D, D, I])
+    sig("legacy_lbfgs_step", [H, I])
+    for g in ("get_point", "get_delta_point", "get_gradient", "get_delta_gradient", "get_direction", "get_scalars"):
+        sig("legacy_lbfgs_" + g, [H, c_double_p])
+    sig("legacy_lbfgs_get_history", [H, c_double_p, c_double_p])
+    sig("legacy_lbfgs_destroy", [H], None)
+
     dev = [] if cpu else [I]
     sig("objective", [I, I, I64, I, I64, I64, c_double_p, c_double_p] + dev)
     sig("gradient", [I, I, I64, I, I64, I64, c_double_p, c_double_p] + dev)
@@ -108,6 +116,9 @@ def bind(lib, cpu: bool):
         sig("lbfgs_set_stream", [H, C.c_void_p])
         sig("lbfgs_step_async", [H, I])
         sig("lbfgs_sync", [H])
+        sig("legacy_lbfgs_set_stream", [H, C.c_void_p])
+        sig("legacy_lbfgs_step_async", [H, I])
+        sig("legacy_lbfgs_sync", [H])
         sig("gd_set_stream", [H, C.c_void_p])
         sig("gd_step_async", [H, I])
         sig("gd_sync", [H])

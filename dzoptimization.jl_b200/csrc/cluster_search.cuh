@@ -24,9 +24,9 @@ constexpr int kClusterThreads = 512;
 
 // shared-memory exchange area of one CTA
 struct ClusterRed {
-    double warp_part[3][16];               // [quantity][warp]
+    double warp_part[4][16];               // [quantity][warp]
     unsigned warp_flag[16];
-    double cta_part[2][3][kClusterCtas];   // [parity][quantity][source CTA]   (written by peers)
+    double cta_part[2][4][kClusterCtas];   // [parity][quantity][source CTA]   (written by peers)
     unsigned cta_flag[2][kClusterCtas];
     int parity;
 };

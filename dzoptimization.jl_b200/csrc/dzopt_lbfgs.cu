@@ -2,7 +2,7 @@
 #include <new>
 
 #include "host_common.h"
-#include "lbfgs_kernels.cuh"
+#include "legacy_lbfgs.cuh"
 
 using namespace dzo;
 
@@ -216,6 +216,132 @@ int dzo_adgd_get_scalars(dzo_adgd* o, double* s) {
     AdgdCtrl c;
     DZO_TRY(ad_read(o, &c, o->ctrl, sizeof c));
     s[0] = c.f; s[1] = c.df; s[2] = c.cur; s[3] = c.prev; s[4] = (double)c.iter; s[5] = (double)c.stuck;
+    return DZO_OK;
+}
+}  // extern "C"
+
+// ============================================================================= legacy LBFGSOptimizer (legacy/DZOptimization.jl:458-695)
+struct dzo_legacy_lbfgs {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int64_t n = 0;
+    int m = 0, max_increases = 0, decor = 0;
+    double l2 = 0.0, lo = 0.0, hi = 0.0;
+    double *x = nullptr, *dx = nullptr, *g = nullptr, *dg = nullptr, *d = nullptr, *S = nullptr, *Y = nullptr;
+    LegacyCtrl* ctrl = nullptr;
+};
+static void free_legacy(dzo_legacy_lbfgs* o) {
+    if (!o) return;
+    cudaSetDevice(o->device);
+    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->d, o->S, o->Y, o->ctrl};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (o->own_stream) cudaStreamDestroy(o->own_stream);
+    delete o;
+}
+static int legacy_launch(dzo_legacy_lbfgs* o, int mode, int k, double L0) {
+    LegacyArgs a;
+    a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.d = o->d; a.S = o->S; a.Y = o->Y; a.ctrl = o->ctrl;
+    a.n = o->n; a.m = o->m; a.ksteps = k; a.max_increases = o->max_increases; a.mode = mode; a.decor = o->decor;
+    a.initial_step_length = L0; a.l2 = o->l2; a.lo = o->lo; a.hi = o->hi;
+    cluster_legacy_lbfgs_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+extern "C" {
+int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constraint, int64_t obj_param, int64_t n,
+                            const double* x0, double initial_step_length, int history_length, int max_increases,
+                            int decor, double l2_lambda, double box_lower, double box_upper, int device) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = nullptr;
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, 1));
+    if (objective != DZO_OBJ_ROSENBROCK) return fail(DZO_ERR_UNSUPPORTED, "legacy LBFGSOptimizer device objective: DZO_OBJ_ROSENBROCK");
+    if (decor & ~(DZO_DECOR_L2 | DZO_DECOR_BOX)) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown decorator bits");
+    if ((decor & DZO_DECOR_L2) && l2_lambda != l2_lambda) return fail(DZO_ERR_INVALID_ARGUMENT, "lambda is NaN");
+    if ((decor & DZO_DECOR_BOX) && !(box_lower <= box_upper)) return fail(DZO_ERR_INVALID_ARGUMENT, "box needs lower_bound <= upper_bound");
+    if (history_length < 1 || history_length > DZO_LBFGS_MAX_HISTORY)                            // :528
+        return fail(DZO_ERR_INVALID_ARGUMENT, "history_length must be in [1, %d]", DZO_LBFGS_MAX_HISTORY);
+    DZO_TRY(use_device(device));
+    dzo_legacy_lbfgs* o = new (std::nothrow) dzo_legacy_lbfgs();
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->device = device; o->n = n; o->m = history_length; o->max_increases = max_increases; o->decor = decor;
+    o->l2 = l2_lambda; o->lo = box_lower; o->hi = box_upper;
+    auto bail = [&](int code) { free_legacy(o); return code; };
+    if (cudaStreamCreateWithFlags(&o->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "cudaStreamCreate failed"));
+    o->stream = o->own_stream;
+    const size_t vb = (size_t)n * 8;
+    double** vecs[] = {&o->x, &o->dx, &o->g, &o->dg, &o->d};
+    for (double** v : vecs)
+        if (cudaMalloc((void**)v, vb) != cudaSuccess) return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+    if (cudaMalloc((void**)&o->S, vb * history_length) != cudaSuccess || cudaMalloc((void**)&o->Y, vb * history_length) != cudaSuccess ||
+        cudaMalloc((void**)&o->ctrl, sizeof(LegacyCtrl)) != cudaSuccess)
+        return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+    if (cudaMemcpyAsync(o->x, x0, vb, cudaMemcpyHostToDevice, o->stream) != cudaSuccess ||
+        cudaMemsetAsync(o->S, 0, vb * history_length, o->stream) != cudaSuccess ||
+        cudaMemsetAsync(o->Y, 0, vb * history_length, o->stream) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "initial copies failed"));
+    int rc = legacy_launch(o, 1, 0, initial_step_length);
+    if (rc) return bail(rc);
+    if (cudaStreamSynchronize(o->stream) != cudaSuccess)
+        return bail(fail(DZO_ERR_CUDA, "constructor kernel failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = o;
+    return DZO_OK;
+}
+void dzo_legacy_lbfgs_destroy(dzo_legacy_lbfgs* o) { free_legacy(o); }
+int dzo_legacy_lbfgs_set_stream(dzo_legacy_lbfgs* o, void* cuda_stream) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    o->stream = cuda_stream ? (cudaStream_t)cuda_stream : o->own_stream;
+    return DZO_OK;
+}
+int dzo_legacy_lbfgs_step_async(dzo_legacy_lbfgs* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    DZO_TRY(use_device(o->device));
+    if (k == 0) return DZO_OK;
+    return legacy_launch(o, 0, k, 0.0);
+}
+int dzo_legacy_lbfgs_sync(dzo_legacy_lbfgs* o) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+int dzo_legacy_lbfgs_step(dzo_legacy_lbfgs* o, int k) {
+    DZO_TRY(dzo_legacy_lbfgs_step_async(o, k));
+    return dzo_legacy_lbfgs_sync(o);
+}
+static int lg_read(dzo_legacy_lbfgs* o, void* dst, const void* src, size_t bytes) {
+    if (!o || !dst) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+#define DZO_LG_VEC(name, field)                                                   \
+    int name(dzo_legacy_lbfgs* o, double* out) {                                  \
+        if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");             \
+        return lg_read(o, out, o->field, (size_t)o->n * 8);                       \
+    }
+DZO_LG_VEC(dzo_legacy_lbfgs_get_point, x)
+DZO_LG_VEC(dzo_legacy_lbfgs_get_delta_point, dx)
+DZO_LG_VEC(dzo_legacy_lbfgs_get_gradient, g)
+DZO_LG_VEC(dzo_legacy_lbfgs_get_delta_gradient, dg)
+DZO_LG_VEC(dzo_legacy_lbfgs_get_direction, d)
+#undef DZO_LG_VEC
+int dzo_legacy_lbfgs_get_scalars(dzo_legacy_lbfgs* o, double* s) {
+    if (!o || !s) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    LegacyCtrl c;
+    DZO_TRY(lg_read(o, &c, o->ctrl, sizeof c));
+    s[0] = c.f; s[1] = c.df; s[2] = c.L; s[3] = (double)c.iter; s[4] = (double)(c.term != 0); s[5] = (double)c.hist_count;
+    return DZO_OK;
+}
+int dzo_legacy_lbfgs_get_history(dzo_legacy_lbfgs* o, double* rho, double* alpha) {
+    if (!o || !rho || !alpha) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    LegacyCtrl c;
+    DZO_TRY(lg_read(o, &c, o->ctrl, sizeof c));
+    for (int i = 0; i < o->m; ++i) { rho[i] = c.rho[i]; alpha[i] = c.alpha[i]; }
     return DZO_OK;
 }
 }  // extern "C"

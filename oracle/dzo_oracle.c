@@ -128,6 +128,9 @@ static void gemv_rows_(int order, int64_t n, int64_t r0, int64_t r1, const doubl
 typedef struct {
     int objective, constraint, order;
     int64_t n, dim;
+    /* decorators (legacy/DZOptimization.jl:222-296); zero = undecorated */
+    int decor;
+    double l2_lambda, box_lo, box_hi;
 } problem_t;
 
 /* rosenbrock_function  legacy/ExampleFunctions.jl:10-15, one pair term */
@@ -179,7 +182,7 @@ static double riesz_energy_tree(const double* p, int64_t dim, int64_t np) {
     return tree_combine(part);
 }
 
-static double objective_(const problem_t* P, const double* x) {
+static double base_objective_(const problem_t* P, const double* x) {
     if (P->objective == DZO_OBJ_ROSENBROCK) {
         /* [GLUE] extended Rosenbrock: sum over pairs k ascending */
         const int64_t m = P->n / 2;
@@ -200,7 +203,7 @@ static double objective_(const problem_t* P, const double* x) {
 
 /* rosenbrock_gradient!  legacy/ExampleFunctions.jl:17-24;  riesz_gradient!  :47-83;
  * with DZO_CONSTRAINT_SPHERE followed by constrain_riesz_gradient_sphere! :361-374. */
-static void gradient_(const problem_t* P, double* g, const double* x) {
+static void base_gradient_(const problem_t* P, double* g, const double* x) {
     if (P->objective == DZO_OBJ_ROSENBROCK) {
         for (int64_t k = 0; k < P->n / 2; ++k) {
             const double xx = x[2 * k], y = x[2 * k + 1];
@@ -250,7 +253,7 @@ static void gradient_(const problem_t* P, double* g, const double* x) {
 
 /* constraint_function!(x)::Bool.  NONE: x -> true.  SPHERE [GLUE, SURVEY.md 8.0]:
  * each column p <- p * (1/sqrt(sum p^2)); returns true. */
-static int constraint_(const problem_t* P, double* x) {
+static int base_constraint_(const problem_t* P, double* x) {
     if (P->constraint == DZO_CONSTRAINT_NONE) return 1;
     const int64_t dim = P->dim, np = P->n / P->dim;
     for (int64_t j = 0; j < np; ++j) {
@@ -260,6 +263,35 @@ static int constraint_(const problem_t* P, double* x) {
         for (int64_t k = 0; k < dim; ++k) x[k + j * dim] *= inv;
     }
     return 1;
+}
+
+/* Decorators  legacy/DZOptimization.jl:222-296.  [GLUE] composition order:
+ * objective = L2RegularizationWrapper(f, lambda); gradient! = UniformBoxGradientWrapper(
+ * L2GradientWrapper(g!, lambda), lo, hi); constraint! = UniformBoxConstraint(lo, hi) after the
+ * objective's own constraint. */
+static double objective_(const problem_t* P, const double* x) {
+    const double f = base_objective_(P, x);
+    if (P->decor & DZO_DECOR_L2) return f + P->l2_lambda * norm2_(P->order, x, P->n);  /* :233-234 */
+    return f;
+}
+static void gradient_(const problem_t* P, double* g, const double* x) {
+    base_gradient_(P, g, x);
+    if (P->decor & DZO_DECOR_L2) {                                   /* :243-251 axpy!(g, 2 lambda, x) */
+        const double a = P->l2_lambda + P->l2_lambda;
+        for (int64_t i = 0; i < P->n; ++i) g[i] += a * x[i];
+    }
+    if (P->decor & DZO_DECOR_BOX)                                    /* :281-296 */
+        for (int64_t i = 0; i < P->n; ++i)
+            if (((x[i] <= P->box_lo) && (g[i] >= 0.0)) || ((x[i] >= P->box_hi) && (g[i] <= 0.0))) g[i] = 0.0;
+}
+static inline double julia_clamp(double x, double lo, double hi) { /* Base.clamp: ifelse(x > hi, hi, ifelse(x < lo, lo, x)) */
+    return (x > hi) ? hi : ((x < lo) ? lo : x);
+}
+static int constraint_(const problem_t* P, double* x) {
+    const int ok = base_constraint_(P, x);
+    if (P->decor & DZO_DECOR_BOX)                                    /* :263-272, returns true */
+        for (int64_t i = 0; i < P->n; ++i) x[i] = julia_clamp(x[i], P->box_lo, P->box_hi);
+    return ok;
 }
 
 static int arrays_equal(const double* a, const double* b, int64_t n) { /* Julia == on arrays */
@@ -392,7 +424,7 @@ static void quadratic_line_search(ray_t* r, double f0, double t1, int max_increa
 int dzo_cpu_line_search(int objective, int constraint, int64_t obj_param, int order, int64_t n,
                         const double* x, const double* dir, double f0, double t1,
                         double* t_best, double* f_best) {
-    problem_t P = {objective, constraint, order, n, obj_param > 0 ? obj_param : 1};
+    problem_t P = {objective, constraint, order, n, obj_param > 0 ? obj_param : 1, 0, 0.0, 0.0, 0.0};
     double* w = (double*)malloc((size_t)(2 * n + 1) * sizeof(double));
     if (!w) return fail(DZO_ERR_ALLOC, "line_search: out of memory");
     ray_t r = {&P, x, dir, w, w + n, -1.0, 0};
@@ -806,7 +838,7 @@ int dzo_cpu_objective(int objective, int constraint, int64_t obj_param, int orde
     int rc = check_problem(objective, constraint, obj_param, n, batch);
     if (rc) return rc;
     if (!x || !f) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
-    problem_t P = {objective, constraint, order, n, obj_param > 0 ? obj_param : 1};
+    problem_t P = {objective, constraint, order, n, obj_param > 0 ? obj_param : 1, 0, 0.0, 0.0, 0.0};
     for (int64_t p = 0; p < batch; ++p) f[p] = objective_(&P, x + p * n);
     return DZO_OK;
 }
@@ -815,7 +847,7 @@ int dzo_cpu_gradient(int objective, int constraint, int64_t obj_param, int order
     int rc = check_problem(objective, constraint, obj_param, n, batch);
     if (rc) return rc;
     if (!x || !g) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
-    problem_t P = {objective, constraint, order, n, obj_param > 0 ? obj_param : 1};
+    problem_t P = {objective, constraint, order, n, obj_param > 0 ? obj_param : 1, 0, 0.0, 0.0, 0.0};
     for (int64_t p = 0; p < batch; ++p) gradient_(&P, g + p * n, x + p * n);
     return DZO_OK;
 }
@@ -1233,5 +1265,176 @@ int dzo_cpu_adgd_get_scalars(dzo_cpu_adgd* o, double* s) {
 void dzo_cpu_adgd_destroy(dzo_cpu_adgd* o) {
     if (!o) return;
     free(o->x); free(o->dx); free(o->g); free(o->dg);
+    free(o);
+}
+
+/* ======================================================================= legacy LBFGSOptimizer
+ * legacy/DZOptimization.jl:458-695 (struct :458-486, ctor :489-548, step! :565-695): QuadraticLineSearch along the stored
+ * direction, retry along the rescaled gradient when it fails (:589-610, history reset), cyclic
+ * history buffer (column c = (iteration_count - 1) mod m, :641-643), two-loop correction exactly as
+ * written (:656-680 -- note `axpy!(d, alpha, dg_c)` ADDS alpha*dg, unlike the textbook recursion;
+ * the descent check :683-692 then falls back to the scaled negative gradient), natural step size
+ * delta_overlap / norm2(delta_gradient) (:669-670). */
+struct dzo_cpu_legacy_lbfgs {
+    problem_t P;
+    int m, max_increases;
+    double *x, *dx, *g, *dg, *d, *S, *Y, *scratch;
+    double rho[DZO_LBFGS_MAX_HISTORY], alpha[DZO_LBFGS_MAX_HISTORY];
+    double f, df, L;
+    int64_t iter, hist_count;
+    int term;
+};
+
+static int check_decor(int objective, int decor, double l2_lambda, double lo, double hi) {
+    if (decor & ~(DZO_DECOR_L2 | DZO_DECOR_BOX)) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown decorator bits");
+    if (decor && objective != DZO_OBJ_ROSENBROCK) return fail(DZO_ERR_UNSUPPORTED, "decorators: DZO_OBJ_ROSENBROCK only");
+    if ((decor & DZO_DECOR_L2) && l2_lambda != l2_lambda) return fail(DZO_ERR_INVALID_ARGUMENT, "lambda is NaN");
+    if ((decor & DZO_DECOR_BOX) && !(lo <= hi)) return fail(DZO_ERR_INVALID_ARGUMENT, "box needs lower_bound <= upper_bound");
+    return DZO_OK;
+}
+
+int dzo_cpu_legacy_lbfgs_create(dzo_cpu_legacy_lbfgs** out, int objective, int constraint, int64_t obj_param, int64_t n,
+                                const double* x0, double initial_step_length, int history_length, int max_increases,
+                                int decor, double l2_lambda, double box_lower, double box_upper, int order) {
+    if (!out || !x0) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    *out = NULL;
+    int rc = check_problem(objective, constraint, obj_param, n, 1);
+    if (rc) return rc;
+    rc = check_decor(objective, decor, l2_lambda, box_lower, box_upper);
+    if (rc) return rc;
+    if (history_length < 1 || history_length > DZO_LBFGS_MAX_HISTORY) return fail(DZO_ERR_INVALID_ARGUMENT, "history_length must be in [1, 64]"); /* :528 */
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    dzo_cpu_legacy_lbfgs* o = (dzo_cpu_legacy_lbfgs*)calloc(1, sizeof *o);
+    if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
+    o->P.objective = objective; o->P.constraint = constraint; o->P.order = order; o->P.n = n;
+    o->P.dim = obj_param > 0 ? obj_param : 1;
+    o->P.decor = decor; o->P.l2_lambda = l2_lambda; o->P.box_lo = box_lower; o->P.box_hi = box_upper;
+    o->m = history_length; o->max_increases = max_increases;
+    o->x = (double*)malloc((size_t)n * 8); o->dx = (double*)calloc((size_t)n, 8);
+    o->g = (double*)malloc((size_t)n * 8); o->dg = (double*)calloc((size_t)n, 8);
+    o->d = (double*)calloc((size_t)n, 8);
+    o->S = (double*)calloc((size_t)n * (size_t)history_length, 8);
+    o->Y = (double*)calloc((size_t)n * (size_t)history_length, 8);
+    o->scratch = (double*)malloc((size_t)n * 2 * 8);
+    if (!o->x || !o->dx || !o->g || !o->dg || !o->d || !o->S || !o->Y || !o->scratch) { dzo_cpu_legacy_lbfgs_destroy(o); return fail(DZO_ERR_ALLOC, "out of memory"); }
+    memcpy(o->x, x0, (size_t)n * 8);                                                    /* :499 collect */
+    if (!constraint_(&o->P, o->x)) { dzo_cpu_legacy_lbfgs_destroy(o); return fail(DZO_ERR_CONSTRAINT_FAILED, "constraint_function! failed on the initial point"); } /* :500 */
+    o->f = objective_(&o->P, o->x);                                                     /* :503 */
+    gradient_(&o->P, o->g, o->x);                                                       /* :507-508 */
+    const double inv_gradient_norm = 1.0 / sqrt(norm2_(order, o->g, n));                /* :512 */
+    if (isfinite(inv_gradient_norm)) {                                                  /* :514-517 */
+        const double a = -initial_step_length * inv_gradient_norm;
+        for (int64_t i = 0; i < n; ++i) o->d[i] = o->g[i];
+        for (int64_t i = 0; i < n; ++i) o->d[i] *= a;
+    }
+    o->term = (!isfinite(o->f)) || (!isfinite(inv_gradient_norm));                      /* :524-526 */
+    *out = o;
+    return DZO_OK;
+}
+
+static int legacy_search_(dzo_cpu_legacy_lbfgs* o, double* step_size, double* objective_value) {
+    ray_t r = {&o->P, o->x, o->d, o->scratch, o->scratch + o->P.n, +1.0, 0};
+    quadratic_line_search(&r, o->f, 1.0, o->max_increases, step_size, objective_value);
+    return !(*step_size == 0.0 || !(*objective_value < o->f));                          /* :589-590 */
+}
+
+static void legacy_lbfgs_step_one(dzo_cpu_legacy_lbfgs* o) {
+    if (o->term) return;                                                                /* :578 */
+    const problem_t* P = &o->P;
+    const int64_t n = P->n;
+    const int order = P->order, m = o->m;
+    double *x = o->x, *dx = o->dx, *g = o->g, *dg = o->dg, *d = o->d;
+    double step_size, objective_value;
+    if (!legacy_search_(o, &step_size, &objective_value)) {                             /* :584-590 */
+        const double a = -o->L * (1.0 / sqrt(norm2_(order, g, n)));                     /* :594-595 */
+        for (int64_t i = 0; i < n; ++i) d[i] = g[i];                                    /* :593 */
+        for (int64_t i = 0; i < n; ++i) d[i] *= a;
+        if (!legacy_search_(o, &step_size, &objective_value)) {                         /* :596-605 */
+            o->term = 1;
+            return;
+        }
+        o->hist_count = 0;                                                              /* :609 */
+    }
+    o->iter += 1;                                                                       /* :611 */
+    memcpy(dx, x, (size_t)n * 8);                                                       /* :614 */
+    for (int64_t i = 0; i < n; ++i) x[i] += step_size * d[i];                           /* :615 */
+    constraint_(P, x);                                                                  /* :616 */
+    for (int64_t i = 0; i < n; ++i) dx[i] = x[i] - dx[i];                               /* :619 */
+    const double step_length = sqrt(norm2_(order, dx, n));                              /* :620-621 */
+    o->L = step_length;
+    o->df = objective_value - o->f;                                                     /* :624-626 */
+    o->f = objective_value;
+    memcpy(dg, g, (size_t)n * 8);                                                       /* :629 */
+    gradient_(P, g, x);                                                                 /* :630 */
+    for (int64_t i = 0; i < n; ++i) dg[i] = g[i] - dg[i];                               /* :631 */
+    const double inv_gradient_norm = 1.0 / sqrt(norm2_(order, g, n));                   /* :634 */
+    if (!isfinite(inv_gradient_norm)) {                                                 /* :635-638 */
+        o->term = 1;
+        return;
+    }
+    int c = (int)((o->iter - 1) % m);                                                   /* :641 (0-based) */
+    memcpy(o->S + (size_t)c * n, dx, (size_t)n * 8);                                    /* :642-643 */
+    memcpy(o->Y + (size_t)c * n, dg, (size_t)n * 8);
+    const double delta_overlap = dot_(order, dx, dg, n);                                /* :646 */
+    o->rho[c] = 1.0 / delta_overlap;                                                    /* :647 */
+    const int64_t hist_count = (o->hist_count + 1 < m) ? o->hist_count + 1 : m;         /* :650-653 */
+    const int64_t hist_end = o->iter, hist_begin = hist_end - hist_count + 1;
+    o->hist_count = hist_count;
+    memcpy(d, g, (size_t)n * 8);                                                        /* :656 */
+    for (int64_t it = hist_end; it >= hist_begin; --it) {                               /* :659-666 */
+        c = (int)((it - 1) % m);
+        const double alpha = o->rho[c] * dot_(order, d, o->S + (size_t)c * n, n);
+        o->alpha[c] = alpha;
+        const double* y = o->Y + (size_t)c * n;
+        for (int64_t i = 0; i < n; ++i) d[i] += alpha * y[i];
+    }
+    const double gamma = delta_overlap / norm2_(order, dg, n);                          /* :669-670 */
+    for (int64_t i = 0; i < n; ++i) d[i] *= gamma;
+    for (int64_t it = hist_begin; it <= hist_end; ++it) {                               /* :673-680 */
+        c = (int)((it - 1) % m);
+        const double beta = o->alpha[c] - o->rho[c] * dot_(order, d, o->Y + (size_t)c * n, n);
+        const double* s = o->S + (size_t)c * n;
+        for (int64_t i = 0; i < n; ++i) d[i] += beta * s[i];
+    }
+    for (int64_t i = 0; i < n; ++i) d[i] = -d[i];                                       /* :683-684 negate! */
+    const double gradient_overlap = dot_(order, d, g, n);
+    if (!isfinite(gradient_overlap)) {                                                  /* :687-688 */
+        o->term = 1;
+    } else if (gradient_overlap >= 0.0) {                                               /* :689-692 */
+        const double a = -step_length * inv_gradient_norm;
+        for (int64_t i = 0; i < n; ++i) d[i] = a * g[i];
+    }
+}
+
+int dzo_cpu_legacy_lbfgs_step(dzo_cpu_legacy_lbfgs* o, int k) {
+    if (!o || k < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    for (int s = 0; s < k; ++s) legacy_lbfgs_step_one(o);
+    return DZO_OK;
+}
+#define LLGET(name, field)                                                              \
+    int name(dzo_cpu_legacy_lbfgs* o, double* out) {                                    \
+        if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");          \
+        memcpy(out, o->field, (size_t)o->P.n * 8);                                      \
+        return DZO_OK;                                                                  \
+    }
+LLGET(dzo_cpu_legacy_lbfgs_get_point, x)
+LLGET(dzo_cpu_legacy_lbfgs_get_delta_point, dx)
+LLGET(dzo_cpu_legacy_lbfgs_get_gradient, g)
+LLGET(dzo_cpu_legacy_lbfgs_get_delta_gradient, dg)
+LLGET(dzo_cpu_legacy_lbfgs_get_direction, d)
+#undef LLGET
+int dzo_cpu_legacy_lbfgs_get_scalars(dzo_cpu_legacy_lbfgs* o, double* s) {
+    if (!o || !s) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    s[0] = o->f; s[1] = o->df; s[2] = o->L; s[3] = (double)o->iter; s[4] = (double)o->term; s[5] = (double)o->hist_count;
+    return DZO_OK;
+}
+int dzo_cpu_legacy_lbfgs_get_history(dzo_cpu_legacy_lbfgs* o, double* rho, double* alpha) {
+    if (!o || !rho || !alpha) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    for (int i = 0; i < o->m; ++i) { rho[i] = o->rho[i]; alpha[i] = o->alpha[i]; }
+    return DZO_OK;
+}
+void dzo_cpu_legacy_lbfgs_destroy(dzo_cpu_legacy_lbfgs* o) {
+    if (!o) return;
+    free(o->x); free(o->dx); free(o->g); free(o->dg); free(o->d); free(o->S); free(o->Y); free(o->scratch);
     free(o);
 }

@@ -681,3 +681,148 @@ class LiveAdGDOptimizer:
         self.delta_gradient = [1.0 * a + (-1.0) * b for a, b in zip(g, self.delta_gradient)]
         self.iteration_count += 1
         return self
+
+
+# ------------------------------------------------------------------ legacy decorators (:222-296)
+class L2Regularized:
+    """L2RegularizationWrapper (:228-234) + L2GradientWrapper (:237-251) around an objective object."""
+
+    def __init__(self, fn, lam):
+        self.fn, self.lam, self.tree = fn, lam, fn.tree
+
+    def constraint(self, x):
+        return self.fn.constraint(x)
+
+    def f(self, x):
+        return self.fn.f(x) + self.lam * norm2(x, self.tree)
+
+    def g(self, g, x):
+        self.fn.g(g, x)
+        a = self.lam + self.lam
+        for i in range(len(g)):
+            g[i] += a * x[i]
+
+
+class UniformBox:
+    """UniformBoxConstraint (:257-272) + UniformBoxGradientWrapper (:275-296) around an objective object."""
+
+    def __init__(self, fn, lower_bound, upper_bound):
+        self.fn, self.lo, self.hi, self.tree = fn, lower_bound, upper_bound, fn.tree
+
+    def constraint(self, x):
+        ok = self.fn.constraint(x)
+        for i in range(len(x)):
+            v = x[i]
+            x[i] = self.hi if v > self.hi else (self.lo if v < self.lo else v)  # Base.clamp
+        return ok
+
+    def f(self, x):
+        return self.fn.f(x)
+
+    def g(self, g, x):
+        self.fn.g(g, x)
+        for i in range(len(g)):
+            if (x[i] <= self.lo and g[i] >= 0.0) or (x[i] >= self.hi and g[i] <= 0.0):
+                g[i] = 0.0
+
+
+# ------------------------------------------------------------------ legacy L-BFGS (:458-695)
+class LegacyLBFGSOptimizer:
+    """legacy/DZOptimization.jl:458-695: cyclic history columns, gradient retry, two-loop as written."""
+
+    def __init__(self, fn, x0, initial_step_length, history_length, max_increases=0, tree=True):  # :489-548
+        self.fn, self.tree, self.max_increases = fn, tree, max_increases
+        n = len(x0)
+        self.current_point = list(x0)
+        assert fn.constraint(self.current_point)
+        self.delta_point = [0.0] * n
+        self.current_objective_value = fn.f(self.current_point)
+        self.delta_objective_value = 0.0
+        self.current_gradient = [0.0] * n
+        fn.g(self.current_gradient, self.current_point)
+        self.delta_gradient = [0.0] * n
+        self.last_step_length = 0.0
+        inv_gradient_norm = _div(1.0, math.sqrt(norm2(self.current_gradient, tree)))
+        self.next_step_direction = [0.0] * n
+        if math.isfinite(inv_gradient_norm):
+            a = -initial_step_length * inv_gradient_norm
+            self.next_step_direction = [gi * a for gi in self.current_gradient]
+        self.iteration_count = 0
+        self.has_terminated = (not math.isfinite(self.current_objective_value)
+                               or not math.isfinite(inv_gradient_norm))
+        assert history_length > 0
+        m = history_length
+        self._alpha = [0.0] * m
+        self._rho = [0.0] * m
+        self._dp_hist = [[0.0] * n for _ in range(m)]   # column c of _delta_point_history
+        self._dg_hist = [[0.0] * n for _ in range(m)]
+        self._history_count = 0
+
+    def _search(self):
+        f0 = self.current_objective_value
+        t, fv = quadratic_line_search(Ray(self.fn, self.current_point, self.next_step_direction, +1.0),
+                                      f0, 1.0, self.max_increases)
+        return t, fv, not (t == 0.0 or not (fv < f0))
+
+    def step(self):  # :565-695
+        if self.has_terminated:
+            return self
+        x, g = self.current_point, self.current_gradient
+        n, m, tree = len(x), len(self._alpha), self.tree
+        step_size, objective_value, ok = self._search()
+        if not ok:
+            a = -self.last_step_length * _div(1.0, math.sqrt(norm2(g, tree)))
+            self.next_step_direction = [gi * a for gi in g]
+            step_size, objective_value, ok = self._search()
+            if not ok:
+                self.has_terminated = True
+                return self
+            self._history_count = 0
+        self.iteration_count += 1
+        d = self.next_step_direction
+        old = list(x)
+        for i in range(n):
+            x[i] += step_size * d[i]
+        assert self.fn.constraint(x)
+        self.delta_point = [x[i] - old[i] for i in range(n)]
+        step_length = math.sqrt(norm2(self.delta_point, tree))
+        self.last_step_length = step_length
+        self.delta_objective_value = objective_value - self.current_objective_value
+        self.current_objective_value = objective_value
+        gold = list(g)
+        self.fn.g(g, x)
+        self.delta_gradient = [g[i] - gold[i] for i in range(n)]
+        inv_gradient_norm = _div(1.0, math.sqrt(norm2(g, tree)))
+        if not math.isfinite(inv_gradient_norm):
+            self.has_terminated = True
+            return self
+        c = (self.iteration_count - 1) % m
+        self._dp_hist[c] = list(self.delta_point)
+        self._dg_hist[c] = list(self.delta_gradient)
+        delta_overlap = dot(self.delta_point, self.delta_gradient, tree)
+        self._rho[c] = _div(1.0, delta_overlap)
+        hist_count = min(self._history_count + 1, m)
+        hist_end = self.iteration_count
+        hist_begin = hist_end - hist_count + 1
+        self._history_count = hist_count
+        d = list(g)
+        for it in range(hist_end, hist_begin - 1, -1):
+            c = (it - 1) % m
+            alpha = self._rho[c] * dot(d, self._dp_hist[c], tree)
+            self._alpha[c] = alpha
+            d = [di + alpha * yi for di, yi in zip(d, self._dg_hist[c])]
+        gamma = _div(delta_overlap, norm2(self.delta_gradient, tree))
+        d = [di * gamma for di in d]
+        for it in range(hist_begin, hist_end + 1):
+            c = (it - 1) % m
+            beta = self._alpha[c] - self._rho[c] * dot(d, self._dg_hist[c], tree)
+            d = [di + beta * si for di, si in zip(d, self._dp_hist[c])]
+        d = [-di for di in d]
+        gradient_overlap = dot(d, g, tree)
+        if not math.isfinite(gradient_overlap):
+            self.has_terminated = True
+        elif gradient_overlap >= 0.0:
+            a = -step_length * inv_gradient_norm
+            d = [a * gi for gi in g]
+        self.next_step_direction = d
+        return self

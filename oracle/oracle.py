@@ -341,3 +341,65 @@ class AdGD:
             self.close()
         except Exception:
             pass
+
+
+DECOR_NONE, DECOR_L2, DECOR_BOX = 0, 1, 2
+
+
+class LegacyLBFGS:
+    """legacy LBFGSOptimizer (legacy/DZOptimization.jl:458-695) with the optional L2 / box decorators
+    (:222-296), one problem; x0: (n,)"""
+
+    _PFX = "dzo_cpu_legacy_lbfgs_"
+
+    def __init__(self, objective, x0, step, history_length, max_increases=0, l2_lambda=None, box=None, order=TREE):
+        a = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+        self.n, self.m = a.size, int(history_length)
+        self._h = None
+        h = C.c_void_p()
+        decor = (DECOR_L2 if l2_lambda is not None else 0) | (DECOR_BOX if box is not None else 0)
+        lo, hi = box if box is not None else (0.0, 0.0)
+        _check(lib().dzo_cpu_legacy_lbfgs_create(C.byref(h), objective, CONSTRAINT_NONE, 0, self.n, _dp(a), float(step),
+                                                 self.m, int(max_increases), decor,
+                                                 float(l2_lambda if l2_lambda is not None else 0.0), float(lo), float(hi), order))
+        self._h = h
+
+    def _vec(self, name):
+        out = np.empty(self.n)
+        _check(getattr(lib(), self._PFX + name)(self._h, _dp(out)))
+        return out
+
+    point = property(lambda s: s._vec("get_point"))
+    delta_point = property(lambda s: s._vec("get_delta_point"))
+    gradient = property(lambda s: s._vec("get_gradient"))
+    delta_gradient = property(lambda s: s._vec("get_delta_gradient"))
+    direction = property(lambda s: s._vec("get_direction"))
+
+    @property
+    def scalars(self):
+        """(f, df, last_step_length, iteration_count, has_terminated, _history_count)"""
+        out = np.empty(6)
+        _check(getattr(lib(), self._PFX + "get_scalars")(self._h, _dp(out)))
+        return out
+
+    @property
+    def history(self):
+        """(_rho, _alpha), physical column order"""
+        rho, alpha = np.zeros(self.m), np.zeros(self.m)
+        _check(getattr(lib(), self._PFX + "get_history")(self._h, _dp(rho), _dp(alpha)))
+        return rho, alpha
+
+    def step(self, k=1):
+        _check(getattr(lib(), self._PFX + "step")(self._h, int(k)))
+        return self
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            getattr(lib(), self._PFX + "destroy")(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
