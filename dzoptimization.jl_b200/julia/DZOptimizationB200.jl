@@ -20,7 +20,8 @@
 # versions of legacy/ExampleFunctions.jl exported below; anything else raises ArgumentError.
 module DZOptimizationB200
 
-export BFGSOptimizer, GradientDescentOptimizer, LBFGSOptimizer, AdGDOptimizer, QuadraticLineSearch, step!, StepType, NullStep,
+export BFGSOptimizer, GradientDescentOptimizer, LBFGSOptimizer, AdGDOptimizer, LegacyLBFGSOptimizer, L2RegularizationWrapper,
+    L2GradientWrapper, UniformBoxConstraint, UniformBoxGradientWrapper, QuadraticLineSearch, step!, StepType, NullStep,
     GradientDescentStep, BFGSStep, NULL_CONSTRAINT, SPHERE_CONSTRAINT,
     accelerated_pairwise_radial_energy, accelerated_pairwise_radial_gradient!, accelerated_pairwise_radial_hvp!
 
@@ -311,6 +312,80 @@ function Base.getproperty(opt::AdGDOptimizer, s::Symbol)
     s === :previous_step_size && return fill(sc[4])                                 # :196
     s === :iteration_count && return fill(Int(sc[5]))                               # :186
     (s === :is_stuck || s === :has_converged) && return fill(sc[6] != 0)            # :185
+    return getfield(opt, s)
+end
+
+# ================================================================== legacy decorators (legacy/DZOptimization.jl:222-296)
+# The reference wraps callables; here the wrappers are peeled into decorator bits for the device objective.
+struct L2RegularizationWrapper{F}; objective_function::F; lambda::Float64; end           # :228-234
+struct L2GradientWrapper{G}; gradient_function!::G; lambda::Float64; end                 # :237-251
+struct UniformBoxConstraint; lower_bound::Float64; upper_bound::Float64; end            # :257-272
+struct UniformBoxGradientWrapper{G}; gradient_function!::G; lower_bound::Float64; upper_bound::Float64; end   # :275-296
+
+function resolve_decorated(c!, f, g!)
+    lam_f = lam_g = nothing
+    box_c = box_g = nothing
+    if f isa L2RegularizationWrapper; lam_f = f.lambda; f = f.objective_function; end
+    if g! isa UniformBoxGradientWrapper; box_g = (g!.lower_bound, g!.upper_bound); g! = g!.gradient_function!; end
+    if g! isa L2GradientWrapper; lam_g = g!.lambda; g! = g!.gradient_function!; end
+    g! isa UniformBoxGradientWrapper && throw(ArgumentError("device order is UniformBoxGradientWrapper(L2GradientWrapper(g!, lambda), lo, hi)"))
+    if c! isa UniformBoxConstraint; box_c = (c!.lower_bound, c!.upper_bound); c! = NULL_CONSTRAINT; end
+    c! === nothing && (c! = NULL_CONSTRAINT)
+    lam_f == lam_g || throw(ArgumentError("L2RegularizationWrapper and L2GradientWrapper must share one lambda"))
+    box_c == box_g || throw(ArgumentError("UniformBoxConstraint and UniformBoxGradientWrapper must share their bounds"))
+    obj, cid = resolve(f, g!, c!)
+    return obj, cid, lam_f, box_c
+end
+
+# ================================================================== legacy LBFGSOptimizer (legacy/DZOptimization.jl:458-695)
+# (the live package's optimizer of the same name is LBFGSOptimizer above)
+mutable struct LegacyLBFGSOptimizer
+    handle::Ptr{Cvoid}
+    n::Int
+    m::Int
+end
+function LegacyLBFGSOptimizer(c!, f, g!, ls::QuadraticLineSearch, x0::Vector{Float64}, step::Float64,
+    history_length::Int; device::Integer=0)                                         # :489-548
+    obj, cid, lam, box = resolve_decorated(c!, f, g!)
+    @assert history_length > 0                                                       # :528
+    decor = (lam === nothing ? 0 : 1) | (box === nothing ? 0 : 2)
+    lo, hi = box === nothing ? (0.0, 0.0) : box
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dzo_legacy_lbfgs_create, libdzopt), Cint,
+        (Ref{Ptr{Cvoid}}, Cint, Cint, Int64, Int64, Ptr{Float64}, Float64, Cint, Cint, Cint, Float64, Float64, Float64, Cint),
+        h, obj, cid, 0, length(x0), x0, step, history_length, ls.max_increases, decor,
+        lam === nothing ? 0.0 : lam, lo, hi, device))
+    opt = LegacyLBFGSOptimizer(h[], length(x0), history_length)
+    finalizer(o -> ccall((:dzo_legacy_lbfgs_destroy, libdzopt), Cvoid, (Ptr{Cvoid},), getfield(o, :handle)), opt)
+    return opt
+end
+LegacyLBFGSOptimizer(f, g!, ls::QuadraticLineSearch, x0::Vector{Float64}, step::Float64, history_length::Int; kw...) =
+    LegacyLBFGSOptimizer(NULL_CONSTRAINT, f, g!, ls, x0, step, history_length; kw...)   # :551-562
+function step!(opt::LegacyLBFGSOptimizer)                                           # :565-695
+    check(ccall((:dzo_legacy_lbfgs_step, libdzopt), Cint, (Ptr{Cvoid}, Cint), getfield(opt, :handle), 1))
+    return opt
+end
+function Base.getproperty(opt::LegacyLBFGSOptimizer, s::Symbol)
+    h, n, m = getfield(opt, :handle), getfield(opt, :n), getfield(opt, :m)
+    vec(sym) = (out = Vector{Float64}(undef, n); check(ccall((sym, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, out)); out)
+    s === :current_point && return vec(:dzo_legacy_lbfgs_get_point)                 # :461
+    s === :delta_point && return vec(:dzo_legacy_lbfgs_get_delta_point)             # :462
+    s === :current_gradient && return vec(:dzo_legacy_lbfgs_get_gradient)           # :469
+    s === :delta_gradient && return vec(:dzo_legacy_lbfgs_get_delta_gradient)       # :470
+    s === :next_step_direction && return vec(:dzo_legacy_lbfgs_get_direction)       # :473
+    if s === :_rho || s === :_alpha                                                 # :480-481
+        rho, alpha = Vector{Float64}(undef, m), Vector{Float64}(undef, m)
+        check(ccall((:dzo_legacy_lbfgs_get_history, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h, rho, alpha))
+        return s === :_rho ? rho : alpha
+    end
+    sc = Vector{Float64}(undef, 6)
+    check(ccall((:dzo_legacy_lbfgs_get_scalars, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, sc))
+    s === :current_objective_value && return fill(sc[1])                            # :465
+    s === :delta_objective_value && return fill(sc[2])                              # :466
+    s === :last_step_length && return fill(sc[3])                                   # :474
+    s === :iteration_count && return fill(Int(sc[4]))                               # :477
+    (s === :has_terminated || s === :has_converged) && return fill(sc[5] != 0)      # :478
+    s === :_history_count && return fill(Int(sc[6]))                                # :484
     return getfield(opt, s)
 end
 
