@@ -125,6 +125,7 @@ def bind(lib, cpu: bool):
         sig("gd_info", [H, c_i64_p, c_i64_p, c_int_p])
         sig("identity", [I64, c_double_p, I])
         sig("bench_kernel", [I, I64, I, I, c_float_p, I])
+        sig("dev_selftest_ieee_fast", [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), I])
         sig("set_tuning", [C.c_char_p, I])
         V = C.c_void_p
         sig("pairwise_workspace_bytes", [I64], C.c_uint64)

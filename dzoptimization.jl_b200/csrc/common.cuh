@@ -3,7 +3,8 @@
 // Arithmetic policy: the legacy Julia on this path contains no muladd and no
 // @simd reductions, so nothing may be contracted into FMA.  The whole library is compiled
 // with -fmad=false; double-precision '/' and sqrt() are IEEE-correct in CUDA regardless of
-// flags.  Never use rsqrt()/__drcp_* here.
+// flags.  Never use rsqrt()/__drcp_* here; the only approximate instructions in the library are inside
+// ieee_fast.cuh, which replicates the compiler's own IEEE sqrt / division fast paths and is self-tested on the device.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

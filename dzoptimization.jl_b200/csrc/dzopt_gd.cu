@@ -396,3 +396,17 @@ int riesz_dev_line_search(int constraint, int64_t dim, int order, int64_t n, con
 }
 
 }  // namespace dzo
+
+// ============================================================================= ieee_fast.cuh self-test
+extern "C" int dzo_dev_selftest_ieee_fast(uint64_t count, uint64_t seed, uint64_t* mismatches, int device) {
+    if (!mismatches) return dzo::fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(dzo::use_device(device));
+    dzo::DevBuf b;
+    DZO_TRY(b.alloc(8));
+    DZO_CUDA(cudaMemset(b.p, 0, 8));
+    dzo::ieee_fast_selftest_kernel<<<148 * 8, 256>>>(count, seed, b.as<unsigned long long>());
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    DZO_CUDA(cudaMemcpy(mismatches, b.p, 8, cudaMemcpyDeviceToHost));
+    return DZO_OK;
+}

@@ -17,6 +17,7 @@
 #pragma once
 #include <cooperative_groups.h>
 
+#include "ieee_fast.cuh"
 #include "large_bfgs.cuh"
 
 namespace dzo {
@@ -54,6 +55,8 @@ struct RieszGdArgs {
 };
 
 constexpr int kRieszSegWarps = 32;   // warps per CTA, each with a private staging buffer
+constexpr int kRieszBatch = 4;       // energy pair terms whose sqrt / reciprocal chains run interleaved
+constexpr int kRieszGradBatch = 2;   // same for the gradient (sqrt, reciprocal, division per term)
 
 template <int DIM>
 struct RieszDev {
@@ -99,16 +102,41 @@ struct RieszDev {
                     double wj[DIM];
                     trial_point(a, dir, j, alpha, pmode, wj);
                     double seg = 0.0;
-                    // the sqrt / division of different sources are independent (ILP); only the adds are ordered
-#pragma unroll 4
-                    for (int i = 0; i < lim; ++i) {
+                    // the sqrt / reciprocal chains of kRieszBatch sources run interleaved (ieee_fast.cuh); only the
+                    // adds are ordered
+                    int i = 0;
+                    for (; i + kRieszBatch <= lim; i += kRieszBatch) {
+                        double ds[kRieszBatch], t[kRieszBatch];
+                        bool safe = true;
+#pragma unroll
+                        for (int u = 0; u < kRieszBatch; ++u) {
+                            double dist_sq = 0.0;
+#pragma unroll
+                            for (int k = 0; k < DIM; ++k) {
+                                const double dist = buf[(i + u) * DIM + k] - wj[k];   // points[k,i] - points[k,j]  :37
+                                dist_sq += dist * dist;
+                            }
+                            ds[u] = dist_sq;
+                            safe &= ieee_fast_safe(dist_sq);
+                        }
+                        if (safe) {
+#pragma unroll
+                            for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_rsqrt_operators(ds[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < kRieszBatch; ++u) seg += t[u];     // rsqrt(dist_sq)  :41
+                    }
+                    for (; i < lim; ++i) {
                         double dist_sq = 0.0;
 #pragma unroll
                         for (int k = 0; k < DIM; ++k) {
-                            const double dist = buf[i * DIM + k] - wj[k];     // points[k,i] - points[k,j]  :37
+                            const double dist = buf[i * DIM + k] - wj[k];
                             dist_sq += dist * dist;
                         }
-                        seg += 1.0 / sqrt(dist_sq);                            // rsqrt(dist_sq)  :41
+                        seg += ieee_rsqrt_operators(dist_sq);
                     }
                     a.segE[(long long)it.y * a.N + j] = seg;
                 }
@@ -180,21 +208,54 @@ struct RieszDev {
                 double xj[DIM], part[DIM];
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) { xj[k] = a.x[(long long)j * DIM + k]; part[k] = 0.0; }
-#pragma unroll 4
-                for (int i = 0; i < cnt; ++i) {
-                    if (i0 + i == j) continue;                                 // :55, :69 (i != j)
+                int i = 0;
+                for (; i + kRieszGradBatch <= cnt; i += kRieszGradBatch) {
+                    double ds[kRieszGradBatch], c[kRieszGradBatch];
+                    bool safe = true;
+#pragma unroll
+                    for (int u = 0; u < kRieszGradBatch; ++u) {
+                        double dist_sq = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) {
+                            const double dist = buf[(i + u) * DIM + k] - xj[k];
+                            dist_sq += dist * dist;
+                        }
+                        ds[u] = (i0 + i + u == j) ? 1.0 : dist_sq;             // the skipped self term (:55, :69) rides along as 1.0
+                        safe &= ieee_fast_safe(ds[u]);
+                    }
+                    if (safe) {
+#pragma unroll
+                        for (int u = 0; u < kRieszGradBatch; ++u) {
+                            const double inv_dist = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));   // :61
+                            c[u] = ieee_fast_div(inv_dist, ds[u]);                          // :62
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < kRieszGradBatch; ++u) c[u] = ieee_inv_cubed_operators(ds[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < kRieszGradBatch; ++u) {
+                        if (i0 + i + u == j) continue;                         // :55, :69 (i != j)
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) {
+                            const double dist = buf[(i + u) * DIM + k] - xj[k];
+                            part[k] += dist * c[u];                            // :65
+                        }
+                    }
+                }
+                for (; i < cnt; ++i) {
+                    if (i0 + i == j) continue;
                     double dist_sq = 0.0;
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) {
                         const double dist = buf[i * DIM + k] - xj[k];
                         dist_sq += dist * dist;
                     }
-                    const double inv_dist = 1.0 / sqrt(dist_sq);               // :61
-                    const double inv_dist_cubed = inv_dist / dist_sq;          // :62
+                    const double inv_dist_cubed = ieee_inv_cubed_operators(dist_sq);
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) {
                         const double dist = buf[i * DIM + k] - xj[k];
-                        part[k] += dist * inv_dist_cubed;                      // :65
+                        part[k] += dist * inv_dist_cubed;
                     }
                 }
 #pragma unroll
