@@ -27,13 +27,14 @@ struct dzo_gd {
     int2* e_items = nullptr;
     int n_e_items = 0;
     unsigned* counter = nullptr;
+    unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
     int grid = 0;
 };
 
 static void free_gd(dzo_gd* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter,
+    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter, o->prof,
                     o->f, o->df, o->L, o->iter, o->term};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -154,6 +155,11 @@ static int gd_launch(dzo_gd* o, int mode, int k, double L0) {
     if (o->objective == DZO_OBJ_RIESZ) {
         RieszGdArgs a = riesz_args(o, mode, k);
         a.initial_step_length = L0;
+        if (g_tuning.riesz_profile && mode == 0) {
+            if (!o->prof) DZO_TRY(dmalloc(&o->prof, (size_t)1 + 2 * kRieszProfCap));
+            DZO_CUDA(cudaMemsetAsync(o->prof, 0, 8, o->stream));
+            a.prof = o->prof;
+        }
         void* params[] = {&a};
         DZO_CUDA(cudaLaunchCooperativeKernel(riesz_kernel_for((int)o->dim), dim3(o->grid), dim3(1024), params,
                                              riesz_gd_smem((int)o->dim), o->stream));
@@ -274,6 +280,19 @@ DZO_GD_SCALAR(dzo_gd_get_iteration_count, int64_t, c.iter, iter)
 DZO_GD_SCALAR(dzo_gd_get_terminated, uint8_t, c.term != 0, term)
 #undef DZO_GD_SCALAR
 
+int dzo_gd_get_phase_log(dzo_gd* o, uint64_t* events, int64_t cap_events, int64_t* count) {
+    if (!o || !events || !count || cap_events < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    *count = 0;
+    if (!o->prof) return DZO_OK;
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    unsigned long long k = 0;
+    DZO_CUDA(cudaMemcpy(&k, o->prof, 8, cudaMemcpyDeviceToHost));
+    if (k > (unsigned long long)cap_events) k = (unsigned long long)cap_events;
+    if (k) DZO_CUDA(cudaMemcpy(events, o->prof + 1, (size_t)k * 16, cudaMemcpyDeviceToHost));
+    *count = (int64_t)k;
+    return DZO_OK;
+}
 int dzo_gd_info(dzo_gd* o, int64_t* n, int64_t* batch, int* order) {
     if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
     if (n) *n = o->n;

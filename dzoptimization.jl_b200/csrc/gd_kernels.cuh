@@ -50,9 +50,27 @@ struct RieszGdArgs {
                                   // 5 = the O(n)/O(N^2) stage of a BFGS step! (search, decision, bookkeeping),
                                   // 6 = BFGSOptimizer constructor
     double ls_f0, ls_t1, ls_sign; // mode 4 inputs; result in fbox[1], fbox[2]
+    unsigned long long* prof;     // optional phase log of the leader thread: [0] = events, then (id, %globaltimer ns) pairs
     LargeCtrl* bctrl;             // modes 5, 6: the BFGS control block shared with the n^2 sweep kernels
     double* sd;                   // mode 5: step_direction / overlap  (legacy/DZOptimization.jl:874)
 };
+
+constexpr int kRieszProfCap = 8192;  // events of the optional phase log
+// phase ids: 1 step begin, 2 energy begin, 3 leader's own energy items done, 4 first energy barrier passed,
+// 5 energy end (rows + tree + barrier), 6 line search end, 7 point update + barrier, 8 leader's own gradient items
+// done, 9 gradient barrier passed, 10 gradient rows + barrier, 11 step end
+DZO_DEVINL void riesz_prof_mark(const RieszGdArgs& a, int id) {
+    if (a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned long long k = a.prof[0];
+        if (k < (unsigned long long)kRieszProfCap) {
+            a.prof[1 + 2 * k] = (unsigned long long)id;
+            a.prof[2 + 2 * k] = t;
+            a.prof[0] = k + 1;
+        }
+    }
+}
 
 constexpr int kRieszSegWarps = 32;   // warps per CTA, each with a private staging buffer
 constexpr int kRieszBatch = 4;       // energy pair terms whose sqrt / reciprocal chains run interleaved
@@ -183,9 +201,14 @@ struct RieszDev {
 
     static DZO_DEVINL double energy(const RieszGdArgs& a, cg::grid_group& grid, const double* dir, double alpha, int pmode,
                                     double* wsm, double* sm) {
+        riesz_prof_mark(a, 2);
         energy_segments(a, dir, alpha, pmode, wsm);
+        riesz_prof_mark(a, 3);
         grid.sync();
-        return energy_finish(a, grid, sm);
+        riesz_prof_mark(a, 4);
+        const double f = energy_finish(a, grid, sm);
+        riesz_prof_mark(a, 5);
+        return f;
     }
 
     // ---- riesz_gradient! (:47-83) at the stored points + tangent projection (:361-374)
@@ -565,7 +588,9 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         const long long iter = __ldcg(&a.ctrl->iter);
         long long evals = 0;
         double step_size, objective_value;
+        riesz_prof_mark(a, 1);
         R::line_search(a, grid, a.d, f0, 1.0, 1.0, wsm, sm, step_size, objective_value, evals);   // :405-407
+        riesz_prof_mark(a, 6);
         if (step_size == 0.0 || !(objective_value < f0)) {                     // :410-414
             if (leader) a.ctrl->term = 1;
             continue;                                   // next iteration's barrier publishes the flag
@@ -582,10 +607,14 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             for (int k = 0; k < DIM; ++k) a.x[(long long)j * DIM + k] = w[k];
         }
         grid.sync();
+        riesz_prof_mark(a, 7);
         R::gradient_segments(a, wsm);                                          // :434
+        riesz_prof_mark(a, 8);
         grid.sync();
+        riesz_prof_mark(a, 9);
         R::gradient_rows(a, true);                                             // :433-435
         grid.sync();
+        riesz_prof_mark(a, 10);
         const double step_length = sqrt(cta_tree_dot(a.dx, a.dx, n, sm));      // :424
         const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :438
         const bool ok = isfinite(inv_gradient_norm);
@@ -601,6 +630,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             a.ctrl->evals += evals;
             if (!ok) a.ctrl->term = 1;                                         // :439-442
         }
+        riesz_prof_mark(a, 11);
     }
 }
 
