@@ -27,6 +27,7 @@ struct dzo_gd {
     int2* e_items = nullptr;
     int n_e_items = 0;
     unsigned* counter = nullptr;
+    unsigned* rbcnt = nullptr;
     unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
     int grid = 0;
 };
@@ -34,7 +35,7 @@ struct dzo_gd {
 static void free_gd(dzo_gd* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter, o->prof,
+    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter, o->rbcnt, o->prof,
                     o->f, o->df, o->L, o->iter, o->term};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -84,6 +85,7 @@ struct RieszWork {
     int2* e_items = nullptr;
     int n_e_items = 0;
     unsigned* counter = nullptr;
+    unsigned* rbcnt = nullptr;
     int grid = 0;
     void* kernel = nullptr;
     size_t smem = 0;
@@ -92,7 +94,11 @@ struct RieszWork {
         if (!kernel) return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
         const int nseg = (N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
         DZO_TRY(dmalloc(&segE, (size_t)nseg * N));
-        DZO_TRY(dmalloc(&rowE, (size_t)N));
+        DZO_TRY(dmalloc(&rowE, (size_t)2 * N));              // double-buffered by evaluation parity
+        DZO_CUDA(cudaMemset(rowE, 0, (size_t)2 * N * sizeof(double)));
+        const int nrb = (N + 31) / 32;
+        DZO_TRY(dmalloc(&rbcnt, (size_t)2 * nrb));           // items finished per row block: energy | gradient
+        DZO_CUDA(cudaMemset(rbcnt, 0, (size_t)2 * nrb * sizeof(unsigned)));
         DZO_TRY(dmalloc(&segG, (size_t)nseg * N * dim));
         DZO_TRY(dmalloc(&fbox, 4));
         DZO_TRY(dmalloc(&counter, 1));
@@ -114,14 +120,14 @@ struct RieszWork {
         return DZO_OK;
     }
     void release() {
-        void* ptrs[] = {segE, rowE, segG, fbox, e_items, counter};
+        void* ptrs[] = {segE, rowE, segG, fbox, e_items, counter, rbcnt};
         for (void* p : ptrs)
             if (p) cudaFree(p);
-        segE = rowE = segG = fbox = nullptr; e_items = nullptr; counter = nullptr;
+        segE = rowE = segG = fbox = nullptr; e_items = nullptr; counter = nullptr; rbcnt = nullptr;
     }
     void fill(RieszGdArgs& a) const {
         a.segE = segE; a.rowE = rowE; a.segG = segG; a.e_items = e_items; a.n_e_items = n_e_items;
-        a.counter = counter; a.fbox = fbox;
+        a.counter = counter; a.fbox = fbox; a.rbcnt = rbcnt; a.dscale = 1.0;
     }
     int launch(RieszGdArgs& a, cudaStream_t stream) const {
         void* params[] = {&a};
@@ -135,7 +141,7 @@ static RieszGdArgs riesz_args(const dzo_gd* o, int mode, int k) {
     memset(&a, 0, sizeof a);
     a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg;
     a.segE = o->segE; a.rowE = o->rowE; a.segG = o->segG; a.e_items = o->e_items; a.n_e_items = o->n_e_items;
-    a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox;
+    a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox; a.rbcnt = o->rbcnt; a.dscale = 1.0;
     a.N = (int)(o->n / o->dim); a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.max_increases = o->max_increases;
     a.ksteps = k; a.mode = mode;
     return a;
@@ -208,7 +214,7 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         RieszWork w;
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
-        o->n_e_items = w.n_e_items; o->counter = w.counter; o->grid = w.grid;
+        o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->grid = w.grid;
     }
     if (cudaMemcpyAsync(o->x, x0, nb * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)   // :339 collect
         return bail(fail(DZO_ERR_CUDA, "H2D copy of x0 failed"));

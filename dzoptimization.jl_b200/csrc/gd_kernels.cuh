@@ -36,13 +36,15 @@ struct GdCtrl {
 struct RieszGdArgs {
     double *x, *g, *d, *dx, *dg;  // dim x N column-major (point j contiguous)
     double *segE;                 // [nseg][N]       energy segment partials
-    double *rowE;                 // [N]             row energies
+    double *rowE;                 // [2][N]          row energies, double-buffered by the parity of the evaluation count
+    unsigned* rbcnt;              // [2][nrb]        items finished per 32-row block (energy | gradient); zero between uses
     double *segG;                 // [nseg][N][DIM]  gradient segment partials
     const int2* e_items;          // (row block, segment) items of the strict lower triangle
     int n_e_items;
     GdCtrl* ctrl;
-    unsigned* counter;            // last-CTA-done counter (zero between uses)
-    double* fbox;                 // broadcast slot for the reduced energy
+    unsigned* counter;            // (unused by the kernel since the row sums moved into the segment phase)
+    double* fbox;                 // result slots of the kernel-level modes 2 and 4
+    double dscale;                // the direction actually used is dscale * dir[e] (1.0, or alpha with dir = g: see mode 0)
     int N, sphere, max_increases, ksteps;
     double initial_step_length;
     int mode;                     // 0 = k GD step! calls, 1 = GD constructor, 2 = one energy evaluation of x,
@@ -86,7 +88,7 @@ struct RieszDev {
         for (int k = 0; k < DIM; ++k) w[k] = a.x[(long long)j * DIM + k];
         if (pmode == 2) return;
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) w[k] = w[k] + alpha * dir[(long long)j * DIM + k];   // legacy/Kernels.jl:127-135
+        for (int k = 0; k < DIM; ++k) w[k] = w[k] + alpha * (a.dscale * dir[(long long)j * DIM + k]);   // legacy/Kernels.jl:127-135
         if (a.sphere) {                                                                    // [GLUE] SURVEY 8.0
             double s = 0.0;
 #pragma unroll
@@ -98,7 +100,9 @@ struct RieszDev {
     }
 
     // ---- riesz_energy (legacy/ExampleFunctions.jl:30-45), phase 1: segment partials
-    static DZO_DEVINL void energy_segments(const RieszGdArgs& a, const double* dir, double alpha, int pmode, double* wsm) {
+    // The warp that finishes the LAST item of a 32-row block (per-block counter, threadfence pattern) adds that
+    // block's segment partials in ascending order and stores the row energies: no grid barrier between the two.
+    static DZO_DEVINL void energy_segments(const RieszGdArgs& a, const double* dir, double alpha, int pmode, int par, double* wsm) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
         for (int idx = blockIdx.x + gridDim.x * warp; idx < a.n_e_items; idx += gridDim.x * kRieszSegWarps) {
@@ -159,60 +163,66 @@ struct RieszDev {
                     a.segE[(long long)it.y * a.N + j] = seg;
                 }
             }
-        }
-    }
-
-    // phase 2: rows, then (last CTA to arrive) the canonical tree.  Returns after the grid barrier
-    // with the energy, identical on every thread of the grid.
-    static DZO_DEVINL double energy_finish(const RieszGdArgs& a, cg::grid_group& grid, double* sm) {
-        __shared__ int s_last;
-        for (int j = blockIdx.x * 1024 + threadIdx.x; j < a.N; j += gridDim.x * 1024) {
-            double ej = 0.0;
-            for (int s0 = 0; s0 < j; s0 += DZO_RIESZ_SEG) {
-                const double seg = __ldcg(&a.segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
-                ej = (s0 == 0) ? seg : ej + seg;
-            }
-            a.rowE[j] = ej;
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
-        __syncthreads();
-        if (s_last) {
             __threadfence();
-            double p[1][4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double acc = 0.0;
-                for (int j = threadIdx.x + 1024 * q; j < a.N; j += DZO_TREE_WIDTH) acc += __ldcg(&a.rowE[j]);
-                p[0][q] = acc;
+            __syncwarp();
+            unsigned last = 0;
+            if (lane == 0) {
+                const int jmax = min(a.N, it.x * 32 + 32) - 1;
+                const unsigned expected = (unsigned)((jmax + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG);
+                last = (atomicAdd(&a.rbcnt[it.x], 1u) == expected - 1u);
             }
-            double out[1];
-            cta1024_tree_reduce<1>(p, sm, out);
-            if (threadIdx.x == 0) {
-                a.fbox[0] = out[0];
-                *a.counter = 0;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
                 __threadfence();
+                if (j < a.N) {
+                    double ej = 0.0;
+                    for (int s0 = 0; s0 < j; s0 += DZO_RIESZ_SEG) {
+                        const double seg = __ldcg(&a.segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
+                        ej = (s0 == 0) ? seg : ej + seg;
+                    }
+                    a.rowE[(long long)par * a.N + j] = ej;
+                }
+                if (lane == 0) a.rbcnt[it.x] = 0;      // next use is behind at least one grid barrier
             }
         }
-        grid.sync();
-        return __ldcg(&a.fbox[0]);
     }
 
-    static DZO_DEVINL double energy(const RieszGdArgs& a, cg::grid_group& grid, const double* dir, double alpha, int pmode,
+    // phase 2 (after ONE grid barrier): every CTA runs the canonical tree over the row energies itself (32 KB from L2
+    // at N = 4096), so the value is identical on every thread of the grid without a broadcast or a second barrier.
+    static DZO_DEVINL double energy_finish(const RieszGdArgs& a, int par, double* sm) {
+        const double* rowE = a.rowE + (long long)par * a.N;
+        double p[1][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double acc = 0.0;
+            for (int j = threadIdx.x + 1024 * q; j < a.N; j += DZO_TREE_WIDTH) acc += __ldcg(&rowE[j]);
+            p[0][q] = acc;
+        }
+        double out[1];
+        cta1024_tree_reduce<1>(p, sm, out);
+        return out[0];
+    }
+
+    // `epar` counts the evaluations of this launch (identical on every CTA); its parity selects the rowE buffer, so a
+    // CTA that is still reducing evaluation k cannot be overtaken by the row stores of evaluation k+1.
+    static DZO_DEVINL double energy(const RieszGdArgs& a, cg::grid_group& grid, int& epar, const double* dir, double alpha, int pmode,
                                     double* wsm, double* sm) {
+        const int par = epar & 1;
+        epar += 1;
         riesz_prof_mark(a, 2);
-        energy_segments(a, dir, alpha, pmode, wsm);
+        energy_segments(a, dir, alpha, pmode, par, wsm);
         riesz_prof_mark(a, 3);
         grid.sync();
         riesz_prof_mark(a, 4);
-        const double f = energy_finish(a, grid, sm);
+        const double f = energy_finish(a, par, sm);
         riesz_prof_mark(a, 5);
         return f;
     }
 
     // ---- riesz_gradient! (:47-83) at the stored points + tangent projection (:361-374)
-    static DZO_DEVINL void gradient_segments(const RieszGdArgs& a, double* wsm) {
+    // As for the energy, the warp finishing the last segment item of a 32-row block combines that block's rows
+    // (ascending segment order), projects, and writes g (and dg = g_new - g_old when with_delta).
+    static DZO_DEVINL void gradient_segments(const RieszGdArgs& a, double* wsm, bool with_delta) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
         const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
@@ -284,34 +294,41 @@ struct RieszDev {
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) a.segG[((long long)s * a.N + j) * DIM + k] = part[k];
             }
+            __threadfence();
+            __syncwarp();
+            unsigned last = 0;
+            if (lane == 0) last = (atomicAdd(&a.rbcnt[nrb + rb], 1u) == (unsigned)nseg - 1u);
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                if (j < a.N) gradient_row(a, j, nseg, with_delta);
+                if (lane == 0) a.rbcnt[nrb + rb] = 0;
+            }
         }
     }
-    // rows: combine, project, write g (and dg = g_new - g_old when with_delta)
-    static DZO_DEVINL void gradient_rows(const RieszGdArgs& a, bool with_delta) {
-        const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
-        for (int j = blockIdx.x * 1024 + threadIdx.x; j < a.N; j += gridDim.x * 1024) {
-            double acc[DIM], xj[DIM];
+    // one row: combine, project, write g (and dg = g_new - g_old when with_delta)
+    static DZO_DEVINL void gradient_row(const RieszGdArgs& a, int j, int nseg, bool with_delta) {
+        double acc[DIM], xj[DIM];
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) {
-                acc[k] = __ldcg(&a.segG[((long long)0 * a.N + j) * DIM + k]);
-                xj[k] = a.x[(long long)j * DIM + k];
-            }
-            for (int s = 1; s < nseg; ++s)
+        for (int k = 0; k < DIM; ++k) {
+            acc[k] = __ldcg(&a.segG[((long long)0 * a.N + j) * DIM + k]);
+            xj[k] = a.x[(long long)j * DIM + k];
+        }
+        for (int s = 1; s < nseg; ++s)
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) acc[k] += __ldcg(&a.segG[((long long)s * a.N + j) * DIM + k]);
-            if (a.sphere) {
-                double overlap = 0.0;
+            for (int k = 0; k < DIM; ++k) acc[k] += __ldcg(&a.segG[((long long)s * a.N + j) * DIM + k]);
+        if (a.sphere) {
+            double overlap = 0.0;
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) overlap += xj[k] * acc[k];
+            for (int k = 0; k < DIM; ++k) overlap += xj[k] * acc[k];
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) acc[k] -= overlap * xj[k];
-            }
+            for (int k = 0; k < DIM; ++k) acc[k] -= overlap * xj[k];
+        }
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) {
-                const long long e = (long long)j * DIM + k;
-                if (with_delta) a.dg[e] = acc[k] - a.g[e];                     // :433-435
-                a.g[e] = acc[k];
-            }
+        for (int k = 0; k < DIM; ++k) {
+            const long long e = (long long)j * DIM + k;
+            if (with_delta) a.dg[e] = acc[k] - a.g[e];                         // :433-435
+            a.g[e] = acc[k];
         }
     }
 
@@ -321,12 +338,12 @@ struct RieszDev {
         for (int j = threadIdx.x; j < a.N; j += 1024) {
             if (what == 0) {            // step_is_zero: all(dir == 0)  :71-85
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) bad |= !(dir[(long long)j * DIM + k] == 0.0);
+                for (int k = 0; k < DIM; ++k) bad |= !(a.dscale * dir[(long long)j * DIM + k] == 0.0);
             } else if (what == 1) {     // !point_changed: all(x == x + alpha*dir) before the constraint  :73-80
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) {
                     const double xx = a.x[(long long)j * DIM + k];
-                    bad |= (xx != xx + alpha * dir[(long long)j * DIM + k]);
+                    bad |= (xx != xx + alpha * (a.dscale * dir[(long long)j * DIM + k]));
                 }
             } else if (what == 2) {     // new_point == initial_point after the constraint  :119
                 double w[DIM];
@@ -345,7 +362,7 @@ struct RieszDev {
     }
 
     // QuadraticLineSearch (:191-216) over find_three_point_bracket (:49-172), first trial step t1
-    static DZO_DEVINL void line_search(const RieszGdArgs& a, cg::grid_group& grid, const double* dir, double f0, double t1,
+    static DZO_DEVINL void line_search(const RieszGdArgs& a, cg::grid_group& grid, int& epar, const double* dir, double f0, double t1,
                                        double sign, double* wsm, double* sm, double& t_best, double& f_best,
                                        long long& evals) {
         double x1 = 0.0, f1 = f0, x2 = 0.0, f2 = f0;
@@ -366,7 +383,7 @@ struct RieszDev {
             }
             if (capped) break;
             if (small && all_points(a, dir, sign * step, 0.0, 2)) break;       // :107-123
-            double fa = energy(a, grid, dir, sign * step, 0, wsm, sm);         // :126
+            double fa = energy(a, grid, epar, dir, sign * step, 0, wsm, sm);         // :126
             ++evals;
             if (fa <= f0) {                                                    // :130
                 int num_increases = 0;
@@ -374,7 +391,7 @@ struct RieszDev {
                 for (;;) {                                                     // :143-156
                     const double ds = step + step;
                     num_increases += 1;
-                    const double fb = energy(a, grid, dir, sign * ds, 0, wsm, sm);
+                    const double fb = energy(a, grid, epar, dir, sign * ds, 0, wsm, sm);
                     ++evals;
                     --cap;
                     if (((a.max_increases > 0) && (num_increases >= a.max_increases)) || !isfinite(fb) || fb > fa ||
@@ -389,7 +406,7 @@ struct RieszDev {
                 cap = DZO_LINESEARCH_CAP;
                 for (;;) {
                     const double hs = 0.5 * step;
-                    const double fb = energy(a, grid, dir, sign * hs, 0, wsm, sm);
+                    const double fb = energy(a, grid, epar, dir, sign * hs, 0, wsm, sm);
                     ++evals;
                     --cap;
                     if (fb <= f0 || cap == 0) {
@@ -411,7 +428,7 @@ struct RieszDev {
             const double twice_delta_1 = delta_1 + delta_1;
             const double delta_ratio = (twice_delta_1 + sum_deltas) / (sum_deltas + sum_deltas);
             const double xq = delta_ratio * x1;
-            const double fq = energy(a, grid, dir, sign * xq, 0, wsm, sm);
+            const double fq = energy(a, grid, epar, dir, sign * xq, 0, wsm, sm);
             ++evals;
             if (fq < fb) { xb = xq; fb = fq; }
         }
@@ -420,32 +437,55 @@ struct RieszDev {
     }
 };
 
+// dx . dx and g . g in one pass over the canonical tree (every CTA computes both itself)
+DZO_DEVINL void cta_tree_norms2(const double* __restrict__ v, const double* __restrict__ w, long long n, double* sm,
+                                double& vv, double& ww) {
+    double p[2][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double av = 0.0, aw = 0.0;
+        for (long long k = threadIdx.x + 1024 * q; 2 * k < n; k += DZO_TREE_WIDTH) {
+            av += v[2 * k] * v[2 * k];
+            aw += w[2 * k] * w[2 * k];
+            if (2 * k + 1 < n) {
+                av += v[2 * k + 1] * v[2 * k + 1];
+                aw += w[2 * k + 1] * w[2 * k + 1];
+            }
+        }
+        p[0][q] = av;
+        p[1][q] = aw;
+    }
+    double out[2];
+    cta1024_tree_reduce<2>(p, sm, out);
+    vv = out[0];
+    ww = out[1];
+}
+
 template <int DIM>
 static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sm = reinterpret_cast<double*>(smem_raw);          // 132 doubles: tree reduction scratch
-    double* wsm = sm + 136;                                    // 32 warps x 128 x DIM staging
+    double* sm = reinterpret_cast<double*>(smem_raw);          // 2 x 132 doubles: tree reduction scratch
+    double* wsm = sm + 272;                                    // 32 warps x 128 x DIM staging
     cg::grid_group grid = cg::this_grid();
     using R = RieszDev<DIM>;
     const long long n = (long long)a.N * DIM;
     const long long gtid = (long long)blockIdx.x * 1024 + threadIdx.x, gsize = (long long)gridDim.x * 1024;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
+    int epar = 0;                                               // energy evaluations of this launch (rowE parity)
 
     if (a.mode == 2) {                                          // dzo_dev_objective: f(x) as given
-        const double f = R::energy(a, grid, a.x, 0.0, 2, wsm, sm);
+        const double f = R::energy(a, grid, epar, a.x, 0.0, 2, wsm, sm);
         if (leader) a.fbox[1] = f;
         return;
     }
     if (a.mode == 3) {                                          // dzo_dev_gradient
-        R::gradient_segments(a, wsm);
-        grid.sync();
-        R::gradient_rows(a, false);
+        R::gradient_segments(a, wsm, false);
         return;
     }
     if (a.mode == 4) {                                          // dzo_dev_line_search
         double tb, fb;
         long long ev = 0;
-        R::line_search(a, grid, a.d, a.ls_f0, a.ls_t1, a.ls_sign, wsm, sm, tb, fb, ev);
+        R::line_search(a, grid, epar, a.d, a.ls_f0, a.ls_t1, a.ls_sign, wsm, sm, tb, fb, ev);
         if (leader) { a.fbox[1] = tb; a.fbox[2] = fb; }
         return;
     }
@@ -462,10 +502,8 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             }
         for (long long e = gtid; e < n; e += gsize) { a.dx[e] = 0.0; a.dg[e] = 0.0; }   // :777-778
         grid.sync();
-        const double f0 = R::energy(a, grid, a.x, 0.0, 2, wsm, sm);            // :772
-        R::gradient_segments(a, wsm);                                          // :775-776
-        grid.sync();
-        R::gradient_rows(a, false);
+        const double f0 = R::energy(a, grid, epar, a.x, 0.0, 2, wsm, sm);      // :772
+        R::gradient_segments(a, wsm, false);                                   // :775-776
         grid.sync();
         for (long long e = gtid; e < n; e += gsize) a.d[e] = a.g[e];           // :784 next_step_direction = copy(gradient)
         if (leader) {
@@ -491,11 +529,13 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         const long long iter0 = __ldcg(&a.bctrl->iter), calls0 = __ldcg(&a.bctrl->calls), evals0 = __ldcg(&a.bctrl->evals);
         long long evals = 0;
         grid.sync();                       // every CTA holds the control block before the leader may rewrite it
-        const double grad_norm = sqrt(cta_tree_dot(a.g, a.g, n, sm));          // :921
-        const double bfgs_norm = sqrt(cta_tree_dot(a.d, a.d, n, sm));          // :928
+        double gg, dd;
+        cta_tree_norms2(a.g, a.d, n, sm, gg, dd);
+        const double grad_norm = sqrt(gg);                                     // :921
+        const double bfgs_norm = sqrt(dd);                                     // :928
         double grad_step_length, grad_obj, bfgs_step_length, bfgs_obj;
-        R::line_search(a, grid, a.g, f0, step_length / grad_norm, -1.0, wsm, sm, grad_step_length, grad_obj, evals);  // :922-925
-        R::line_search(a, grid, a.d, f0, step_length / bfgs_norm, -1.0, wsm, sm, bfgs_step_length, bfgs_obj, evals);  // :929-932
+        R::line_search(a, grid, epar, a.g, f0, step_length / grad_norm, -1.0, wsm, sm, grad_step_length, grad_obj, evals);  // :922-925
+        R::line_search(a, grid, epar, a.d, f0, step_length / bfgs_norm, -1.0, wsm, sm, bfgs_step_length, bfgs_obj, evals);  // :929-932
         int kind;
         double alpha, fnew, Lnew;
         if (bfgs_obj < f0 && !(bfgs_obj > grad_obj)) {                         // :934
@@ -525,9 +565,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             for (int k = 0; k < DIM; ++k) a.x[(long long)j * DIM + k] = w[k];
         }
         grid.sync();                                   // every CTA is done reading the old gradient as `dir`
-        R::gradient_segments(a, wsm);                                          // :948
-        grid.sync();
-        R::gradient_rows(a, true);                                             // dg = (-g_old) + g_new  :944, :950
+        R::gradient_segments(a, wsm, true);                                    // :948, dg = (-g_old) + g_new  :944, :950
         grid.sync();
         double overlap = 0.0;
         if (kind == DZO_STEP_BFGS) {
@@ -560,10 +598,8 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             }
         for (long long e = gtid; e < n; e += gsize) { a.dx[e] = 0.0; a.dg[e] = 0.0; a.d[e] = 0.0; }
         grid.sync();
-        const double f0 = R::energy(a, grid, a.x, 0.0, 2, wsm, sm);            // :343
-        R::gradient_segments(a, wsm);                                          // :347-348
-        grid.sync();
-        R::gradient_rows(a, false);
+        const double f0 = R::energy(a, grid, epar, a.x, 0.0, 2, wsm, sm);      // :343
+        R::gradient_segments(a, wsm, false);                                   // :347-348
         grid.sync();
         const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :352
         if (isfinite(inv_gradient_norm)) {                                     // :354-357
@@ -579,25 +615,29 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         return;
     }
 
-    // ---- k step! calls  (:393-449)
+    // ---- k step! calls  (:393-449).  The scalars a step hands to the next (f, iteration count, has_terminated and the
+    // factor alpha of next_step_direction = alpha * gradient) are identical on every CTA -- they all come out of
+    // grid-wide reductions each CTA finishes itself -- so they travel in registers and the steps of one launch need no
+    // barrier between them: the next line search reads its direction as alpha * g[e] (the very product stored in d[e]).
+    int term = __ldcg(&a.ctrl->term);
+    double f0 = __ldcg(&a.ctrl->f);
+    long long iter = __ldcg(&a.ctrl->iter);
+    const double* dir = a.d;
     for (int s = 0; s < a.ksteps; ++s) {
-        grid.sync();                                   // ctrl, x, d, g of the previous step are complete
-        const int term = __ldcg(&a.ctrl->term);
         if (term) break;                                                       // :402
-        const double f0 = __ldcg(&a.ctrl->f);
-        const long long iter = __ldcg(&a.ctrl->iter);
         long long evals = 0;
         double step_size, objective_value;
         riesz_prof_mark(a, 1);
-        R::line_search(a, grid, a.d, f0, 1.0, 1.0, wsm, sm, step_size, objective_value, evals);   // :405-407
+        R::line_search(a, grid, epar, dir, f0, 1.0, 1.0, wsm, sm, step_size, objective_value, evals);   // :405-407
         riesz_prof_mark(a, 6);
         if (step_size == 0.0 || !(objective_value < f0)) {                     // :410-414
+            term = 1;
             if (leader) a.ctrl->term = 1;
-            continue;                                   // next iteration's barrier publishes the flag
+            break;
         }
         for (int j = (int)gtid; j < a.N; j += (int)gsize) {                    // :418-423
             double w[DIM];
-            R::trial_point(a, a.d, j, step_size, 0, w);                        // x += step*d ; constraint!(x)
+            R::trial_point(a, dir, j, step_size, 0, w);                        // x += step*d ; constraint!(x)
 #pragma unroll
             for (int k = 0; k < DIM; ++k) {
                 const long long e = (long long)j * DIM + k;
@@ -608,20 +648,18 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         }
         grid.sync();
         riesz_prof_mark(a, 7);
-        R::gradient_segments(a, wsm);                                          // :434
+        R::gradient_segments(a, wsm, true);                                    // :433-435
         riesz_prof_mark(a, 8);
         grid.sync();
-        riesz_prof_mark(a, 9);
-        R::gradient_rows(a, true);                                             // :433-435
-        grid.sync();
         riesz_prof_mark(a, 10);
-        const double step_length = sqrt(cta_tree_dot(a.dx, a.dx, n, sm));      // :424
-        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :438
+        double dxdx, gg;
+        cta_tree_norms2(a.dx, a.g, n, sm, dxdx, gg);
+        const double step_length = sqrt(dxdx);                                 // :424
+        const double inv_gradient_norm = 1.0 / sqrt(gg);                       // :438
         const bool ok = isfinite(inv_gradient_norm);
-        if (ok) {
-            const double alpha = -step_length * inv_gradient_norm;             // :445-446
+        const double alpha = -step_length * inv_gradient_norm;                 // :445-446
+        if (ok)
             for (long long e = gtid; e < n; e += gsize) a.d[e] = alpha * a.g[e];
-        }
         if (leader) {
             a.ctrl->iter = iter + 1;                                           // :415
             a.ctrl->L = step_length;                                           // :425
@@ -630,11 +668,16 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             a.ctrl->evals += evals;
             if (!ok) a.ctrl->term = 1;                                         // :439-442
         }
+        iter += 1;
+        f0 = objective_value;
+        if (!ok) term = 1;
+        dir = a.g;                         // d[e] == alpha * g[e] bit for bit; g is complete behind the barrier above
+        a.dscale = alpha;
         riesz_prof_mark(a, 11);
     }
 }
 
-inline size_t riesz_gd_smem(int dim) { return sizeof(double) * (136 + (size_t)kRieszSegWarps * DZO_RIESZ_SEG * dim); }
+inline size_t riesz_gd_smem(int dim) { return sizeof(double) * (272 + (size_t)kRieszSegWarps * DZO_RIESZ_SEG * dim); }
 
 // ============================================================================= Rosenbrock GD, one CTA
 struct VecGdArgs {

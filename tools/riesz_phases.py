@@ -20,9 +20,9 @@ cnt = C.c_int64()
 assert dz.lib().dzo_gd_get_phase_log(o._h, ev.ctypes.data_as(C.POINTER(C.c_uint64)), 8192, C.byref(cnt)) == 0
 ev = ev[:2 * cnt.value].reshape(-1, 2)
 names = {(1, 2): "line search bookkeeping before an energy", (5, 2): "bookkeeping between energies", (2, 3): "energy: leader's own items",
-         (3, 4): "energy: wait + barrier 1", (4, 5): "energy: rows + tree + barrier 2", (5, 6): "line search tail",
-         (6, 7): "point update + barrier", (7, 8): "gradient: leader's own items", (8, 9): "gradient: wait + barrier",
-         (9, 10): "gradient rows + barrier", (10, 11): "dots + direction", (11, 1): "step-top barrier"}
+         (3, 4): "energy: wait + barrier", (4, 5): "energy: tree over the rows (per CTA)", (5, 6): "line search tail",
+         (6, 7): "point update + barrier", (7, 8): "gradient: leader's own items", (8, 10): "gradient: wait + barrier",
+         (10, 11): "dots + direction", (11, 1): "hand-off to the next step"}
 tot, num = defaultdict(float), defaultdict(int)
 for (a, ta), (b, tb) in zip(ev[:-1], ev[1:]):
     key = (int(a), int(b))
