@@ -31,7 +31,7 @@ import numpy as np
 from . import _capi
 
 __all__ = [
-    "LBFGSOptimizer", "AdGDOptimizer", "LegacyLBFGSOptimizer",
+    "LBFGSOptimizer", "AdGDOptimizer", "LegacyLBFGSOptimizer", "LineSearchEvaluator",
     "L2RegularizationWrapper", "L2GradientWrapper", "UniformBoxConstraint", "UniformBoxGradientWrapper",
     "accelerated_pairwise_radial_energy", "accelerated_pairwise_radial_gradient_", "accelerated_pairwise_radial_hvp_",
     "BFGSOptimizer", "GradientDescentOptimizer", "QuadraticLineSearch", "step_",
@@ -788,6 +788,46 @@ class LegacyLBFGSOptimizer:
             self.close()
         except Exception:
             pass
+
+
+class LineSearchEvaluator:
+    """struct LineSearchEvaluator of the LIVE package, src/DZOptimization.jl:12-26.
+
+    ``LineSearchEvaluator(c_, f, g_, initial_point, initial_objective_value, initial_gradient, step_direction,
+    overlap)`` (:29-63); calling ``lse(step_size, compute_gradient)`` (:66-92) fills ``trial_point``,
+    ``trial_objective_value``, ``improvement_ratio`` and, with ``compute_gradient``, ``trial_gradient`` and
+    ``slope_ratio``, and returns the trial objective value.  One cluster launch per call."""
+
+    def __init__(self, constraint_function_, objective_function, gradient_function_, initial_point,
+                 initial_objective_value, initial_gradient, step_direction, overlap, device=0):
+        c = NULL_CONSTRAINT if constraint_function_ is None else constraint_function_
+        self._obj, self._cid = _resolve(objective_function, gradient_function_, c)
+        self.current_point = np.ascontiguousarray(initial_point, dtype=np.float64)
+        self.current_gradient = np.ascontiguousarray(initial_gradient, dtype=np.float64)
+        self.step_direction = np.ascontiguousarray(step_direction, dtype=np.float64)
+        if not (self.current_point.shape == self.current_gradient.shape == self.step_direction.shape):
+            raise AssertionError("point_axes == axes(initial_gradient) == axes(step_direction)")   # @assert :41-43
+        self.current_objective_value = np.array(float(initial_objective_value))
+        self.overlap = np.array(float(overlap))
+        self.trial_point = np.empty_like(self.current_point)
+        self.trial_gradient = np.empty_like(self.current_point)
+        self.trial_objective_value = np.array(np.nan)
+        self.improvement_ratio = np.array(np.nan)
+        self.slope_ratio = np.array(np.nan)
+        self._device = int(device)
+
+    def __call__(self, step_size, compute_gradient):
+        res = np.empty(3)
+        _check(lib().dzo_line_search_evaluate(self._obj, self._cid, 0, ORDER_TREE, self.current_point.size,
+                                              _dp(self.current_point), float(self.current_objective_value[()]),
+                                              _dp(self.step_direction), float(self.overlap[()]), float(step_size),
+                                              1 if compute_gradient else 0, _dp(self.trial_point),
+                                              _dp(self.trial_gradient), _dp(res), self._device))
+        self.trial_objective_value[()] = res[0]
+        self.improvement_ratio[()] = res[1]
+        if compute_gradient:
+            self.slope_ratio[()] = res[2]
+        return float(res[0])
 
 
 def step_(opt):

@@ -94,6 +94,7 @@ def bind(lib, cpu: bool):
                                    c_double_p, c_double_p, I])
     sig("line_search", [I, I, I64, I, I64, c_double_p, c_double_p, D, D, c_double_p, c_double_p] + dev)
 
+    sig("line_search_evaluate", [I, I, I64, I, I64, c_double_p, D, c_double_p, D, D, I, c_double_p, c_double_p, c_double_p] + dev)
     P = c_double_p
     sig("pairwise_energy", [I, I, I64, P, P, P, P, P] + dev)
     sig("pairwise_gradient", [I, I, I64, P, P, P, P, P, P] + dev)
@@ -144,7 +145,7 @@ class _DevAlias:
     """The header spells kernel-level CUDA entry points ``dzo_dev_<name>``; present them
     under the same short names the oracle uses (``dzo_cpu_<name>``) so bind() is uniform."""
 
-    _DEV = {"objective", "gradient", "dot", "gemv", "update_inverse_hessian", "line_search",
+    _DEV = {"objective", "gradient", "dot", "gemv", "update_inverse_hessian", "line_search", "line_search_evaluate",
             "identity", "pairwise_energy", "pairwise_gradient", "pairwise_hvp"}
 
     def __init__(self, lib):

@@ -345,3 +345,32 @@ int dzo_legacy_lbfgs_get_history(dzo_legacy_lbfgs* o, double* rho, double* alpha
     return DZO_OK;
 }
 }  // extern "C"
+
+// ============================================================================= live LineSearchEvaluator (src/DZOptimization.jl:12-92)
+extern "C" int dzo_dev_line_search_evaluate(int objective, int constraint, int64_t obj_param, int order, int64_t n,
+                                            const double* x, double f_old, const double* dir, double overlap,
+                                            double step_size, int compute_gradient, double* trial_point,
+                                            double* trial_gradient, double* results3, int device) {
+    if (!x || !dir || !trial_point || !results3 || (compute_gradient && !trial_gradient))
+        return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    DZO_TRY(check_problem(objective, constraint, obj_param, n, 1));
+    if (objective != DZO_OBJ_ROSENBROCK) return fail(DZO_ERR_UNSUPPORTED, "LineSearchEvaluator device objective: DZO_OBJ_ROSENBROCK");
+    if (order != DZO_ORDER_TREE) return fail(DZO_ERR_UNSUPPORTED, "device LineSearchEvaluator computes in DZO_ORDER_TREE");
+    DZO_TRY(use_device(device));
+    DevBuf dx, dd, dt, dg, dout;
+    const size_t vb = (size_t)n * 8;
+    DZO_TRY(dx.alloc(vb)); DZO_TRY(dd.alloc(vb)); DZO_TRY(dt.alloc(vb)); DZO_TRY(dg.alloc(vb)); DZO_TRY(dout.alloc(24));
+    DZO_CUDA(cudaMemcpy(dx.p, x, vb, cudaMemcpyHostToDevice));
+    DZO_CUDA(cudaMemcpy(dd.p, dir, vb, cudaMemcpyHostToDevice));
+    LseArgs a;
+    a.x = dx.as<double>(); a.dir = dd.as<double>(); a.trial = dt.as<double>(); a.trial_g = dg.as<double>();
+    a.out3 = dout.as<double>(); a.n = n; a.f_old = f_old; a.overlap = overlap; a.step = step_size;
+    a.compute_gradient = compute_gradient ? 1 : 0;
+    cluster_lse_kernel<<<kClusterCtas, kClusterThreads>>>(a);
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaDeviceSynchronize());
+    DZO_CUDA(cudaMemcpy(trial_point, dt.p, vb, cudaMemcpyDeviceToHost));
+    if (compute_gradient) DZO_CUDA(cudaMemcpy(trial_gradient, dg.p, vb, cudaMemcpyDeviceToHost));
+    DZO_CUDA(cudaMemcpy(results3, dout.p, 24, cudaMemcpyDeviceToHost));
+    return DZO_OK;
+}

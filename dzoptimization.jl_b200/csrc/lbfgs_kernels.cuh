@@ -298,3 +298,49 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
 }
 
 }  // namespace dzo
+
+// ============================================================================= live LineSearchEvaluator (:12-92)
+// (lse::LineSearchEvaluator)(step_size, compute_gradient)  src/DZOptimization.jl:66-92 as one cluster launch:
+// trial_point = x + step*dir (:70-71), f_new (:81), improvement_ratio (:85), and with compute_gradient the trial
+// gradient (:88) and slope_ratio = dot(trial_gradient, dir) / overlap (:89-90).  out3 = { f_new, improvement_ratio,
+// slope_ratio (NaN-free only when compute_gradient) }.
+namespace dzo {
+struct LseArgs {
+    const double *x, *dir;
+    double *trial, *trial_g, *out3;
+    long long n;
+    double f_old, overlap, step;
+    int compute_gradient;
+};
+static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
+    cluster_lse_kernel(LseArgs a) {
+    __shared__ ClusterRed R;
+    cg::cluster_group cluster = cg::this_cluster();
+    const long long m2 = a.n >> 1;
+    const long long v = (long long)cluster.block_rank() * kClusterThreads + threadIdx.x;
+    if (threadIdx.x == 0) R.parity = 0;
+    __syncthreads();
+    cluster.sync();
+    double acc = 0.0, ov = 0.0;
+    for (long long k = v; k < m2; k += DZO_TREE_WIDTH) {
+        const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+        const double2 dd = reinterpret_cast<const double2*>(a.dir)[k];
+        const double w0 = xx.x + a.step * dd.x, w1 = xx.y + a.step * dd.y;                      // :70-71 copy! + axpy!
+        reinterpret_cast<double2*>(a.trial)[k] = make_double2(w0, w1);
+        acc += RosenbrockVec::term(w0, w1);                                                     // :81
+        if (a.compute_gradient) {
+            const double2 tg = RosenbrockVec::grad(w0, w1);                                     // :88
+            reinterpret_cast<double2*>(a.trial_g)[k] = tg;
+            ov += tg.x * dd.x; ov += tg.y * dd.y;                                               // :89
+        }
+    }
+    double p[2] = {acc, ov};
+    unsigned fl = 0;
+    cluster_tree_reduce<2>(cluster, R, p, fl);
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+        a.out3[0] = p[0];
+        a.out3[1] = (p[0] - a.f_old) / (a.step * a.overlap);                                    // :85
+        a.out3[2] = a.compute_gradient ? p[1] / a.overlap : 0.0;                                // :90
+    }
+}
+}  // namespace dzo

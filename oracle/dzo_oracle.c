@@ -1438,3 +1438,34 @@ void dzo_cpu_legacy_lbfgs_destroy(dzo_cpu_legacy_lbfgs* o) {
     free(o->x); free(o->dx); free(o->g); free(o->dg); free(o->d); free(o->S); free(o->Y); free(o->scratch);
     free(o);
 }
+
+/* ======================================================================= live LineSearchEvaluator
+ * (lse::LineSearchEvaluator)(step_size, compute_gradient)  src/DZOptimization.jl:66-92.  LinearAlgebra.axpy! / dot
+ * are BLAS in the reference -> un-fused x + step*dir and dot_ here.  results3 = { f_new (:81), improvement_ratio
+ * (:85), slope_ratio (:90; 0 when compute_gradient is false -- the reference leaves the field untouched) }.
+ * A failing constraint (:72-79) cannot occur with the device objectives (NONE, or SPHERE which returns true). */
+int dzo_cpu_line_search_evaluate(int objective, int constraint, int64_t obj_param, int order, int64_t n,
+                                 const double* x, double f_old, const double* dir, double overlap, double step_size,
+                                 int compute_gradient, double* trial_point, double* trial_gradient, double* results3) {
+    if (!x || !dir || !trial_point || !results3 || (compute_gradient && !trial_gradient))
+        return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    int rc = check_problem(objective, constraint, obj_param, n, 1);
+    if (rc) return rc;
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    problem_t P = {objective, constraint, order, n, obj_param > 0 ? obj_param : 1, 0, 0.0, 0.0, 0.0};
+    for (int64_t i = 0; i < n; ++i) trial_point[i] = x[i];                              /* :70 copy! */
+    for (int64_t i = 0; i < n; ++i) trial_point[i] += step_size * dir[i];               /* :71 axpy! */
+    if (!constraint_(&P, trial_point)) {                                                /* :72-79 */
+        results3[0] = INFINITY; results3[1] = -INFINITY; results3[2] = INFINITY;
+        return DZO_OK;
+    }
+    const double f_new = objective_(&P, trial_point);                                   /* :81 */
+    results3[0] = f_new;
+    results3[1] = (f_new - f_old) / (step_size * overlap);                              /* :85 */
+    results3[2] = 0.0;
+    if (compute_gradient) {
+        gradient_(&P, trial_gradient, trial_point);                                     /* :88 */
+        results3[2] = dot_(order, trial_gradient, dir, n) / overlap;                    /* :89-90 */
+    }
+    return DZO_OK;
+}

@@ -826,3 +826,21 @@ class LegacyLBFGSOptimizer:
             d = [a * gi for gi in g]
         self.next_step_direction = d
         return self
+
+
+# ------------------------------------------------------------------ live LineSearchEvaluator (src/DZOptimization.jl:12-92)
+def live_line_search_evaluate(fn, x, f_old, direction, overlap, step_size, compute_gradient, tree=True):
+    """(lse)(step_size, compute_gradient) :66-92 -> (trial_point, trial_gradient | None, f_new, improvement_ratio, slope_ratio | None)"""
+    trial = list(x)
+    for i in range(len(trial)):
+        trial[i] += step_size * direction[i]
+    if not fn.constraint(trial):
+        return trial, None, INF, -INF, INF
+    f_new = fn.f(trial)
+    improvement_ratio = _div(f_new - f_old, step_size * overlap)
+    if not compute_gradient:
+        return trial, None, f_new, improvement_ratio, None
+    tg = [0.0] * len(trial)
+    fn.g(tg, trial)
+    slope_ratio = _div(dot(tg, direction, tree), overlap)
+    return trial, tg, f_new, improvement_ratio, slope_ratio

@@ -403,3 +403,15 @@ class LegacyLBFGS:
             self.close()
         except Exception:
             pass
+
+
+def line_search_evaluate(objective, x, f_old, direction, overlap, step_size, compute_gradient, order=TREE):
+    """live LineSearchEvaluator call (src/DZOptimization.jl:66-92) -> (trial_point, trial_gradient | None,
+    (f_new, improvement_ratio, slope_ratio))"""
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    d = np.ascontiguousarray(direction, dtype=np.float64).reshape(-1)
+    tp, tg, res = np.empty(x.size), np.empty(x.size), np.empty(3)
+    _check(lib().dzo_cpu_line_search_evaluate(objective, CONSTRAINT_NONE, 0, order, x.size, _dp(x), float(f_old), _dp(d),
+                                              float(overlap), float(step_size), 1 if compute_gradient else 0, _dp(tp),
+                                              _dp(tg), _dp(res)))
+    return tp, (tg if compute_gradient else None), res

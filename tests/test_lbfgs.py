@@ -129,3 +129,49 @@ def test_gpu_adgd_trace(gpu, orc, n):
     opt.step(200); ref.step(200)
     compare("fused")
     assert float(opt.current_objective_value[()]) < orc.objective(ROSEN, x0, orc.TREE)[0]
+
+
+# ----------------------------------------------------------------------------- live LineSearchEvaluator (:12-92)
+@pytest.mark.parametrize("n,tree", [(2, False), (10, True), (64, True)])
+def test_line_search_evaluator_c_oracle_equals_python_restatement(orc, n, tree):
+    import dzo_oracle_py as P
+    x = _x0(orc, n, 9)
+    fn = P.Rosenbrock(tree)
+    g = [0.0] * n
+    fn.g(g, list(x))
+    d = -np.array(g)
+    order = orc.TREE if tree else orc.SEQ
+    f_old = fn.f(list(x))
+    overlap = P.dot(g, list(d), tree)
+    for step, cg in ((1e-3, True), (1e-4, False), (0.5, True)):
+        tp, tg, res = orc.line_search_evaluate(ROSEN, x, f_old, d, overlap, step, cg, order)
+        ptp, ptg, pf, pir, psr = P.live_line_search_evaluate(fn, list(x), f_old, list(d), overlap, step, cg, tree)
+        assert_bitwise(tp, np.array(ptp), "trial point")
+        assert res[0] == pf and res[1] == pir
+        if cg:
+            assert_bitwise(tg, np.array(ptg), "trial gradient")
+            assert res[2] == psr
+    # a small step along -g decreases f: Armijo ratio in (0, 1], curvature ratio below 1
+    tp, tg, res = orc.line_search_evaluate(ROSEN, x, f_old, d, overlap, 1e-6, True, order)
+    assert 0.0 < res[1] <= 1.0 + 1e-6 and res[2] < 1.0 + 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 34, 4096, 20000])
+def test_gpu_line_search_evaluator(gpu, orc, n):
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x = _x0(orc, n, 9)
+    g = orc.gradient(ROSEN, x[None, :], orc.TREE)[0]
+    f_old = orc.objective(ROSEN, x[None, :], orc.TREE)[0]
+    d = -g
+    overlap = float(orc.dot(g, d, orc.TREE))
+    lse = dz.LineSearchEvaluator(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x, f_old, g, d, overlap)
+    for step, cg in ((1e-3, True), (1e-4, False), (0.5, True), (0.0, True)):
+        f_new = lse(step, cg)
+        tp, tg, res = orc.line_search_evaluate(ROSEN, x, f_old, d, overlap, step, cg, orc.TREE)
+        assert_bitwise(lse.trial_point, tp, f"step {step}: trial point")
+        assert_bitwise([f_new, float(lse.improvement_ratio[()])], res[:2], f"step {step}: f_new, improvement_ratio")
+        if cg:
+            assert_bitwise(lse.trial_gradient, tg, f"step {step}: trial gradient")
+            assert_bitwise(float(lse.slope_ratio[()]), res[2], f"step {step}: slope_ratio")
