@@ -40,7 +40,8 @@ __all__ = [
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "csrc", "libdzopt_b200.so")
+#: DZOPT_B200_LIB selects another build of the same library (A/B measurements of compile-time variants)
+lib_path = os.environ.get("DZOPT_B200_LIB") or os.path.join(_HERE, "csrc", "libdzopt_b200.so")
 _lib = None
 
 # include/dzopt.h constants

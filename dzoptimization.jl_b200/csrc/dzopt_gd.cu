@@ -28,6 +28,7 @@ struct dzo_gd {
     int n_e_items = 0;
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
+    int esplit = 2, gcnt_off = 0;
     unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
     int grid = 0;
 };
@@ -53,15 +54,15 @@ static int dmalloc(T** p, size_t count) {
     return DZO_OK;
 }
 
-// (row block of 32 rows, segment of 128 sources) items that contain at least one pair i < j,
+// (row block of `rows` rows, segment of 128 sources) items that contain at least one pair i < j,
 // heaviest first so the round-robin over warps stays balanced
-static std::vector<int2> energy_items(int N) {
+static std::vector<int2> energy_items(int N, int rows) {
     std::vector<int2> full, diag;
-    const int nrb = (N + 31) / 32;
+    const int nrb = (N + rows - 1) / rows;
     for (int rb = 0; rb < nrb; ++rb) {
-        const int jmax = std::min(N, rb * 32 + 32) - 1;
+        const int jmax = std::min(N, rb * rows + rows) - 1;
         for (int s = 0; s * DZO_RIESZ_SEG < jmax; ++s) {
-            const bool whole = (s + 1) * DZO_RIESZ_SEG <= rb * 32;
+            const bool whole = (s + 1) * DZO_RIESZ_SEG <= rb * rows;
             (whole ? full : diag).push_back(make_int2(rb, s));
         }
     }
@@ -86,6 +87,7 @@ struct RieszWork {
     int n_e_items = 0;
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
+    int esplit = 2, gcnt_off = 0;
     int grid = 0;
     void* kernel = nullptr;
     size_t smem = 0;
@@ -96,14 +98,15 @@ struct RieszWork {
         DZO_TRY(dmalloc(&segE, (size_t)nseg * N));
         DZO_TRY(dmalloc(&rowE, (size_t)2 * N));              // double-buffered by evaluation parity
         DZO_CUDA(cudaMemset(rowE, 0, (size_t)2 * N * sizeof(double)));
-        const int nrb = (N + 31) / 32;
-        DZO_TRY(dmalloc(&rbcnt, (size_t)2 * nrb));           // items finished per row block: energy | gradient
-        DZO_CUDA(cudaMemset(rbcnt, 0, (size_t)2 * nrb * sizeof(unsigned)));
+        esplit = (g_tuning.riesz_esplit == 2) ? 2 : 1;   // measured: 2 lanes per row is 11 % slower (the loops are issue-bound, not latency-bound)
+        gcnt_off = (N + 15) / 16;
+        DZO_TRY(dmalloc(&rbcnt, (size_t)2 * gcnt_off));      // items finished per row block: energy | gradient
+        DZO_CUDA(cudaMemset(rbcnt, 0, (size_t)2 * gcnt_off * sizeof(unsigned)));
         DZO_TRY(dmalloc(&segG, (size_t)nseg * N * dim));
         DZO_TRY(dmalloc(&fbox, 4));
         DZO_TRY(dmalloc(&counter, 1));
         DZO_CUDA(cudaMemset(counter, 0, sizeof(unsigned)));
-        std::vector<int2> items = energy_items(N);
+        std::vector<int2> items = energy_items(N, esplit == 2 ? 16 : 32);
         n_e_items = (int)items.size();
         DZO_TRY(dmalloc(&e_items, items.size()));
         if (!items.empty())
@@ -127,7 +130,7 @@ struct RieszWork {
     }
     void fill(RieszGdArgs& a) const {
         a.segE = segE; a.rowE = rowE; a.segG = segG; a.e_items = e_items; a.n_e_items = n_e_items;
-        a.counter = counter; a.fbox = fbox; a.rbcnt = rbcnt; a.dscale = 1.0;
+        a.counter = counter; a.fbox = fbox; a.rbcnt = rbcnt; a.dscale = 1.0; a.esplit = esplit; a.gcnt_off = gcnt_off;
     }
     int launch(RieszGdArgs& a, cudaStream_t stream) const {
         void* params[] = {&a};
@@ -141,7 +144,7 @@ static RieszGdArgs riesz_args(const dzo_gd* o, int mode, int k) {
     memset(&a, 0, sizeof a);
     a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg;
     a.segE = o->segE; a.rowE = o->rowE; a.segG = o->segG; a.e_items = o->e_items; a.n_e_items = o->n_e_items;
-    a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox; a.rbcnt = o->rbcnt; a.dscale = 1.0;
+    a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox; a.rbcnt = o->rbcnt; a.dscale = 1.0; a.esplit = o->esplit; a.gcnt_off = o->gcnt_off;
     a.N = (int)(o->n / o->dim); a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.max_increases = o->max_increases;
     a.ksteps = k; a.mode = mode;
     return a;
@@ -214,7 +217,7 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         RieszWork w;
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
-        o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->grid = w.grid;
+        o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->esplit = w.esplit; o->gcnt_off = w.gcnt_off; o->grid = w.grid;
     }
     if (cudaMemcpyAsync(o->x, x0, nb * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)   // :339 collect
         return bail(fail(DZO_ERR_CUDA, "H2D copy of x0 failed"));

@@ -44,6 +44,8 @@ struct RieszGdArgs {
     GdCtrl* ctrl;
     unsigned* counter;            // (unused by the kernel since the row sums moved into the segment phase)
     double* fbox;                 // result slots of the kernel-level modes 2 and 4
+    int esplit;                   // 1: energy items of 32 rows x 128 sources, one lane per row; 2: 16 rows, two lanes per row
+    int gcnt_off;                 // offset of the gradient counters inside rbcnt
     double dscale;                // the direction actually used is dscale * dir[e] (1.0, or alpha with dir = g: see mode 0)
     int N, sphere, max_increases, ksteps;
     double initial_step_length;
@@ -75,8 +77,14 @@ DZO_DEVINL void riesz_prof_mark(const RieszGdArgs& a, int id) {
 }
 
 constexpr int kRieszSegWarps = 32;   // warps per CTA, each with a private staging buffer
-constexpr int kRieszBatch = 4;       // energy pair terms whose sqrt / reciprocal chains run interleaved
-constexpr int kRieszGradBatch = 2;   // same for the gradient (sqrt, reciprocal, division per term)
+#ifndef DZO_RIESZ_BATCH
+#define DZO_RIESZ_BATCH 4
+#endif
+#ifndef DZO_RIESZ_GRAD_BATCH
+#define DZO_RIESZ_GRAD_BATCH 2
+#endif
+constexpr int kRieszBatch = DZO_RIESZ_BATCH;            // energy pair terms whose sqrt / reciprocal chains run interleaved
+constexpr int kRieszGradBatch = DZO_RIESZ_GRAD_BATCH;   // same for the gradient (sqrt, reciprocal, division per term)
 
 template <int DIM>
 struct RieszDev {
@@ -187,6 +195,95 @@ struct RieszDev {
         }
     }
 
+    // Two lanes per row (esplit = 2): an item is 16 rows x 128 sources; lane l < 16 takes the even sources of row l,
+    // lane l + 16 the odd ones, kRieszBatch terms each per round, and lane l adds the 2*kRieszBatch values in source
+    // order (the odd ones arrive by shuffle).  Twice as many items as with one lane per row, so nearly every warp of
+    // the grid has one (2112 -> 4224 items for 4736 warps at N = 4096) and the serial chain per lane halves.
+    static DZO_DEVINL void energy_segments_split(const RieszGdArgs& a, const double* dir, double alpha, int pmode, int par,
+                                                 double* wsm) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int half = lane >> 4;
+        double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
+        for (int idx = blockIdx.x + gridDim.x * warp; idx < a.n_e_items; idx += gridDim.x * kRieszSegWarps) {
+            const int2 it = a.e_items[idx];                  // (16-row block, segment)
+            const int i0 = it.y * DZO_RIESZ_SEG;
+            const int cnt = min(DZO_RIESZ_SEG, a.N - i0);
+            __syncwarp();
+            for (int q = lane; q < cnt; q += 32) {
+                double w[DIM];
+                trial_point(a, dir, i0 + q, alpha, pmode, w);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) buf[q * DIM + k] = w[k];
+            }
+            __syncwarp();
+            const int j = it.x * 16 + (lane & 15);
+            const int lim = (j < a.N) ? max(0, min(cnt, j - i0)) : 0;   // sources i < j inside this segment
+            const int lim_max = __reduce_max_sync(0xffffffffu, lim);
+            double wj[DIM];
+            if (j < a.N) trial_point(a, dir, j, alpha, pmode, wj);
+            else {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) wj[k] = 0.0;
+            }
+            double seg = 0.0;
+            for (int base = 0; base < lim_max; base += 2 * kRieszBatch) {
+                double ds[kRieszBatch], t[kRieszBatch];
+                bool safe = true;
+#pragma unroll
+                for (int u = 0; u < kRieszBatch; ++u) {
+                    const int i = base + 2 * u + half;
+                    double dist_sq = 0.0;
+                    if (i < lim) {
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) {
+                            const double dist = buf[i * DIM + k] - wj[k];         // points[k,i] - points[k,j]  :37
+                            dist_sq += dist * dist;
+                        }
+                    } else {
+                        dist_sq = 1.0;                                            // placeholder, never added
+                    }
+                    ds[u] = dist_sq;
+                    safe &= ieee_fast_safe(dist_sq);
+                }
+                if (safe) {
+#pragma unroll
+                    for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_rsqrt_operators(ds[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < kRieszBatch; ++u) {
+                    const double odd = __shfl_down_sync(0xffffffffu, t[u], 16);
+                    if (base + 2 * u < lim) seg += t[u];                          // rsqrt(dist_sq)  :41 (even source)
+                    if (base + 2 * u + 1 < lim) seg += odd;                       //                     (odd source)
+                }
+            }
+            if (half == 0 && lim > 0) a.segE[(long long)it.y * a.N + j] = seg;
+            __threadfence();
+            __syncwarp();
+            unsigned last = 0;
+            if (lane == 0) {
+                const int jmax = min(a.N, it.x * 16 + 16) - 1;
+                const unsigned expected = (unsigned)((jmax + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG);
+                last = (atomicAdd(&a.rbcnt[it.x], 1u) == expected - 1u);
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                if (half == 0 && j < a.N) {
+                    double ej = 0.0;
+                    for (int s0 = 0; s0 < j; s0 += DZO_RIESZ_SEG) {
+                        const double sg = __ldcg(&a.segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
+                        ej = (s0 == 0) ? sg : ej + sg;
+                    }
+                    a.rowE[(long long)par * a.N + j] = ej;
+                }
+                if (lane == 0) a.rbcnt[it.x] = 0;
+            }
+        }
+    }
+
     // phase 2 (after ONE grid barrier): every CTA runs the canonical tree over the row energies itself (32 KB from L2
     // at N = 4096), so the value is identical on every thread of the grid without a broadcast or a second barrier.
     static DZO_DEVINL double energy_finish(const RieszGdArgs& a, int par, double* sm) {
@@ -210,7 +307,8 @@ struct RieszDev {
         const int par = epar & 1;
         epar += 1;
         riesz_prof_mark(a, 2);
-        energy_segments(a, dir, alpha, pmode, par, wsm);
+        if (a.esplit == 2) energy_segments_split(a, dir, alpha, pmode, par, wsm);
+        else energy_segments(a, dir, alpha, pmode, par, wsm);
         riesz_prof_mark(a, 3);
         grid.sync();
         riesz_prof_mark(a, 4);
@@ -297,12 +395,12 @@ struct RieszDev {
             __threadfence();
             __syncwarp();
             unsigned last = 0;
-            if (lane == 0) last = (atomicAdd(&a.rbcnt[nrb + rb], 1u) == (unsigned)nseg - 1u);
+            if (lane == 0) last = (atomicAdd(&a.rbcnt[a.gcnt_off + rb], 1u) == (unsigned)nseg - 1u);
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {
                 __threadfence();
                 if (j < a.N) gradient_row(a, j, nseg, with_delta);
-                if (lane == 0) a.rbcnt[nrb + rb] = 0;
+                if (lane == 0) a.rbcnt[a.gcnt_off + rb] = 0;
             }
         }
     }
@@ -622,6 +720,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
     int term = __ldcg(&a.ctrl->term);
     double f0 = __ldcg(&a.ctrl->f);
     long long iter = __ldcg(&a.ctrl->iter);
+    long long evals_total = __ldcg(&a.ctrl->evals);
     const double* dir = a.d;
     for (int s = 0; s < a.ksteps; ++s) {
         if (term) break;                                                       // :402
@@ -665,9 +764,10 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             a.ctrl->L = step_length;                                           // :425
             a.ctrl->df = objective_value - f0;                                 // :428-429
             a.ctrl->f = objective_value;                                       // :430
-            a.ctrl->evals += evals;
+            a.ctrl->evals = evals_total + evals;
             if (!ok) a.ctrl->term = 1;                                         // :439-442
         }
+        evals_total += evals;
         iter += 1;
         f0 = objective_value;
         if (!ok) term = 1;
