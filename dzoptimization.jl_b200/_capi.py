@@ -117,6 +117,7 @@ def bind(lib, cpu: bool):
         sig("lbfgs_set_stream", [H, C.c_void_p])
         sig("lbfgs_step_async", [H, I])
         sig("lbfgs_sync", [H])
+        sig("lbfgs_info", [H, c_i64_p, c_int_p, c_int_p])
         sig("legacy_lbfgs_set_stream", [H, C.c_void_p])
         sig("legacy_lbfgs_step_async", [H, I])
         sig("legacy_lbfgs_sync", [H])

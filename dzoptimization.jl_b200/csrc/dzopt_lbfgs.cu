@@ -2,6 +2,7 @@
 #include <new>
 
 #include "host_common.h"
+#include "grid_lbfgs.cuh"
 #include "legacy_lbfgs.cuh"
 
 using namespace dzo;
@@ -13,12 +14,17 @@ struct dzo_lbfgs {
     int m = 0;
     double *x = nullptr, *dx = nullptr, *g = nullptr, *dg = nullptr, *d = nullptr, *S = nullptr, *Y = nullptr;
     LbfgsCtrl* ctrl = nullptr;
+    // n > DZO_TREE_BLOCK: cooperative grid of clusters, one cluster per block (grid_lbfgs.cuh)
+    bool use_grid = false;
+    int nblocks = 0, nclusters = 0;
+    double* part = nullptr;
+    unsigned* fpart = nullptr;
 };
 
 static void free_lbfgs(dzo_lbfgs* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->d, o->S, o->Y, o->ctrl};
+    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->d, o->S, o->Y, o->ctrl, o->part, o->fpart};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
@@ -26,6 +32,24 @@ static void free_lbfgs(dzo_lbfgs* o) {
 }
 
 static int lbfgs_launch(dzo_lbfgs* o, int mode, int k, double L0) {
+    if (o->use_grid) {
+        GridLbfgsArgs g;
+        g.x = o->x; g.dx = o->dx; g.g = o->g; g.dg = o->dg; g.d = o->d; g.S = o->S; g.Y = o->Y; g.ctrl = o->ctrl;
+        g.part = o->part; g.fpart = o->fpart; g.n = o->n; g.m = o->m; g.ksteps = k; g.nblocks = o->nblocks;
+        g.mode = mode; g.initial_step_length = L0;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)(o->nclusters * kClusterCtas));
+        cfg.blockDim = dim3(kClusterThreads);
+        cfg.stream = o->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_lbfgs_kernel, g));
+        return DZO_OK;
+    }
     LbfgsArgs a;
     a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.d = o->d; a.S = o->S; a.Y = o->Y; a.ctrl = o->ctrl;
     a.n = o->n; a.m = o->m; a.ksteps = k; a.initial_step_length = L0; a.mode = mode;
@@ -64,6 +88,27 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         cudaMemsetAsync(o->S, 0, vb * history_length, o->stream) != cudaSuccess ||
         cudaMemsetAsync(o->Y, 0, vb * history_length, o->stream) != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "initial copies failed"));
+    if (n > DZO_TREE_BLOCK) {
+        // one cluster per block of DZO_TREE_BLOCK elements, as many clusters as are co-resident (cooperative launch)
+        o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(kClusterCtas * 64);
+        cfg.blockDim = dim3(kClusterThreads);
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, grid_lbfgs_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+            cudaGetLastError();
+            return bail(fail(DZO_ERR_CUDA, "no co-resident clusters for the grid-wide L-BFGS kernel"));
+        }
+        o->nclusters = o->nblocks < max_clusters ? o->nblocks : max_clusters;
+        if (o->nblocks > kGridMaxBlocks || o->nblocks > kGridOwn * o->nclusters)
+            return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d blocks; the grid-wide L-BFGS kernel holds at most %d",
+                             (long long)n, o->nblocks, kGridOwn * o->nclusters));
+        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * 3 * kGridMaxBlocks) != cudaSuccess ||
+            cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxBlocks) != cudaSuccess)
+            return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+        o->use_grid = true;
+    }
     int rc = lbfgs_launch(o, 1, 0, initial_step_length);
     if (rc) return bail(rc);
     if (cudaStreamSynchronize(o->stream) != cudaSuccess)
@@ -130,6 +175,13 @@ DZO_LB_SCALAR(dzo_lbfgs_get_iteration_count, int64_t, c.iter)
 DZO_LB_SCALAR(dzo_lbfgs_get_stuck, uint8_t, c.stuck != 0)
 #undef DZO_LB_SCALAR
 
+int dzo_lbfgs_info(dzo_lbfgs* o, int64_t* n, int* order, int* clusters) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    if (n) *n = o->n;
+    if (order) *order = DZO_ORDER_TREE_BLOCKED;          // == DZO_ORDER_TREE for n <= DZO_TREE_BLOCK
+    if (clusters) *clusters = o->use_grid ? o->nclusters : 1;
+    return DZO_OK;
+}
 int dzo_lbfgs_get_rho_history(dzo_lbfgs* o, int64_t* count, double* rho) {
     if (!o || !count || !rho) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     LbfgsCtrl c;

@@ -535,23 +535,31 @@ struct RieszDev {
     }
 };
 
-// dx . dx and g . g in one pass over the canonical tree (every CTA computes both itself)
+// dx . dx and g . g in one pass over the canonical tree (every CTA computes both itself).  The loop runs over rounds
+// of 4096 pairs with the four virtual threads of a thread side by side, so the 16 loads of a round are in flight
+// together (two L2 round trips at n = 12288 instead of six); each accumulator still sees its pairs in ascending order.
 DZO_DEVINL void cta_tree_norms2(const double* __restrict__ v, const double* __restrict__ w, long long n, double* sm,
                                 double& vv, double& ww) {
     double p[2][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        double av = 0.0, aw = 0.0;
-        for (long long k = threadIdx.x + 1024 * q; 2 * k < n; k += DZO_TREE_WIDTH) {
-            av += v[2 * k] * v[2 * k];
-            aw += w[2 * k] * w[2 * k];
-            if (2 * k + 1 < n) {
-                av += v[2 * k + 1] * v[2 * k + 1];
-                aw += w[2 * k + 1] * w[2 * k + 1];
-            }
+    for (int q = 0; q < 4; ++q) { p[0][q] = 0.0; p[1][q] = 0.0; }
+    for (long long base = 0; 2 * base < n; base += DZO_TREE_WIDTH) {
+        double a0[4], a1[4], b0[4], b1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long k = base + threadIdx.x + 1024 * q;
+            const bool in0 = 2 * k < n, in1 = 2 * k + 1 < n;
+            a0[q] = in0 ? v[2 * k] : 0.0;
+            b0[q] = in0 ? w[2 * k] : 0.0;
+            a1[q] = in1 ? v[2 * k + 1] : 0.0;
+            b1[q] = in1 ? w[2 * k + 1] : 0.0;
         }
-        p[0][q] = av;
-        p[1][q] = aw;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long k = base + threadIdx.x + 1024 * q;
+            if (2 * k < n) { p[0][q] += a0[q] * a0[q]; p[1][q] += b0[q] * b0[q]; }
+            if (2 * k + 1 < n) { p[0][q] += a1[q] * a1[q]; p[1][q] += b1[q] * b1[q]; }
+        }
     }
     double out[2];
     cta1024_tree_reduce<2>(p, sm, out);

@@ -21,6 +21,8 @@ struct LbfgsCtrl {
     int pad;
     double rho[DZO_LBFGS_MAX_HISTORY];       // rho_history, PHYSICAL slots       :342
     long long evals;
+    double yy;                               // grid-wide kernel only: dot(y, y) of the newest history entry (:443), computed
+                                             // in the accept pass that wrote y -- the same sum the next step! would redo
 };
 
 struct LbfgsArgs {

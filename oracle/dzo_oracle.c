@@ -90,6 +90,18 @@ static double dot_(int order, const double* v, const double* w, int64_t n) {
         return result;
     }
     double p[DZO_TREE_WIDTH];
+    if (order == DZO_ORDER_TREE_BLOCKED) { /* blocks of DZO_TREE_BLOCK elements, block results added in ascending order */
+        double total = 0.0;
+        for (int64_t b0 = 0; b0 < n || b0 == 0; b0 += DZO_TREE_BLOCK) {
+            const int64_t b1 = (b0 + DZO_TREE_BLOCK < n) ? b0 + DZO_TREE_BLOCK : n;
+            for (int i = 0; i < DZO_TREE_WIDTH; ++i) p[i] = 0.0;
+            for (int64_t e = b0; e < b1; ++e) p[((e - b0) >> 1) & (DZO_TREE_WIDTH - 1)] += v[e] * w[e];
+            const double t = tree_combine(p);
+            total = (b0 == 0) ? t : total + t;
+            if (n == 0) break;
+        }
+        return total;
+    }
     for (int i = 0; i < DZO_TREE_WIDTH; ++i) p[i] = 0.0;
     for (int64_t e = 0; e < n; ++e) p[(e >> 1) & (DZO_TREE_WIDTH - 1)] += v[e] * w[e];
     return tree_combine(p);
@@ -192,6 +204,19 @@ static double base_objective_(const problem_t* P, const double* x) {
             return result;
         }
         double p[DZO_TREE_WIDTH];
+        if (P->order == DZO_ORDER_TREE_BLOCKED) { /* blocks of DZO_TREE_BLOCK / 2 pairs */
+            const int64_t pb = DZO_TREE_BLOCK / 2;
+            double total = 0.0;
+            for (int64_t k0 = 0; k0 < m || k0 == 0; k0 += pb) {
+                const int64_t k1 = (k0 + pb < m) ? k0 + pb : m;
+                for (int i = 0; i < DZO_TREE_WIDTH; ++i) p[i] = 0.0;
+                for (int64_t k = k0; k < k1; ++k) p[(k - k0) & (DZO_TREE_WIDTH - 1)] += rosen_term(x[2 * k], x[2 * k + 1]);
+                const double t = tree_combine(p);
+                total = (k0 == 0) ? t : total + t;
+                if (m == 0) break;
+            }
+            return total;
+        }
         for (int i = 0; i < DZO_TREE_WIDTH; ++i) p[i] = 0.0;
         for (int64_t k = 0; k < m; ++k) p[k & (DZO_TREE_WIDTH - 1)] += rosen_term(x[2 * k], x[2 * k + 1]);
         return tree_combine(p);
@@ -1031,7 +1056,7 @@ int dzo_cpu_lbfgs_create(dzo_cpu_lbfgs** out, int objective, int constraint, int
     if (rc) return rc;
     if (history_length < 1 || history_length > DZO_LBFGS_MAX_HISTORY) return fail(DZO_ERR_INVALID_ARGUMENT, "history_length must be in [1, 64]");
     if (!(initial_step_length > 0.0)) return fail(DZO_ERR_INVALID_ARGUMENT, "initial_step_length must be positive"); /* :375 */
-    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE && order != DZO_ORDER_TREE_BLOCKED) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
     dzo_cpu_lbfgs* o = (dzo_cpu_lbfgs*)calloc(1, sizeof *o);
     if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
     o->P.objective = objective; o->P.constraint = constraint; o->P.order = order; o->P.n = n;

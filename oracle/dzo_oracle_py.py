@@ -44,13 +44,31 @@ def _tree_combine(p):
     return p[0]
 
 
-def ksum(terms, tree, owner=lambda k: k):
-    """Sum an iterable of terms: left-to-right (legacy/Kernels.jl:12-20) or canonical tree."""
+TREE_BLOCK = 65536
+BLOCKED = 2   # tree == BLOCKED: DZO_ORDER_TREE_BLOCKED (include/dzopt.h)
+
+
+def ksum(terms, tree, owner=lambda k: k, block_terms=TREE_BLOCK):
+    """Sum an iterable of terms: left-to-right (legacy/Kernels.jl:12-20), canonical tree, or -- tree == BLOCKED --
+    canonical tree per block of `block_terms` consecutive terms with the block results added in ascending order."""
     if not tree:
         r = 0.0
         for t in terms:
             r += t
         return r
+    if tree == BLOCKED and tree is not True:
+        total, p, filled, first = 0.0, [0.0] * TREE_WIDTH, 0, True
+        for t in terms:
+            p[owner(filled) % TREE_WIDTH] += t
+            filled += 1
+            if filled == block_terms:
+                b = _tree_combine(p)
+                total = b if first else total + b
+                first, p, filled = False, [0.0] * TREE_WIDTH, 0
+        if filled or first:
+            b = _tree_combine(p)
+            total = b if first else total + b
+        return total
     p = [0.0] * TREE_WIDTH
     for k, t in enumerate(terms):
         p[owner(k) % TREE_WIDTH] += t
@@ -58,7 +76,7 @@ def ksum(terms, tree, owner=lambda k: k):
 
 
 def dot(v, w, tree=False):
-    return ksum((a * b for a, b in zip(v, w)), tree, owner=lambda e: e // 2)
+    return ksum((a * b for a, b in zip(v, w)), tree, owner=lambda e: e // 2, block_terms=TREE_BLOCK)
 
 
 def norm2(x, tree=False):
@@ -97,7 +115,7 @@ class Rosenbrock:
             t1 = 1 - x
             t2 = y - x * x
             return t1 * t1 + 100 * (t2 * t2)
-        return ksum((term(k) for k in range(len(v) // 2)), self.tree)
+        return ksum((term(k) for k in range(len(v) // 2)), self.tree, block_terms=TREE_BLOCK // 2)
 
     def g(self, g, v):
         for k in range(len(v) // 2):

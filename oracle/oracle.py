@@ -21,7 +21,7 @@ _spec.loader.exec_module(_capi)
 
 OBJ_ROSENBROCK, OBJ_RIESZ = 1, 2
 CONSTRAINT_NONE, CONSTRAINT_SPHERE = 0, 1
-SEQ, TREE = 0, 1
+SEQ, TREE, TREE_BLOCKED = 0, 1, 2
 
 _lib = None
 

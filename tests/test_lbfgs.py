@@ -175,3 +175,69 @@ def test_gpu_line_search_evaluator(gpu, orc, n):
         if cg:
             assert_bitwise(lse.trial_gradient, tg, f"step {step}: trial gradient")
             assert_bitwise(float(lse.slope_ratio[()]), res[2], f"step {step}: slope_ratio")
+
+
+# ----------------------------------------------------------------------------- DZO_ORDER_TREE_BLOCKED (n > 65536)
+def test_blocked_order_is_the_tree_order_up_to_one_block(orc):
+    import ctypes as C
+    x, y = _x0(orc, 70000, 11), _x0(orc, 70000, 12)
+    out = C.c_double()
+    for n in (2, 4097, 65536):
+        orc.lib().dzo_cpu_dot(orc.TREE_BLOCKED, n, orc._dp(x), orc._dp(y), C.byref(out))
+        assert out.value == float(orc.dot(x[:n], y[:n], orc.TREE))
+        assert orc.objective(ROSEN, x[None, :n - n % 2], orc.TREE_BLOCKED)[0] == orc.objective(ROSEN, x[None, :n - n % 2], orc.TREE)[0]
+    # above one block: block results added in ascending order (checked against a numpy-free restatement)
+    import dzo_oracle_py as P
+    orc.lib().dzo_cpu_dot(orc.TREE_BLOCKED, 70000, orc._dp(x), orc._dp(y), C.byref(out))
+    assert out.value == P.dot(list(x), list(y), P.BLOCKED)
+    b0 = float(orc.dot(x[:65536], y[:65536], orc.TREE)); b1 = float(orc.dot(x[65536:], y[65536:], orc.TREE))
+    assert out.value == b0 + b1
+    assert orc.objective(ROSEN, x[None, :], orc.TREE_BLOCKED)[0] == P.Rosenbrock(P.BLOCKED).f(list(x))
+
+
+def test_lbfgs_blocked_c_oracle_equals_python_restatement(orc):
+    import dzo_oracle_py as P
+    n = 65536 + 40
+    x0 = _x0(orc, n, 3)
+    py = P.LiveLBFGSOptimizer(P.Rosenbrock(P.BLOCKED), list(x0), 0.5, 2, P.BLOCKED)
+    c = orc.LBFGS(ROSEN, x0, 0.5, 2, orc.TREE_BLOCKED)
+    for it in range(3):
+        py.step(); c.step(1)
+        assert_bitwise(c.point, np.array(py.current_point), f"iter {it} point")
+        assert_bitwise(c.direction, np.array(py.step_direction), f"iter {it} direction")
+        assert c.objective == py.current_objective_value
+        assert_bitwise(c.rho_history, np.array(py.rho), "rho history")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(65538, 2), (131072, 3), (200000, 5), (1 << 20, 10)])
+def test_gpu_lbfgs_grid_wide_trace(gpu, orc, n, m):
+    """n > DZO_TREE_BLOCK: cooperative grid, one cluster per block, DZO_ORDER_TREE_BLOCKED; bitwise vs the oracle."""
+    import ctypes as C
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n, 5)
+    opt = dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, m)
+    order, clusters = C.c_int(), C.c_int()
+    assert dz.lib().dzo_lbfgs_info(opt._h, None, C.byref(order), C.byref(clusters)) == 0
+    assert order.value == 2 and clusters.value == min((n + 65535) // 65536, clusters.value) and clusters.value > 1
+    ref = orc.LBFGS(ROSEN, x0, 1.0, m, orc.TREE_BLOCKED)
+
+    def compare(tag):
+        assert_bitwise(opt.current_point, ref.point, f"{tag}: point")
+        assert_bitwise(opt.delta_point, ref.delta_point, f"{tag}: delta_point")
+        assert_bitwise(opt.current_gradient, ref.gradient, f"{tag}: gradient")
+        assert_bitwise(opt.delta_gradient, ref.delta_gradient, f"{tag}: delta_gradient")
+        assert_bitwise(opt.step_direction, ref.direction, f"{tag}: direction")
+        assert float(opt.current_objective_value[()]) == ref.objective
+        assert float(opt.delta_objective_value[()]) == ref.delta_objective
+        assert int(opt.iteration_count[()]) == ref.iteration_count and bool(opt.is_stuck[()]) == ref.stuck
+        assert_bitwise(opt.rho_history, ref.rho_history, f"{tag}: rho")
+
+    compare("ctor")
+    steps = 6 if n >= (1 << 20) else 12
+    for it in range(steps):
+        dz.step_(opt); ref.step(1)
+        compare(f"n={n} iter {it}")
+    opt.step(15); ref.step(15)            # 15 step! calls in one cooperative launch
+    compare("fused")
