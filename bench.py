@@ -21,6 +21,7 @@ Numbers on the JSON line
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -475,28 +476,50 @@ def bench_pairwise(dz, orc, torch, cpu=True):
 
 def bench_lbfgs(dz, orc, torch, stream, cpu=True):
     """the live package's LBFGSOptimizer (the package's own answer for large n) on
-    extended Rosenbrock n = 2^20, history 10: k step! calls in ONE cluster-kernel launch."""
+    extended Rosenbrock n = 2^20, history 10: k step! calls in ONE cooperative launch (one 8-CTA cluster per block of
+    65536 elements, DZO_ORDER_TREE_BLOCKED).  Algorithmic traffic per step! with a full history and one line-search
+    trial: (8m + 13) n-vectors = d = g and s_0.d (3), 2m fused correction passes (4 each, the last one also reads x),
+    accept pass (3 reads, 6 writes); the direction vector itself stays L2-resident."""
     EF = dz.ExampleFunctions
     n, m, k = 1 << 20, 10, 50
     x0 = 4.0 * orc.pcg_fill(n, 9) - 2.0
     opt = dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, m)
     opt.set_stream(stream.cuda_stream)
-    opt.step(5)
+    opt.step(12)
     it0 = int(opt.iteration_count[()])
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream); opt.step_async(k); e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     done = int(opt.iteration_count[()]) - it0
+    bytes_per_step = 8 * n * (8 * m + 13)
+    clusters = C.c_int()
+    dz.lib().dzo_lbfgs_info(opt._h, None, None, C.byref(clusters))
     out = {"n": n, "history_length": m, "steps": done, "ms_per_step": ms / max(done, 1), "steps_per_s": 1e3 * done / ms,
-           "objective": float(opt.current_objective_value[()])}
+           "objective": float(opt.current_objective_value[()]), "clusters": clusters.value,
+           "algorithmic_bytes_per_step": bytes_per_step,
+           "achieved_gbs": bytes_per_step * done / (ms * 1e-3) / 1e9, "order": "DZO_ORDER_TREE_BLOCKED"}
     opt.close()
     if cpu:
-        ref = orc.LBFGS(orc.OBJ_ROSENBROCK, x0, 1.0, m, orc.TREE)
+        ref = orc.LBFGS(orc.OBJ_ROSENBROCK, x0, 1.0, m, orc.TREE_BLOCKED)
         ref.step(5)
         t0 = time.perf_counter(); ref.step(5); dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"ms_per_step": 1e3 * dt / 5, "cores": 1, "kind": "port",
                                "sample": "5 step! calls of the same problem, oracle single thread"}
+    # SURVEY 8f rank 3: the legacy LBFGSOptimizer (quadratic line search, cyclic history) on one cluster
+    n2 = 65536
+    x1 = 4.0 * orc.pcg_fill(n2, 9) - 2.0
+    leg = dz.LegacyLBFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, dz.QuadraticLineSearch(0), x1, 1.0, m)
+    leg.set_stream(stream.cuda_stream)
+    leg.step(12)
+    it0 = int(leg.iteration_count[()])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); leg.step_async(k); e1.record(stream)
+    torch.cuda.synchronize()
+    done2 = int(leg.iteration_count[()]) - it0
+    out["legacy_lbfgs"] = {"n": n2, "history_length": m, "steps": done2, "ms_per_step": e0.elapsed_time(e1) / max(done2, 1),
+                           "objective": float(leg.current_objective_value[()])}
+    leg.close()
     return out
 
 
