@@ -16,7 +16,7 @@ struct dzo_lbfgs {
     LbfgsCtrl* ctrl = nullptr;
     // n > DZO_TREE_BLOCK: cooperative grid of clusters, one cluster per block (grid_lbfgs.cuh)
     bool use_grid = false;
-    int nblocks = 0, nclusters = 0;
+    int nblocks = 0, nclusters = 0;          // nclusters: CTAs of the cooperative grid
     double* part = nullptr;
     unsigned* fpart = nullptr;
 };
@@ -39,7 +39,7 @@ static int lbfgs_launch(dzo_lbfgs* o, int mode, int k, double L0) {
         g.mode = mode; g.initial_step_length = L0;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3((unsigned)(o->nclusters * kClusterCtas));
+        cfg.gridDim = dim3((unsigned)o->nclusters);
         cfg.blockDim = dim3(kClusterThreads);
         cfg.stream = o->stream;
         cudaLaunchAttribute attr[1];
@@ -47,7 +47,8 @@ static int lbfgs_launch(dzo_lbfgs* o, int mode, int k, double L0) {
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_lbfgs_kernel, g));
+        if (8 * o->nblocks <= o->nclusters) DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_lbfgs_kernel<1>, g));   // direction in registers
+        else DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_lbfgs_kernel<kGridOwnMax>, g));
         return DZO_OK;
     }
     LbfgsArgs a;
@@ -89,23 +90,21 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         cudaMemsetAsync(o->Y, 0, vb * history_length, o->stream) != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "initial copies failed"));
     if (n > DZO_TREE_BLOCK) {
-        // one cluster per block of DZO_TREE_BLOCK elements, as many clusters as are co-resident (cooperative launch)
+        // eight 512-thread CTAs per block of DZO_TREE_BLOCK elements, as many CTAs as are co-resident (cooperative launch)
         o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(kClusterCtas * 64);
-        cfg.blockDim = dim3(kClusterThreads);
-        int max_clusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, grid_lbfgs_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_lbfgs_kernel<kGridOwnMax>, kClusterThreads, 0) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
-            return bail(fail(DZO_ERR_CUDA, "no co-resident clusters for the grid-wide L-BFGS kernel"));
+            return bail(fail(DZO_ERR_CUDA, "the grid-wide L-BFGS kernel does not fit on this device"));
         }
-        o->nclusters = o->nblocks < max_clusters ? o->nblocks : max_clusters;
-        if (o->nblocks > kGridMaxBlocks || o->nblocks > kGridOwn * o->nclusters)
-            return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d blocks; the grid-wide L-BFGS kernel holds at most %d",
-                             (long long)n, o->nblocks, kGridOwn * o->nclusters));
-        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * 3 * kGridMaxBlocks) != cudaSuccess ||
-            cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxBlocks) != cudaSuccess)
+        const int resident = per_sm * sms;
+        o->nclusters = 8 * o->nblocks < resident ? 8 * o->nblocks : resident;      // CTAs of the grid
+        if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nclusters)
+            return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d CTA shares; the grid-wide L-BFGS kernel holds at most %d",
+                             (long long)n, 8 * o->nblocks, kGridOwnMax * o->nclusters));
+        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * 3 * kGridMaxParts) != cudaSuccess ||
+            cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
         o->use_grid = true;
     }
@@ -179,7 +178,7 @@ int dzo_lbfgs_info(dzo_lbfgs* o, int64_t* n, int* order, int* clusters) {
     if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
     if (n) *n = o->n;
     if (order) *order = DZO_ORDER_TREE_BLOCKED;          // == DZO_ORDER_TREE for n <= DZO_TREE_BLOCK
-    if (clusters) *clusters = o->use_grid ? o->nclusters : 1;
+    if (clusters) *clusters = o->use_grid ? o->nclusters : kClusterCtas;
     return DZO_OK;
 }
 int dzo_lbfgs_get_rho_history(dzo_lbfgs* o, int64_t* count, double* rho) {

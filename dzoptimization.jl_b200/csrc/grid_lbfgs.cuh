@@ -1,28 +1,32 @@
 // grid_lbfgs.cuh -- the live LBFGSOptimizer step! (src/DZOptimization.jl:454-509) for n > DZO_TREE_BLOCK on the
-// WHOLE GPU: a cooperative grid of 8-CTA clusters, one cluster per block of DZO_TREE_BLOCK elements.
+// WHOLE GPU: one cooperative grid, eight 512-thread CTAs per block of DZO_TREE_BLOCK elements.
 //
 // cluster_lbfgs_kernel (lbfgs_kernels.cuh) runs a step on one cluster = 8 SMs, which caps an O(n*m) step at what
 // 8 SMs can pull out of L2 (n = 2^20, m = 10: 1.98 ms per step, ~0.5 TB/s).  DZO_ORDER_TREE_BLOCKED (include/dzopt.h)
-// keeps the canonical tree inside a block of 65536 elements and adds the block results in ascending order, so
-// every block can live on its own cluster: thread v of the cluster IS virtual thread v of that block's tree and
-// owns its 8 element pairs of every vector (between reductions a thread only re-reads what it wrote itself).
-// A reduction = in-cluster DSMEM tree (cluster_search.cuh) -> one double per block in global memory -> ONE grid
-// barrier -> every thread adds the <= 64 block values in ascending order.  The block values are double-buffered
-// by the parity of the reduction count so that a cluster racing ahead cannot overwrite what a slower one still reads.
+// keeps the canonical tree inside a block of 65536 elements and adds the block results in ascending order, so the
+// blocks can live on different SMs.  A CTA owns an EIGHTH of a block: its 512 threads are the virtual threads
+// 512*part .. 512*part+511 of that block's tree and own their 8 element pairs of every vector (between reductions a
+// thread only re-reads what it wrote itself).  A reduction = lane bits by shuffle, warp bits through shared memory
+// -> one double per CTA in global memory -> ONE grid barrier -> warp 0 of every CTA fetches all CTA values side by
+// side, finishes each block's tree (the three CTA bits, ascending) and adds the blocks in ascending order.  The CTA
+// values are double-buffered by the parity of the reduction count so that a CTA racing ahead cannot overwrite what a
+// slower one still reads.  (A first version used one 8-CTA cluster per block with DSMEM for the CTA bits; only 15
+// such clusters are co-resident on a B200, one short of the 16 blocks of n = 2^20.)
 #pragma once
 #include "lbfgs_kernels.cuh"
 
 namespace dzo {
 
 constexpr int kGridMaxBlocks = 1024;                     // n <= 64 Mi elements
+constexpr int kGridMaxParts = 8 * kGridMaxBlocks;        // CTA values per quantity
 constexpr long long kBlockPairs = DZO_TREE_BLOCK / 2;    // 32768 pairs = 8 per virtual thread
 
 struct GridLbfgsArgs {
     double *x, *dx, *g, *dg, *d;
     double *S, *Y;                           // m x n, physical slot p at S + p*n
     LbfgsCtrl* ctrl;
-    double* part;                            // [2][3][kGridMaxBlocks] block results (parity, quantity, block)
-    unsigned* fpart;                         // [2][kGridMaxBlocks]    block flag words
+    double* part;                            // [2][3][kGridMaxParts] CTA results (parity, quantity, eighth)
+    unsigned* fpart;                         // [2][kGridMaxParts]    CTA flag words
     long long n;
     int m, ksteps, nblocks;
     int mode;                                // 0 = steps, 1 = constructor
@@ -31,57 +35,79 @@ struct GridLbfgsArgs {
 
 struct GridCtx {
     cg::grid_group grid;
-    cg::cluster_group cluster;
-    ClusterRed* R;
-    int nclusters, cid, nblocks;
-    long long v;                             // virtual thread of this thread inside a block
+    int nctas, cta, nblocks;                 // eighth e of the vector (block e / 8, part e % 8) belongs to CTA e mod nctas
     int red;                                 // reductions so far (parity)
-    double* s_out;                           // shared: totals of the last reduction
+    double* s_warp;                          // shared [3][16]: warp partials
+    unsigned* s_wflag;                       // shared [16]
+    double* s_out;                           // shared [3]: totals of the last reduction
     unsigned* s_flags;
 };
 
-// Reduce K per-block accumulators (acc[k][j] = this thread's partial of quantity k for its j-th owned block) and OR
-// the per-block flag words.  Returns the totals in out[k], the OR in flags; identical on every thread of the grid.
+// Reduce K per-eighth accumulators (acc[k][j] = this thread's partial of quantity k for the j-th eighth its CTA owns)
+// and OR the flag words.  Returns the totals in out[k], the OR in flags; identical on every thread of the grid.
 template <int K, int MAXB>
 DZO_DEVINL void grid_reduce(GridCtx& c, const GridLbfgsArgs& a, double (&acc)[K][MAXB], unsigned (&fl)[MAXB], double (&out)[K],
                             unsigned& flags) {
     const int par = c.red & 1;
     c.red += 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < MAXB; ++j) {
-        const int b = c.cid + j * c.nclusters;
-        if (b < c.nblocks) {                 // uniform over the cluster
-            double p[K];
+        const int e = c.cta + j * c.nctas;
+        if (e < 8 * c.nblocks) {             // uniform over the CTA
 #pragma unroll
-            for (int k = 0; k < K; ++k) p[k] = acc[k][j];
-            unsigned f = fl[j];
-            cluster_tree_reduce<K>(c.cluster, *c.R, p, f);
-            if (c.cluster.block_rank() == 0 && threadIdx.x == 0) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) a.part[(par * 3 + k) * kGridMaxBlocks + b] = p[k];
-                a.fpart[par * kGridMaxBlocks + b] = f;
+            for (int k = 0; k < K; ++k) {
+                const double sv = warp_butterfly_desc(acc[k][j]);                 // bits 4,3,2,1,0
+                if (lane == 0) c.s_warp[k * 16 + warp] = sv;
             }
+            const unsigned wf = __reduce_or_sync(0xffffffffu, fl[j]);
+            if (lane == 0) c.s_wflag[warp] = wf;
+            __syncthreads();
+            if (warp == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double v = c.s_warp[k * 16 + (lane & 15)];
+#pragma unroll
+                    for (int o = 1; o < 16; o <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);   // bits 5,6,7,8
+                    if (lane == 0) a.part[(par * 3 + k) * kGridMaxParts + e] = v;
+                }
+                unsigned f = c.s_wflag[lane & 15];
+                f = __reduce_or_sync(0xffffffffu, f);
+                if (lane == 0) a.fpart[par * kGridMaxParts + e] = f;
+            }
+            __syncthreads();                 // s_warp may be reused by the next owned eighth
         }
     }
     c.grid.sync();
-    // warp 0 of every CTA fetches the block values side by side (one L2 round trip per 32 blocks -- a thread adding
-    // them one load at a time would wait out a full L2 latency per block) and adds them in ascending block order
-    const int lane = threadIdx.x & 31;
+    // warp 0 of every CTA fetches the CTA values side by side (one L2 round trip per 16 blocks -- a thread adding
+    // them one load at a time would wait out a full L2 latency per value): lane l holds CTA values 4l .. 4l+3 of
+    // the round, i.e. half a block; bits 9, 10 inside the lane, bit 11 across the lane pair, blocks in ascending order
     if (threadIdx.x < 32) {
         double tot[K];
         unsigned f = 0;
-        for (int b0 = 0; b0 < c.nblocks; b0 += 32) {
-            const int b = b0 + lane;
-            double val[K];
+        for (int b0 = 0; b0 < c.nblocks; b0 += 16) {
+            const int e0 = 8 * b0 + 4 * lane;
+            const bool in = (e0 < 8 * c.nblocks);
+            double half[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) val[k] = (b < c.nblocks) ? __ldcg(&a.part[(par * 3 + k) * kGridMaxBlocks + b]) : 0.0;
-            const unsigned fv = (b < c.nblocks) ? __ldcg(&a.fpart[par * kGridMaxBlocks + b]) : 0u;
+            for (int k = 0; k < K; ++k) {
+                const double* q = a.part + (par * 3 + k) * kGridMaxParts + e0;
+                const double c0 = in ? __ldcg(&q[0]) : 0.0, c1 = in ? __ldcg(&q[1]) : 0.0;
+                const double c2 = in ? __ldcg(&q[2]) : 0.0, c3 = in ? __ldcg(&q[3]) : 0.0;
+                half[k] = (c0 + c1) + (c2 + c3);                                  // bits 9, 10
+            }
+            unsigned fv = 0;
+            if (in) {
+                const unsigned* fq = a.fpart + par * kGridMaxParts + e0;
+                fv = __ldcg(&fq[0]) | __ldcg(&fq[1]) | __ldcg(&fq[2]) | __ldcg(&fq[3]);
+            }
             f |= __reduce_or_sync(0xffffffffu, fv);
-            const int cnt = min(32, c.nblocks - b0);
-            for (int i = 0; i < cnt; ++i) {
+            const int cnt = min(16, c.nblocks - b0);
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const double x = __shfl_sync(0xffffffffu, val[k], i);
+            for (int k = 0; k < K; ++k) {
+                const double blockv = half[k] + __shfl_down_sync(0xffffffffu, half[k], 1);   // bit 11 (valid on even lanes)
+                for (int i = 0; i < cnt; ++i) {
+                    const double x = __shfl_sync(0xffffffffu, blockv, 2 * i);
                     tot[k] = (b0 == 0 && i == 0) ? x : tot[k] + x;
                 }
             }
@@ -99,51 +125,75 @@ DZO_DEVINL void grid_reduce(GridCtx& c, const GridLbfgsArgs& a, double (&acc)[K]
     // the next write to s_out sits behind the next grid barrier
 }
 
-constexpr int kGridOwn = 8;   // blocks one cluster may own: n <= 8 * nclusters * 65536 (9.4 Mi elements on 18 clusters)
+constexpr int kGridOwnMax = 8;   // eighths one CTA may own: n <= nctas * 65536 elements (148 CTAs: 9.7 Mi)
 
-// for (own pairs) body: j = index of the owned block (compile-time after unrolling, so per-block accumulators stay in
-// registers), k = global pair index
+// for (own pairs) body: j = index of the owned eighth (compile-time after unrolling, so per-eighth accumulators stay in
+// registers), k = global pair index.  Eighth e: block e / 8, virtual threads 512 * (e % 8) + threadIdx.x.
 #define DZO_GRID_OWN_PAIRS(c, m2, j, k)                                                                              \
     _Pragma("unroll") for (int j = 0; j < kGridOwn; ++j)                                                             \
-        if ((c).cid + j * (c).nclusters < (c).nblocks)                                                               \
-            for (long long k = (long long)((c).cid + j * (c).nclusters) * kBlockPairs + (c).v,                       \
-                           e__ = (long long)((c).cid + j * (c).nclusters + 1) * kBlockPairs;                         \
-                 k < e__ && k < (m2); k += DZO_TREE_WIDTH)
+        if ((c).cta + j * (c).nctas < 8 * (c).nblocks)                                                               \
+            for (long long e__ = (c).cta + j * (c).nctas, k = (e__ >> 3) * kBlockPairs + (e__ & 7) * 512 + threadIdx.x, \
+                           i__ = 0;                                                                                  \
+                 i__ < 8 && k < (m2); ++i__, k += DZO_TREE_WIDTH)
 
-DZO_DEVINL double grid_dot(GridCtx& c, const GridLbfgsArgs& a, const double* __restrict__ u, const double* __restrict__ w) {
-    const long long m2 = a.n >> 1;
-    double acc[1][kGridOwn];
-    unsigned fl[kGridOwn];
+// Own pairs with a compile-time position: f(j, i, k) -- j = owned block, i = position of the pair inside the thread's
+// share of the block (only meaningful for OWN == 1, where the loop is fully unrolled), k = global pair index.
+template <int OWN, class F>
+DZO_DEVINL void own_pairs_idx(const GridCtx& c, long long m2, F&& f) {
+    if constexpr (OWN == 1) {
+        if (c.cta < 8 * c.nblocks) {
 #pragma unroll
-    for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; fl[j] = 0; }
-    DZO_GRID_OWN_PAIRS(c, m2, j, k) {
-        const double2 uu = reinterpret_cast<const double2*>(u)[k];
-        const double2 ww = reinterpret_cast<const double2*>(w)[k];
-        acc[0][j] += uu.x * ww.x;
-        acc[0][j] += uu.y * ww.y;
+            for (int i = 0; i < 8; ++i) {
+                const long long k = (long long)(c.cta >> 3) * kBlockPairs + (c.cta & 7) * 512 + threadIdx.x + (long long)DZO_TREE_WIDTH * i;
+                if (k < m2) f(0, i, k);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < OWN; ++j) {
+            const long long e = c.cta + j * c.nctas;
+            if (e < 8 * c.nblocks) {
+                long long k = (e >> 3) * kBlockPairs + (e & 7) * 512 + threadIdx.x;
+                for (int i = 0; i < 8 && k < m2; ++i, k += DZO_TREE_WIDTH) f(j, 0, k);
+            }
+        }
     }
-    double out[1];
-    unsigned f;
-    grid_reduce<1, kGridOwn>(c, a, acc, fl, out, f);
-    return out[0];
 }
 
-static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
-    grid_lbfgs_kernel(GridLbfgsArgs a) {
-    __shared__ ClusterRed R;
+// The direction vector while compute_lbfgs_step_direction! runs: with one eighth per CTA (OWN == 1: n <= nctas * 8192,
+// e.g. n = 2^20 on 128 CTAs) a thread's 8 pairs stay in REGISTERS across the 2m + 1 passes, so a pass only streams
+// the history vectors; otherwise the vector lives in global memory (L2-resident).
+template <int OWN>
+struct DirRegs {
+    double2 r[OWN == 1 ? 8 : 1];
+    DZO_DEVINL double2 get(const double* d, int i, long long k) const {
+        if constexpr (OWN == 1) return r[i];
+        else return reinterpret_cast<const double2*>(d)[k];
+    }
+    DZO_DEVINL void set(double* d, int i, long long k, double2 v, bool to_global) {
+        if constexpr (OWN == 1) {
+            r[i] = v;
+            if (to_global) reinterpret_cast<double2*>(d)[k] = v;
+        } else {
+            reinterpret_cast<double2*>(d)[k] = v;
+        }
+    }
+};
+
+template <int OWN>
+static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(GridLbfgsArgs a) {
+    constexpr int kGridOwn = OWN;          // the macros and arrays below size themselves by it
     __shared__ LbfgsCtrl sc;
     __shared__ double alpha[DZO_LBFGS_MAX_HISTORY];
+    __shared__ double s_warp[3 * 16];
+    __shared__ unsigned s_wflag[16];
     __shared__ double s_out[3];
     __shared__ unsigned s_flags;
-    GridCtx c{cg::this_grid(), cg::this_cluster(), &R, 0, 0, a.nblocks, 0, 0, s_out, &s_flags};
-    c.nclusters = (int)(gridDim.x / kClusterCtas);
-    c.cid = (int)(blockIdx.x / kClusterCtas);
-    c.v = (long long)c.cluster.block_rank() * kClusterThreads + threadIdx.x;
+    GridCtx c{cg::this_grid(), (int)gridDim.x, (int)blockIdx.x, a.nblocks, 0, s_warp, s_wflag, s_out, &s_flags};
     const long long n = a.n, m2 = n >> 1;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
-    if (threadIdx.x == 0) { sc = *a.ctrl; R.parity = 0; }
+    if (threadIdx.x == 0) sc = *a.ctrl;
     __syncthreads();
-    c.cluster.sync();
     c.grid.sync();                 // every CTA holds the control block before the leader may rewrite it
 
     if (a.mode == 1) {
@@ -200,17 +250,18 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
             unsigned fl[kGridOwn];
             double out[1];
             unsigned f;
+            DirRegs<OWN> D;
 #pragma unroll
             for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; fl[j] = 0; }
             {
                 const double* s0 = a.S + (long long)head * n;
-                DZO_GRID_OWN_PAIRS(c, m2, j, k) {                                               // d = g, and s_0 . d  (:439)
+                own_pairs_idx<OWN>(c, m2, [&](int j, int i, long long k) {                      // d = g, and s_0 . d  (:439)
                     const double2 gg = reinterpret_cast<const double2*>(a.g)[k];
                     const double2 ss = reinterpret_cast<const double2*>(s0)[k];
-                    reinterpret_cast<double2*>(a.d)[k] = gg;
+                    D.set(a.d, i, k, gg, false);
                     acc[0][j] += ss.x * gg.x;
                     acc[0][j] += ss.y * gg.y;
-                }
+                });
             }
             grid_reduce<1, kGridOwn>(c, a, acc, fl, out, f);
             double al = out[0] / sc.rho[head];
@@ -226,16 +277,16 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
                 const double* nxt = last ? (a.Y + (long long)pn * n) : (a.S + (long long)pn * n);
 #pragma unroll
                 for (int j = 0; j < kGridOwn; ++j) acc[0][j] = 0.0;
-                DZO_GRID_OWN_PAIRS(c, m2, j, k) {
-                    double2 dd = reinterpret_cast<double2*>(a.d)[k];
+                own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
+                    double2 dd = D.get(a.d, q, k);
                     const double2 yy = reinterpret_cast<const double2*>(y)[k];
                     const double2 nn = reinterpret_cast<const double2*>(nxt)[k];
                     dd.x += na * yy.x; dd.y += na * yy.y;                                       // :440
                     if (last) { dd.x *= cc; dd.y *= cc; }                                       // :443
-                    reinterpret_cast<double2*>(a.d)[k] = dd;
+                    D.set(a.d, q, k, dd, false);
                     acc[0][j] += nn.x * dd.x;                                                   // s_{i+1} . d (:439) or y_{cnt-1} . d (:446)
                     acc[0][j] += nn.y * dd.y;
-                }
+                });
                 grid_reduce<1, kGridOwn>(c, a, acc, fl, out, f);
                 if (last) beta = out[0] / sc.rho[p];
                 else al = out[0] / sc.rho[pn];
@@ -250,29 +301,29 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
                 if (i > 0) {
                     const int pn = (head + i - 1) % m;
                     const double* yn = a.Y + (long long)pn * n;
-                    DZO_GRID_OWN_PAIRS(c, m2, j, k) {
-                        double2 dd = reinterpret_cast<double2*>(a.d)[k];
+                    own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
+                        double2 dd = D.get(a.d, q, k);
                         const double2 ss = reinterpret_cast<const double2*>(sp)[k];
                         const double2 yy = reinterpret_cast<const double2*>(yn)[k];
                         dd.x += na * ss.x; dd.y += na * ss.y;                                   // :447
-                        reinterpret_cast<double2*>(a.d)[k] = dd;
+                        D.set(a.d, q, k, dd, false);
                         acc[0][j] += yy.x * dd.x;                                               // y_{i-1} . d  (:446)
                         acc[0][j] += yy.y * dd.y;
-                    }
+                    });
                     grid_reduce<1, kGridOwn>(c, a, acc, fl, out, f);
                     beta = out[0] / sc.rho[pn];
                 } else {
                     // last correction fused with the first trial of take_backtracking_step!(opt, 1, d)  (:124-138)
-                    DZO_GRID_OWN_PAIRS(c, m2, j, k) {
-                        double2 dd = reinterpret_cast<double2*>(a.d)[k];
+                    own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
+                        double2 dd = D.get(a.d, q, k);
                         const double2 ss = reinterpret_cast<const double2*>(sp)[k];
                         const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
                         dd.x += na * ss.x; dd.y += na * ss.y;                                   // :447
-                        reinterpret_cast<double2*>(a.d)[k] = dd;
+                        D.set(a.d, q, k, dd, true);                                             // step_direction as the host reads it
                         const double w0 = xx.x + step * dd.x, w1 = xx.y + step * dd.y;         // :124 axpy!
                         if (!julia_isequal(w0, xx.x) || !julia_isequal(w1, xx.y)) fl[j] |= 1u;  // :128
                         acc[0][j] += RosenbrockVec::term(w0, w1);                               // :138
-                    }
+                    });
                     grid_reduce<1, kGridOwn>(c, a, acc, fl, pr_out, pr_flags);
                     have_probe = true;
                 }
