@@ -88,3 +88,42 @@ def test_line_search_restatements_agree(orc, data):
     got = orc.line_search(ROSEN, np.array(x), np.array(d), f0, t1, orc.SEQ)
     assert (np.array(got).view(np.uint64) == np.array(ref, dtype=np.float64).view(np.uint64)).all() or (
         all(math.isnan(a) and math.isnan(b) or a == b for a, b in zip(got, ref)))
+
+
+@settings(**{**COMMON, "max_examples": 12})
+@given(data=st.data())
+def test_legacy_lbfgs_restatements_agree(orc, data):
+    """legacy LBFGSOptimizer (legacy/DZOptimization.jl:458-695) with arbitrary decorators, history lengths and starts"""
+    import dzo_oracle_py as P
+    n = 2 * data.draw(st.integers(min_value=1, max_value=5))
+    tree = data.draw(st.booleans())
+    x0 = [data.draw(coord) for _ in range(n)]
+    L0 = data.draw(step_len)
+    m = data.draw(st.integers(min_value=1, max_value=4))
+    mi = data.draw(st.integers(min_value=0, max_value=3))
+    lam = data.draw(st.sampled_from([None, 0.0, 0.25, 1e3]))
+    box = data.draw(st.sampled_from([None, (-0.5, 0.8), (0.0, 0.0), (-1e9, 1e9), (1.0, 1.0)]))
+    fn = P.Rosenbrock(tree)
+    if lam is not None:
+        fn = P.L2Regularized(fn, lam)
+    if box is not None:
+        fn = P.UniformBox(fn, *box)
+    py = P.LegacyLBFGSOptimizer(fn, list(x0), L0, m, mi, tree)
+    c = orc.LegacyLBFGS(ROSEN, np.array(x0), L0, m, mi, lam, box, orc.TREE if tree else orc.SEQ)
+
+    def same(a, b):     # NaN payloads are not part of the contract
+        a, b = np.array(a, dtype=np.float64), np.array(b, dtype=np.float64)
+        assert ((a.view(np.uint64) == b.view(np.uint64)) | (np.isnan(a) & np.isnan(b))).all()
+
+    for it in range(6):
+        py.step(); c.step(1)
+        same(c.point, py.current_point)
+        same(c.direction, py.next_step_direction)
+        same(c.gradient, py.current_gradient)
+        s = c.scalars
+        same(s[:3], [py.current_objective_value, py.delta_objective_value, py.last_step_length])
+        assert int(s[3]) == py.iteration_count and bool(s[4]) == py.has_terminated and int(s[5]) == py._history_count
+        rho, alpha = c.history
+        same(rho, py._rho); same(alpha, py._alpha)
+        if py.has_terminated:
+            break
