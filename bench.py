@@ -507,8 +507,8 @@ def bench_lbfgs(dz, orc, torch, stream, cpu=True):
         t0 = time.perf_counter(); ref.step(5); dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"ms_per_step": 1e3 * dt / 5, "cores": 1, "kind": "port",
                                "sample": "5 step! calls of the same problem, oracle single thread"}
-    # the legacy LBFGSOptimizer (quadratic line search, cyclic history) on one cluster
-    n2 = 65536
+    # the legacy LBFGSOptimizer (quadratic line search, cyclic history), same grid-wide machinery
+    n2 = 1 << 20
     x1 = 4.0 * orc.pcg_fill(n2, 9) - 2.0
     leg = dz.LegacyLBFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, dz.QuadraticLineSearch(0), x1, 1.0, m)
     leg.set_stream(stream.cuda_stream)

@@ -4,6 +4,7 @@
 #include "host_common.h"
 #include "grid_lbfgs.cuh"
 #include "legacy_lbfgs.cuh"
+#include "grid_legacy_lbfgs.cuh"
 
 using namespace dzo;
 
@@ -103,7 +104,7 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nclusters)
             return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d CTA shares; the grid-wide L-BFGS kernel holds at most %d",
                              (long long)n, 8 * o->nblocks, kGridOwnMax * o->nclusters));
-        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * 3 * kGridMaxParts) != cudaSuccess ||
+        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
             cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
         o->use_grid = true;
@@ -280,11 +281,16 @@ struct dzo_legacy_lbfgs {
     double l2 = 0.0, lo = 0.0, hi = 0.0;
     double *x = nullptr, *dx = nullptr, *g = nullptr, *dg = nullptr, *d = nullptr, *S = nullptr, *Y = nullptr;
     LegacyCtrl* ctrl = nullptr;
+    // n > DZO_TREE_BLOCK: cooperative grid, eight CTAs per block (grid_legacy_lbfgs.cuh)
+    bool use_grid = false;
+    int nblocks = 0, nctas = 0;
+    double* part = nullptr;
+    unsigned* fpart = nullptr;
 };
 static void free_legacy(dzo_legacy_lbfgs* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->d, o->S, o->Y, o->ctrl};
+    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->d, o->S, o->Y, o->ctrl, o->part, o->fpart};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
@@ -295,6 +301,22 @@ static int legacy_launch(dzo_legacy_lbfgs* o, int mode, int k, double L0) {
     a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.d = o->d; a.S = o->S; a.Y = o->Y; a.ctrl = o->ctrl;
     a.n = o->n; a.m = o->m; a.ksteps = k; a.max_increases = o->max_increases; a.mode = mode; a.decor = o->decor;
     a.initial_step_length = L0; a.l2 = o->l2; a.lo = o->lo; a.hi = o->hi;
+    if (o->use_grid) {
+        GridLegacyArgs ga;
+        ga.a = a; ga.part = o->part; ga.fpart = o->fpart; ga.nblocks = o->nblocks;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)o->nctas);
+        cfg.blockDim = dim3(kClusterThreads);
+        cfg.stream = o->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_legacy_lbfgs_kernel, ga));
+        return DZO_OK;
+    }
     cluster_legacy_lbfgs_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;
@@ -332,6 +354,24 @@ int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constrain
         cudaMemsetAsync(o->S, 0, vb * history_length, o->stream) != cudaSuccess ||
         cudaMemsetAsync(o->Y, 0, vb * history_length, o->stream) != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "initial copies failed"));
+    if (n > DZO_TREE_BLOCK) {
+        o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_legacy_lbfgs_kernel, kClusterThreads, 0) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
+            cudaGetLastError();
+            return bail(fail(DZO_ERR_CUDA, "the grid-wide legacy L-BFGS kernel does not fit on this device"));
+        }
+        const int resident = per_sm * sms;
+        o->nctas = 8 * o->nblocks < resident ? 8 * o->nblocks : resident;
+        if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nctas)
+            return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d CTA shares; the grid-wide legacy L-BFGS kernel holds at most %d",
+                             (long long)n, 8 * o->nblocks, kGridOwnMax * o->nctas));
+        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
+            cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
+            return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+        o->use_grid = true;
+    }
     int rc = legacy_launch(o, 1, 0, initial_step_length);
     if (rc) return bail(rc);
     if (cudaStreamSynchronize(o->stream) != cudaSuccess)

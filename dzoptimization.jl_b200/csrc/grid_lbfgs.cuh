@@ -19,13 +19,14 @@ namespace dzo {
 
 constexpr int kGridMaxBlocks = 1024;                     // n <= 64 Mi elements
 constexpr int kGridMaxParts = 8 * kGridMaxBlocks;        // CTA values per quantity
+constexpr int kGridQ = 4;                                // quantities one reduction can carry
 constexpr long long kBlockPairs = DZO_TREE_BLOCK / 2;    // 32768 pairs = 8 per virtual thread
 
 struct GridLbfgsArgs {
     double *x, *dx, *g, *dg, *d;
     double *S, *Y;                           // m x n, physical slot p at S + p*n
     LbfgsCtrl* ctrl;
-    double* part;                            // [2][3][kGridMaxParts] CTA results (parity, quantity, eighth)
+    double* part;                            // [2][kGridQ][kGridMaxParts] CTA results (parity, quantity, eighth)
     unsigned* fpart;                         // [2][kGridMaxParts]    CTA flag words
     long long n;
     int m, ksteps, nblocks;
@@ -37,17 +38,18 @@ struct GridCtx {
     cg::grid_group grid;
     int nctas, cta, nblocks;                 // eighth e of the vector (block e / 8, part e % 8) belongs to CTA e mod nctas
     int red;                                 // reductions so far (parity)
-    double* s_warp;                          // shared [3][16]: warp partials
+    double* part;                            // global [2][kGridQ][kGridMaxParts]
+    unsigned* fpart;                         // global [2][kGridMaxParts]
+    double* s_warp;                          // shared [kGridQ][16]: warp partials
     unsigned* s_wflag;                       // shared [16]
-    double* s_out;                           // shared [3]: totals of the last reduction
+    double* s_out;                           // shared [kGridQ]: totals of the last reduction
     unsigned* s_flags;
 };
 
 // Reduce K per-eighth accumulators (acc[k][j] = this thread's partial of quantity k for the j-th eighth its CTA owns)
 // and OR the flag words.  Returns the totals in out[k], the OR in flags; identical on every thread of the grid.
 template <int K, int MAXB>
-DZO_DEVINL void grid_reduce(GridCtx& c, const GridLbfgsArgs& a, double (&acc)[K][MAXB], unsigned (&fl)[MAXB], double (&out)[K],
-                            unsigned& flags) {
+DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[MAXB], double (&out)[K], unsigned& flags) {
     const int par = c.red & 1;
     c.red += 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -69,11 +71,11 @@ DZO_DEVINL void grid_reduce(GridCtx& c, const GridLbfgsArgs& a, double (&acc)[K]
                     double v = c.s_warp[k * 16 + (lane & 15)];
 #pragma unroll
                     for (int o = 1; o < 16; o <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);   // bits 5,6,7,8
-                    if (lane == 0) a.part[(par * 3 + k) * kGridMaxParts + e] = v;
+                    if (lane == 0) c.part[(par * kGridQ + k) * kGridMaxParts + e] = v;
                 }
                 unsigned f = c.s_wflag[lane & 15];
                 f = __reduce_or_sync(0xffffffffu, f);
-                if (lane == 0) a.fpart[par * kGridMaxParts + e] = f;
+                if (lane == 0) c.fpart[par * kGridMaxParts + e] = f;
             }
             __syncthreads();                 // s_warp may be reused by the next owned eighth
         }
@@ -91,14 +93,14 @@ DZO_DEVINL void grid_reduce(GridCtx& c, const GridLbfgsArgs& a, double (&acc)[K]
             double half[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double* q = a.part + (par * 3 + k) * kGridMaxParts + e0;
+                const double* q = c.part + (par * kGridQ + k) * kGridMaxParts + e0;
                 const double c0 = in ? __ldcg(&q[0]) : 0.0, c1 = in ? __ldcg(&q[1]) : 0.0;
                 const double c2 = in ? __ldcg(&q[2]) : 0.0, c3 = in ? __ldcg(&q[3]) : 0.0;
                 half[k] = (c0 + c1) + (c2 + c3);                                  // bits 9, 10
             }
             unsigned fv = 0;
             if (in) {
-                const unsigned* fq = a.fpart + par * kGridMaxParts + e0;
+                const unsigned* fq = c.fpart + par * kGridMaxParts + e0;
                 fv = __ldcg(&fq[0]) | __ldcg(&fq[1]) | __ldcg(&fq[2]) | __ldcg(&fq[3]);
             }
             f |= __reduce_or_sync(0xffffffffu, fv);
@@ -185,11 +187,11 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
     constexpr int kGridOwn = OWN;          // the macros and arrays below size themselves by it
     __shared__ LbfgsCtrl sc;
     __shared__ double alpha[DZO_LBFGS_MAX_HISTORY];
-    __shared__ double s_warp[3 * 16];
+    __shared__ double s_warp[kGridQ * 16];
     __shared__ unsigned s_wflag[16];
-    __shared__ double s_out[3];
+    __shared__ double s_out[kGridQ];
     __shared__ unsigned s_flags;
-    GridCtx c{cg::this_grid(), (int)gridDim.x, (int)blockIdx.x, a.nblocks, 0, s_warp, s_wflag, s_out, &s_flags};
+    GridCtx c{cg::this_grid(), (int)gridDim.x, (int)blockIdx.x, a.nblocks, 0, a.part, a.fpart, s_warp, s_wflag, s_out, &s_flags};
     const long long n = a.n, m2 = n >> 1;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
     if (threadIdx.x == 0) sc = *a.ctrl;
@@ -214,7 +216,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
         }
         double out[2];
         unsigned f;
-        grid_reduce<2, kGridOwn>(c, a, acc, fl, out, f);
+        grid_reduce<2, kGridOwn>(c, acc, fl, out, f);
         const double gnorm = sqrt(out[1]);                                                      // :376
         const bool stuck = (gnorm == 0.0);                                                      // :377
         const double cc = -a.initial_step_length / gnorm;
@@ -263,7 +265,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                     acc[0][j] += ss.y * gg.y;
                 });
             }
-            grid_reduce<1, kGridOwn>(c, a, acc, fl, out, f);
+            grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
             double al = out[0] / sc.rho[head];
             const double cc = -sc.rho[head] / sc.yy;                                            // :443 (dot(y_0, y_0) cached)
             double beta = 0.0;
@@ -287,7 +289,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                     acc[0][j] += nn.x * dd.x;                                                   // s_{i+1} . d (:439) or y_{cnt-1} . d (:446)
                     acc[0][j] += nn.y * dd.y;
                 });
-                grid_reduce<1, kGridOwn>(c, a, acc, fl, out, f);
+                grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
                 if (last) beta = out[0] / sc.rho[p];
                 else al = out[0] / sc.rho[pn];
             }
@@ -310,7 +312,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                         acc[0][j] += yy.x * dd.x;                                               // y_{i-1} . d  (:446)
                         acc[0][j] += yy.y * dd.y;
                     });
-                    grid_reduce<1, kGridOwn>(c, a, acc, fl, out, f);
+                    grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
                     beta = out[0] / sc.rho[pn];
                 } else {
                     // last correction fused with the first trial of take_backtracking_step!(opt, 1, d)  (:124-138)
@@ -324,7 +326,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                         if (!julia_isequal(w0, xx.x) || !julia_isequal(w1, xx.y)) fl[j] |= 1u;  // :128
                         acc[0][j] += RosenbrockVec::term(w0, w1);                               // :138
                     });
-                    grid_reduce<1, kGridOwn>(c, a, acc, fl, pr_out, pr_flags);
+                    grid_reduce<1, kGridOwn>(c, acc, fl, pr_out, pr_flags);
                     have_probe = true;
                 }
             }
@@ -343,7 +345,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                     if (!julia_isequal(w0, xx.x) || !julia_isequal(w1, xx.y)) fl[j] |= 1u;      // :128
                     acc[0][j] += RosenbrockVec::term(w0, w1);                                   // :138
                 }
-                grid_reduce<1, kGridOwn>(c, a, acc, fl, pr_out, pr_flags);
+                grid_reduce<1, kGridOwn>(c, acc, fl, pr_out, pr_flags);
             }
             have_probe = false;
             if (!(pr_flags & 1u)) break;                                                        // :128-131 stuck
@@ -389,7 +391,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
         }
         double out[2];
         unsigned f;
-        grid_reduce<2, kGridOwn>(c, a, acc, fl, out, f);
+        grid_reduce<2, kGridOwn>(c, acc, fl, out, f);
         const double rho_new = out[0];
         if (threadIdx.x == 0) {
             sc.yy = out[1];

@@ -1328,7 +1328,7 @@ int dzo_cpu_legacy_lbfgs_create(dzo_cpu_legacy_lbfgs** out, int objective, int c
     rc = check_decor(objective, decor, l2_lambda, box_lower, box_upper);
     if (rc) return rc;
     if (history_length < 1 || history_length > DZO_LBFGS_MAX_HISTORY) return fail(DZO_ERR_INVALID_ARGUMENT, "history_length must be in [1, 64]"); /* :528 */
-    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE && order != DZO_ORDER_TREE_BLOCKED) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
     dzo_cpu_legacy_lbfgs* o = (dzo_cpu_legacy_lbfgs*)calloc(1, sizeof *o);
     if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
     o->P.objective = objective; o->P.constraint = constraint; o->P.order = order; o->P.n = n;

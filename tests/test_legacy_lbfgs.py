@@ -165,3 +165,27 @@ def test_gpu_legacy_lbfgs_degenerate_starts(gpu, orc):
         for it in range(30):
             gpu.step_(opt); ref.step(1)
             _compare(opt, ref, f"iter {it}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,mi,lam,box", [(65538, 2, 0, None, None), (131072, 3, 2, 0.1, None), (200000, 5, 0, None, (-0.5, 0.8)),
+                                            (1 << 20, 10, 0, 0.01, (-1.0, 0.5)), (3_000_000, 2, 0, None, None)])
+def test_gpu_legacy_lbfgs_grid_wide_trace(gpu, orc, n, m, mi, lam, box):
+    """n > DZO_TREE_BLOCK: cooperative grid, eight CTAs per block, DZO_ORDER_TREE_BLOCKED; bitwise vs the oracle."""
+    x0 = _x0(orc, n, 5)
+    opt, _unused = _gpu_pair(gpu, orc, x0[:4], 1, 0, None, None)      # (exercise the small path once more)
+    opt.close()
+    EF = gpu.ExampleFunctions
+    f, g, c = EF.rosenbrock_function, EF.rosenbrock_gradient_, gpu.NULL_CONSTRAINT
+    if lam is not None:
+        f, g = gpu.L2RegularizationWrapper(f, lam), gpu.L2GradientWrapper(g, lam)
+    if box is not None:
+        g, c = gpu.UniformBoxGradientWrapper(g, *box), gpu.UniformBoxConstraint(*box)
+    opt = gpu.LegacyLBFGSOptimizer(c, f, g, gpu.QuadraticLineSearch(mi), x0, 1.0, m)
+    ref = orc.LegacyLBFGS(ROSEN, x0, 1.0, m, mi, lam, box, orc.TREE_BLOCKED)
+    _compare(opt, ref, "ctor")
+    for it in range(4 if n >= (1 << 20) else 10):
+        gpu.step_(opt); ref.step(1)
+        _compare(opt, ref, f"n={n} iter {it}")
+    opt.step(12); ref.step(12)
+    _compare(opt, ref, "fused")
