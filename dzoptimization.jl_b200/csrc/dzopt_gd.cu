@@ -9,6 +9,14 @@
 
 using namespace dzo;
 
+// grid-wide GradientDescentOptimizer for extended Rosenbrock, n > DZO_TREE_BLOCK (dzopt_lbfgs.cu)
+namespace dzo {
+int grid_gd_attach(int64_t n, int device, void** out, double** scal);
+void grid_gd_detach(void* p);
+int grid_gd_launch(void* p, int mode, int k, cudaStream_t stream, double* x, double* dx, double* g, double* dg, double* d,
+                   int64_t n, int max_increases, double L0);
+}
+
 // ============================================================================= handle
 struct dzo_gd {
     int device = 0;
@@ -31,6 +39,9 @@ struct dzo_gd {
     int esplit = 2, gcnt_off = 0;
     unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
     int grid = 0;
+    // Rosenbrock, n > DZO_TREE_BLOCK: cooperative grid, DZO_ORDER_TREE_BLOCKED
+    void* gridgd = nullptr;
+    double* gscal = nullptr;              // { f, df, L, iteration_count, has_terminated, evals } (owned by gridgd)
 };
 
 static void free_gd(dzo_gd* o) {
@@ -40,6 +51,7 @@ static void free_gd(dzo_gd* o) {
                     o->f, o->df, o->L, o->iter, o->term};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    if (o->gridgd) grid_gd_detach(o->gridgd);
     if (o->own_stream) cudaStreamDestroy(o->own_stream);
     delete o;
 }
@@ -174,6 +186,8 @@ static int gd_launch(dzo_gd* o, int mode, int k, double L0) {
                                              riesz_gd_smem((int)o->dim), o->stream));
         return DZO_OK;
     }
+    if (o->gridgd)
+        return grid_gd_launch(o->gridgd, mode, k, o->stream, o->x, o->dx, o->g, o->dg, o->d, o->n, o->max_increases, L0);
     VecGdArgs a;
     a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg; a.ctrl = o->ctrl; a.n = o->n;
     a.max_increases = o->max_increases; a.ksteps = k; a.initial_step_length = L0; a.mode = mode;
@@ -218,6 +232,9 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
         o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->esplit = w.esplit; o->gcnt_off = w.gcnt_off; o->grid = w.grid;
+    }
+    if (!o->small && objective == DZO_OBJ_ROSENBROCK && n > DZO_TREE_BLOCK) {
+        if ((rc = grid_gd_attach(n, device, &o->gridgd, &o->gscal))) return bail(rc);
     }
     if (cudaMemcpyAsync(o->x, x0, nb * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)   // :339 collect
         return bail(fail(DZO_ERR_CUDA, "H2D copy of x0 failed"));
@@ -278,7 +295,13 @@ DZO_GD_VEC(dzo_gd_get_direction, d)
         if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");    \
         if (o->small) return gd_read(o, out, o->field, (size_t)o->batch * sizeof(type));   \
         GdCtrl c;                                                                 \
-        DZO_TRY(gd_read(o, &c, o->ctrl, sizeof c));                               \
+        if (o->gridgd) {                                                          \
+            double s6[6];                                                         \
+            DZO_TRY(gd_read(o, s6, o->gscal, sizeof s6));                         \
+            c.f = s6[0]; c.df = s6[1]; c.L = s6[2]; c.iter = (long long)s6[3]; c.term = (int)s6[4]; \
+        } else {                                                                  \
+            DZO_TRY(gd_read(o, &c, o->ctrl, sizeof c));                           \
+        }                                                                         \
         *out = (type)(expr);                                                      \
         return DZO_OK;                                                            \
     }
@@ -306,7 +329,7 @@ int dzo_gd_info(dzo_gd* o, int64_t* n, int64_t* batch, int* order) {
     if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
     if (n) *n = o->n;
     if (batch) *batch = o->batch;
-    if (order) *order = o->small ? DZO_ORDER_SEQUENTIAL : DZO_ORDER_TREE;
+    if (order) *order = o->small ? DZO_ORDER_SEQUENTIAL : (o->gridgd ? DZO_ORDER_TREE_BLOCKED : DZO_ORDER_TREE);
     return DZO_OK;
 }
 

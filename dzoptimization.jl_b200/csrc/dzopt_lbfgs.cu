@@ -300,7 +300,7 @@ static int legacy_launch(dzo_legacy_lbfgs* o, int mode, int k, double L0) {
     LegacyArgs a;
     a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.d = o->d; a.S = o->S; a.Y = o->Y; a.ctrl = o->ctrl;
     a.n = o->n; a.m = o->m; a.ksteps = k; a.max_increases = o->max_increases; a.mode = mode; a.decor = o->decor;
-    a.initial_step_length = L0; a.l2 = o->l2; a.lo = o->lo; a.hi = o->hi;
+    a.initial_step_length = L0; a.l2 = o->l2; a.lo = o->lo; a.hi = o->hi; a.algo = 0;
     if (o->use_grid) {
         GridLegacyArgs ga;
         ga.a = a; ga.part = o->part; ga.fpart = o->fpart; ga.nblocks = o->nblocks;
@@ -465,3 +465,79 @@ extern "C" int dzo_dev_line_search_evaluate(int objective, int constraint, int64
     DZO_CUDA(cudaMemcpy(results3, dout.p, 24, cudaMemcpyDeviceToHost));
     return DZO_OK;
 }
+
+
+// ============================================================================= GradientDescentOptimizer, Rosenbrock, n > DZO_TREE_BLOCK
+// (hook used by dzopt_gd.cu: the grid-wide legacy kernel with algo = 1)
+namespace dzo {
+struct GridGd {
+    int nblocks = 0, nctas = 0;
+    double* part = nullptr;
+    unsigned* fpart = nullptr;
+    LegacyCtrl* lctrl = nullptr;
+    double* scal = nullptr;      // { f, df, L, iteration_count, has_terminated, evals } for the getters of dzopt_gd.cu
+};
+static __global__ void grid_gd_publish_kernel(const LegacyCtrl* c, double* s) {
+    s[0] = c->f; s[1] = c->df; s[2] = c->L; s[3] = (double)c->iter; s[4] = (double)(c->term != 0); s[5] = (double)c->evals;
+}
+void grid_gd_detach(void* p) {
+    GridGd* h = static_cast<GridGd*>(p);
+    if (!h) return;
+    void* ptrs[] = {h->part, h->fpart, h->lctrl, h->scal};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    delete h;
+}
+int grid_gd_attach(int64_t n, int device, void** out, double** scal) {
+    *out = nullptr;
+    GridGd* h = new (std::nothrow) GridGd();
+    if (!h) return fail(DZO_ERR_ALLOC, "out of memory");
+    h->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_legacy_lbfgs_kernel, kClusterThreads, 0) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
+        cudaGetLastError();
+        delete h;
+        return fail(DZO_ERR_CUDA, "the grid-wide GD kernel does not fit on this device");
+    }
+    const int resident = per_sm * sms;
+    h->nctas = 8 * h->nblocks < resident ? 8 * h->nblocks : resident;
+    if (h->nblocks > kGridMaxBlocks || 8 * h->nblocks > kGridOwnMax * h->nctas) {
+        delete h;
+        return fail(DZO_ERR_UNSUPPORTED, "n = %lld is too large for the grid-wide GD kernel", (long long)n);
+    }
+    if (cudaMalloc((void**)&h->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
+        cudaMalloc((void**)&h->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess ||
+        cudaMalloc((void**)&h->lctrl, sizeof(LegacyCtrl)) != cudaSuccess || cudaMalloc((void**)&h->scal, 6 * sizeof(double)) != cudaSuccess) {
+        grid_gd_detach(h);
+        return fail(DZO_ERR_ALLOC, "cudaMalloc failed");
+    }
+    *out = h;
+    *scal = h->scal;
+    return DZO_OK;
+}
+int grid_gd_launch(void* p, int mode, int k, cudaStream_t stream, double* x, double* dx, double* g, double* dg, double* d,
+                   int64_t n, int max_increases, double L0) {
+    GridGd* h = static_cast<GridGd*>(p);
+    GridLegacyArgs ga;
+    memset(&ga, 0, sizeof ga);
+    ga.a.x = x; ga.a.dx = dx; ga.a.g = g; ga.a.dg = dg; ga.a.d = d; ga.a.S = nullptr; ga.a.Y = nullptr;   // no history in GD mode
+    ga.a.ctrl = h->lctrl; ga.a.n = n; ga.a.m = 1; ga.a.ksteps = k; ga.a.max_increases = max_increases; ga.a.mode = mode;
+    ga.a.decor = 0; ga.a.algo = 1; ga.a.initial_step_length = L0;
+    ga.part = h->part; ga.fpart = h->fpart; ga.nblocks = h->nblocks;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)h->nctas);
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_legacy_lbfgs_kernel, ga));
+    grid_gd_publish_kernel<<<1, 1, 0, stream>>>(h->lctrl, h->scal);
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+}  // namespace dzo

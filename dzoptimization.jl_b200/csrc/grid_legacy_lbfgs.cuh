@@ -3,6 +3,8 @@
 // (eight 512-thread CTAs per 65536-element block, one grid barrier per reduction) under the control flow of
 // cluster_legacy_lbfgs_kernel (legacy_lbfgs.cuh).  Every pass over the direction of the two-loop correction also
 // accumulates the dot product the next stage needs.
+// a.algo == 1 runs step!(::GradientDescentOptimizer) (legacy/DZOptimization.jl:393-449) on the same machinery: the same
+// constructor and line search, no gradient retry, no history, next_step_direction = -(step length / |g|) * g.
 #pragma once
 #include "grid_lbfgs.cuh"
 #include "legacy_lbfgs.cuh"
@@ -211,6 +213,11 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
         double step_size, objective_value;
         grid_legacy_line_search(c, m2, D, a.x, a.d, f0, a.max_increases, step_size, objective_value, evals);   // :584-586
         bool reset_history = false;
+        if (a.algo == 1 && (step_size == 0.0 || !(objective_value < f0))) {                     // GD :410-414
+            if (threadIdx.x == 0) { sc.term = 1; sc.evals += evals; }
+            __syncthreads();
+            break;
+        }
         if (step_size == 0.0 || !(objective_value < f0)) {                                      // :589-590
             double acc[1][kGridOwn];
             unsigned fl[kGridOwn];
@@ -260,8 +267,10 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
                 reinterpret_cast<double2*>(a.dx)[k] = dxv;
                 reinterpret_cast<double2*>(a.g)[k] = gn;
                 reinterpret_cast<double2*>(a.dg)[k] = dgv;
-                reinterpret_cast<double2*>(Snew)[k] = dxv;                                      // :642-643 (unused once terminated)
-                reinterpret_cast<double2*>(Ynew)[k] = dgv;
+                if (a.algo == 0) {
+                    reinterpret_cast<double2*>(Snew)[k] = dxv;                                  // :642-643 (unused once terminated)
+                    reinterpret_cast<double2*>(Ynew)[k] = dgv;
+                }
                 acc[0][j] += dxv.x * dxv.x; acc[0][j] += dxv.y * dxv.y;
                 acc[1][j] += gn.x * gn.x;   acc[1][j] += gn.y * gn.y;
                 acc[2][j] += dxv.x * dgv.x; acc[2][j] += dxv.y * dgv.y;
@@ -284,6 +293,15 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
             if (threadIdx.x == 0) sc.term = 1;
             __syncthreads();
             break;
+        }
+        if (a.algo == 1) {                                                                      // GD :445-446
+            const double cc = -step_length * inv_gradient_norm;
+            DZO_GRID_OWN_PAIRS(c, m2, j, k) {
+                const double2 gg = reinterpret_cast<const double2*>(a.g)[k];
+                reinterpret_cast<double2*>(a.d)[k] = make_double2(cc * gg.x, cc * gg.y);
+            }
+            __syncthreads();
+            continue;
         }
         const double delta_overlap = q4[2];                                                     // :646
         const double rho_new = 1.0 / delta_overlap;                                             // :647

@@ -31,6 +31,7 @@ struct LegacyArgs {
     long long n;
     int m, ksteps, max_increases, mode;      // mode 0 = steps, 1 = constructor
     int decor;
+    int algo;                                // 0 = legacy L-BFGS; 1 = GradientDescentOptimizer (grid-wide kernel only)
     double initial_step_length, l2, lo, hi;
 };
 

@@ -737,7 +737,7 @@ int dzo_cpu_gd_create(dzo_cpu_gd** out, int objective, int constraint, int64_t o
     *out = NULL;
     int rc = check_problem(objective, constraint, obj_param, n, batch);
     if (rc) return rc;
-    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE)
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE && order != DZO_ORDER_TREE_BLOCKED)
         return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
     if (nthreads < 1) nthreads = 1;
     dzo_cpu_gd* o = (dzo_cpu_gd*)calloc(1, sizeof *o);
