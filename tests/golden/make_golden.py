@@ -106,5 +106,66 @@ def main():
     print("wrote golden.json:", {k: (len(v) if isinstance(v, list) else "ok") for k, v in g.items()})
 
 
+def legacy_trace(x0, step, m, mi, lam, box, tree, iters):
+    fn = P.Rosenbrock(tree)
+    if lam is not None:
+        fn = P.L2Regularized(fn, lam)
+    if box is not None:
+        fn = P.UniformBox(fn, *box)
+    opt = P.LegacyLBFGSOptimizer(fn, list(x0), step, m, mi, tree)
+    rows = []
+    for _ in range(iters):
+        opt.step()
+        rows.append({"f": float(opt.current_objective_value).hex(), "L": float(opt.last_step_length).hex(),
+                     "iter": opt.iteration_count, "term": opt.has_terminated, "hist": opt._history_count})
+        if opt.has_terminated:
+            break
+    return {"x0": hx(x0), "step": step, "m": m, "max_increases": mi, "lambda": lam, "box": box, "tree": tree, "rows": rows,
+            "final_x": hx(opt.current_point), "final_d": hx(opt.next_step_direction), "rho": hx(opt._rho), "alpha": hx(opt._alpha)}
+
+
+def live_lbfgs_trace(x0, step, m, tree, iters):
+    opt = P.LiveLBFGSOptimizer(P.Rosenbrock(tree), list(x0), step, m, tree)
+    rows = []
+    for _ in range(iters):
+        opt.step()
+        rows.append({"f": float(opt.current_objective_value).hex(), "iter": opt.iteration_count, "stuck": opt.is_stuck})
+    return {"x0": hx(x0), "step": step, "m": m, "rows": rows, "final_x": hx(opt.current_point),
+            "final_d": hx(opt.step_direction), "rho": hx(opt.rho)}
+
+
+def main_next():
+    """Fixtures of the SURVEY 8f rows (second file so that golden.json stays byte-identical)."""
+    g = {}
+    u = [4.0 * a - 2.0 for a in P.pcg_fill(64, 5)]
+    g["legacy_lbfgs"] = [legacy_trace(u[:n], 1.0, m, mi, lam, box, True, 25)
+                         for n, m, mi, lam, box in ((2, 3, 0, None, None), (16, 5, 0, None, None), (34, 4, 2, 0.1, None),
+                                                    (64, 3, 0, None, [-0.5, 0.8]), (16, 1, 0, 0.01, [-1.0, 0.5]))]
+    g["live_lbfgs"] = [live_lbfgs_trace(u[:n], 1.0, m, True, 25) for n, m in ((2, 2), (34, 5), (64, 3))]
+    # DZO_ORDER_TREE_BLOCKED above one block: dot and extended Rosenbrock of 70000 elements
+    n = 70000
+    a = P.pcg_fill(2 * n, 11)
+    x = [4.0 * t - 2.0 for t in a[:n]]
+    y = [4.0 * t - 2.0 for t in a[n:]]
+    g["blocked_n70000"] = {"seed": 11, "dot": P.dot(x, y, P.BLOCKED).hex(), "rosenbrock": P.Rosenbrock(P.BLOCKED).f(x).hex()}
+    # live LineSearchEvaluator
+    fn = P.Rosenbrock(True)
+    x = u[:34]
+    gr = [0.0] * 34
+    fn.g(gr, x)
+    d = [-t for t in gr]
+    f_old = fn.f(x)
+    overlap = P.dot(gr, d, True)
+    tp, tg, f_new, ir, sr = P.live_line_search_evaluate(fn, x, f_old, d, overlap, 1e-3, True, True)
+    g["line_search_evaluator_n34"] = {"x": hx(x), "f_old": f_old.hex(), "overlap": overlap.hex(), "step": 1e-3,
+                                      "trial_point": hx(tp), "trial_gradient": hx(tg), "f_new": f_new.hex(),
+                                      "improvement_ratio": ir.hex(), "slope_ratio": sr.hex()}
+    with open(os.path.join(HERE, "golden_next.json"), "w") as f:
+        json.dump(g, f, indent=0, sort_keys=True)
+    print("wrote golden_next.json:", {k: (len(v) if isinstance(v, list) else "ok") for k, v in g.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--next-only" not in sys.argv:
+        main()
+    main_next()
