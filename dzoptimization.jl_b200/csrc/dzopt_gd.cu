@@ -9,7 +9,7 @@
 
 using namespace dzo;
 
-// grid-wide GradientDescentOptimizer for extended Rosenbrock, n > DZO_TREE_BLOCK (dzopt_lbfgs.cu)
+// GradientDescentOptimizer for extended Rosenbrock, n > 32, on the legacy L-BFGS kernels with algo = 1 (dzopt_lbfgs.cu)
 namespace dzo {
 int grid_gd_attach(int64_t n, int device, void** out, double** scal);
 void grid_gd_detach(void* p);
@@ -39,7 +39,7 @@ struct dzo_gd {
     int esplit = 2, gcnt_off = 0;
     unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
     int grid = 0;
-    // Rosenbrock, n > DZO_TREE_BLOCK: cooperative grid, DZO_ORDER_TREE_BLOCKED
+    // Rosenbrock, n > 32: cluster kernel up to n = DZO_TREE_BLOCK, cooperative grid above (DZO_ORDER_TREE_BLOCKED)
     void* gridgd = nullptr;
     double* gscal = nullptr;              // { f, df, L, iteration_count, has_terminated, evals } (owned by gridgd)
 };
@@ -233,7 +233,7 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
         o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->esplit = w.esplit; o->gcnt_off = w.gcnt_off; o->grid = w.grid;
     }
-    if (!o->small && objective == DZO_OBJ_ROSENBROCK && n > DZO_TREE_BLOCK) {
+    if (!o->small && objective == DZO_OBJ_ROSENBROCK) {       // one 8-CTA cluster up to n = DZO_TREE_BLOCK, the whole grid above
         if ((rc = grid_gd_attach(n, device, &o->gridgd, &o->gscal))) return bail(rc);
     }
     if (cudaMemcpyAsync(o->x, x0, nb * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)   // :339 collect

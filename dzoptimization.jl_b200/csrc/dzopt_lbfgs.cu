@@ -493,6 +493,15 @@ int grid_gd_attach(int64_t n, int device, void** out, double** scal) {
     GridGd* h = new (std::nothrow) GridGd();
     if (!h) return fail(DZO_ERR_ALLOC, "out of memory");
     h->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
+    if (h->nblocks == 1) {       // one block: the 8-CTA cluster kernel (DSMEM reductions), no grid-wide scratch
+        if (cudaMalloc((void**)&h->lctrl, sizeof(LegacyCtrl)) != cudaSuccess || cudaMalloc((void**)&h->scal, 6 * sizeof(double)) != cudaSuccess) {
+            grid_gd_detach(h);
+            return fail(DZO_ERR_ALLOC, "cudaMalloc failed");
+        }
+        *out = h;
+        *scal = h->scal;
+        return DZO_OK;
+    }
     int per_sm = 0, sms = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_legacy_lbfgs_kernel, kClusterThreads, 0) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
@@ -525,6 +534,13 @@ int grid_gd_launch(void* p, int mode, int k, cudaStream_t stream, double* x, dou
     ga.a.ctrl = h->lctrl; ga.a.n = n; ga.a.m = 1; ga.a.ksteps = k; ga.a.max_increases = max_increases; ga.a.mode = mode;
     ga.a.decor = 0; ga.a.algo = 1; ga.a.initial_step_length = L0;
     ga.part = h->part; ga.fpart = h->fpart; ga.nblocks = h->nblocks;
+    if (h->nblocks == 1) {
+        cluster_legacy_lbfgs_kernel<<<kClusterCtas, kClusterThreads, 0, stream>>>(ga.a);
+        DZO_CUDA(cudaGetLastError());
+        grid_gd_publish_kernel<<<1, 1, 0, stream>>>(h->lctrl, h->scal);
+        DZO_CUDA(cudaGetLastError());
+        return DZO_OK;
+    }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)h->nctas);

@@ -31,7 +31,8 @@ struct LegacyArgs {
     long long n;
     int m, ksteps, max_increases, mode;      // mode 0 = steps, 1 = constructor
     int decor;
-    int algo;                                // 0 = legacy L-BFGS; 1 = GradientDescentOptimizer (grid-wide kernel only)
+    int algo;                                // 0 = legacy L-BFGS; 1 = GradientDescentOptimizer (legacy/DZOptimization.jl:393-449):
+                                             //     same constructor and line search, no gradient retry, no history
     double initial_step_length, l2, lo, hi;
 };
 
@@ -224,6 +225,11 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
         double step_size, objective_value;
         legacy_line_search(cluster, R, D, a.x, a.d, n, f0, a.max_increases, step_size, objective_value, evals);   // :584-586
         bool reset_history = false;
+        if (a.algo == 1 && (step_size == 0.0 || !(objective_value < f0))) {                     // GradientDescentOptimizer :410-414
+            if (threadIdx.x == 0) { sc.term = 1; sc.evals += evals; }
+            __syncthreads();
+            break;
+        }
         if (step_size == 0.0 || !(objective_value < f0)) {                                      // :589-590
             const double gn2 = cluster_dot(cluster, R, a.g, a.g, n);
             const double c = -sc.L * (1.0 / sqrt(gn2));                                         // :594-595
@@ -255,8 +261,10 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
             reinterpret_cast<double2*>(a.dx)[k] = dxv;
             reinterpret_cast<double2*>(a.g)[k] = gn;
             reinterpret_cast<double2*>(a.dg)[k] = dgv;
-            reinterpret_cast<double2*>(Snew)[k] = dxv;                                          // :642-643 (unused once terminated)
-            reinterpret_cast<double2*>(Ynew)[k] = dgv;
+            if (a.algo == 0) {
+                reinterpret_cast<double2*>(Snew)[k] = dxv;                                      // :642-643 (unused once terminated)
+                reinterpret_cast<double2*>(Ynew)[k] = dgv;
+            }
             q[0] += dxv.x * dxv.x; q[0] += dxv.y * dxv.y;
             q[1] += gn.x * gn.x;   q[1] += gn.y * gn.y;
             q[2] += dxv.x * dgv.x; q[2] += dxv.y * dgv.y;
@@ -278,6 +286,12 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
             if (threadIdx.x == 0) sc.term = 1;
             __syncthreads();
             break;
+        }
+        if (a.algo == 1) {                                                                      // GradientDescentOptimizer :445-446
+            const double c = -step_length * inv_gradient_norm;
+            DZO_OWN_ELEMENTS(e, n, v) a.d[e] = c * a.g[e];
+            __syncthreads();
+            continue;
         }
         const double delta_overlap = q[2];                                                      // :646
         const double rho_new = 1.0 / delta_overlap;                                             // :647
