@@ -200,11 +200,15 @@ struct dzo_adgd {
     int64_t n = 0;
     double *x = nullptr, *dx = nullptr, *g = nullptr, *dg = nullptr;
     AdgdCtrl* ctrl = nullptr;
+    // n > DZO_TREE_BLOCK: cooperative grid (grid_adgd_kernel)
+    int nblocks = 0, nctas = 0;
+    double* part = nullptr;
+    unsigned* fpart = nullptr;
 };
 static void free_adgd(dzo_adgd* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->ctrl};
+    void* ptrs[] = {o->x, o->dx, o->g, o->dg, o->ctrl, o->part, o->fpart};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (o->stream) cudaStreamDestroy(o->stream);
@@ -214,6 +218,22 @@ static int adgd_launch(dzo_adgd* o, int mode, int k, double L0) {
     AdgdArgs a;
     a.x = o->x; a.dx = o->dx; a.g = o->g; a.dg = o->dg; a.ctrl = o->ctrl; a.n = o->n; a.ksteps = k; a.mode = mode;
     a.initial_step_length = L0;
+    if (o->nblocks > 1) {
+        GridAdgdArgs ga;
+        ga.a = a; ga.part = o->part; ga.fpart = o->fpart; ga.nblocks = o->nblocks;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)o->nctas);
+        cfg.blockDim = dim3(kClusterThreads);
+        cfg.stream = o->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_adgd_kernel, ga));
+        return DZO_OK;
+    }
     cluster_adgd_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;
@@ -238,6 +258,22 @@ int dzo_adgd_create(dzo_adgd** out, int objective, int constraint, int64_t obj_p
     if (cudaMalloc((void**)&o->ctrl, sizeof(AdgdCtrl)) != cudaSuccess) return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
     if (cudaMemcpyAsync(o->x, x0, (size_t)n * 8, cudaMemcpyHostToDevice, o->stream) != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "H2D copy failed"));
+    o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
+    if (o->nblocks > 1) {
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_adgd_kernel, kClusterThreads, 0) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
+            cudaGetLastError();
+            return bail(fail(DZO_ERR_CUDA, "the grid-wide AdGD kernel does not fit on this device"));
+        }
+        const int resident = per_sm * sms;
+        o->nctas = 8 * o->nblocks < resident ? 8 * o->nblocks : resident;
+        if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nctas)
+            return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld is too large for the grid-wide AdGD kernel", (long long)n));
+        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
+            cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
+            return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
+    }
     int rc = adgd_launch(o, 1, 0, initial_step_length);
     if (rc) return bail(rc);
     if (cudaStreamSynchronize(o->stream) != cudaSuccess) return bail(fail(DZO_ERR_CUDA, "constructor kernel failed"));

@@ -409,3 +409,124 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
 }
 
 }  // namespace dzo
+
+// ============================================================================= live AdGDOptimizer (:179-312), n > DZO_TREE_BLOCK
+// The same control flow as cluster_adgd_kernel (lbfgs_kernels.cuh) on the cooperative grid / blocked tree.
+namespace dzo {
+struct GridAdgdArgs {
+    AdgdArgs a;
+    double* part;
+    unsigned* fpart;
+    int nblocks;
+};
+static __global__ void __launch_bounds__(kClusterThreads, 1) grid_adgd_kernel(GridAdgdArgs ga) {
+    constexpr int kGridOwn = kGridOwnMax;
+    const AdgdArgs& a = ga.a;
+    __shared__ AdgdCtrl sc;
+    __shared__ double s_warp[kGridQ * 16];
+    __shared__ unsigned s_wflag[16];
+    __shared__ double s_out[kGridQ];
+    __shared__ unsigned s_flags;
+    GridCtx c{cg::this_grid(), (int)gridDim.x, (int)blockIdx.x, ga.nblocks, 0, ga.part, ga.fpart, s_warp, s_wflag, s_out, &s_flags};
+    const long long m2 = a.n >> 1;
+    const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
+    if (threadIdx.x == 0 && a.mode == 0) sc = *a.ctrl;
+    __syncthreads();
+    c.grid.sync();
+    double acc[2][kGridOwn];
+    unsigned fl[kGridOwn];
+    double out[2];
+    unsigned f;
+    if (a.mode == 1) {                                                                          // :201-271
+#pragma unroll
+        for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; acc[1][j] = 0.0; fl[j] = 0; }
+        DZO_GRID_OWN_PAIRS(c, m2, j, k) {
+            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+            const double2 gg = RosenbrockVec::grad(xx.x, xx.y);                                 // :265
+            reinterpret_cast<double2*>(a.g)[k] = gg;
+            reinterpret_cast<double2*>(a.dx)[k] = make_double2(0.0, 0.0);
+            reinterpret_cast<double2*>(a.dg)[k] = make_double2(0.0, 0.0);
+            acc[0][j] += RosenbrockVec::term(xx.x, xx.y);                                       // :260
+            acc[1][j] += gg.x * gg.x; acc[1][j] += gg.y * gg.y;
+        }
+        grid_reduce<2, kGridOwn>(c, acc, fl, out, f);
+        const double gnorm = sqrt(out[1]);                                                      // :233
+        if (leader) {
+            AdgdCtrl t;
+            t.f = out[0]; t.df = 0.0; t.iter = 0; t.pad = 0;
+            t.stuck = (gnorm == 0.0);                                                           // :234
+            t.cur = t.prev = t.stuck ? 0.0 : a.initial_step_length / gnorm;                     // :235-236
+            *a.ctrl = t;
+        }
+        return;
+    }
+    const double inv_sqrt_two = sqrt(0.5);
+    for (int step_i = 0; step_i < a.ksteps; ++step_i) {
+        if (sc.stuck) break;                                                                    // :276-278
+        const double previous = sc.prev, current = sc.cur;
+        double next = current;
+        if (sc.iter > 0) {                                                                      // :288-297
+            const double theta = current / previous;
+            next *= sqrt(1.0 + theta);
+#pragma unroll
+            for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; acc[1][j] = 0.0; fl[j] = 0; }
+            DZO_GRID_OWN_PAIRS(c, m2, j, k) {
+                const double2 dgv = reinterpret_cast<const double2*>(a.dg)[k];
+                const double2 dxv = reinterpret_cast<const double2*>(a.dx)[k];
+                acc[0][j] += dgv.x * dgv.x; acc[0][j] += dgv.y * dgv.y;
+                acc[1][j] += dxv.x * dxv.x; acc[1][j] += dxv.y * dxv.y;
+            }
+            grid_reduce<2, kGridOwn>(c, acc, fl, out, f);
+            const double dgn = sqrt(out[0]);
+            if (dgn != 0.0) {
+                const double inv_L = sqrt(out[1]) / dgn;
+                next = julia_min(next, inv_sqrt_two * inv_L);
+            }
+        }
+        // take_backtracking_step!(opt, -next, current_gradient)  :301, :107-154
+        double step = -next, nxt = 0.0;
+        bool accepted = false;
+        for (;;) {
+#pragma unroll
+            for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; acc[1][j] = 0.0; fl[j] = 0; }
+            DZO_GRID_OWN_PAIRS(c, m2, j, k) {
+                const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+                const double2 gg = reinterpret_cast<const double2*>(a.g)[k];
+                const double w0 = xx.x + step * gg.x, w1 = xx.y + step * gg.y;
+                if (!julia_isequal(w0, xx.x) || !julia_isequal(w1, xx.y)) fl[j] |= 1u;
+                acc[0][j] += RosenbrockVec::term(w0, w1);
+            }
+            grid_reduce<2, kGridOwn>(c, acc, fl, out, f);
+            if (!(f & 1u)) break;
+            nxt = out[0];
+            if (nxt < sc.f) { accepted = true; break; }
+            step *= 0.5;
+        }
+        if (!accepted) {
+            DZO_GRID_OWN_PAIRS(c, m2, j, k) reinterpret_cast<double2*>(a.dx)[k] = reinterpret_cast<const double2*>(a.x)[k];
+            if (threadIdx.x == 0) { sc.stuck = 1; sc.prev = current; sc.cur = next; }
+            __syncthreads();
+            break;
+        }
+        DZO_GRID_OWN_PAIRS(c, m2, j, k) {
+            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+            const double2 go = reinterpret_cast<const double2*>(a.g)[k];
+            double2 xn, dxv, dgv;
+            xn.x = xx.x + step * go.x; xn.y = xx.y + step * go.y;
+            dxv.x = 1.0 * xn.x + (-1.0) * xx.x; dxv.y = 1.0 * xn.y + (-1.0) * xx.y;
+            const double2 gn = RosenbrockVec::grad(xn.x, xn.y);
+            dgv.x = 1.0 * gn.x + (-1.0) * go.x; dgv.y = 1.0 * gn.y + (-1.0) * go.y;
+            reinterpret_cast<double2*>(a.x)[k] = xn;
+            reinterpret_cast<double2*>(a.dx)[k] = dxv;
+            reinterpret_cast<double2*>(a.g)[k] = gn;
+            reinterpret_cast<double2*>(a.dg)[k] = dgv;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            sc.df = nxt - sc.f; sc.f = nxt; sc.prev = current; sc.cur = next; sc.iter += 1;     // :298-299, :310
+        }
+        __syncthreads();
+    }
+    if (leader) *a.ctrl = sc;
+}
+}  // namespace dzo

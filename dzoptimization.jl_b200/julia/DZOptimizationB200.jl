@@ -20,7 +20,8 @@
 # versions of legacy/ExampleFunctions.jl exported below; anything else raises ArgumentError.
 module DZOptimizationB200
 
-export BFGSOptimizer, GradientDescentOptimizer, LBFGSOptimizer, AdGDOptimizer, LegacyLBFGSOptimizer, L2RegularizationWrapper,
+export BFGSOptimizer, GradientDescentOptimizer, LBFGSOptimizer, AdGDOptimizer, LegacyLBFGSOptimizer, LineSearchEvaluator,
+    L2RegularizationWrapper,
     L2GradientWrapper, UniformBoxConstraint, UniformBoxGradientWrapper, QuadraticLineSearch, step!, StepType, NullStep,
     GradientDescentStep, BFGSStep, NULL_CONSTRAINT, SPHERE_CONSTRAINT,
     accelerated_pairwise_radial_energy, accelerated_pairwise_radial_gradient!, accelerated_pairwise_radial_hvp!
@@ -387,6 +388,41 @@ function Base.getproperty(opt::LegacyLBFGSOptimizer, s::Symbol)
     (s === :has_terminated || s === :has_converged) && return fill(sc[5] != 0)      # :478
     s === :_history_count && return fill(Int(sc[6]))                                # :484
     return getfield(opt, s)
+end
+
+# ================================================================== LineSearchEvaluator (live src/DZOptimization.jl:12-92)
+struct LineSearchEvaluator
+    objective::Cint
+    constraint::Cint
+    current_point::Vector{Float64}
+    current_objective_value::Array{Float64,0}
+    current_gradient::Vector{Float64}
+    step_direction::Vector{Float64}
+    overlap::Array{Float64,0}
+    trial_point::Vector{Float64}
+    trial_objective_value::Array{Float64,0}
+    trial_gradient::Vector{Float64}
+    improvement_ratio::Array{Float64,0}
+    slope_ratio::Array{Float64,0}
+end
+function LineSearchEvaluator(c!, f, g!, x::Vector{Float64}, fx::Float64, gx::Vector{Float64}, dir::Vector{Float64},
+    overlap::Float64)                                                                # :29-63
+    obj, cid = resolve(f, g!, c! === nothing ? NULL_CONSTRAINT : c!)
+    @assert axes(x) == axes(gx) == axes(dir)                                         # :41-43
+    return LineSearchEvaluator(obj, cid, x, fill(fx), gx, dir, fill(overlap), similar(x), Array{Float64,0}(undef),
+        similar(gx), Array{Float64,0}(undef), Array{Float64,0}(undef))
+end
+function (lse::LineSearchEvaluator)(step_size::Float64, compute_gradient::Bool)      # :66-92
+    res = Vector{Float64}(undef, 3)
+    check(ccall((:dzo_dev_line_search_evaluate, libdzopt), Cint,
+        (Cint, Cint, Int64, Cint, Int64, Ptr{Float64}, Float64, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64},
+            Ptr{Float64}, Ptr{Float64}, Cint),
+        lse.objective, lse.constraint, 0, 1, length(lse.current_point), lse.current_point, lse.current_objective_value[],
+        lse.step_direction, lse.overlap[], step_size, compute_gradient ? 1 : 0, lse.trial_point, lse.trial_gradient, res, 0))
+    lse.trial_objective_value[] = res[1]
+    lse.improvement_ratio[] = res[2]
+    compute_gradient && (lse.slope_ratio[] = res[3])
+    return res[1]
 end
 
 # ================================================================== pairwise radial kernels (live src/ExampleFunctions.jl)

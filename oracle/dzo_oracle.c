@@ -1203,7 +1203,7 @@ int dzo_cpu_adgd_create(dzo_cpu_adgd** out, int objective, int constraint, int64
     int rc = check_problem(objective, constraint, obj_param, n, 1);
     if (rc) return rc;
     if (!(initial_step_length > 0.0)) return fail(DZO_ERR_INVALID_ARGUMENT, "initial_step_length must be positive"); /* :232 */
-    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
+    if (order != DZO_ORDER_SEQUENTIAL && order != DZO_ORDER_TREE && order != DZO_ORDER_TREE_BLOCKED) return fail(DZO_ERR_INVALID_ARGUMENT, "unknown summation order");
     dzo_cpu_adgd* o = (dzo_cpu_adgd*)calloc(1, sizeof *o);
     if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
     o->P.objective = objective; o->P.constraint = constraint; o->P.order = order; o->P.n = n;

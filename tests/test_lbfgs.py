@@ -241,3 +241,28 @@ def test_gpu_lbfgs_grid_wide_trace(gpu, orc, n, m):
         compare(f"n={n} iter {it}")
     opt.step(15); ref.step(15)            # 15 step! calls in one cooperative launch
     compare("fused")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [65538, 200000, 1 << 20])
+def test_gpu_adgd_grid_wide_trace(gpu, orc, n):
+    """AdGD above n = 65536: cooperative grid, DZO_ORDER_TREE_BLOCKED; bitwise vs the oracle."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n, 8) * 0.5
+    opt = dz.AdGDOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1e-3)
+    ref = orc.AdGD(ROSEN, x0, 1e-3, orc.TREE_BLOCKED)
+
+    def compare(tag):
+        assert_bitwise(opt.current_point, ref.point, f"{tag}: point")
+        assert_bitwise(opt.delta_point, ref.delta_point, f"{tag}: delta_point")
+        assert_bitwise(opt.current_gradient, ref.gradient, f"{tag}: gradient")
+        assert_bitwise(opt.delta_gradient, ref.delta_gradient, f"{tag}: delta_gradient")
+        assert_bitwise(opt._scalars(), ref.scalars, f"{tag}: scalars")
+
+    compare("ctor")
+    for it in range(8):
+        dz.step_(opt); ref.step(1)
+        compare(f"n={n} iter {it}")
+    opt.step(40); ref.step(40)
+    compare("fused")
