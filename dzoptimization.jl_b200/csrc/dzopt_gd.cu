@@ -82,12 +82,19 @@ static std::vector<int2> energy_items(int N, int rows) {
     return full;
 }
 
+// one translation unit per instance (riesz_dim<N>.cu)
+namespace dzo {
+void* riesz_kernel_dim1();
+void* riesz_kernel_dim2();
+void* riesz_kernel_dim3();
+void* riesz_kernel_dim4();
+}
 static void* riesz_kernel_for(int dim) {
     switch (dim) {
-        case 1: return (void*)riesz_gd_kernel<1>;
-        case 2: return (void*)riesz_gd_kernel<2>;
-        case 3: return (void*)riesz_gd_kernel<3>;
-        case 4: return (void*)riesz_gd_kernel<4>;
+        case 1: return riesz_kernel_dim1();
+        case 2: return riesz_kernel_dim2();
+        case 3: return riesz_kernel_dim3();
+        case 4: return riesz_kernel_dim4();
         default: return nullptr;
     }
 }

@@ -8,6 +8,13 @@
 
 using namespace dzo;
 
+// the grid-wide kernels live in grid_lbfgs_tu.cu / grid_legacy_tu.cu
+namespace dzo {
+void* grid_lbfgs_kernel_ptr(int own);
+void* grid_adgd_kernel_ptr();
+void* grid_legacy_kernel_ptr();
+}
+
 struct dzo_lbfgs {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -48,8 +55,8 @@ static int lbfgs_launch(dzo_lbfgs* o, int mode, int k, double L0) {
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (8 * o->nblocks <= o->nclusters) DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_lbfgs_kernel<1>, g));   // direction in registers
-        else DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_lbfgs_kernel<kGridOwnMax>, g));
+        void* params[] = {&g};
+        DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_lbfgs_kernel_ptr(8 * o->nblocks <= o->nclusters ? 1 : kGridOwnMax), params));   // own = 1: direction in registers
         return DZO_OK;
     }
     LbfgsArgs a;
@@ -94,7 +101,7 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         // eight 512-thread CTAs per block of DZO_TREE_BLOCK elements, as many CTAs as are co-resident (cooperative launch)
         o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
         int per_sm = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_lbfgs_kernel<kGridOwnMax>, kClusterThreads, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_lbfgs_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
             return bail(fail(DZO_ERR_CUDA, "the grid-wide L-BFGS kernel does not fit on this device"));
@@ -231,7 +238,8 @@ static int adgd_launch(dzo_adgd* o, int mode, int k, double L0) {
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_adgd_kernel, ga));
+        void* params[] = {&ga};
+        DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_adgd_kernel_ptr(), params));
         return DZO_OK;
     }
     cluster_adgd_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
@@ -261,7 +269,7 @@ int dzo_adgd_create(dzo_adgd** out, int objective, int constraint, int64_t obj_p
     o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
     if (o->nblocks > 1) {
         int per_sm = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_adgd_kernel, kClusterThreads, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_adgd_kernel_ptr(), kClusterThreads, 0) != cudaSuccess ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
             return bail(fail(DZO_ERR_CUDA, "the grid-wide AdGD kernel does not fit on this device"));
@@ -350,7 +358,8 @@ static int legacy_launch(dzo_legacy_lbfgs* o, int mode, int k, double L0) {
         attr[0].val.cooperative = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_legacy_lbfgs_kernel, ga));
+        void* params[] = {&ga};
+        DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_legacy_kernel_ptr(), params));
         return DZO_OK;
     }
     cluster_legacy_lbfgs_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
@@ -393,7 +402,7 @@ int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constrain
     if (n > DZO_TREE_BLOCK) {
         o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
         int per_sm = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_legacy_lbfgs_kernel, kClusterThreads, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(), kClusterThreads, 0) != cudaSuccess ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
             return bail(fail(DZO_ERR_CUDA, "the grid-wide legacy L-BFGS kernel does not fit on this device"));
@@ -539,7 +548,7 @@ int grid_gd_attach(int64_t n, int device, void** out, double** scal) {
         return DZO_OK;
     }
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_legacy_lbfgs_kernel, kClusterThreads, 0) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(), kClusterThreads, 0) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
         cudaGetLastError();
         delete h;
@@ -587,7 +596,8 @@ int grid_gd_launch(void* p, int mode, int k, cudaStream_t stream, double* x, dou
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DZO_CUDA(cudaLaunchKernelEx(&cfg, grid_legacy_lbfgs_kernel, ga));
+    void* params[] = {&ga};
+    DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_legacy_kernel_ptr(), params));
     grid_gd_publish_kernel<<<1, 1, 0, stream>>>(h->lctrl, h->scal);
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;

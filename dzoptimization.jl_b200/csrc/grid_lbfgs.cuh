@@ -419,6 +419,7 @@ struct GridAdgdArgs {
     unsigned* fpart;
     int nblocks;
 };
+template <int INSTANCE>   // compiled in grid_lbfgs_tu.cu only
 static __global__ void __launch_bounds__(kClusterThreads, 1) grid_adgd_kernel(GridAdgdArgs ga) {
     constexpr int kGridOwn = kGridOwnMax;
     const AdgdArgs& a = ga.a;

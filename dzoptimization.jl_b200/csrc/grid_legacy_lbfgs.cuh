@@ -19,7 +19,8 @@ struct GridLegacyArgs {
 };
 
 // bit 0: any(x != x + alpha*dir)   bit 1: any(dir != 0)
-DZO_DEVINL unsigned grid_point_flags(GridCtx& c, long long m2, const double* __restrict__ x, const double* __restrict__ dir,
+// (out of line: the line search calls these from a dozen sites and each expands to an 8-way unrolled pass)
+static __device__ __noinline__ unsigned grid_point_flags(GridCtx& c, long long m2, const double* __restrict__ x, const double* __restrict__ dir,
                                      double alpha) {
     constexpr int kGridOwn = kGridOwnMax;
     double acc[1][kGridOwn];
@@ -40,7 +41,7 @@ DZO_DEVINL unsigned grid_point_flags(GridCtx& c, long long m2, const double* __r
 
 // lse(alpha), see legacy_probe (legacy_lbfgs.cuh) for the flag bits
 template <int MODE>
-DZO_DEVINL double grid_legacy_probe(GridCtx& c, long long m2, const LegacyDecor& D, const double* __restrict__ x,
+static __device__ __noinline__ double grid_legacy_probe(GridCtx& c, long long m2, const LegacyDecor& D, const double* __restrict__ x,
                                     const double* __restrict__ dir, double alpha, double alpha_ref, unsigned& flags) {
     constexpr int kGridOwn = kGridOwnMax;
     double acc[2][kGridOwn];
@@ -147,6 +148,7 @@ DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDe
     f_best = fb;
 }
 
+template <int INSTANCE>   // a template only so that the kernel is compiled in ONE translation unit (grid_legacy_tu.cu)
 static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_kernel(GridLegacyArgs ga) {
     constexpr int kGridOwn = kGridOwnMax;
     const LegacyArgs& a = ga.a;

@@ -1,0 +1,6 @@
+// riesz_dim1.cu -- instantiates riesz_gd_kernel<1> in its own translation unit (each instance takes ptxas about a
+// minute; four units compile in parallel).  dzopt_gd.cu launches it through the pointer returned here.
+#include "gd_kernels.cuh"
+namespace dzo {
+void* riesz_kernel_dim1() { return (void*)riesz_gd_kernel<1>; }
+}
