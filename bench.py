@@ -68,8 +68,9 @@ def oracle_mod():
     return oracle
 
 
-def x0_batch(orc, batch, seed):
-    return (4.0 * orc.pcg_fill(batch * N_SMALL, seed) - 2.0).reshape(batch, N_SMALL)
+def x0_batch(gen, batch, seed):
+    """gen: anything with pcg_fill(count, seed) -- the product package in the GPU arm, the oracle in the reference arm"""
+    return (4.0 * gen.pcg_fill(batch * N_SMALL, seed) - 2.0).reshape(batch, N_SMALL)
 
 
 class ClockSampler:
@@ -194,7 +195,8 @@ def run_gpu(args):
     for kv in args.tune:
         k, v = kv.split("=")
         dz.set_tuning(k, int(v))
-    orc = oracle_mod()  # input generator (PCG) and, on rank 0, the cpu_baseline leg
+    # the checker: only the cpu_baseline legs below touch it (inputs come from the product's own dz.pcg_fill)
+    orc = oracle_mod() if (rank == 0 and world == 1 and not args.skip_cpu) else None
     peak, peak_src = load_peaks()
     K, W = args.steps, args.warmup
 
@@ -217,7 +219,7 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    x0 = x0_batch(orc, BATCH, 2024 + rank)
+    x0 = x0_batch(dz, BATCH, 2024 + rank)
     x0_pinned = torch.from_numpy(x0).pin_memory()
     x0_host = x0_pinned.numpy()
     stream = torch.cuda.Stream()      # a real (non-default) stream: handle 0 would mean "the handle's own stream"
@@ -363,7 +365,7 @@ def bench_large(dz, orc, torch, stream, peak, device, cpu=True):
     import ctypes as C
     EF = dz.ExampleFunctions
     n = LARGE_N
-    x0 = 4.0 * orc.pcg_fill(n, 1) - 2.0
+    x0 = 4.0 * dz.pcg_fill(n, 1) - 2.0
     opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, device=device)
     opt.set_stream(stream.cuda_stream)
     opt.step(3)
@@ -415,7 +417,7 @@ def bench_riesz(dz, orc, torch, stream, device, cpu=True):
     and pair terms/s.  Inputs per SURVEY 8d: PCG seed 3 uniform in [-1,1)^3, normalised; initial step 1e-3."""
     EF = dz.ExampleFunctions
     N = 4096
-    p = 2.0 * orc.pcg_fill(3 * N, 3).reshape(N, 3) - 1.0
+    p = 2.0 * dz.pcg_fill(3 * N, 3).reshape(N, 3) - 1.0
     p = p / np.sqrt((p * p).sum(axis=1, keepdims=True))
     opt = dz.GradientDescentOptimizer(dz.SPHERE_CONSTRAINT, EF.riesz_energy, EF.riesz_gradient_,
                                       dz.QuadraticLineSearch(0), p, 1e-3, device=device)
@@ -449,7 +451,7 @@ def bench_pairwise(dz, orc, torch, cpu=True):
     EF = dz.ExampleFunctions
     n = 16384
     L = 1.2 * n ** (1.0 / 3.0)
-    p = orc.pcg_fill(3 * n, 21).reshape(3, n) * L
+    p = dz.pcg_fill(3 * n, 21).reshape(3, n) * L
     t = [torch.from_numpy(a.copy()).cuda() for a in p]
     g = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(3)]
     out = {"n": n, "potential": "lennard_jones"}
@@ -483,7 +485,7 @@ def bench_lbfgs(dz, orc, torch, stream, cpu=True):
     HBM fraction is reported for orientation, not as the bound."""
     EF = dz.ExampleFunctions
     n, m, k = 1 << 20, 10, 50
-    x0 = 4.0 * orc.pcg_fill(n, 9) - 2.0
+    x0 = 4.0 * dz.pcg_fill(n, 9) - 2.0
     opt = dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, m)
     opt.set_stream(stream.cuda_stream)
     opt.step(12)
@@ -509,7 +511,7 @@ def bench_lbfgs(dz, orc, torch, stream, cpu=True):
                                "sample": "5 step! calls of the same problem, oracle single thread"}
     # the legacy LBFGSOptimizer (quadratic line search, cyclic history), same grid-wide machinery
     n2 = 1 << 20
-    x1 = 4.0 * orc.pcg_fill(n2, 9) - 2.0
+    x1 = 4.0 * dz.pcg_fill(n2, 9) - 2.0
     leg = dz.LegacyLBFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, dz.QuadraticLineSearch(0), x1, 1.0, m)
     leg.set_stream(stream.cuda_stream)
     leg.step(12)
@@ -528,7 +530,7 @@ def bench_readme(dz, orc):
     """BASELINE configs[0]: README Rosenbrock n=2 from rand(2), step 1.0, run to has_converged -- the
     reference's own CPU-runnable case (README.md:49-66 reports 2.8 us min / 5.6 us median per optimisation
     on an unspecified CPU).  Oracle: 1000 PCG seeds, one thread; GPU: the same 1000 problems as one batch."""
-    x0 = np.stack([orc.pcg_fill(2, s) for s in range(1000)])
+    x0 = np.stack([dz.pcg_fill(2, s) for s in range(1000)])
     t0 = time.perf_counter()
     ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0, 1.0, order=orc.SEQ, nthreads=1)
     while ref.count_active():

@@ -29,6 +29,7 @@ from types import SimpleNamespace
 import numpy as np
 
 from . import _capi
+from .pcg import pcg_fill  # noqa: F401  (legacy/PCG.jl:7-22, the input generator of bench.py and the tools)
 
 __all__ = [
     "LBFGSOptimizer", "AdGDOptimizer", "LegacyLBFGSOptimizer", "LineSearchEvaluator",
@@ -36,7 +37,7 @@ __all__ = [
     "accelerated_pairwise_radial_energy", "accelerated_pairwise_radial_gradient_", "accelerated_pairwise_radial_hvp_",
     "BFGSOptimizer", "GradientDescentOptimizer", "QuadraticLineSearch", "step_",
     "ExampleFunctions", "NULL_CONSTRAINT", "SPHERE_CONSTRAINT", "StepType",
-    "DZOptError", "lib", "lib_path",
+    "DZOptError", "lib", "lib_path", "pcg_fill",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

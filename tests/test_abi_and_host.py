@@ -128,3 +128,18 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_product_pcg_generator_equals_the_oracle_and_the_golden_vectors(dz, orc):
+    """dzoptimization.jl_b200/pcg.py (legacy/PCG.jl:7-22, numpy): the inputs of bench.py come from the product, not
+    from oracle/; bit-identical to dzo_cpu_pcg_fill and to the committed golden vectors."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "golden.json")) as f:
+        golden = json.load(f)["pcg"]
+    for seed, vals in golden.items():
+        assert [float(v).hex() for v in dz.pcg_fill(8, int(seed))] == vals
+    for count, seed in ((1, 0), (4095, 3), (4096, 2024), (4097, 5), (10000, 2 ** 63 + 5), (300000, 9)):
+        assert np.array_equal(dz.pcg_fill(count, seed), orc.pcg_fill(count, seed))
+    assert dz.pcg_fill(0, 1).size == 0
