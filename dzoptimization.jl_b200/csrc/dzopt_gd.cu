@@ -37,6 +37,8 @@ struct dzo_gd {
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
     int esplit = 2, gcnt_off = 0;
+    int2* g_jobs = nullptr;
+    int n_g_jobs = 0, gvariant = 0;
     unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
     int grid = 0;
     // Rosenbrock, n > 32: cluster kernel up to n = DZO_TREE_BLOCK, cooperative grid above (DZO_ORDER_TREE_BLOCKED)
@@ -47,7 +49,7 @@ struct dzo_gd {
 static void free_gd(dzo_gd* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter, o->rbcnt, o->prof,
+    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter, o->rbcnt, o->prof, o->g_jobs,
                     o->f, o->df, o->L, o->iter, o->term};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -68,6 +70,16 @@ static int dmalloc(T** p, size_t count) {
 
 // (row block of `rows` rows, segment of 128 sources) items that contain at least one pair i < j,
 // heaviest first so the round-robin over warps stays balanced
+// gradient tile jobs (a, b), a <= b over the segments of 128 points: off-diagonal (two families of partials) first
+static std::vector<int2> gradient_jobs(int N) {
+    const int nseg = (N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
+    std::vector<int2> jobs;
+    for (int a = 0; a < nseg; ++a)
+        for (int b = a + 1; b < nseg; ++b) jobs.push_back(make_int2(a, b));
+    for (int a = 0; a < nseg; ++a) jobs.push_back(make_int2(a, a));
+    return jobs;
+}
+
 static std::vector<int2> energy_items(int N, int rows) {
     std::vector<int2> full, diag;
     const int nrb = (N + rows - 1) / rows;
@@ -107,6 +119,8 @@ struct RieszWork {
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
     int esplit = 2, gcnt_off = 0;
+    int2* g_jobs = nullptr;
+    int n_g_jobs = 0, gvariant = 0;
     int grid = 0;
     void* kernel = nullptr;
     size_t smem = 0;
@@ -130,6 +144,12 @@ struct RieszWork {
         DZO_TRY(dmalloc(&e_items, items.size()));
         if (!items.empty())
             DZO_CUDA(cudaMemcpy(e_items, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        gvariant = g_tuning.riesz_gvariant ? 1 : 0;
+        std::vector<int2> jobs = gradient_jobs(N);
+        n_g_jobs = (int)jobs.size();
+        DZO_TRY(dmalloc(&g_jobs, jobs.size()));
+        if (!jobs.empty())
+            DZO_CUDA(cudaMemcpy(g_jobs, jobs.data(), jobs.size() * sizeof(int2), cudaMemcpyHostToDevice));
         smem = riesz_gd_smem(dim);
         DZO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaDeviceProp prop;
@@ -142,14 +162,15 @@ struct RieszWork {
         return DZO_OK;
     }
     void release() {
-        void* ptrs[] = {segE, rowE, segG, fbox, e_items, counter, rbcnt};
+        void* ptrs[] = {segE, rowE, segG, fbox, e_items, counter, rbcnt, g_jobs};
         for (void* p : ptrs)
             if (p) cudaFree(p);
-        segE = rowE = segG = fbox = nullptr; e_items = nullptr; counter = nullptr; rbcnt = nullptr;
+        segE = rowE = segG = fbox = nullptr; e_items = nullptr; counter = nullptr; rbcnt = nullptr; g_jobs = nullptr;
     }
     void fill(RieszGdArgs& a) const {
         a.segE = segE; a.rowE = rowE; a.segG = segG; a.e_items = e_items; a.n_e_items = n_e_items;
         a.counter = counter; a.fbox = fbox; a.rbcnt = rbcnt; a.dscale = 1.0; a.esplit = esplit; a.gcnt_off = gcnt_off;
+        a.g_jobs = g_jobs; a.n_g_jobs = n_g_jobs; a.gvariant = gvariant;
     }
     int launch(RieszGdArgs& a, cudaStream_t stream) const {
         void* params[] = {&a};
@@ -164,6 +185,7 @@ static RieszGdArgs riesz_args(const dzo_gd* o, int mode, int k) {
     a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg;
     a.segE = o->segE; a.rowE = o->rowE; a.segG = o->segG; a.e_items = o->e_items; a.n_e_items = o->n_e_items;
     a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox; a.rbcnt = o->rbcnt; a.dscale = 1.0; a.esplit = o->esplit; a.gcnt_off = o->gcnt_off;
+    a.g_jobs = o->g_jobs; a.n_g_jobs = o->n_g_jobs; a.gvariant = o->gvariant;
     a.N = (int)(o->n / o->dim); a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.max_increases = o->max_increases;
     a.ksteps = k; a.mode = mode;
     return a;
@@ -239,6 +261,7 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
         o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->esplit = w.esplit; o->gcnt_off = w.gcnt_off; o->grid = w.grid;
+        o->g_jobs = w.g_jobs; o->n_g_jobs = w.n_g_jobs; o->gvariant = w.gvariant;
     }
     if (!o->small && objective == DZO_OBJ_ROSENBROCK) {       // one 8-CTA cluster up to n = DZO_TREE_BLOCK, the whole grid above
         if ((rc = grid_gd_attach(n, device, &o->gridgd, &o->gscal))) return bail(rc);

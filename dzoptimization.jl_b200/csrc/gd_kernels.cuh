@@ -44,6 +44,9 @@ struct RieszGdArgs {
     GdCtrl* ctrl;
     unsigned* counter;            // (unused by the kernel since the row sums moved into the segment phase)
     double* fbox;                 // result slots of the kernel-level modes 2 and 4
+    const int2* g_jobs;           // gradient tile jobs (segment a, segment b), a <= b  (gvariant 1)
+    int n_g_jobs;
+    int gvariant;                 // 0: (32 rows x 128 sources) warp items; 1: symmetric 128 x 128 CTA tiles
     int esplit;                   // 1: energy items of 32 rows x 128 sources, one lane per row; 2: 16 rows, two lanes per row
     int gcnt_off;                 // offset of the gradient counters inside rbcnt
     double dscale;                // the direction actually used is dscale * dir[e] (1.0, or alpha with dir = g: see mode 0)
@@ -404,6 +407,128 @@ struct RieszDev {
             }
         }
     }
+    // ---- riesz_gradient!, symmetric CTA tiles (gvariant 1).  The pair weight inv_dist_cubed(i, j) is the same number
+    // for row j / source i and for row i / source j (dist_sq is a sum of squares of exactly negated differences), and the
+    // products dist * weight of the two uses are exact negations of each other.  A CTA therefore computes the weights of
+    // a whole (segment a) x (segment b) tile ONCE into shared memory -- 16 per thread, 4 at a time through the interleaved
+    // IEEE fast paths -- and then BOTH families of segment partials that need them: rows of a over the sources of b and
+    // rows of b over the sources of a, each lane walking its 128 sources in ascending order (the reference order of
+    // :55-81 inside a segment), one warp per (32 rows, component).  38 -> ~24 FP64 instructions per ordered pair term.
+    static DZO_DEVINL void gradient_tiles(const RieszGdArgs& a, double* wsm, bool with_delta) {
+        constexpr int LD = DZO_RIESZ_SEG + 1;                       // padded leading dimension (conflict-free columns)
+        double* Cw = wsm;                                            // [128][129] pair weights
+        double* PA = wsm + DZO_RIESZ_SEG * LD;                       // [128][DIM] points of segment a
+        double* PB = PA + DZO_RIESZ_SEG * DIM;                       // [128][DIM] points of segment b
+        __shared__ int s_fin[8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
+        for (int job = blockIdx.x; job < a.n_g_jobs; job += gridDim.x) {
+            const int2 t = a.g_jobs[job];
+            const int ta = t.x, tb = t.y;
+            const int a0 = ta * DZO_RIESZ_SEG, b0 = tb * DZO_RIESZ_SEG;
+            const int na = min(DZO_RIESZ_SEG, a.N - a0), nb = min(DZO_RIESZ_SEG, a.N - b0);
+            __syncthreads();                                         // the previous job's readers are done with the tile
+            for (int e = threadIdx.x; e < na * DIM; e += 1024) PA[e] = a.x[(long long)a0 * DIM + e];
+            for (int e = threadIdx.x; e < nb * DIM; e += 1024) PB[e] = a.x[(long long)b0 * DIM + e];
+            __syncthreads();
+            // weights: warp w owns tile rows 4w .. 4w+3, lane the columns lane, lane+32, lane+64, lane+96
+#pragma unroll 1
+            for (int r = 0; r < 4; ++r) {
+                const int jj = 4 * warp + r;
+                if (jj >= na) break;                                 // uniform over the warp
+                double pj[DIM];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) pj[k] = PA[jj * DIM + k];
+                double ds[4], c[4];
+                bool safe = true;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ii = lane + 32 * u;
+                    double dist_sq = 1.0;                            // placeholder for the self pair and for columns past nb
+                    if (ii < nb && !(ta == tb && ii == jj)) {
+                        dist_sq = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) {
+                            const double dist = PB[ii * DIM + k] - pj[k];
+                            dist_sq += dist * dist;
+                        }
+                    }
+                    ds[u] = dist_sq;
+                    safe &= ieee_fast_safe(dist_sq);
+                }
+                if (safe) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[u] = ieee_fast_div(ieee_fast_rcp(ieee_fast_sqrt(ds[u])), ds[u]);   // :61-62
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[u] = ieee_inv_cubed_operators(ds[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) Cw[jj * LD + lane + 32 * u] = c[u];
+            }
+            __syncthreads();
+            // segment partials: warps [0, 4*DIM) rows of a over the sources of b, warps [4*DIM, 8*DIM) rows of b over a
+            if (warp < 8 * DIM) {
+                const int side = warp / (4 * DIM), q = (warp % (4 * DIM)) / DIM, k = warp % DIM;
+                const int row = 32 * q + lane;
+                if (side == 0) {
+                    if (row < na) {
+                        const double xr = PA[row * DIM + k];
+                        const int self = (ta == tb) ? row : -1;
+                        double part = 0.0;
+                        int ii = 0;
+                        for (; ii + 8 <= nb; ii += 8) {              // 16 shared-memory loads in flight, adds in order
+                            double term[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) term[u] = (PB[(ii + u) * DIM + k] - xr) * Cw[row * LD + ii + u];   // :65
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                if (ii + u != self) part += term[u];                   // :55, :69 (i != j)
+                        }
+                        for (; ii < nb; ++ii)
+                            if (ii != self) part += (PB[ii * DIM + k] - xr) * Cw[row * LD + ii];
+                        a.segG[((long long)tb * a.N + (a0 + row)) * DIM + k] = part;
+                    }
+                } else if (ta != tb) {
+                    if (row < nb) {
+                        const double xr = PB[row * DIM + k];
+                        double part = 0.0;
+                        int jj = 0;
+                        for (; jj + 8 <= na; jj += 8) {
+                            double term[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) term[u] = (PA[(jj + u) * DIM + k] - xr) * Cw[(jj + u) * LD + row];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) part += term[u];
+                        }
+                        for (; jj < na; ++jj) part += (PA[jj * DIM + k] - xr) * Cw[jj * LD + row];
+                        a.segG[((long long)ta * a.N + (b0 + row)) * DIM + k] = part;
+                    }
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x < 8) {
+                const int side = threadIdx.x >> 2, q = threadIdx.x & 3;
+                const bool valid = (side == 0) ? (32 * q < na) : (ta != tb && 32 * q < nb);
+                int fin = 0;
+                if (valid) {
+                    const int rb = (side == 0 ? ta : tb) * (DZO_RIESZ_SEG / 32) + q;
+                    fin = (atomicAdd(&a.rbcnt[a.gcnt_off + rb], 1u) == (unsigned)nseg - 1u);
+                    if (fin) a.rbcnt[a.gcnt_off + rb] = 0;
+                }
+                s_fin[threadIdx.x] = fin;
+            }
+            __syncthreads();
+            if (warp < 8 && s_fin[warp]) {                          // this job completed the row block: combine its rows
+                __threadfence();
+                const int rb = ((warp >> 2) == 0 ? ta : tb) * (DZO_RIESZ_SEG / 32) + (warp & 3);
+                const int j = rb * 32 + lane;
+                if (j < a.N) gradient_row(a, j, nseg, with_delta);
+            }
+        }
+    }
+
     // one row: combine, project, write g (and dg = g_new - g_old when with_delta)
     static DZO_DEVINL void gradient_row(const RieszGdArgs& a, int j, int nseg, bool with_delta) {
         double acc[DIM], xj[DIM];
@@ -428,6 +553,11 @@ struct RieszDev {
             if (with_delta) a.dg[e] = acc[k] - a.g[e];                         // :433-435
             a.g[e] = acc[k];
         }
+    }
+
+    static DZO_DEVINL void gradient(const RieszGdArgs& a, double* wsm, bool with_delta) {
+        if (a.gvariant == 1) gradient_tiles(a, wsm, with_delta);
+        else gradient_segments(a, wsm, with_delta);
     }
 
     // every CTA scans all points (N/1024 per thread): cheap, avoids a grid barrier
@@ -585,7 +715,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         return;
     }
     if (a.mode == 3) {                                          // dzo_dev_gradient
-        R::gradient_segments(a, wsm, false);
+        R::gradient(a, wsm, false);
         return;
     }
     if (a.mode == 4) {                                          // dzo_dev_line_search
@@ -609,7 +739,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         for (long long e = gtid; e < n; e += gsize) { a.dx[e] = 0.0; a.dg[e] = 0.0; }   // :777-778
         grid.sync();
         const double f0 = R::energy(a, grid, epar, a.x, 0.0, 2, wsm, sm);      // :772
-        R::gradient_segments(a, wsm, false);                                   // :775-776
+        R::gradient(a, wsm, false);                                   // :775-776
         grid.sync();
         for (long long e = gtid; e < n; e += gsize) a.d[e] = a.g[e];           // :784 next_step_direction = copy(gradient)
         if (leader) {
@@ -671,7 +801,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
             for (int k = 0; k < DIM; ++k) a.x[(long long)j * DIM + k] = w[k];
         }
         grid.sync();                                   // every CTA is done reading the old gradient as `dir`
-        R::gradient_segments(a, wsm, true);                                    // :948, dg = (-g_old) + g_new  :944, :950
+        R::gradient(a, wsm, true);                                    // :948, dg = (-g_old) + g_new  :944, :950
         grid.sync();
         double overlap = 0.0;
         if (kind == DZO_STEP_BFGS) {
@@ -705,7 +835,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         for (long long e = gtid; e < n; e += gsize) { a.dx[e] = 0.0; a.dg[e] = 0.0; a.d[e] = 0.0; }
         grid.sync();
         const double f0 = R::energy(a, grid, epar, a.x, 0.0, 2, wsm, sm);      // :343
-        R::gradient_segments(a, wsm, false);                                   // :347-348
+        R::gradient(a, wsm, false);                                   // :347-348
         grid.sync();
         const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :352
         if (isfinite(inv_gradient_norm)) {                                     // :354-357
@@ -755,7 +885,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         }
         grid.sync();
         riesz_prof_mark(a, 7);
-        R::gradient_segments(a, wsm, true);                                    // :433-435
+        R::gradient(a, wsm, true);                                    // :433-435
         riesz_prof_mark(a, 8);
         grid.sync();
         riesz_prof_mark(a, 10);
@@ -785,7 +915,11 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
     }
 }
 
-inline size_t riesz_gd_smem(int dim) { return sizeof(double) * (272 + (size_t)kRieszSegWarps * DZO_RIESZ_SEG * dim); }
+inline size_t riesz_gd_smem(int dim) {
+    const size_t staging = (size_t)kRieszSegWarps * DZO_RIESZ_SEG * dim;                                  // per-warp source staging
+    const size_t tile = (size_t)DZO_RIESZ_SEG * (DZO_RIESZ_SEG + 1) + 2 * (size_t)DZO_RIESZ_SEG * dim;     // gradient tile + 2 point sets
+    return sizeof(double) * (272 + (staging > tile ? staging : tile));
+}
 
 // ============================================================================= Rosenbrock GD, one CTA
 struct VecGdArgs {

@@ -61,6 +61,8 @@ struct Tuning {
     int sharded_variant = 0;  // row-sharded gathers: 0 = fused into the producing kernels over peer memory, 1 = ncclAllGather
     int search_variant = 0;   // large-n O(n) stage: 0 = 8-CTA cluster + DSMEM reductions, 1 = single 1024-thread CTA
     int riesz_esplit = 1;     // lanes per row in the Riesz energy items (1 or 2), read when an optimizer is created
+    int riesz_gvariant = 0;   // Riesz gradient: 0 = (32 rows x 128 sources) warp items, 1 = symmetric 128 x 128 CTA tiles (each pair
+                              // weight computed once; measured 0.183 vs 0.177 ms per GD step at N = 4096, so not the default)
     int riesz_profile = 0;    // 1: the cooperative Riesz kernel logs (phase id, %globaltimer) events of its leader thread
     int batched_variant = 0;  // 0 = hybrid kernel for n in {2,4,8,16}, 1 = lanes-per-problem kernel everywhere
 };
