@@ -217,12 +217,7 @@ static int gd_launch(dzo_gd* o, int mode, int k, double L0) {
     }
     if (o->gridgd)
         return grid_gd_launch(o->gridgd, mode, k, o->stream, o->x, o->dx, o->g, o->dg, o->d, o->n, o->max_increases, L0);
-    VecGdArgs a;
-    a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg; a.ctrl = o->ctrl; a.n = o->n;
-    a.max_increases = o->max_increases; a.ksteps = k; a.initial_step_length = L0; a.mode = mode;
-    vec_gd_kernel<<<1, 1024, 0, o->stream>>>(a);
-    DZO_CUDA(cudaGetLastError());
-    return DZO_OK;
+    return fail(DZO_ERR_UNSUPPORTED, "no device kernel for this objective / size");
 }
 
 extern "C" {

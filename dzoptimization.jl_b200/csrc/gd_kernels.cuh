@@ -13,7 +13,7 @@
 //                        thread j mod 4096)                                     [oracle riesz_energy_tree]
 //       gradient G_j   = sum over segments (ascending) of sequential partials skipping i == j,
 //                        then the tangent projection g_j -= (p_j . g_j) p_j      [oracle gradient_]
-// (2) extended Rosenbrock at any n > 32: one 1024-thread CTA does the whole step!.
+// (2) extended Rosenbrock at n > 32 runs on the legacy L-BFGS kernels with algo = 1 (legacy_lbfgs.cuh, grid_legacy_lbfgs.cuh).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -419,9 +419,12 @@ struct RieszDev {
         double* Cw = wsm;                                            // [128][129] pair weights
         double* PA = wsm + DZO_RIESZ_SEG * LD;                       // [128][DIM] points of segment a
         double* PB = PA + DZO_RIESZ_SEG * DIM;                       // [128][DIM] points of segment b
-        __shared__ int s_fin[8];
+        __shared__ int s_done[64];                                  // at most 8 per tile, 528 tiles / 148 CTAs at N = 4096
+        __shared__ int s_ndone;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
+        if (threadIdx.x == 0) s_ndone = 0;
+        __syncthreads();
         for (int job = blockIdx.x; job < a.n_g_jobs; job += gridDim.x) {
             const int2 t = a.g_jobs[job];
             const int ta = t.x, tb = t.y;
@@ -506,25 +509,31 @@ struct RieszDev {
                     }
                 }
             }
-            __threadfence();
+            if (warp < 8 * DIM) __threadfence();                    // the writers of segG
             __syncthreads();
             if (threadIdx.x < 8) {
                 const int side = threadIdx.x >> 2, q = threadIdx.x & 3;
                 const bool valid = (side == 0) ? (32 * q < na) : (ta != tb && 32 * q < nb);
-                int fin = 0;
                 if (valid) {
                     const int rb = (side == 0 ? ta : tb) * (DZO_RIESZ_SEG / 32) + q;
-                    fin = (atomicAdd(&a.rbcnt[a.gcnt_off + rb], 1u) == (unsigned)nseg - 1u);
-                    if (fin) a.rbcnt[a.gcnt_off + rb] = 0;
+                    if (atomicAdd(&a.rbcnt[a.gcnt_off + rb], 1u) == (unsigned)nseg - 1u) {
+                        a.rbcnt[a.gcnt_off + rb] = 0;
+                        s_done[atomicAdd(&s_ndone, 1)] = rb;        // this job completed the row block: combine its rows later
+                    }
                 }
-                s_fin[threadIdx.x] = fin;
             }
             __syncthreads();
-            if (warp < 8 && s_fin[warp]) {                          // this job completed the row block: combine its rows
-                __threadfence();
-                const int rb = ((warp >> 2) == 0 ? ta : tb) * (DZO_RIESZ_SEG / 32) + (warp & 3);
-                const int j = rb * 32 + lane;
-                if (j < a.N) gradient_row(a, j, nseg, with_delta);
+            if (s_ndone > 56 || job + (int)gridDim.x >= a.n_g_jobs) {
+                // combine the row blocks this CTA completed, one warp each -- after its last tile, so that no tile waits
+                // for a combination (or earlier when the list is about to overflow: 8 entries per tile at most)
+                const int ndone = s_ndone;
+                for (int e = warp; e < ndone; e += 32) {
+                    __threadfence();
+                    const int j = s_done[e] * 32 + lane;
+                    if (j < a.N) gradient_row(a, j, nseg, with_delta);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) s_ndone = 0;
             }
         }
     }
@@ -919,90 +928,6 @@ inline size_t riesz_gd_smem(int dim) {
     const size_t staging = (size_t)kRieszSegWarps * DZO_RIESZ_SEG * dim;                                  // per-warp source staging
     const size_t tile = (size_t)DZO_RIESZ_SEG * (DZO_RIESZ_SEG + 1) + 2 * (size_t)DZO_RIESZ_SEG * dim;     // gradient tile + 2 point sets
     return sizeof(double) * (272 + (staging > tile ? staging : tile));
-}
-
-// ============================================================================= Rosenbrock GD, one CTA
-struct VecGdArgs {
-    double *x, *g, *d, *dx, *dg;
-    GdCtrl* ctrl;
-    long long n;
-    int max_increases, ksteps;
-    double initial_step_length;
-    int mode;  // 0 = steps, 1 = constructor
-};
-
-static __global__ void __launch_bounds__(1024, 1) vec_gd_kernel(VecGdArgs a) {
-    __shared__ double sm[132];
-    const long long n = a.n, m = n >> 1;
-    if (a.mode == 1) {                                                         // :330-374
-        ProbeFlags fl;
-        const double f0 = cta_probe_rosenbrock<2>(a.x, a.x, m, 0.0, 0.0, sm, fl);   // :343
-        for (long long k = threadIdx.x; k < m; k += 1024) {
-            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
-            reinterpret_cast<double2*>(a.g)[k] = RosenbrockVec::grad(xx.x, xx.y);    // :347-348
-            reinterpret_cast<double2*>(a.dx)[k] = make_double2(0.0, 0.0);
-            reinterpret_cast<double2*>(a.dg)[k] = make_double2(0.0, 0.0);
-            reinterpret_cast<double2*>(a.d)[k] = make_double2(0.0, 0.0);
-        }
-        __syncthreads();
-        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));  // :352
-        if (isfinite(inv_gradient_norm)) {
-            const double alpha = -a.initial_step_length * inv_gradient_norm;
-            for (long long e = threadIdx.x; e < n; e += 1024) a.d[e] = a.g[e] * alpha;
-        }
-        if (threadIdx.x == 0) {
-            GdCtrl c;
-            c.f = f0; c.df = 0.0; c.L = 0.0; c.iter = 0; c.pad = 0; c.evals = 1;
-            c.term = (!isfinite(f0)) || (!isfinite(inv_gradient_norm));
-            *a.ctrl = c;
-        }
-        return;
-    }
-    __shared__ GdCtrl sc;
-    if (threadIdx.x == 0) sc = *a.ctrl;
-    __syncthreads();
-    for (int s = 0; s < a.ksteps; ++s) {
-        if (sc.term) break;                                                    // :402
-        const double f0 = sc.f;
-        long long evals = 0;
-        double step_size, objective_value;
-        cta_line_search_rosenbrock(a.x, a.d, n, f0, 1.0, 1.0, a.max_increases, sm, step_size, objective_value, evals);
-        __syncthreads();
-        if (step_size == 0.0 || !(objective_value < f0)) {                     // :410-414
-            if (threadIdx.x == 0) sc.term = 1;
-            __syncthreads();
-            break;
-        }
-        for (long long k = threadIdx.x; k < m; k += 1024) {                    // each thread owns its pairs
-            const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
-            const double2 dd = reinterpret_cast<const double2*>(a.d)[k];
-            const double2 go = reinterpret_cast<const double2*>(a.g)[k];
-            double2 xn;
-            xn.x = xx.x + step_size * dd.x;                                    // :419
-            xn.y = xx.y + step_size * dd.y;
-            const double2 gn = RosenbrockVec::grad(xn.x, xn.y);                // :434
-            reinterpret_cast<double2*>(a.dx)[k] = make_double2(xn.x - xx.x, xn.y - xx.y);   // :423
-            reinterpret_cast<double2*>(a.dg)[k] = make_double2(gn.x - go.x, gn.y - go.y);   // :435
-            reinterpret_cast<double2*>(a.x)[k] = xn;
-            reinterpret_cast<double2*>(a.g)[k] = gn;
-        }
-        __syncthreads();
-        const double step_length = sqrt(cta_tree_dot(a.dx, a.dx, n, sm));      // :424
-        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :438
-        const bool ok = isfinite(inv_gradient_norm);
-        if (ok) {
-            const double alpha = -step_length * inv_gradient_norm;             // :445-446
-            for (long long e = threadIdx.x; e < n; e += 1024) a.d[e] = alpha * a.g[e];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            sc.iter += 1; sc.L = step_length; sc.df = objective_value - f0; sc.f = objective_value;
-            sc.evals += evals;
-            if (!ok) sc.term = 1;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *a.ctrl = sc;
 }
 
 }  // namespace dzo
