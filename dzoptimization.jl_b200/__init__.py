@@ -414,6 +414,29 @@ class BFGSOptimizer(_Optimizer):
     @property
     def last_step_type(self): return self._scalar("get_step_type", np.int32, _capi.c_i32_p)
 
+    def reuse_host_buffers(self, enable: bool = True):
+        """Cached page-locked field buffers (see _Optimizer).  For a batched optimizer the two fields of the README loop
+        -- ``has_converged[]`` and ``current_objective_value[]`` -- additionally become ZERO-COPY MIRRORS
+        (dzo_bfgs_mirror_fields): the step kernel itself stores them into the cached host arrays while it runs, and
+        reading them only synchronises."""
+        self._unmirror()
+        super().reuse_host_buffers(enable)
+        if enable and self._batched:
+            f = self._out("get_objective", self._batch, np.float64)
+            t = self._out("get_terminated", self._batch, np.uint8)
+            _check(lib().dzo_bfgs_mirror_fields(self._h, _dp(f), t.ctypes.data_as(_capi.c_u8_p)))
+            self._mirrored = True
+        return self
+
+    def _unmirror(self):
+        if getattr(self, "_mirrored", False) and getattr(self, "_h", None):
+            lib().dzo_bfgs_mirror_fields(self._h, None, None)      # before the buffers go back to the recycling pool
+        self._mirrored = False
+
+    def _release_cache(self):
+        self._unmirror()
+        super()._release_cache()
+
     def inverse_hessian(self, problem: int = 0):
         """approximate_inverse_hessian (:746) of one problem as an (n, n) array.  It is bitwise
         symmetric, so the column-major device matrix and this C-order view coincide."""

@@ -22,6 +22,8 @@ struct BatchedArgs {
     int* type;
     unsigned char* term;
     unsigned long long* probes;  // optional statistics (may be null): objective evaluations
+    double* f_host;              // optional zero-copy mirrors in page-locked HOST memory (may be null): the step kernel
+    unsigned char* term_host;    //   stores f / has_terminated there too, so the fields cross PCIe while it runs
     int n;
     long long batch;
     int ksteps;
@@ -377,8 +379,12 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kern
             A.L[p] = L;
             A.iter[p] = iter;
             A.type[p] = type;
+            if (A.f_host) A.f_host[p] = f0;
         }
-        if (term) A.term[p] = 1;
+        if (term) {
+            A.term[p] = 1;
+            if (A.term_host) A.term_host[p] = 1;
+        }
         if (A.probes) atomicAdd(A.probes, G.probes);
         if (!waited) mbar_wait(bar, 0);  // never leave with an async copy still targeting our smem
         if (H_dirty) bulk_wait_read0();

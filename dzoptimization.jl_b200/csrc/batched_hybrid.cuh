@@ -350,8 +350,12 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid_kernel(
             A.L[p] = L;
             A.iter[p] = iter;
             A.type[p] = type;
+            if (A.f_host) A.f_host[p] = f0;       // 32 lanes = 256 contiguous bytes of posted PCIe writes
         }
-        if (term) A.term[p] = 1;
+        if (term) {
+            A.term[p] = 1;
+            if (A.term_host) A.term_host[p] = 1;
+        }
     }
 }
 

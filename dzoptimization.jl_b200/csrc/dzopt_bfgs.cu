@@ -96,6 +96,8 @@ struct dzo_bfgs {
     long long* iter = nullptr;
     int* type = nullptr;
     unsigned char* term = nullptr;
+    double* f_host = nullptr;            // dzo_bfgs_mirror_fields: page-locked host mirrors written by the step kernels
+    unsigned char* term_host = nullptr;
     unsigned long long* counter = nullptr;
     // large path
     double *sd = nullptr, *t = nullptr, *partial = nullptr;
@@ -194,6 +196,7 @@ static BatchedArgs batched_args(const dzo_bfgs* o, int ksteps) {
     BatchedArgs A;
     A.x = o->x; A.g = o->g; A.d = o->d; A.dx = o->dx; A.dg = o->dg; A.H = o->H; A.f = o->f; A.L = o->L;
     A.iter = o->iter; A.type = o->type; A.term = o->term; A.probes = nullptr;
+    A.f_host = o->f_host; A.term_host = o->term_host;
     A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps; A.prefetch_rounds = g_tuning.batched_prefetch;
     return A;
 }
@@ -685,8 +688,39 @@ int dzo_bfgs_get_inverse_hessian(dzo_bfgs* o, int64_t problem, double* out) {
     if (o->small) return read_back(o, out, o->H + (size_t)problem * o->n * o->n, (size_t)o->n * o->n * 8);
     return read_back(o, out, o->H, (size_t)o->rows * (size_t)o->n * 8);
 }
+// the mirrored fields are already in the caller's buffer once the stream has drained
+static int mirror_sync(dzo_bfgs* o) {
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    return DZO_OK;
+}
+int dzo_bfgs_mirror_fields(dzo_bfgs* o, double* objective_host, uint8_t* terminated_host) {
+    if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
+    if (!o->small) return fail(DZO_ERR_UNSUPPORTED, "field mirrors: batched (n <= 32) optimizers only");
+    DZO_TRY(use_device(o->device));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    o->f_host = nullptr; o->term_host = nullptr;
+    if (!objective_host && !terminated_host) return DZO_OK;
+    void* ptrs[2] = {objective_host, terminated_host};
+    for (void* p : ptrs) {
+        if (!p) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost || at.devicePointer != p) {
+            cudaGetLastError();
+            return fail(DZO_ERR_INVALID_ARGUMENT, "field mirrors must be page-locked host memory the device can address "
+                                                  "(dzo_host_alloc, or cudaHostRegister with the mapped flag)");
+        }
+    }
+    // bring the mirrors up to date, then let the step kernels maintain them
+    if (objective_host) DZO_CUDA(cudaMemcpyAsync(objective_host, o->f, (size_t)o->batch * 8, cudaMemcpyDeviceToHost, o->stream));
+    if (terminated_host) DZO_CUDA(cudaMemcpyAsync(terminated_host, o->term, (size_t)o->batch, cudaMemcpyDeviceToHost, o->stream));
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    o->f_host = objective_host; o->term_host = terminated_host;
+    return DZO_OK;
+}
 int dzo_bfgs_get_objective(dzo_bfgs* o, double* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small && out == o->f_host) return mirror_sync(o);
     if (o->small) return read_back(o, out, o->f, (size_t)o->batch * 8);
     LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.f; return DZO_OK;
 }
@@ -707,6 +741,7 @@ int dzo_bfgs_get_iteration_count(dzo_bfgs* o, int64_t* out) {
 }
 int dzo_bfgs_get_terminated(dzo_bfgs* o, uint8_t* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small && out == o->term_host) return mirror_sync(o);
     if (o->small) return read_back(o, out, o->term, (size_t)o->batch);
     LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = (uint8_t)(c.term != 0); return DZO_OK;
 }
@@ -769,6 +804,9 @@ int dzo_bfgs_set_state(dzo_bfgs* o, const double* point, const double* inverse_h
         bool bad = false;
         DZO_TRY(any_nan(o, o->f, o->batch, &bad));
         if (bad) return fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the restored point");   // :829
+        if (o->f_host) DZO_CUDA(cudaMemcpyAsync(o->f_host, o->f, (size_t)o->batch * 8, cudaMemcpyDeviceToHost, o->stream));
+        if (o->term_host) DZO_CUDA(cudaMemcpyAsync(o->term_host, o->term, (size_t)o->batch, cudaMemcpyDeviceToHost, o->stream));
+        if (o->f_host || o->term_host) DZO_CUDA(cudaStreamSynchronize(o->stream));
         return DZO_OK;
     }
     // large: the caller passes the full n x n matrix; keep rows [row0, row0+rows) of every column
@@ -1075,7 +1113,7 @@ int dzo_host_alloc(void** out, uint64_t bytes) {
         cudaGetLastError();
         return fail(DZO_ERR_NO_DEVICE, "no CUDA device available");
     }
-    if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         return fail(DZO_ERR_ALLOC, "cudaHostAlloc of %llu bytes failed", (unsigned long long)bytes);
     }

@@ -231,6 +231,31 @@ function current_objective_values(opt::BatchedBFGSOptimizer)
     check(ccall((:dzo_bfgs_get_objective, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), opt.handle, out))
     return out
 end
+# Zero-copy mirrors of the two fields the README loop reads every iteration: the step kernels store
+# current_objective_value / has_terminated of every problem into page-locked host Vectors while they run, and the two
+# accessors below only synchronise (dzo_bfgs_mirror_fields, include/dzopt.h).  The Vectors wrap dzo_host_alloc memory
+# and stay valid until `unmirror_fields!` or finalisation.
+function mirror_fields!(opt::BatchedBFGSOptimizer)
+    pf, pt = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:dzo_host_alloc, libdzopt), Cint, (Ref{Ptr{Cvoid}}, UInt64), pf, 8 * opt.batch))
+    check(ccall((:dzo_host_alloc, libdzopt), Cint, (Ref{Ptr{Cvoid}}, UInt64), pt, opt.batch))
+    f = unsafe_wrap(Array, Ptr{Float64}(pf[]), opt.batch)
+    t = unsafe_wrap(Array, Ptr{UInt8}(pt[]), opt.batch)
+    check(ccall((:dzo_bfgs_mirror_fields, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}), opt.handle, f, t))
+    return f, t
+end
+function unmirror_fields!(opt::BatchedBFGSOptimizer, f::Vector{Float64}, t::Vector{UInt8})
+    check(ccall((:dzo_bfgs_mirror_fields, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}), opt.handle, C_NULL, C_NULL))
+    ccall((:dzo_host_free, libdzopt), Cint, (Ptr{Cvoid},), pointer(f))
+    ccall((:dzo_host_free, libdzopt), Cint, (Ptr{Cvoid},), pointer(t))
+    return nothing
+end
+# after step!(opt): the mirrors are current once these return
+mirrored_objective_values!(opt::BatchedBFGSOptimizer, f::Vector{Float64}) =
+    (check(ccall((:dzo_bfgs_get_objective, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Float64}), opt.handle, f)); f)
+mirrored_terminated!(opt::BatchedBFGSOptimizer, t::Vector{UInt8}) =
+    (check(ccall((:dzo_bfgs_get_terminated, libdzopt), Cint, (Ptr{Cvoid}, Ptr{UInt8}), opt.handle, t)); t)
+
 function count_active(opt::BatchedBFGSOptimizer)
     c = Ref{Int64}(0)
     check(ccall((:dzo_bfgs_count_active, libdzopt), Cint, (Ptr{Cvoid}, Ref{Int64}), opt.handle, c))

@@ -429,3 +429,36 @@ def test_large_awkward_inputs(gpu, orc, L0):
     for it in range(10):
         dz.step_(opt); ref.step(1)
         _compare_state(opt, ref, False, f"L0={L0} iter {it}")
+
+
+@pytest.mark.parametrize("n,batch", [(2, 1000), (16, 5000), (6, 777)])
+def test_zero_copy_field_mirrors_equal_the_device_fields(gpu, orc, n, batch):
+    """dzo_bfgs_mirror_fields: the step kernels store current_objective_value / has_terminated into page-locked host
+    buffers while they run; the mirrored reads must equal ordinary copies of the device fields after every step!."""
+    import ctypes as C
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = (4.0 * orc.pcg_fill(n * batch, 31) - 2.0).reshape(batch, n)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    opt.reuse_host_buffers(True)
+    ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0, 1.0, order=orc.SEQ)
+    f_copy, t_copy = np.empty(batch), np.empty(batch, dtype=np.uint8)
+    for it in range(60):
+        k = 1 if it < 40 else 7
+        opt.step(k); ref.step(k)
+        f_mirror = opt.current_objective_value           # only synchronises
+        t_mirror = opt.has_converged
+        assert dz.lib().dzo_bfgs_get_objective(opt._h, f_copy.ctypes.data_as(dz._capi.c_double_p)) == 0
+        assert dz.lib().dzo_bfgs_get_terminated(opt._h, t_copy.ctypes.data_as(dz._capi.c_u8_p)) == 0
+        assert_bitwise(f_mirror, f_copy, f"iter {it}: mirrored objective")
+        assert np.array_equal(t_mirror.view(np.uint8), t_copy), f"iter {it}: mirrored has_terminated"
+        assert_bitwise(f_mirror, ref.objective, f"iter {it}: objective vs oracle")
+        assert np.array_equal(t_mirror, ref.terminated)
+    assert t_copy.sum() > 0 or n == 16          # some problems have terminated (n = 2, 6 converge within the run)
+    # pageable memory is refused, (NULL, NULL) clears the mirrors
+    pageable = np.empty(batch)
+    assert dz.lib().dzo_bfgs_mirror_fields(opt._h, pageable.ctypes.data_as(dz._capi.c_double_p), None) == -1
+    assert dz.lib().dzo_bfgs_mirror_fields(opt._h, None, None) == 0
+    opt._mirrored = False
+    opt.step(1); ref.step(1)
+    assert_bitwise(opt.current_objective_value, ref.objective, "after clearing the mirrors")
