@@ -424,8 +424,10 @@ class BFGSOptimizer(_Optimizer):
         if enable and self._batched:
             f = self._out("get_objective", self._batch, np.float64)
             t = self._out("get_terminated", self._batch, np.uint8)
-            _check(lib().dzo_bfgs_mirror_fields(self._h, _dp(f), t.ctypes.data_as(_capi.c_u8_p)))
-            self._mirrored = True
+            rc = lib().dzo_bfgs_mirror_fields(self._h, _dp(f), t.ctypes.data_as(_capi.c_u8_p))
+            if rc != -5:                 # DZO_ERR_UNSUPPORTED (generic batched kernel): ordinary copies into the cache
+                _check(rc)
+            self._mirrored = (rc == 0)
         return self
 
     def _unmirror(self):

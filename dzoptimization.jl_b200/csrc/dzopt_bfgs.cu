@@ -697,6 +697,8 @@ static int mirror_sync(dzo_bfgs* o) {
 int dzo_bfgs_mirror_fields(dzo_bfgs* o, double* objective_host, uint8_t* terminated_host) {
     if (!o) return fail(DZO_ERR_INVALID_ARGUMENT, "null handle");
     if (!o->small) return fail(DZO_ERR_UNSUPPORTED, "field mirrors: batched (n <= 32) optimizers only");
+    if (o->objective != DZO_OBJ_ROSENBROCK && (objective_host || terminated_host))
+        return fail(DZO_ERR_UNSUPPORTED, "field mirrors: the warp-resident batched kernels (DZO_OBJ_ROSENBROCK) only");
     DZO_TRY(use_device(o->device));
     DZO_CUDA(cudaStreamSynchronize(o->stream));
     o->f_host = nullptr; o->term_host = nullptr;

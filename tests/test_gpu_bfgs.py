@@ -462,3 +462,20 @@ def test_zero_copy_field_mirrors_equal_the_device_fields(gpu, orc, n, batch):
     opt._mirrored = False
     opt.step(1); ref.step(1)
     assert_bitwise(opt.current_objective_value, ref.objective, "after clearing the mirrors")
+
+
+def test_field_mirrors_are_refused_where_no_kernel_maintains_them(gpu, orc):
+    """Batched Riesz BFGS runs on the generic one-thread-per-problem kernel, which does not write mirrors: the C entry
+    point refuses, the Python twin falls back to ordinary copies into its cached buffers, and the reads stay correct."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    pts = (2.0 * orc.pcg_fill(40 * 6, 33) - 1.0).reshape(40, 2, 3)
+    pts /= np.sqrt((pts * pts).sum(axis=2, keepdims=True))
+    opt = dz.BFGSOptimizer(EF.riesz_energy, EF.riesz_gradient_, dz.SPHERE_CONSTRAINT, pts, 1e-2, batched=True)
+    opt.reuse_host_buffers(True)
+    assert opt._mirrored is False
+    ref = orc.BFGS(orc.OBJ_RIESZ, pts.reshape(40, 6), 1e-2, order=orc.SEQ, constraint=orc.CONSTRAINT_SPHERE, dim=3)
+    for it in range(5):
+        opt.step(1); ref.step(1)
+        assert_bitwise(opt.current_objective_value, ref.objective, f"iter {it}: objective")
+        assert np.array_equal(opt.has_converged, ref.terminated)
