@@ -12,7 +12,7 @@ using namespace dzo;
 namespace dzo {
 void* grid_lbfgs_kernel_ptr(int own);
 void* grid_adgd_kernel_ptr();
-void* grid_legacy_kernel_ptr();
+void* grid_legacy_kernel_ptr(int own);
 }
 
 struct dzo_lbfgs {
@@ -359,7 +359,7 @@ static int legacy_launch(dzo_legacy_lbfgs* o, int mode, int k, double L0) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         void* params[] = {&ga};
-        DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_legacy_kernel_ptr(), params));
+        DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_legacy_kernel_ptr(8 * o->nblocks <= o->nctas ? 1 : kGridOwnMax), params));
         return DZO_OK;
     }
     cluster_legacy_lbfgs_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(a);
@@ -402,7 +402,7 @@ int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constrain
     if (n > DZO_TREE_BLOCK) {
         o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
         int per_sm = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(), kClusterThreads, 0) != cudaSuccess ||
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
             return bail(fail(DZO_ERR_CUDA, "the grid-wide legacy L-BFGS kernel does not fit on this device"));
@@ -548,7 +548,7 @@ int grid_gd_attach(int64_t n, int device, void** out, double** scal) {
         return DZO_OK;
     }
     int per_sm = 0, sms = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(), kClusterThreads, 0) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
         cudaGetLastError();
         delete h;
@@ -597,7 +597,7 @@ int grid_gd_launch(void* p, int mode, int k, cudaStream_t stream, double* x, dou
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     void* params[] = {&ga};
-    DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_legacy_kernel_ptr(), params));
+    DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_legacy_kernel_ptr(8 * h->nblocks <= h->nctas ? 1 : kGridOwnMax), params));
     grid_gd_publish_kernel<<<1, 1, 0, stream>>>(h->lctrl, h->scal);
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;

@@ -19,10 +19,11 @@ struct GridLegacyArgs {
 };
 
 // bit 0: any(x != x + alpha*dir)   bit 1: any(dir != 0)
-// (out of line: the line search calls these from a dozen sites and each expands to an 8-way unrolled pass)
+// (out of line: the line search calls these from a dozen sites and each expands to an OWN-way unrolled pass)
+template <int OWN>
 static __device__ __noinline__ unsigned grid_point_flags(GridCtx& c, long long m2, const double* __restrict__ x, const double* __restrict__ dir,
                                      double alpha) {
-    constexpr int kGridOwn = kGridOwnMax;
+    constexpr int kGridOwn = OWN;
     double acc[1][kGridOwn];
     unsigned fl[kGridOwn];
 #pragma unroll
@@ -40,10 +41,10 @@ static __device__ __noinline__ unsigned grid_point_flags(GridCtx& c, long long m
 }
 
 // lse(alpha), see legacy_probe (legacy_lbfgs.cuh) for the flag bits
-template <int MODE>
+template <int MODE, int OWN>
 static __device__ __noinline__ double grid_legacy_probe(GridCtx& c, long long m2, const LegacyDecor& D, const double* __restrict__ x,
                                     const double* __restrict__ dir, double alpha, double alpha_ref, unsigned& flags) {
-    constexpr int kGridOwn = kGridOwnMax;
+    constexpr int kGridOwn = OWN;
     double acc[2][kGridOwn];
     unsigned fl[kGridOwn];
 #pragma unroll
@@ -75,6 +76,7 @@ static __device__ __noinline__ double grid_legacy_probe(GridCtx& c, long long m2
 
 // QuadraticLineSearch(max_increases)(lse, f0, _)  :191-216 with find_three_point_bracket :49-172 (first step 1);
 // the same control flow as legacy_line_search (legacy_lbfgs.cuh)
+template <int OWN>
 DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDecor& D, const double* __restrict__ x,
                                         const double* __restrict__ dir, double f0, int max_increases, double& t_best,
                                         double& f_best, long long& evals) {
@@ -83,18 +85,18 @@ DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDe
     do {
         if (!isfinite(f0)) break;                                         // :64-66
         double step = 1.0;
-        unsigned fl = grid_point_flags(c, m2, x, dir, step);
+        unsigned fl = grid_point_flags<OWN>(c, m2, x, dir, step);
         if (!(fl & 2u)) break;                                            // :71-85 step_is_zero
         int cap = DZO_LINESEARCH_CAP;
         bool capped = false, small = false;
         while (!(fl & 1u)) {                                              // :91-101
             step += step;
             small = true;
-            fl = grid_point_flags(c, m2, x, dir, step);
+            fl = grid_point_flags<OWN>(c, m2, x, dir, step);
             if (--cap == 0) { capped = true; break; }
         }
         if (capped) break;
-        double fa = grid_legacy_probe<0>(c, m2, D, x, dir, step, 0.0, pf);   // :104, :126
+        double fa = grid_legacy_probe<0, OWN>(c, m2, D, x, dir, step, 0.0, pf);   // :104, :126
         if (small && !(pf & 4u)) break;                                   // :107-123
         ++evals;
         if (fa <= f0) {                                                   // :130
@@ -103,7 +105,7 @@ DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDe
             for (;;) {                                                    // :143-156
                 const double ds = step + step;
                 num_increases += 1;
-                const double fb = grid_legacy_probe<1>(c, m2, D, x, dir, ds, step, pf);
+                const double fb = grid_legacy_probe<1, OWN>(c, m2, D, x, dir, ds, step, pf);
                 ++evals;
                 --cap;
                 if (((max_increases > 0) && (num_increases >= max_increases)) || !isfinite(fb) || fb > fa || !(pf & 2u) ||
@@ -118,7 +120,7 @@ DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDe
             cap = DZO_LINESEARCH_CAP;
             for (;;) {
                 const double hs = 0.5 * step;
-                const double fb = grid_legacy_probe<0>(c, m2, D, x, dir, hs, 0.0, pf);
+                const double fb = grid_legacy_probe<0, OWN>(c, m2, D, x, dir, hs, 0.0, pf);
                 ++evals;
                 --cap;
                 if (fb <= f0 || cap == 0) {
@@ -140,7 +142,7 @@ DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDe
         const double twice_delta_1 = delta_1 + delta_1;
         const double delta_ratio = (twice_delta_1 + sum_deltas) / (sum_deltas + sum_deltas);
         const double xq = delta_ratio * x1;
-        const double fq = grid_legacy_probe<0>(c, m2, D, x, dir, xq, 0.0, pf);
+        const double fq = grid_legacy_probe<0, OWN>(c, m2, D, x, dir, xq, 0.0, pf);
         ++evals;
         if (fq < fb) { xb = xq; fb = fq; }
     }
@@ -148,9 +150,9 @@ DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDe
     f_best = fb;
 }
 
-template <int INSTANCE>   // a template only so that the kernel is compiled in ONE translation unit (grid_legacy_tu.cu)
+template <int OWN>   // eighths one CTA may own (1: n <= CTAs * 8192); compiled in ONE translation unit (grid_legacy_tu.cu)
 static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_kernel(GridLegacyArgs ga) {
-    constexpr int kGridOwn = kGridOwnMax;
+    constexpr int kGridOwn = OWN;
     const LegacyArgs& a = ga.a;
     __shared__ LegacyCtrl sc;
     __shared__ double s_warp[kGridQ * 16];
@@ -213,7 +215,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
         const double f0 = sc.f;
         long long evals = 0;
         double step_size, objective_value;
-        grid_legacy_line_search(c, m2, D, a.x, a.d, f0, a.max_increases, step_size, objective_value, evals);   // :584-586
+        grid_legacy_line_search<OWN>(c, m2, D, a.x, a.d, f0, a.max_increases, step_size, objective_value, evals);   // :584-586
         bool reset_history = false;
         if (a.algo == 1 && (step_size == 0.0 || !(objective_value < f0))) {                     // GD :410-414
             if (threadIdx.x == 0) { sc.term = 1; sc.evals += evals; }
@@ -237,7 +239,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
                 const double2 gg = reinterpret_cast<const double2*>(a.g)[k];
                 reinterpret_cast<double2*>(a.d)[k] = make_double2(gg.x * cc, gg.y * cc);
             }
-            grid_legacy_line_search(c, m2, D, a.x, a.d, f0, a.max_increases, step_size, objective_value, evals);   // :596-598
+            grid_legacy_line_search<OWN>(c, m2, D, a.x, a.d, f0, a.max_increases, step_size, objective_value, evals);   // :596-598
             if (step_size == 0.0 || !(objective_value < f0)) {                                  // :601-605
                 if (threadIdx.x == 0) { sc.term = 1; sc.evals += evals; }
                 __syncthreads();
