@@ -15,29 +15,33 @@
 #pragma once
 #include "common.cuh"
 
+#include "ieee_fast.cuh"
+
 namespace dzo {
 
 struct LennardJones {
-    static DZO_DEVINL double energy(double r2) {             // lj_energy  :16-27
-        const double inv_r2 = 1.0 / r2;
+    // every radial function starts with inv_r2 = 1 / r2; the *_inv forms take it as given so that a batch of pair terms
+    // can obtain its reciprocals through the interleavable IEEE fast path (ieee_fast.cuh) -- same operations, same bits
+    static DZO_DEVINL double energy_inv(double inv_r2) {     // lj_energy  :16-27
         const double inv_r4 = inv_r2 * inv_r2;
         const double inv_r6 = inv_r4 * inv_r2;
         return 4.0 * fma(inv_r6, inv_r6, -inv_r6);
     }
-    static DZO_DEVINL double first(double r2) {              // lj_first_derivative  :30-47
-        const double inv_r2 = 1.0 / r2;
+    static DZO_DEVINL double first_inv(double inv_r2) {      // lj_first_derivative  :30-47
         const double inv_r4 = inv_r2 * inv_r2;
         const double inv_r6 = inv_r4 * inv_r2;
         const double inv_r8 = inv_r4 * inv_r4;
         return -12.0 * fma(inv_r8, inv_r6 + inv_r6, -inv_r8);
     }
-    static DZO_DEVINL double second(double r2) {             // lj_second_derivative  :50-72
-        const double inv_r2 = 1.0 / r2;
+    static DZO_DEVINL double second_inv(double inv_r2) {     // lj_second_derivative  :50-72
         const double inv_r4 = inv_r2 * inv_r2;
         const double inv_r8 = inv_r4 * inv_r4;
         const double inv_r10 = inv_r8 * inv_r2;
         return 48.0 * fma(3.5, inv_r8 * inv_r8, -inv_r10);
     }
+    static DZO_DEVINL double energy(double r2) { return energy_inv(1.0 / r2); }
+    static DZO_DEVINL double first(double r2) { return first_inv(1.0 / r2); }
+    static DZO_DEVINL double second(double r2) { return second_inv(1.0 / r2); }
 };
 
 struct PairwiseArgs {
@@ -65,6 +69,49 @@ DZO_DEVINL void pair_term(bool self, double xi, double yi, double zi, double ui,
         const double os = overlap * s;
         const double g = os + os;                                            // :413 twice(overlap * s)
         ax += f * du + g * dx; ay += f * dv + g * dy; az += f * dw + g * dz; // :416-418
+    }
+}
+
+// Four consecutive sources at once: the four reciprocals run interleaved through ieee_fast_rcp (the compiler's own
+// 1.0 / r2 puts a slow-path branch between neighbouring terms, which serialises their FP64 chains); the accumulation
+// stays in source order.  A batch with an r2 outside [2^-500, 2^500) falls back to the operator.
+template <int WHAT, class Pot>
+DZO_DEVINL void pair_terms4(long long j0, long long i, double xi, double yi, double zi, double ui, double vi, double wi,
+                            const double* sx, const double* sy, const double* sz, const double* su, const double* sv,
+                            const double* sw, double& ax, double& ay, double& az) {
+    double dx[4], dy[4], dz[4], rr[4], inv[4];
+    bool safe = true;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        dx[u] = xi - sx[u]; dy[u] = yi - sy[u]; dz[u] = zi - sz[u];
+        const double r2 = dx[u] * dx[u] + dy[u] * dy[u] + dz[u] * dz[u];
+        rr[u] = (j0 + u == i) ? 1.0 : r2;                                     // the self term is skipped below
+        safe &= ieee_fast_safe(rr[u]);
+    }
+    if (safe) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) inv[u] = ieee_fast_rcp(rr[u]);
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) inv[u] = 1.0 / rr[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const bool self = (j0 + u == i);
+        if (WHAT == 0) {
+            ax += self ? 0.0 : Pot::energy_inv(inv[u]);                       // :145
+        } else if (WHAT == 1) {
+            const double f = self ? 0.0 : Pot::first_inv(inv[u]);             // :253
+            ax += f * dx[u]; ay += f * dy[u]; az += f * dz[u];                // :254-256
+        } else {
+            const double du = ui - su[u], dv = vi - sv[u], dw = wi - sw[u];
+            const double f = self ? 0.0 : Pot::first_inv(inv[u]);             // :409
+            const double sd = self ? 0.0 : Pot::second_inv(inv[u]);           // :410
+            const double overlap = dx[u] * du + dy[u] * dv + dz[u] * dw;      // :411
+            const double os = overlap * sd;
+            const double g = os + os;                                         // :413
+            ax += f * du + g * dx[u]; ay += f * dv + g * dy[u]; az += f * dw + g * dz[u];   // :416-418
+        }
     }
 }
 
@@ -98,8 +145,11 @@ static __global__ void __launch_bounds__(kPairSeqThreads) pairwise_seq_kernel(Pa
         __syncthreads();
         const int cnt = (int)((a.n - t0 < kPairSeqThreads) ? (a.n - t0) : kPairSeqThreads);
         if (valid) {
-#pragma unroll 4
-            for (int jj = 0; jj < cnt; ++jj)
+            int jj = 0;
+            for (; jj + 4 <= cnt; jj += 4)
+                pair_terms4<WHAT, Pot>(t0 + jj, i, xi, yi, zi, ui, vi, wi, sx + jj, sy + jj, sz + jj, su + (WHAT == 2 ? jj : 0),
+                                       sv + (WHAT == 2 ? jj : 0), sw + (WHAT == 2 ? jj : 0), ax, ay, az);
+            for (; jj < cnt; ++jj)
                 pair_term<WHAT, Pot>(t0 + jj == i, xi, yi, zi, ui, vi, wi, sx[jj], sy[jj], sz[jj],
                                      WHAT == 2 ? su[jj] : 0.0, WHAT == 2 ? sv[jj] : 0.0, WHAT == 2 ? sw[jj] : 0.0, ax, ay, az);
         }
@@ -138,8 +188,12 @@ static __global__ void __launch_bounds__(32 * PairTreeWarps<WHAT>::value) pairwi
             }
             __syncwarp();
             if (valid) {
-#pragma unroll 4
-                for (int jj = 0; jj < cnt; ++jj)
+                int jj = 0;
+                for (; jj + 4 <= cnt; jj += 4)
+                    pair_terms4<WHAT, Pot>(j0 + jj, i, xi, yi, zi, ui, vi, wi, &src[warp][0][jj], &src[warp][1][jj],
+                                           &src[warp][2][jj], &src[warp][WHAT == 2 ? 3 : 0][jj], &src[warp][WHAT == 2 ? 4 : 0][jj],
+                                           &src[warp][WHAT == 2 ? 5 : 0][jj], ax, ay, az);
+                for (; jj < cnt; ++jj)
                     pair_term<WHAT, Pot>(j0 + jj == i, xi, yi, zi, ui, vi, wi, src[warp][0][jj], src[warp][1][jj],
                                          src[warp][2][jj], WHAT == 2 ? src[warp][3][jj] : 0.0,
                                          WHAT == 2 ? src[warp][4][jj] : 0.0, WHAT == 2 ? src[warp][5][jj] : 0.0, ax, ay, az);
