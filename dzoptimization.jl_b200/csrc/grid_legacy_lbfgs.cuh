@@ -324,14 +324,15 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
         unsigned f;
 #pragma unroll
         for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; fl[j] = 0; }
+        DirRegs<OWN> Dr;                       // OWN == 1: the direction lives in registers across the 2m + 1 passes
         {
             const double* s0 = a.S + (long long)((hist_end - 1) % m) * n;
-            DZO_GRID_OWN_PAIRS(c, m2, j, k) {                                                   // :656 d = g, and d . S_c of the first stage
+            own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {                          // :656 d = g, and d . S_c of the first stage
                 const double2 gg = reinterpret_cast<const double2*>(a.g)[k];
                 const double2 ss = reinterpret_cast<const double2*>(s0)[k];
-                reinterpret_cast<double2*>(a.d)[k] = gg;
+                Dr.set(a.d, q, k, gg, false);
                 acc[0][j] += gg.x * ss.x; acc[0][j] += gg.y * ss.y;
-            }
+            });
         }
         grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
         const double gamma = delta_overlap / q4[3];                                             // :669-670
@@ -346,15 +347,15 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
             const double* nxt = last ? (a.Y + (long long)cn * n) : (a.S + (long long)cn * n);
 #pragma unroll
             for (int j = 0; j < kGridOwn; ++j) acc[0][j] = 0.0;
-            DZO_GRID_OWN_PAIRS(c, m2, j, k) {
-                double2 dd = reinterpret_cast<double2*>(a.d)[k];
+            own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
+                double2 dd = Dr.get(a.d, q, k);
                 const double2 yy = reinterpret_cast<const double2*>(y)[k];
                 const double2 nn = reinterpret_cast<const double2*>(nxt)[k];
                 dd.x += alpha * yy.x; dd.y += alpha * yy.y;
                 if (last) { dd.x *= gamma; dd.y *= gamma; }                                     // :669-670 scale!
-                reinterpret_cast<double2*>(a.d)[k] = dd;
+                Dr.set(a.d, q, k, dd, false);
                 acc[0][j] += dd.x * nn.x; acc[0][j] += dd.y * nn.y;
-            }
+            });
             grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
         }
         __syncthreads();                       // sc.alpha[] visible
@@ -367,15 +368,15 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
             const double* nxt = last ? a.g : (a.Y + (long long)((it) % m) * n);                 // Y of it+1, or g for :683-684
 #pragma unroll
             for (int j = 0; j < kGridOwn; ++j) acc[0][j] = 0.0;
-            DZO_GRID_OWN_PAIRS(c, m2, j, k) {
-                double2 dd = reinterpret_cast<double2*>(a.d)[k];
+            own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
+                double2 dd = Dr.get(a.d, q, k);
                 const double2 ss = reinterpret_cast<const double2*>(sp)[k];
                 const double2 nn = reinterpret_cast<const double2*>(nxt)[k];
                 dd.x += beta * ss.x; dd.y += beta * ss.y;
                 if (last) { dd.x = -dd.x; dd.y = -dd.y; }                                       // :683 negate!
-                reinterpret_cast<double2*>(a.d)[k] = dd;
+                Dr.set(a.d, q, k, dd, last);                                                    // the finished direction goes to memory
                 acc[0][j] += dd.x * nn.x; acc[0][j] += dd.y * nn.y;
-            }
+            });
             grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
             if (last) gradient_overlap = out[0];                                                // :684
         }
