@@ -481,6 +481,16 @@ class BFGSOptimizer(_Optimizer):
         _check(lib().dzo_bfgs_count_active(self._h, C.byref(c)))
         return c.value
 
+    STEP_KINDS = ("bfgs_read_h", "bfgs_identity_h", "gradient_descent", "terminate", "idle", "idle_warp")
+
+    def step_kind_counts(self, reset: bool = False) -> dict:
+        """What the step! calls of a batched optimizer did, counted on the device (dzo_bfgs_get_step_kind_counts):
+        BFGS-type steps that read H from HBM / whose H was an implicit identity, gradient-descent steps (:962-986),
+        terminations (:988-990), step! calls on terminated problems (:893).  Running totals."""
+        c = np.zeros(8, dtype=np.int64)
+        _check(lib().dzo_bfgs_get_step_kind_counts(self._h, c.ctypes.data_as(_capi.c_i64_p), int(bool(reset))))
+        return {k: int(v) for k, v in zip(self.STEP_KINDS, c)}
+
     def set_state(self, point, inverse_hessian, delta_point, delta_gradient, last_step_length,
                   last_step_type, iteration_count):
         """Resume from saved fields (README.md:11); semantics of the rebuilding constructor
@@ -527,6 +537,12 @@ class GradientDescentOptimizer(_Optimizer):
 
     @property
     def delta_objective_value(self): return self._scalar("get_delta_objective")
+
+    def evaluation_count(self) -> int:
+        """objective evaluations so far (constructor + line-search probes); one-problem handles"""
+        c = C.c_int64()
+        _check(lib().dzo_gd_get_evaluation_count(self._h, C.byref(c)))
+        return c.value
 
 
 class LBFGSOptimizer:

@@ -114,6 +114,7 @@ def bind(lib, cpu: bool):
         sig("bfgs_info", [H, c_i64_p, c_i64_p, c_int_p, c_i64_p, c_i64_p])
         sig("bfgs_get_step_log", [H, c_i64_p, c_u8_p])
         sig("bfgs_gather_mode", [H, c_int_p])
+        sig("bfgs_get_step_kind_counts", [H, c_i64_p, I])
         sig("bfgs_mirror_fields", [H, c_double_p, c_u8_p])
         sig("lbfgs_set_stream", [H, C.c_void_p])
         sig("lbfgs_step_async", [H, I])
@@ -126,6 +127,7 @@ def bind(lib, cpu: bool):
         sig("gd_step_async", [H, I])
         sig("gd_sync", [H])
         sig("gd_info", [H, c_i64_p, c_i64_p, c_int_p])
+        sig("gd_get_evaluation_count", [H, c_i64_p])
         sig("gd_get_phase_log", [H, C.POINTER(C.c_uint64), I64, c_i64_p])
         sig("identity", [I64, c_double_p, I])
         sig("bench_kernel", [I, I64, I, I, c_float_p, I])

@@ -28,6 +28,9 @@ struct BatchedArgs {
     long long batch;
     int ksteps;
     int prefetch_rounds;  // hybrid kernel: phase-2 rounds whose H tiles are pulled into L2 ahead of use
+    unsigned char* hid;          // optional (may be null): hid[p] != 0 <=> H of problem p is the identity and its copy in
+                                 //   HBM is stale (identity_matrix! :981 / :781-783 not materialised; hybrid kernel only)
+    unsigned long long* stats;   // optional (may be null): HK_COUNT running step-kind counters
 };
 
 constexpr int kBatchedThreads = 256;
@@ -201,8 +204,10 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_init_kern
         A.d[p * n + G.r] = g;                                       // :784 next_step_direction = copy(gradient)
         A.dx[p * n + G.r] = 0.0;                                    // :777
         A.dg[p * n + G.r] = 0.0;                                    // :778
-        double* Hp = A.H + p * n * n;                               // :781-783 identity_matrix!
-        for (int j = 0; j < n; ++j) Hp[G.r + j * n] = (j == G.r) ? 1.0 : 0.0;
+        if (!A.hid) {
+            double* Hp = A.H + p * n * n;                           // :781-783 identity_matrix!
+            for (int j = 0; j < n; ++j) Hp[G.r + j * n] = (j == G.r) ? 1.0 : 0.0;
+        }
     }
     if (G.r == 0) {
         A.f[p] = f0;
@@ -210,6 +215,7 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_init_kern
         A.iter[p] = 0;                                              // :767
         A.type[p] = DZO_STEP_NULL;                                  // :780
         A.term[p] = 0;                                              // :768
+        if (A.hid) A.hid[p] = 1;                                    // H = I, kept implicit (batched_hybrid.cuh)
     }
 }
 
@@ -429,7 +435,20 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_restore_k
     if (G.r == 0) {
         A.f[p] = f0;
         A.term[p] = 0;
+        if (A.hid) A.hid[p] = 0;                                    // the caller's H is in HBM
     }
+}
+
+// identity_matrix! for every problem whose H is still implicit (hid != 0), then clear the flags: run before a
+// kernel that does not know about `hid` takes over a handle (A/B switch of the batched variant).
+static __global__ void materialize_identity_kernel(double* H, unsigned char* hid, int n, long long batch) {
+    const long long nn = (long long)n * n;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nn * batch) return;
+    const long long p = idx / nn;
+    if (!hid[p]) return;
+    const int e = (int)(idx - p * nn);
+    H[idx] = (e / n == e % n) ? 1.0 : 0.0;
 }
 
 // number of problems with has_terminated == false

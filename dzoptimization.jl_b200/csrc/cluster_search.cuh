@@ -328,4 +328,13 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
     if (cluster.block_rank() == 0 && threadIdx.x == 0) a.ctrl->delta_norm = a.ctrl->step_length * a.ctrl->overlap + p[0];
 }
 
+// Row-sharded fused mode, last launch of a step!: the peers' rows of next_step_direction are stored into this GPU's
+// memory by THEIR update kernels, so a drained local stream alone would not mean d is complete.  This one-warp kernel
+// waits for every rank's flag of this step; behind it "stream drained" implies "all slabs have landed"
+// (dzo_bfgs_get_direction / dzo_bfgs_sync right after step!), and the next search kernel's wait is already satisfied.
+static __global__ void __launch_bounds__(32, 1) peer_arrival_kernel(LargeVecs a) {
+    if (a.nranks > 1 && a.ctrl->kind == DZO_STEP_BFGS)
+        peer_wait(a.flags_d, a.nranks, (unsigned long long)a.ctrl->calls, &a.ctrl->pad);
+}
+
 }  // namespace dzo

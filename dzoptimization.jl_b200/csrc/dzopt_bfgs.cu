@@ -99,6 +99,8 @@ struct dzo_bfgs {
     double* f_host = nullptr;            // dzo_bfgs_mirror_fields: page-locked host mirrors written by the step kernels
     unsigned char* term_host = nullptr;
     unsigned long long* counter = nullptr;
+    unsigned char* hid = nullptr;        // batched hybrid kernel: H of problem p is an implicit identity (batched_hybrid.cuh, LAZY)
+    unsigned long long* stats = nullptr; // batched hybrid kernel: running step-kind counters (HK_COUNT words)
     // large path
     double *sd = nullptr, *t = nullptr, *partial = nullptr;
     unsigned* tile_counters = nullptr;
@@ -110,6 +112,7 @@ struct dzo_bfgs {
     // fused gathers over peer memory (CUDA IPC): every rank's t, d and flag words mapped here
     bool pooled = true;                 // device memory from the stream-ordered pool (false: cudaMalloc, IPC-able)
     bool fused = false;
+    bool constructed = false;           // create_common finished: destroy takes part in the ranks' rendezvous
     unsigned long long *flags_t = nullptr, *flags_d = nullptr;   // local, kMaxPeers words each
     unsigned* done = nullptr;
     cudaGraphExec_t step_graph = nullptr;   // one large-n step! (4 launches) captured once, replayed per step
@@ -125,19 +128,32 @@ struct dzo_bfgs {
 // Device memory of a handle comes from the device's stream-ordered pool (cudaMallocAsync) with an
 // unbounded release threshold: constructing optimizer after optimizer in one process reuses the
 // pages instead of paying cudaMalloc / cudaFree of gigabytes each time.
+// Destroying a row-sharded handle is COLLECTIVE (include/dzopt.h): every rank drains its stream (behind
+// peer_arrival_kernel that means all stores INTO this rank's arena have landed and all of this rank's stores into
+// its peers' arenas are complete), closes the peers' mappings, and only after a rendezvous of all ranks -- nobody
+// holds a mapping of anybody's arena any more -- frees the exported arena (the CUDA IPC contract).
 static void free_handle(dzo_bfgs* o) {
     if (!o) return;
     cudaSetDevice(o->device);
+    if (o->own_stream) cudaStreamSynchronize(o->stream);
+    if (o->nranks > 1) {
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p != o->rank && o->peer_arena[p]) { cudaIpcCloseMemHandle(o->peer_arena[p]); o->peer_arena[p] = nullptr; }
+        if (o->constructed && o->comm && o->partial && g_nccl.AllGather && o->own_stream) {
+            // rendezvous: one byte per rank through the scratch that is no longer in use
+            char* scratch = reinterpret_cast<char*>(o->partial);
+            if (g_nccl.AllGather(scratch + o->rank, scratch, 1, /*ncclInt8*/ 0, o->comm, o->own_stream) == 0)
+                cudaStreamSynchronize(o->own_stream);
+        }
+    }
     if (o->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(o->comm);
     if (o->riesz) riesz_bfgs_detach(o->riesz);
     if (o->step_graph) cudaGraphExecDestroy(o->step_graph);
     if (o->arena) { o->t = nullptr; o->d = nullptr; o->flags_t = nullptr; o->flags_d = nullptr; }   // live inside the arena
     void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
-                    o->sd, o->t, o->partial, o->tile_counters, o->ctrl, o->flags_t, o->flags_d, o->done, o->arena};
+                    o->sd, o->t, o->partial, o->tile_counters, o->ctrl, o->flags_t, o->flags_d, o->done, o->arena,
+                    o->hid, o->stats};
     if (o->own_stream) {
-        cudaStreamSynchronize(o->stream);
-        for (int p = 0; p < kMaxPeers; ++p)
-            if (p != o->rank && o->peer_arena[p]) cudaIpcCloseMemHandle(o->peer_arena[p]);
         for (void* p : ptrs) {
             if (!p) continue;
             if (o->pooled) cudaFreeAsync(p, o->own_stream); else cudaFree(p);
@@ -198,6 +214,7 @@ static BatchedArgs batched_args(const dzo_bfgs* o, int ksteps) {
     A.iter = o->iter; A.type = o->type; A.term = o->term; A.probes = nullptr;
     A.f_host = o->f_host; A.term_host = o->term_host;
     A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps; A.prefetch_rounds = g_tuning.batched_prefetch;
+    A.hid = o->hid; A.stats = o->stats;
     return A;
 }
 
@@ -278,15 +295,52 @@ static int launch_hybrid_step(dzo_bfgs* o, int k) {
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;
 }
+template <int N, bool DUAL>
+static int launch_hybrid3_step_(dzo_bfgs* o, int k) {
+    const unsigned grid = (unsigned)((o->batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
+    const size_t smem = hybrid_smem<N>();
+    static bool attr_set[64] = {};
+    if (!attr_set[o->device & 63]) {
+        DZO_CUDA(cudaFuncSetAttribute(bfgs_batched_hybrid3_kernel<N, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[o->device & 63] = true;
+    }
+    bfgs_batched_hybrid3_kernel<N, DUAL><<<grid, kHybridThreads, smem, o->stream>>>(batched_args(o, k));
+    DZO_CUDA(cudaGetLastError());
+    return DZO_OK;
+}
+template <int N>
+static int launch_hybrid3_step(dzo_bfgs* o, int k) {
+    return g_tuning.batched_dual ? launch_hybrid3_step_<N, true>(o, k) : launch_hybrid3_step_<N, false>(o, k);
+}
+static bool hybrid_n(int64_t n) { return n == 2 || n == 4 || n == 8 || n == 16; }
+// a kernel that does not know about implicit identities takes over: write them out, drop the lazy mode for good
+static int materialize_identities(dzo_bfgs* o) {
+    if (!o->hid) return DZO_OK;
+    const long long total = (long long)o->n * o->n * o->batch;
+    materialize_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->H, o->hid, (int)o->n, o->batch);
+    DZO_CUDA(cudaGetLastError());
+    DZO_CUDA(cudaStreamSynchronize(o->stream));
+    if (o->pooled) cudaFreeAsync(o->hid, o->own_stream); else cudaFree(o->hid);
+    o->hid = nullptr;
+    return DZO_OK;
+}
 static int batched_step(dzo_bfgs* o, int k) {
     if (o->objective != DZO_OBJ_ROSENBROCK) return generic_launch(o, 0, k, 0.0);
-    if (g_tuning.batched_variant == 0) {     // thread-per-problem line search + lanes-per-problem H update
+    if (g_tuning.batched_variant == 0 && hybrid_n(o->n)) {   // thread-per-problem dual line search + lanes-per-problem H update
+        switch (o->n) {
+            case 2: return launch_hybrid3_step<2>(o, k);
+            case 4: return launch_hybrid3_step<4>(o, k);
+            case 8: return launch_hybrid3_step<8>(o, k);
+            default: return launch_hybrid3_step<16>(o, k);
+        }
+    }
+    DZO_TRY(materialize_identities(o));
+    if (g_tuning.batched_variant == 2 && hybrid_n(o->n)) {   // second-generation kernel (round 1), kept as the A/B baseline
         switch (o->n) {
             case 2: return launch_hybrid_step<2>(o, k);
             case 4: return launch_hybrid_step<4>(o, k);
             case 8: return launch_hybrid_step<8>(o, k);
-            case 16: return launch_hybrid_step<16>(o, k);
-            default: break;
+            default: return launch_hybrid_step<16>(o, k);
         }
     }
     DZO_LPP_DISPATCH(o, launch_batched_step, o, k)
@@ -392,6 +446,10 @@ static int large_step_once(dzo_bfgs* o) {
     launch_update(sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), o->stream, a);   // :878-886 + :958-960
     DZO_CUDA(cudaGetLastError());
     if (!o->fused) DZO_TRY(allgather_rows(o, o->d));
+    else {
+        peer_arrival_kernel<<<1, 32, 0, o->stream>>>(v);     // drained stream => every peer's rows of d have landed
+        DZO_CUDA(cudaGetLastError());
+    }
     return DZO_OK;
 }
 
@@ -512,8 +570,14 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
         return bail(rc);
     if (o->small) {
         if ((rc = dmalloc(&o->H, nb * (size_t)n)) || (rc = dmalloc(&o->f, (size_t)batch)) || (rc = dmalloc(&o->L, (size_t)batch)) ||
-            (rc = dmalloc(&o->iter, (size_t)batch)) || (rc = dmalloc(&o->type, (size_t)batch)) || (rc = dmalloc(&o->term, (size_t)batch)))
+            (rc = dmalloc(&o->iter, (size_t)batch)) || (rc = dmalloc(&o->type, (size_t)batch)) || (rc = dmalloc(&o->term, (size_t)batch)) ||
+            (rc = dmalloc(&o->stats, (size_t)HK_COUNT)))
             return bail(rc);
+        if (cudaMemsetAsync(o->stats, 0, HK_COUNT * sizeof(unsigned long long), o->stream) != cudaSuccess)
+            return bail(fail(DZO_ERR_CUDA, "memset failed"));
+        // implicit identities (constructor and identity_matrix! after a GD step write no H): hybrid kernel only
+        if (objective == DZO_OBJ_ROSENBROCK && hybrid_n(n) && g_tuning.batched_variant == 0 && g_tuning.batched_lazy)
+            if ((rc = dmalloc(&o->hid, (size_t)batch))) return bail(rc);
     } else {
         const size_t nchunks = (size_t)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
         const size_t rblocks = (size_t)((o->rows + kSweepMinRows - 1) / kSweepMinRows);
@@ -566,6 +630,7 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
         }
         if (bad) return bail(fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the initial point"));
     }
+    o->constructed = true;
     *out = o;
     return DZO_OK;
 }
@@ -685,6 +750,15 @@ DZO_VEC_GETTER(dzo_bfgs_get_direction, d)
 
 int dzo_bfgs_get_inverse_hessian(dzo_bfgs* o, int64_t problem, double* out) {
     if (!o || problem < 0 || problem >= o->batch) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
+    if (o->small && o->hid) {            // an implicit identity is materialised for the caller, not in HBM
+        unsigned char flag = 0;
+        DZO_TRY(read_back(o, &flag, o->hid + problem, 1));
+        if (flag) {
+            for (int64_t j = 0; j < o->n; ++j)
+                for (int64_t i = 0; i < o->n; ++i) out[j * o->n + i] = (i == j) ? 1.0 : 0.0;
+            return DZO_OK;
+        }
+    }
     if (o->small) return read_back(o, out, o->H + (size_t)problem * o->n * o->n, (size_t)o->n * o->n * 8);
     return read_back(o, out, o->H, (size_t)o->rows * (size_t)o->n * 8);
 }
@@ -767,6 +841,18 @@ int dzo_bfgs_get_step_log(dzo_bfgs* o, int64_t* calls, uint8_t* kinds64) {
     LargeCtrl c; DZO_TRY(read_ctrl(o, &c));
     *calls = c.calls;
     memcpy(kinds64, c.kind_log, 64);
+    return DZO_OK;
+}
+int dzo_bfgs_get_step_kind_counts(dzo_bfgs* o, int64_t* counts8, int reset) {
+    if (!o || !counts8) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!o->small || !o->stats) return fail(DZO_ERR_UNSUPPORTED, "step-kind counters exist for batched handles only (large n: dzo_bfgs_get_step_log)");
+    unsigned long long c[HK_COUNT];
+    DZO_TRY(read_back(o, c, o->stats, sizeof c));
+    for (int k = 0; k < 8; ++k) counts8[k] = (k < HK_COUNT) ? (int64_t)c[k] : 0;
+    if (reset) {
+        DZO_CUDA(cudaMemsetAsync(o->stats, 0, sizeof c, o->stream));
+        DZO_CUDA(cudaStreamSynchronize(o->stream));
+    }
     return DZO_OK;
 }
 int dzo_bfgs_gather_mode(dzo_bfgs* o, int* mode) {
@@ -1143,6 +1229,8 @@ int dzo_set_tuning(const char* key, int value) {
         g_tuning.sweep_threads = value; return DZO_OK;
     }
     if (!strcmp(key, "batched_prefetch")) { g_tuning.batched_prefetch = value; return DZO_OK; }
+    if (!strcmp(key, "batched_lazy")) { g_tuning.batched_lazy = value; return DZO_OK; }
+    if (!strcmp(key, "batched_dual")) { g_tuning.batched_dual = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }
 

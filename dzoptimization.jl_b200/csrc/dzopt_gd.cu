@@ -337,6 +337,20 @@ DZO_GD_SCALAR(dzo_gd_get_iteration_count, int64_t, c.iter, iter)
 DZO_GD_SCALAR(dzo_gd_get_terminated, uint8_t, c.term != 0, term)
 #undef DZO_GD_SCALAR
 
+int dzo_gd_get_evaluation_count(dzo_gd* o, int64_t* out) {
+    if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
+    if (o->small) return fail(DZO_ERR_UNSUPPORTED, "evaluation count: one-problem (n > 32) handles only");
+    if (o->gridgd) {
+        double s6[6];
+        DZO_TRY(gd_read(o, s6, o->gscal, sizeof s6));
+        *out = (int64_t)s6[5];
+        return DZO_OK;
+    }
+    GdCtrl c;
+    DZO_TRY(gd_read(o, &c, o->ctrl, sizeof c));
+    *out = (int64_t)c.evals;
+    return DZO_OK;
+}
 int dzo_gd_get_phase_log(dzo_gd* o, uint64_t* events, int64_t cap_events, int64_t* count) {
     if (!o || !events || !count || cap_events < 0) return fail(DZO_ERR_INVALID_ARGUMENT, "bad arguments");
     *count = 0;

@@ -177,6 +177,13 @@ function GradientDescentOptimizer(c!, f, g!, ls::QuadraticLineSearch, x0::Array{
     return GradientDescentOptimizer(h[], size(x0))
 end
 
+# objective evaluations so far (constructor + line-search probes, :36-44) of a one-problem optimizer
+function evaluation_count(opt::GradientDescentOptimizer)
+    c = Ref{Int64}(0)
+    check(ccall((:dzo_gd_get_evaluation_count, libdzopt), Cint, (Ptr{Cvoid}, Ref{Int64}), opt.handle, c))
+    return c[]
+end
+
 function step!(opt::GradientDescentOptimizer)                                       # :393-449
     check(ccall((:dzo_gd_step, libdzopt), Cint, (Ptr{Cvoid}, Cint), opt.handle, 1))
     return opt
@@ -260,6 +267,14 @@ function count_active(opt::BatchedBFGSOptimizer)
     c = Ref{Int64}(0)
     check(ccall((:dzo_bfgs_count_active, libdzopt), Cint, (Ptr{Cvoid}, Ref{Int64}), opt.handle, c))
     return c[]
+end
+
+# What the step! calls did, counted on the device (dzo_bfgs_get_step_kind_counts): BFGS-type steps that read H / whose H
+# was the implicit identity, gradient-descent steps, terminations, step! calls on terminated problems.
+function step_kind_counts(opt::BatchedBFGSOptimizer; reset::Bool=false)
+    c = zeros(Int64, 8)
+    check(ccall((:dzo_bfgs_get_step_kind_counts, libdzopt), Cint, (Ptr{Cvoid}, Ptr{Int64}, Cint), opt.handle, c, reset ? 1 : 0))
+    return (bfgs_read_h=c[1], bfgs_identity_h=c[2], gradient_descent=c[3], terminate=c[4], idle=c[5] + c[6])
 end
 
 # ================================================================== LBFGSOptimizer (live src/DZOptimization.jl:321-509)

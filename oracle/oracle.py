@@ -41,6 +41,32 @@ def lib():
     return _lib
 
 
+NATIVE_FLAGS = "-O3 -march=native -ffp-contract=off -fno-fast-math -fopenmp -fPIC -std=gnu11"
+
+
+def use_native_build():
+    """bench.py's CPU arm: the same source compiled for THIS host's cores (-O3 -march=native, still no contraction
+    and no reassociation, so every bit stays the same -- tests/test_oracle.py asserts it).  Built where it runs (the
+    GPU box's CPU differs from the build container's); must be called before the first oracle call of the process."""
+    global _lib
+    if _lib is not None and getattr(_lib, "_dzo_native", False):
+        return NATIVE_FLAGS
+    out_dir = os.path.join(_HERE, "_build", "native")
+    out = os.path.join(out_dir, "libdzo_oracle_native.so")
+    os.makedirs(out_dir, exist_ok=True)
+    subprocess.run(["gcc"] + NATIVE_FLAGS.split() + ["-shared", "-o", out, os.path.join(_HERE, "dzo_oracle.c"), "-lm"],
+                   check=True, capture_output=True)
+    _lib = _capi.bind(C.CDLL(out), cpu=True)
+    _lib._dzo_native = True
+    return NATIVE_FLAGS
+
+
+def use_default_build():
+    global _lib
+    _lib = None
+    return lib()
+
+
 class OracleError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"oracle error {code}: {msg}")

@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--tune", action="append", default=[], help="key=value for dzo_set_tuning")
     ap.add_argument("--nccl", action="store_true", help="use ncclAllGather instead of the fused peer-memory gathers")
+    ap.add_argument("--delay-rank", type=int, default=-1,
+                    help="--check: this rank sleeps before every step!, the others read next_step_direction right behind theirs")
     args = ap.parse_args()
 
     import torch
@@ -65,15 +67,27 @@ def main():
     assert (r0, r1) == (rank * n // world, (rank + 1) * n // world)
 
     if args.check:
+        # the oracle's whole trace FIRST: nothing but the step! itself may sit between a rank's step! and its read of
+        # next_step_direction (a CPU oracle step in between used to hide a missing wait for the peers' rows)
+        import time
         ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0[None, :], 1.0, order=orc.TREE, nthreads=4)
+        trace = []
+        for it in range(args.steps):
+            ref.step(1)
+            trace.append((ref.point[0], ref.gradient[0], ref.direction[0], float(ref.objective[0]), float(ref.step_length[0])))
+        dist.barrier()
         types = []
         for it in range(args.steps):
-            dz.step_(opt); ref.step(1)
-            assert_bitwise(opt.current_point, ref.point[0], f"rank {rank} iter {it} point")
-            assert_bitwise(opt.current_gradient, ref.gradient[0], f"rank {rank} iter {it} gradient")
-            assert_bitwise(opt.next_step_direction, ref.direction[0], f"rank {rank} iter {it} direction")
-            assert float(opt.current_objective_value[()]) == float(ref.objective[0])
-            assert float(opt.last_step_length[()]) == float(ref.step_length[0])
+            if rank == args.delay_rank:
+                time.sleep(0.25)
+            dz.step_(opt)
+            d_now = opt.next_step_direction          # immediately behind step!: every peer's rows must have landed
+            rp, rg, rd, rf, rl = trace[it]
+            assert_bitwise(d_now, rd, f"rank {rank} iter {it} direction (read right behind step!)")
+            assert_bitwise(opt.current_point, rp, f"rank {rank} iter {it} point")
+            assert_bitwise(opt.current_gradient, rg, f"rank {rank} iter {it} gradient")
+            assert float(opt.current_objective_value[()]) == rf
+            assert float(opt.last_step_length[()]) == rl
             types.append(int(opt.last_step_type[()]))
         assert dz.StepType.BFGSStep in types
         assert_bitwise(opt.inverse_hessian(), ref.inverse_hessian(0)[r0:r1], f"rank {rank} H slab")

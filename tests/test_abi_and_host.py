@@ -143,3 +143,126 @@ def test_product_pcg_generator_equals_the_oracle_and_the_golden_vectors(dz, orc)
     for count, seed in ((1, 0), (4095, 3), (4096, 2024), (4097, 5), (10000, 2 ** 63 + 5), (300000, 9)):
         assert np.array_equal(dz.pcg_fill(count, seed), orc.pcg_fill(count, seed))
     assert dz.pcg_fill(0, 1).size == 0
+
+
+# ----------------------------------------------------------------------------- the Julia wrapper against the header
+def _c_prototypes():
+    """{symbol: (return type, [parameter types])} of include/dzopt.h, comments stripped, names dropped."""
+    import re
+    text = open(os.path.join(ROOT, "include", "dzopt.h")).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    protos = {}
+    for m in re.finditer(r"(?:^|[;}\n])\s*((?:const\s+)?[A-Za-z_][\w]*(?:\s*\*)?)\s+(dzo_\w+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        ret, name, params = m.group(1), m.group(2), m.group(3)
+        plist = []
+        params = " ".join(params.split())
+        if params and params != "void":
+            for prm in params.split(","):
+                prm = prm.strip()
+                stars = prm.count("*")
+                prm = prm.replace("*", " ")
+                toks = [t for t in prm.split() if t != "const"]
+                base = toks[0] if len(toks) <= 2 else " ".join(toks[:-1])
+                if toks[0] == "unsigned" or toks[0] == "struct":
+                    base = " ".join(toks[:2])
+                plist.append(base + "*" * stars)
+        protos[name] = (" ".join(ret.replace("const", "").split()).replace(" *", "*"), plist)
+    return protos
+
+
+# Julia ccall argument type -> the C parameter types it may bind to
+_JL_TO_C = {
+    "Cint": {"int", "int32_t"}, "Int64": {"int64_t"}, "UInt64": {"uint64_t"}, "Float64": {"double"}, "Cstring": {"char*"},
+    "Ptr{Float64}": {"double*"}, "Ptr{Int64}": {"int64_t*"}, "Ref{Int64}": {"int64_t*"}, "Ptr{Int32}": {"int32_t*"},
+    "Ptr{UInt8}": {"uint8_t*", "void*"}, "Ptr{UInt64}": {"uint64_t*"}, "Ref{UInt64}": {"uint64_t*"}, "Ref{Cint}": {"int*"},
+    "Ptr{Cint}": {"int*"}, "Ref{Float64}": {"double*"}, "Ptr{Float32}": {"float*"}, "Ref{Float32}": {"float*"},
+    "Ref{Ptr{Cvoid}}": {"HANDLE**", "void**"}, "Ptr{Cvoid}": {"HANDLE*", "void*", "double*", "uint8_t*"},
+}
+_HANDLES = {"dzo_bfgs", "dzo_gd", "dzo_lbfgs", "dzo_adgd", "dzo_legacy_lbfgs"}
+
+
+def _c_kind(t):
+    base = t.rstrip("*")
+    if base in _HANDLES:
+        return "HANDLE" + "*" * (len(t) - len(base))
+    return t
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip()); cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def test_julia_wrapper_ccalls_match_the_header():
+    """julia/DZOptimizationB200.jl cannot run here (no Julia), so its `ccall`s are checked statically: every symbol it
+    names is declared in include/dzopt.h (and exported by the library), with the same number of arguments and C types the
+    Julia argument tuple can bind to; the symbols passed to its generic (sym) helpers have the (handle, T*) shape."""
+    import re
+    protos = _c_prototypes()
+    assert len(protos) > 100 and "dzo_bfgs_create" in protos and protos["dzo_bfgs_step"] == ("int", ["dzo_bfgs*", "int"])
+    src = open(os.path.join(ROOT, "dzoptimization.jl_b200", "julia", "DZOptimizationB200.jl")).read()
+    src_nc = "\n".join(line.split("#")[0] if "#=" not in line else line for line in src.split("\n"))
+    lib = dz_lib_symbols()
+    checked = 0
+    for m in re.finditer(r"ccall\(\(\s*:(\w+)\s*,\s*libdzopt\s*\)\s*,", src_nc):
+        name = m.group(1)
+        # the balanced argument list of this ccall
+        i = src_nc.index("(", m.start())          # '(' of ccall(
+        depth, j = 0, i
+        while True:
+            depth += src_nc[j] == "("
+            depth -= src_nc[j] == ")"
+            if depth == 0:
+                break
+            j += 1
+        parts = _split_top(src_nc[i + 1:j])
+        ret, argt = parts[1], parts[2]
+        assert argt.startswith("(") and argt.endswith(")"), (name, argt)
+        jl_args = [a for a in _split_top(argt[1:-1]) if a]
+        assert name in protos, f"ccall names {name}, which include/dzopt.h does not declare"
+        assert name in lib, f"{name} is not exported by libdzopt_b200.so"
+        cret, cargs = protos[name]
+        assert len(parts) - 3 == len(jl_args), f"{name}: {len(jl_args)} argument types but {len(parts) - 3} values"
+        assert len(jl_args) == len(cargs), f"{name}: Julia passes {len(jl_args)} arguments, the header declares {len(cargs)}: {cargs}"
+        want_ret = {"Cint": "int", "Cvoid": "void", "Cstring": "char*", "UInt64": "uint64_t"}[ret]
+        assert cret == want_ret, f"{name}: returns {cret}, Julia expects {ret}"
+        for k, (ja, ca) in enumerate(zip(jl_args, cargs)):
+            assert ja in _JL_TO_C, f"{name}: unknown Julia argument type {ja}"
+            assert _c_kind(ca) in _JL_TO_C[ja], f"{name}: argument {k} is `{ca}` in the header, Julia passes {ja}"
+        checked += 1
+    assert checked >= 40
+    # symbols handed to the generic helpers:  vecfield / vec -> (handle, double*),  scalarfield / sc -> (handle, T*)
+    generic = 0
+    for m in re.finditer(r"\b(vecfield|vec|scalarfield|sc)\(\s*(?:opt\s*,\s*)?:(dzo_\w+)\s*(?:,\s*(\w+))?\)", src_nc):
+        helper, name, T = m.groups()
+        assert name in protos and name in lib, f"{name} (used through {helper}) is not in the header / library"
+        cret, cargs = protos[name]
+        assert cret == "int" and len(cargs) == 2 and _c_kind(cargs[0]) == "HANDLE*", (name, cargs)
+        if helper in ("vecfield", "vec"):
+            assert cargs[1] == "double*", (name, cargs)
+        else:
+            assert cargs[1] == {"Float64": "double*", "Int64": "int64_t*", "Int32": "int32_t*", "UInt8": "uint8_t*"}[T], (name, T, cargs)
+        generic += 1
+    assert generic >= 30
+    # and nothing else: every :dzo_ symbol literal of the file went through one of the two checks
+    literals = set(re.findall(r":(dzo_\w+)", src_nc))
+    assert literals <= set(protos), literals - set(protos)
+
+
+def dz_lib_symbols():
+    import subprocess
+    import __graft_entry__ as ge
+    out = subprocess.run(["nm", "-D", "--defined-only", ge.LIB], capture_output=True, text=True, check=True).stdout
+    return {line.split()[-1] for line in out.splitlines() if line.strip()}

@@ -264,9 +264,24 @@ def test_set_state_resume(gpu, orc):
         assert_bitwise(b.current_objective_value, a.current_objective_value, "f after resume")
         assert_bitwise(b.current_gradient, a.current_gradient, "g after resume")
         assert_bitwise(b.next_step_direction, a.next_step_direction, "d after resume")
-        a.step(5); b.step(5)
+        # the oracle's own state-rebuilding constructor (:819-862), fed the oracle's own saved fields
+        order = orc.SEQ if batched else orc.TREE
+        ra = orc.BFGS(ROSEN, x0, 1.0, order=order)
+        ra.step(7)
+        Hr = np.stack([ra.inverse_hessian(p) for p in range(batch)])
+        for got, want, what in ((saved[0], ra.point, "point"), (H.reshape(Hr.shape), Hr, "H"), (saved[2], ra.delta_point, "dx"),
+                                (saved[3], ra.delta_gradient, "dg"), (saved[4], ra.step_length, "L")):
+            assert_bitwise(np.asarray(got).reshape(np.asarray(want).shape), want, f"saved {what} vs oracle")
+        rb = orc.BFGS(ROSEN, x0, 1.0, order=order)
+        rb.set_state(ra.point, Hr, ra.delta_point, ra.delta_gradient, ra.step_length, ra.step_type, ra.iteration_count)
+        _compare_state(b, rb, batched, "after set_state vs the oracle's set_state")
+        for it in range(5):
+            a.step(1); b.step(1); rb.step(1)
+            _compare_state(b, rb, batched, f"resumed iter {it} vs the oracle's resumed optimizer")
         assert_bitwise(b.current_point, a.current_point, "resumed trajectory")
         assert np.array_equal(b.iteration_count, a.iteration_count)
+        for p in (0, batch - 1):
+            assert_bitwise(b.inverse_hessian(p), rb.inverse_hessian(p), "H after resumed steps")
 
 
 def test_run_and_test_invariants_full_size(gpu, orc):
@@ -377,13 +392,20 @@ def test_tuning_variants_do_not_change_any_bit(gpu, orc):
     xb = _x0(orc, 16 * 100, 20).reshape(100, 16)
     rb = orc.BFGS(ROSEN, xb, 1.0)
     rb.step(8)
-    for key, values in (("batched_prefetch", (0, 1, 5, 2)), ("batched_variant", (1, 0))):
+    for key, values in (("batched_prefetch", (0, 1, 5, 2)), ("batched_variant", (1, 2, 0)), ("batched_lazy", (0, 1)), ("batched_dual", (1, 0))):
         for v in values:
             dz.set_tuning(key, v)
             b = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, xb, 1.0, batched=True)
             b.step(8)
             assert_bitwise(b.current_point, rb.point, f"{key}={v}: batched point")
             assert_bitwise(b.inverse_hessian(99), rb.inverse_hessian(99), f"{key}={v}: batched H")
+            # switching the kernel generation in the middle of a run (implicit identities get materialised)
+            dz.set_tuning("batched_variant", 2); b.step(3)
+            dz.set_tuning("batched_variant", 0); b.step(3)
+            r2 = orc.BFGS(ROSEN, xb, 1.0); r2.step(14)
+            assert_bitwise(b.current_point, r2.point, f"{key}={v}: after switching kernels")
+            for p in range(0, 100, 9):
+                assert_bitwise(b.inverse_hessian(p), r2.inverse_hessian(p), f"{key}={v}: H after switching kernels")
             b.close()
 
 
@@ -479,3 +501,92 @@ def test_field_mirrors_are_refused_where_no_kernel_maintains_them(gpu, orc):
         opt.step(1); ref.step(1)
         assert_bitwise(opt.current_objective_value, ref.objective, f"iter {it}: objective")
         assert np.array_equal(opt.has_converged, ref.terminated)
+
+
+# ----------------------------------------------------------------------------- round 2: implicit identities, step kinds, secant condition
+def _oracle_kinds(ref, steps):
+    """per-step kind counts replayed on the oracle: BFGS-type steps split by whether H was the identity going in
+    (previous step gradient-descent or none: :781-783, :981), GD-type, terminating, idle."""
+    out = []
+    prev_type, prev_done = ref.step_type.copy(), ref.terminated.copy()
+    for _ in range(steps):
+        it0 = ref.iteration_count.copy()
+        ref.step(1)
+        moved = ref.iteration_count > it0
+        ty, done = ref.step_type, ref.terminated
+        ident_in = (prev_type != 2)
+        out.append({"bfgs_read_h": int((moved & (ty == 2) & ~ident_in).sum()),
+                    "bfgs_identity_h": int((moved & (ty == 2) & ident_in).sum()),
+                    "gradient_descent": int((moved & (ty == 1)).sum()),
+                    "terminate": int((done & ~prev_done).sum()),
+                    "idle": int(prev_done.sum())})
+        prev_type, prev_done = ty.copy(), done.copy()
+    return out
+
+
+@pytest.mark.parametrize("n,batch", [(16, 4000), (2, 3000), (8, 1000)])
+def test_step_kind_counters_and_implicit_identity(gpu, orc, n, batch):
+    """dzo_bfgs_get_step_kind_counts (what bench.py's roofline is computed from) equals the kinds replayed on the
+    oracle; the inverse Hessian read through the C ABI is the oracle's even while the device keeps H = I implicit."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n * batch, 515).reshape(batch, n)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    ref = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ, nthreads=8)
+    assert_bitwise(opt.inverse_hessian(3), np.eye(n), "H after the constructor (implicit identity)")
+    total = {k: 0 for k in ("bfgs_read_h", "bfgs_identity_h", "gradient_descent", "terminate", "idle")}
+    steps = 45
+    want = _oracle_kinds(ref, steps)
+    for it in range(steps):
+        opt.step(1)
+        got = opt.step_kind_counts()
+        for k in total:
+            total[k] += want[it][k]
+        got_idle = got["idle"] + got["idle_warp"]
+        assert {k: got[k] for k in total if k != "idle"} == {k: total[k] for k in total if k != "idle"}, f"iter {it}"
+        assert got_idle == total["idle"], f"iter {it}: idle"
+    _compare_state(opt, ref, True, "after the counted steps")
+    for p in range(0, batch, max(1, batch // 40)):
+        assert_bitwise(opt.inverse_hessian(p), ref.inverse_hessian(p), f"H[{p}]")
+    assert total["gradient_descent"] > 0 and total["bfgs_identity_h"] > 0 and total["bfgs_read_h"] > 0
+    assert sum(total.values()) == steps * batch
+    # k fused steps in one launch are counted the same way
+    opt.step_kind_counts(reset=True)
+    more = _oracle_kinds(ref, 30)
+    opt.step(30)
+    got = opt.step_kind_counts()
+    for k in ("bfgs_read_h", "bfgs_identity_h", "gradient_descent", "terminate"):
+        assert got[k] == sum(m[k] for m in more), k
+    assert got["idle"] + got["idle_warp"] == sum(m["idle"] for m in more)
+    _compare_state(opt, ref, True, "after the fused counted steps")
+
+
+def _secant_residual(H, dg, dx):
+    """|H dg - dx|_inf / |dx|_inf  -- the secant condition the rank-2 update (:864-889) must restore"""
+    return float(np.abs(H @ dg - dx).max() / np.abs(dx).max())
+
+
+@pytest.mark.parametrize("n,batched", [(16, True), (2048, False)])
+def test_secant_condition_after_every_bfgs_step(gpu, orc, n, batched):
+    """An independent check of update_inverse_hessian! (:864-889) that neither restatement produced: after every
+    BFGS-type step the new inverse Hessian maps delta_gradient to delta_point (H dg = dx, to rounding), and it stays
+    bitwise symmetric.  Checked on the CUDA result itself (the oracle twin is tests/test_oracle.py)."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    batch = 64 if batched else 1
+    x0 = _x0(orc, n * batch, 612).reshape(batch, n)
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0 if batched else x0[0], 1.0, batched=batched)
+    seen = 0
+    for it in range(25 if batched else 12):
+        opt.step(1)
+        ty = np.atleast_1d(opt.last_step_type)
+        moved = np.atleast_1d(opt.iteration_count) == it + 1
+        dx = np.atleast_2d(opt.delta_point); dg = np.atleast_2d(opt.delta_gradient)
+        for p in range(batch):
+            if not (moved[p] and ty[p] == dz.StepType.BFGSStep):
+                continue
+            H = opt.inverse_hessian(p)
+            assert_bitwise(H, H.T, f"iter {it} problem {p}: H symmetric")
+            assert _secant_residual(H, dg[p], dx[p]) < 1e-10, f"iter {it} problem {p}: secant condition"
+            seen += 1
+    assert seen > (100 if batched else 5)

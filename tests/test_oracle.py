@@ -256,3 +256,60 @@ def test_errors_and_edge_cases(orc):
     z.step(1)
     assert z.terminated[0]
     assert math.isfinite(z.objective[0])
+
+
+@pytest.mark.parametrize("n,order_name", [(16, "SEQ"), (2048, "TREE")])
+def test_secant_condition_after_every_bfgs_step(orc, n, order_name):
+    """A check of update_inverse_hessian! (legacy/DZOptimization.jl:864-889) that neither restatement produced: the
+    BFGS update is DEFINED by the secant condition H_new * delta_gradient = delta_point.  After every BFGS-type step
+    the oracle's inverse Hessian satisfies it to rounding (observed 2e-14 ... 5e-13 relative) and is bitwise symmetric.
+    The CUDA twin of this test is tests/test_gpu_bfgs.py::test_secant_condition_after_every_bfgs_step."""
+    order = getattr(orc, order_name)
+    batch = 64 if n == 16 else 1
+    x0 = (4.0 * orc.pcg_fill(n * batch, 612) - 2.0).reshape(batch, n)
+    opt = orc.BFGS(ROSEN, x0, 1.0, order=order, nthreads=4)
+    seen, worst = 0, 0.0
+    for it in range(25 if n == 16 else 12):
+        opt.step(1)
+        ty, moved = opt.step_type, opt.iteration_count == it + 1
+        dx, dg = opt.delta_point, opt.delta_gradient
+        for p in range(batch):
+            if not (moved[p] and ty[p] == 2):
+                continue
+            H = opt.inverse_hessian(p)
+            assert_bitwise(H, H.T, f"iter {it} problem {p}: H symmetric")
+            res = float(np.abs(H @ dg[p] - dx[p]).max() / np.abs(dx[p]).max())
+            worst = max(worst, res)
+            assert res < 1e-10, f"iter {it} problem {p}: secant condition violated ({res:.3e})"
+            seen += 1
+    assert seen > (100 if n == 16 else 5)
+    assert worst > 0.0      # it is a floating-point identity, not an algebraic coincidence of the test
+
+
+def test_native_build_of_the_oracle_is_bit_identical(orc):
+    """bench.py times the oracle compiled with -O3 -march=native (a fairer CPU arm); no contraction, no reassociation:
+    the trace must be the -O2 build's, bit for bit."""
+    x0 = (4.0 * orc.pcg_fill(16 * 300, 2024) - 2.0).reshape(300, 16)
+    a = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ, nthreads=2)
+    a.step(30)
+    pa, fa, Ha = a.point, a.objective, a.inverse_hessian(7)
+    xl = (4.0 * orc.pcg_fill(1500, 1) - 2.0)
+    al = orc.BFGS(ROSEN, xl[None, :], 1.0, order=orc.TREE, nthreads=2)
+    al.step(6)
+    pl, dl = al.point, al.direction
+    a.close(); al.close()
+    try:
+        flags = orc.use_native_build()
+        assert "-march=native" in flags and "-ffp-contract=off" in flags
+        b = orc.BFGS(ROSEN, x0, 1.0, order=orc.SEQ, nthreads=2)
+        b.step(30)
+        assert_bitwise(b.point, pa, "native build: batched point")
+        assert_bitwise(b.objective, fa, "native build: objective")
+        assert_bitwise(b.inverse_hessian(7), Ha, "native build: H")
+        bl = orc.BFGS(ROSEN, xl[None, :], 1.0, order=orc.TREE, nthreads=2)
+        bl.step(6)
+        assert_bitwise(bl.point, pl, "native build: large-n point")
+        assert_bitwise(bl.direction, dl, "native build: large-n direction")
+        b.close(); bl.close()
+    finally:
+        orc.use_default_build()
