@@ -31,6 +31,8 @@ struct BatchedArgs {
     unsigned char* hid;          // optional (may be null): hid[p] != 0 <=> H of problem p is the identity and its copy in
                                  //   HBM is stale (identity_matrix! :981 / :781-783 not materialised; hybrid kernel only)
     unsigned long long* stats;   // optional (may be null): HK_COUNT running step-kind counters
+    unsigned* tile_counter;      // hybrid kernel, persistent grid: next tile of 32 problems (zero between launches); null =
+                                 //   one tile per warp, grid sized to the batch
 };
 
 constexpr int kBatchedThreads = 256;

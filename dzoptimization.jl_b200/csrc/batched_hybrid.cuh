@@ -519,34 +519,80 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid3_kernel
     constexpr int PPR = 32 / N;  // problems per phase-2 round
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     HybridSmem<N>& S = reinterpret_cast<HybridSmem<N>*>(smem_raw)[warp];
-    const long long p0 = ((long long)blockIdx.x * kHybridWarps + warp) * 32;  // first problem of this warp
-    if (p0 >= A.batch) return;
-    const long long p = p0 + lane;
-    const bool valid = p < A.batch;
-    const int nprob = (int)((A.batch - p0 < 32) ? (A.batch - p0) : 32);
     const bool lazy = (A.hid != nullptr);
-
-    bool term = valid ? (A.term[p] != 0) : true;
-    bool ident = (lazy && valid) ? (A.hid[p] != 0) : false;    // H == I and the copy in HBM is stale
-    bool moved_any = false;
     double& cnt_slot = S.X[lane][16];
     cnt_slot = 0.0;                                            // exact for counts < 2^53
     auto count = [&](int k, unsigned ballot) { if (lane == k) cnt_slot += (double)__popc(ballot); };
 
+    // Optional persistent mode ("batched_persistent", off by default): tiles of 32 problems are handed out to WARPS through a
+    // global counter (4 CTAs per SM), so a warp whose line searches finish early takes the next tile instead of waiting for
+    // the slowest warp of its CTA to free the CTA slot, and the partial last wave of the grid disappears.  Measured on the
+    // 1 M x n=16 workload it LOSES to one tile per warp (0.80 vs 0.74 ms per launch; ncu: 2.0 instead of 0.3 no-instruction
+    // stall cycles per issue -- 16 warps at 16 different places of a 54 KB kernel body thrash the instruction cache, while
+    // the warps of freshly launched CTAs walk through it together); kept as a tested variant.  The counter returns to
+    // zero with the last fetch of a launch.
+    const long long ntiles = (A.batch + 31) / 32;
+    const unsigned nwarps_total = gridDim.x * kHybridWarps;
+    auto fetch_tile = [&]() -> long long {
+        if (!A.tile_counter) return ntiles;                    // one tile per warp (A/B baseline)
+        unsigned t = 0;
+        if (lane == 0) {
+            t = atomicAdd(A.tile_counter, 1u);
+            if ((long long)t == ntiles + (long long)nwarps_total - 1) atomicExch(A.tile_counter, 0u);   // the launch's last fetch
+        }
+        t = __shfl_sync(FULL, t, 0);
+        return ((long long)t < ntiles) ? (long long)t : ntiles;
+    };
+    auto read_flags = [&](long long t) -> unsigned {            // has_terminated | (H is an implicit identity) << 1
+        const long long pp = t * 32 + lane;
+        if (t >= ntiles || pp >= A.batch) return 1u;
+        return (A.term[pp] != 0 ? 1u : 0u) | ((lazy && A.hid[pp] != 0) ? 2u : 0u);
+    };
+    long long tile = A.tile_counter ? fetch_tile() : (long long)blockIdx.x * kHybridWarps + warp;
+    if (tile >= ntiles) return;
+    unsigned flags = read_flags(tile);
+
+  while (tile < ntiles) {
+    const long long p0 = tile * 32;                            // first problem of this tile
+    const long long p = p0 + lane;
+    const bool valid = p < A.batch;
+    const int nprob = (int)((A.batch - p0 < 32) ? (A.batch - p0) : 32);
+    long long next_tile = ntiles;
+    unsigned next_flags = 1u;
+    bool have_next = !A.tile_counter;                          // the next tile has been fetched (or there is none to fetch)
+
+    // A tile starts cold: everything it needs first is requested at once -- the three vectors as 16-byte asynchronous
+    // copies straight into the shared tile (24 per lane, no registers held), the scalars as ordinary loads in flight
+    // beside them; the flags were read while the previous tile was in phase 2.
+    auto stage_vectors = [&]() {
+        for (int e2 = lane; e2 < nprob * (N / 2); e2 += 32) {
+            const int q = (2 * e2) / N, i = 2 * e2 - q * N;
+            cp_async16(&S.X[q][i], A.x + p0 * N + 2 * e2);
+            cp_async16(&S.G[q][i], A.g + p0 * N + 2 * e2);
+            cp_async16(&S.D[q][i], A.d + p0 * N + 2 * e2);
+        }
+        cp_async_commit();
+    };
+    __syncwarp();                                              // the previous tile's phase 2 is done with the shared tile
+    stage_vectors();
+    bool term = (flags & 1u) != 0;
+    bool ident = (flags & 2u) != 0;                            // H == I and the copy in HBM is stale
+    bool moved_any = false;
+
     for (int s = 0; s < A.ksteps; ++s) {
         if (!__any_sync(FULL, !term)) {
             if (lane == HK_IDLE_WARP) cnt_slot += (double)nprob * (double)(A.ksteps - s);
+            cp_async_wait_all();                               // nothing may still be landing in the tile when it is reused
             break;
         }
-        // ---------------------------------------------------------------- stage the vectors (coalesced)
-        __syncwarp();
-        for (int e = lane; e < nprob * N; e += 32) {
-            const int q = e / N, i = e - q * N;
-            S.X[q][i] = A.x[p0 * N + e];
-            S.G[q][i] = A.g[p0 * N + e];
-            S.D[q][i] = A.d[p0 * N + e];
+        if (s > 0) {
+            // a later step of the same launch: the vectors were stored by other lanes of this warp in phase 2
+            __threadfence_block();
+            __syncwarp();
+            stage_vectors();
         }
-        __syncwarp();
+        double f0 = valid ? A.f[p] : 0.0;              // (a later step of the same launch reads back its own stores)
+        double L = valid ? A.L[p] : 0.0;
         const double* X = S.X[lane];
         const double* G = S.G[lane];
         const double* D = S.D[lane];
@@ -569,11 +615,11 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid3_kernel
             }
         };
         for (int rr = 0; rr < A.prefetch_rounds; ++rr) prefetch_round(rr);
+        cp_async_wait_all();
+        __syncwarp();
 
         // ---------------------------------------------------------------- phase 1: one thread per problem
         {
-            double f0 = valid ? A.f[p] : 0.0;          // (a later step of the same launch reads back its own stores)
-            double L = valid ? A.L[p] : 0.0;
             int kind = DZO_STEP_NULL;
             double alpha = 0.0, overlap = 0.0;
             double grad_norm = 0.0, bfgs_norm = 0.0;
@@ -668,7 +714,7 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid3_kernel
                 if (kind != DZO_STEP_NULL) {
                     A.f[p] = f0;
                     A.L[p] = L;
-                    A.iter[p] = A.iter[p] + 1;                                            // :940 / :968
+                    atomicAdd(reinterpret_cast<unsigned long long*>(A.iter + p), 1ull);  // :940 / :968 (no load to wait for)
                     A.type[p] = kind;                                                     // :939 / :967
                     moved_any = true;
                 }
@@ -686,6 +732,13 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid3_kernel
             reinterpret_cast<int*>(&S.D[lane][16])[0] = kind | (hsrc << 8);
         }
         __syncwarp();
+        if (!have_next) {
+            // the next tile of this warp: its index and its flags are in flight during phase 2.  (Prefetching its vectors
+            // into L2 as well was measured and removed: 57 us later the lines are gone again -- +0.38 GB of DRAM reads per launch.)
+            have_next = true;
+            next_tile = fetch_tile();
+            next_flags = read_flags(next_tile);
+        }
 
         // ---------------------------------------------------------------- phase 2: N lanes per problem
         // Lane r of problem q owns element r of every vector and row r of H.  Every global access below
@@ -796,6 +849,10 @@ __global__ void __launch_bounds__(kHybridThreads, 4) bfgs_batched_hybrid3_kernel
     }
 
     if (valid && moved_any && A.f_host) A.f_host[p] = A.f[p];     // 32 lanes = 256 contiguous bytes of posted PCIe writes
+    if (!have_next) { next_tile = fetch_tile(); next_flags = read_flags(next_tile); }   // (a tile that was idle on entry)
+    tile = next_tile;
+    flags = next_flags;
+  }
     if (A.stats && lane < HK_COUNT && cnt_slot != 0.0) atomicAdd(A.stats + lane, (unsigned long long)cnt_slot);
 }
 

@@ -127,6 +127,13 @@ DZO_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 
 DZO_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 DZO_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 16-byte asynchronous global -> shared copy (SASS: LDGSTS), L2 only; both addresses 16-byte aligned
+DZO_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+DZO_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DZO_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // streaming (evict-first) 128-bit global access for the n^2 sweeps: H has no reuse inside a sweep
 DZO_DEVINL double2 ldg_stream2(const double* p) {
     double2 r;

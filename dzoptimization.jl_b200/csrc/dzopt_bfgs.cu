@@ -101,6 +101,8 @@ struct dzo_bfgs {
     unsigned long long* counter = nullptr;
     unsigned char* hid = nullptr;        // batched hybrid kernel: H of problem p is an implicit identity (batched_hybrid.cuh, LAZY)
     unsigned long long* stats = nullptr; // batched hybrid kernel: running step-kind counters (HK_COUNT words)
+    unsigned* tilectr = nullptr;         // batched hybrid kernel: tile counter of the persistent grid (zero between launches)
+    int sm_count = 0;
     // large path
     double *sd = nullptr, *t = nullptr, *partial = nullptr;
     unsigned* tile_counters = nullptr;
@@ -152,7 +154,7 @@ static void free_handle(dzo_bfgs* o) {
     if (o->arena) { o->t = nullptr; o->d = nullptr; o->flags_t = nullptr; o->flags_d = nullptr; }   // live inside the arena
     void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
                     o->sd, o->t, o->partial, o->tile_counters, o->ctrl, o->flags_t, o->flags_d, o->done, o->arena,
-                    o->hid, o->stats};
+                    o->hid, o->stats, o->tilectr};
     if (o->own_stream) {
         for (void* p : ptrs) {
             if (!p) continue;
@@ -214,7 +216,7 @@ static BatchedArgs batched_args(const dzo_bfgs* o, int ksteps) {
     A.iter = o->iter; A.type = o->type; A.term = o->term; A.probes = nullptr;
     A.f_host = o->f_host; A.term_host = o->term_host;
     A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps; A.prefetch_rounds = g_tuning.batched_prefetch;
-    A.hid = o->hid; A.stats = o->stats;
+    A.hid = o->hid; A.stats = o->stats; A.tile_counter = nullptr;
     return A;
 }
 
@@ -297,14 +299,20 @@ static int launch_hybrid_step(dzo_bfgs* o, int k) {
 }
 template <int N, bool DUAL>
 static int launch_hybrid3_step_(dzo_bfgs* o, int k) {
-    const unsigned grid = (unsigned)((o->batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
+    unsigned grid = (unsigned)((o->batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
+    BatchedArgs args = batched_args(o, k);
+    const unsigned resident = (unsigned)(o->sm_count > 0 ? o->sm_count : 148) * 4u;   // 4 CTAs per SM (shared tile, registers)
+    if (g_tuning.batched_persistent && grid > resident) {   // persistent CTAs, tiles handed out to warps through a counter
+        grid = resident;
+        args.tile_counter = o->tilectr;
+    }
     const size_t smem = hybrid_smem<N>();
     static bool attr_set[64] = {};
     if (!attr_set[o->device & 63]) {
         DZO_CUDA(cudaFuncSetAttribute(bfgs_batched_hybrid3_kernel<N, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[o->device & 63] = true;
     }
-    bfgs_batched_hybrid3_kernel<N, DUAL><<<grid, kHybridThreads, smem, o->stream>>>(batched_args(o, k));
+    bfgs_batched_hybrid3_kernel<N, DUAL><<<grid, kHybridThreads, smem, o->stream>>>(args);
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;
 }
@@ -571,10 +579,12 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     if (o->small) {
         if ((rc = dmalloc(&o->H, nb * (size_t)n)) || (rc = dmalloc(&o->f, (size_t)batch)) || (rc = dmalloc(&o->L, (size_t)batch)) ||
             (rc = dmalloc(&o->iter, (size_t)batch)) || (rc = dmalloc(&o->type, (size_t)batch)) || (rc = dmalloc(&o->term, (size_t)batch)) ||
-            (rc = dmalloc(&o->stats, (size_t)HK_COUNT)))
+            (rc = dmalloc(&o->stats, (size_t)HK_COUNT)) || (rc = dmalloc(&o->tilectr, (size_t)1)))
             return bail(rc);
-        if (cudaMemsetAsync(o->stats, 0, HK_COUNT * sizeof(unsigned long long), o->stream) != cudaSuccess)
+        if (cudaMemsetAsync(o->stats, 0, HK_COUNT * sizeof(unsigned long long), o->stream) != cudaSuccess ||
+            cudaMemsetAsync(o->tilectr, 0, sizeof(unsigned), o->stream) != cudaSuccess)
             return bail(fail(DZO_ERR_CUDA, "memset failed"));
+        cudaDeviceGetAttribute(&o->sm_count, cudaDevAttrMultiProcessorCount, device);
         // implicit identities (constructor and identity_matrix! after a GD step write no H): hybrid kernel only
         if (objective == DZO_OBJ_ROSENBROCK && hybrid_n(n) && g_tuning.batched_variant == 0 && g_tuning.batched_lazy)
             if ((rc = dmalloc(&o->hid, (size_t)batch))) return bail(rc);
@@ -1231,6 +1241,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "batched_prefetch")) { g_tuning.batched_prefetch = value; return DZO_OK; }
     if (!strcmp(key, "batched_lazy")) { g_tuning.batched_lazy = value; return DZO_OK; }
     if (!strcmp(key, "batched_dual")) { g_tuning.batched_dual = value; return DZO_OK; }
+    if (!strcmp(key, "batched_persistent")) { g_tuning.batched_persistent = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }
 

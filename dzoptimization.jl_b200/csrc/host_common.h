@@ -52,7 +52,8 @@ int check_problem(int objective, int constraint, int64_t obj_param, int64_t n, i
 
 // process-wide tuning knobs (A/B measurements only; never change results)
 struct Tuning {
-    int batched_prefetch = 2;  // hybrid kernel: L2 prefetch distance in phase-2 rounds (measured: 0:0.70 1:0.75 2:0.89 3:0.89 4:0.88 6:0.83 of HBM peak)
+    int batched_prefetch = 3;  // hybrid kernel: L2 prefetch distance in phase-2 rounds (round 2, ms per 1M-problem launch: 1: 1.06,
+                               // 2: 0.740, 3: 0.736, 4: 0.740, 6: 0.766)
     int use_graph = 1;        // large-n step!: replay a captured CUDA graph of its four launches
     int epoch = 0;            // bumped by every dzo_set_tuning call
     int sweep_unroll = 16;    // columns in flight per thread in the n^2 sweeps; measured on one box at n=16384:
@@ -67,6 +68,8 @@ struct Tuning {
     int batched_variant = 0;  // 0 = third-generation hybrid kernel for n in {2,4,8,16}, 1 = lanes-per-problem kernel everywhere,
                               // 2 = second-generation hybrid kernel (round 1; A/B baseline)
     int batched_lazy = 1;     // hybrid kernel: keep H = I implicit (no HBM traffic for identity_matrix!); read at create time
+    int batched_persistent = 0;  // hybrid kernel: 1 = persistent CTAs (4 per SM), tiles of 32 problems handed out to warps through a
+                                 // counter (measured 0.80 vs 0.74 ms per 1M-problem launch: instruction-cache thrash; default off)
     int batched_dual = 0;     // hybrid kernel: 1 = both line searches of a step side by side in one thread (one probe of each
                               // per iteration), 0 = one per-thread state machine over both searches
 };

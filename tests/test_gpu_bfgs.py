@@ -392,7 +392,7 @@ def test_tuning_variants_do_not_change_any_bit(gpu, orc):
     xb = _x0(orc, 16 * 100, 20).reshape(100, 16)
     rb = orc.BFGS(ROSEN, xb, 1.0)
     rb.step(8)
-    for key, values in (("batched_prefetch", (0, 1, 5, 2)), ("batched_variant", (1, 2, 0)), ("batched_lazy", (0, 1)), ("batched_dual", (1, 0))):
+    for key, values in (("batched_prefetch", (0, 1, 5, 3)), ("batched_variant", (1, 2, 0)), ("batched_lazy", (0, 1)), ("batched_dual", (1, 0)), ("batched_persistent", (1, 0))):
         for v in values:
             dz.set_tuning(key, v)
             b = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, xb, 1.0, batched=True)
@@ -590,3 +590,35 @@ def test_secant_condition_after_every_bfgs_step(gpu, orc, n, batched):
             assert _secant_residual(H, dg[p], dx[p]) < 1e-10, f"iter {it} problem {p}: secant condition"
             seen += 1
     assert seen > (100 if batched else 5)
+
+
+def test_persistent_grid_equals_one_tile_per_warp(gpu, orc):
+    """Above 148 x 4 CTAs worth of problems the hybrid kernel runs as a persistent grid whose warps fetch tiles of 32
+    problems from a counter; results (and the step-kind counters) must not depend on who processed which tile, the
+    counter must be back at zero after every launch (three launches in a row), ragged last tile included."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    n, batch = 16, 148 * 4 * 128 + 32 * 7 + 5
+    x0 = _x0(orc, n * batch, 99).reshape(batch, n)
+    dz.set_tuning("batched_persistent", 0)
+    a = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    dz.set_tuning("batched_persistent", 1)
+    b = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    for it in range(3):
+        dz.set_tuning("batched_persistent", 0); a.step(1)
+        dz.set_tuning("batched_persistent", 1); b.step(1)
+        assert_bitwise(b.current_point, a.current_point, f"iter {it}: point")
+        assert_bitwise(b.next_step_direction, a.next_step_direction, f"iter {it}: direction")
+        assert_bitwise(b.current_objective_value, a.current_objective_value, f"iter {it}: objective")
+        assert a.step_kind_counts() == b.step_kind_counts()
+    dz.set_tuning("batched_persistent", 0); a.step(7)
+    dz.set_tuning("batched_persistent", 1); b.step(7)                      # k fused steps per tile
+    assert_bitwise(b.current_point, a.current_point, "fused: point")
+    assert np.array_equal(b.iteration_count, a.iteration_count)
+    sel = np.arange(0, batch, batch // 2000)
+    ref = orc.BFGS(ROSEN, x0[sel], 1.0, order=orc.SEQ, nthreads=8)
+    ref.step(10)
+    assert_bitwise(b.current_point[sel], ref.point, "spot check against the oracle")
+    for p in (0, batch - 1, 75776):
+        assert_bitwise(b.inverse_hessian(p), a.inverse_hessian(p), f"H[{p}]")
+    dz.set_tuning("batched_persistent", 0)

@@ -2,7 +2,7 @@
 
     python tools/batched_ab.py [--batch 1000000] [--steps 20] [--warmup 5] [--configs v0l1p2,v0l0p2,v2l0p2,...]
 
-A config is v<batched_variant>l<batched_lazy>p<batched_prefetch>[d<batched_dual>].  Prints one JSON line per config: ms per step!,
+A config is v<batched_variant>l<batched_lazy>p<batched_prefetch>[d<batched_dual>][s<batched_persistent>].  Prints one JSON line per config: ms per step!,
 the step kinds counted on the device, the algorithmic bytes of that mix and the fraction of the HBM copy peak."""
 import argparse
 import json
@@ -36,9 +36,10 @@ def main():
     torch.cuda.set_stream(stream)
     for rep in range(args.repeat):
         for cfg in args.configs.split(","):
-            m = re.fullmatch(r"v(\d)l(\d)p(\d+)(?:d(\d))?", cfg)
+            m = re.fullmatch(r"v(\d)l(\d)p(\d+)(?:d(\d))?(?:s(\d))?", cfg)
             v, lz, pf = (int(g) for g in m.groups()[:3])
             dual = int(m.group(4) or 0)
+            dz.set_tuning("batched_persistent", int(m.group(5) if m.group(5) is not None else 1))
             dz.set_tuning("batched_variant", v); dz.set_tuning("batched_lazy", lz); dz.set_tuning("batched_prefetch", pf)
             dz.set_tuning("batched_dual", dual)
             opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
