@@ -5,7 +5,7 @@
 
 Workload (N=1): 1,000,000 independent extended-Rosenbrock problems, n=16, x0 = 4u-2 with u from
 the reference's PCG (legacy/PCG.jl, seed 2024+rank), initial step 1.0.  One "step" = one step!
-call on every problem of the batch = ONE launch of bfgs_batched_hybrid3_kernel.  For N>1 every rank
+call on every problem of the batch = ONE launch of bfgs_batched_hybrid_kernel.  For N>1 every rank
 holds its own 1M problems (weak scaling, no collective on the data path).
 
 Numbers on the JSON line
@@ -475,7 +475,7 @@ def run_gpu(args):
 
     if rank == 0:
         table = bytes_by_kind(N_SMALL, lazy)
-        traffic = ncu_traffic("bfgs_batched_hybrid3_kernel<16>")
+        traffic = ncu_traffic("bfgs_batched_hybrid_kernel<16>")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -491,9 +491,9 @@ def run_gpu(args):
                                             "what": "the same loop followed by ONE current_point read (the answer)"},
                     "what": "BFGSOptimizer(host x0) + W+K x [step!; has_converged[]; current_objective_value[]] via the C ABI; the two fields reach the host as zero-copy mirrors (dzo_bfgs_mirror_fields): the step kernel stores them into page-locked host memory, the reads only synchronise"},
             "gpu_launches": K,
-            "gpu_launches_what": "one bfgs_batched_hybrid3_kernel<16> per step! in the timed region of `value`",
+            "gpu_launches_what": "one bfgs_batched_hybrid_kernel<16> per step! in the timed region of `value`",
             "gpu_launches_all_timed_legs": launches,
-            "roofline": {"bound": "hbm", "kernel": "bfgs_batched_hybrid3_kernel<16>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "bfgs_batched_hybrid_kernel<16>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "how": "achieved = sum_kind(count_kind x bytes_kind) / K launches / ms_per_step; counts come from "
                                 "the kernel's own per-launch counters over exactly the timed launches (rank 0)",

@@ -1,16 +1,13 @@
-// batched_bfgs.cuh -- batched small-n BFGS: many independent optimizers, one per lane group.
+// batched_bfgs.cuh -- batched small-n BFGS: the constructor and resume kernels, the lanes-per-problem building blocks
+// (Group, RosenbrockSmall, group_line_search) the kernel-level entry points of small_ops.cuh are made of, and the
+// argument block of the step kernel (batched_hybrid.cuh).
 //
-// Implements, per problem, exactly SURVEY.md 8.0 / legacy/DZOptimization.jl:762-810 (ctor) and
-// :891-994 (step!) with SEQUENTIAL summation order (legacy/Kernels.jl:12-20), so results are
-// bitwise equal to the sequential oracle.
-//
-// Mapping (DESIGN.md "batched kernel"): LPP lanes per problem (n <= LPP, LPP in {2,..,32});
-// lane r owns element r of every vector and ROW r of approximate_inverse_hessian in
-// registers.  A CTA of 256 threads holds 256/LPP problems.  The inverse Hessians of a CTA are
-// staged through shared memory by 1-D bulk async copies (TMA, cp.async.bulk + mbarrier) that
-// are issued before the two line searches and waited on only when the rank-2 update needs
-// them, and are written back by bulk stores.  All cross-lane traffic is warp shuffles or
-// group-private shared-memory broadcast buffers; there is no __syncthreads in the step.
+// Everything here implements, per problem, SURVEY.md 8.0 / legacy/DZOptimization.jl:762-810 (ctor), :819-862 (resume)
+// with SEQUENTIAL summation order (legacy/Kernels.jl:12-20): bitwise equal to the sequential oracle.
+// Mapping: LPP lanes per problem (n <= LPP, LPP in {2,..,32}); lane r owns element r of every vector; a CTA of 256
+// threads holds 256/LPP problems; cross-lane traffic is warp shuffles or group-private shared-memory broadcast buffers.
+// (The first-generation step! kernel that lived here -- LPP lanes per problem for the whole step, H staged through
+// shared memory by cp.async.bulk -- was retired in round 2: 1.63 ms per 1M-problem launch against 0.74 ms.)
 #pragma once
 #include "common.cuh"
 
@@ -21,7 +18,6 @@ struct BatchedArgs {
     long long* iter;
     int* type;
     unsigned char* term;
-    unsigned long long* probes;  // optional statistics (may be null): objective evaluations
     double* f_host;              // optional zero-copy mirrors in page-locked HOST memory (may be null): the step kernel
     unsigned char* term_host;    //   stores f / has_terminated there too, so the fields cross PCIe while it runs
     int n;
@@ -31,8 +27,6 @@ struct BatchedArgs {
     unsigned char* hid;          // optional (may be null): hid[p] != 0 <=> H of problem p is the identity and its copy in
                                  //   HBM is stale (identity_matrix! :981 / :781-783 not materialised; hybrid kernel only)
     unsigned long long* stats;   // optional (may be null): HK_COUNT running step-kind counters
-    unsigned* tile_counter;      // hybrid kernel, persistent grid: next tile of 32 problems (zero between launches); null =
-                                 //   one tile per warp, grid sized to the batch
 };
 
 constexpr int kBatchedThreads = 256;
@@ -221,184 +215,6 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_init_kern
     }
 }
 
-// ----------------------------------------------------------------------------- step! kernel
-template <int LPP, class Obj>
-static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_step_kernel(BatchedArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int PPC = kBatchedThreads / LPP;
-    const int n = A.n;
-    const int nn = n * n;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    double* sH_all = reinterpret_cast<double*>(smem_raw + 16);
-    double* bc_all = sH_all + PPC * nn;
-
-    const int lane = threadIdx.x & 31;
-    const int gi = threadIdx.x / LPP;
-    Group<LPP> G;
-    G.r = threadIdx.x % LPP;
-    G.n = n;
-    G.act = G.r < n;
-    G.mask = (LPP == 32) ? 0xffffffffu : (((1u << LPP) - 1u) << (lane - (lane % LPP)));
-    G.bc = bc_all + gi * (kBcBufs * LPP);
-    G.flip = 0;
-    G.probes = 0;
-    const int r = G.r;
-    double* sH = sH_all + gi * nn;
-
-    if (threadIdx.x == 0) {
-        mbar_init(bar, PPC);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
-    const long long p = (long long)blockIdx.x * PPC + gi;
-    const bool valid = p < A.batch;
-    bool term = valid ? (A.term[p] != 0) : true;
-
-    // Kick off the asynchronous H load (2 KB at n = 16) now; it is consumed only after the
-    // two line searches, so its latency is hidden behind them.
-    if (r == 0) {
-        if (!term) {
-            mbar_arrive_expect_tx(bar, (uint32_t)(nn * sizeof(double)));
-            bulk_g2s(sH, A.H + p * nn, (uint32_t)(nn * sizeof(double)), bar);
-        } else {
-            mbar_arrive(bar);
-        }
-    }
-    if (term) return;  // step! on a terminated optimizer is a no-op (:893)
-
-    double x = 0.0, g = 0.0, d = 0.0, dx = 0.0, dg = 0.0;
-    if (G.act) {
-        x = A.x[p * n + r];
-        g = A.g[p * n + r];
-        d = A.d[p * n + r];
-    }
-    double f0 = A.f[p];
-    double L = A.L[p];
-    long long iter = A.iter[p];
-    int type = DZO_STEP_NULL;
-    bool H_dirty = false;              // sH differs from global
-    bool moved = false;
-    bool waited = false;
-
-    for (int s = 0; s < A.ksteps && !term; ++s) {
-        const double step_length = L;                                   // :918
-        const double grad_norm = sqrt(G.seq_sum(g * g));                // :921
-        double grad_step_length, grad_obj;
-        group_line_search<LPP, Obj>(G, x, g, f0, step_length / grad_norm, grad_step_length, grad_obj);  // :922-925
-        const double bfgs_norm = sqrt(G.seq_sum(d * d));                // :928
-        double bfgs_step_length, bfgs_obj;
-        group_line_search<LPP, Obj>(G, x, d, f0, step_length / bfgs_norm, bfgs_step_length, bfgs_obj);  // :929-932
-
-        if (bfgs_obj < f0 && !(bfgs_obj > grad_obj)) {                  // :934
-            f0 = bfgs_obj;                                              // :937
-            L = bfgs_step_length * bfgs_norm;                           // :938
-            type = DZO_STEP_BFGS;                                       // :939
-            iter += 1;                                                  // :940
-            moved = true;
-            dx = -x;                                                    // :943
-            dg = -g;                                                    // :944
-            const double alpha = -bfgs_step_length;
-            x = x + alpha * d;                                          // :945
-            g = Obj::grad(G, x);                                        // :948
-            dx = dx + x;                                                // :949
-            dg = dg + g;                                                // :950
-            // update_inverse_hessian!(H, -bfgs_step_length, d, dg, scratch)   :864-889
-            const double overlap = G.seq_sum(d * dg);                   // :873
-            const double sd = d * (1.0 / overlap);                      // :874
-            if (!waited) { mbar_wait(bar, 0); waited = true; }
-            double Hrow[LPP];
-#pragma unroll
-            for (int j = 0; j < LPP; ++j) Hrow[j] = (G.act && j < n) ? sH[r + j * n] : 0.0;
-            double* v0 = G.vbuf(0);
-            double* v1 = G.vbuf(1);
-            double* v2 = G.vbuf(2);
-            if (G.act) v0[r] = dg;
-            G.sync();
-            double t = 0.0;                                             // :875  scratch = H * delta_gradient
-#pragma unroll
-            for (int j = 0; j < LPP; ++j)
-                if (j < n) t += Hrow[j] * v0[j];
-            const double delta_norm = alpha * overlap + G.seq_sum(dg * t);  // :876 (seq_sum syncs the group)
-            if (G.act) { v0[r] = g; v1[r] = sd; v2[r] = t; }
-            G.sync();
-            double dnew = 0.0;
-#pragma unroll
-            for (int j = 0; j < LPP; ++j)
-                if (j < n) {
-                    const double sj = v1[j], tj = v2[j];
-                    Hrow[j] += (delta_norm * (sd * sj) - (t * sj + sd * tj));  // :882-884
-                    dnew += Hrow[j] * v0[j];                                  // :958-960  d = H * g
-                }
-            d = dnew;
-            if (G.act) {
-#pragma unroll
-                for (int j = 0; j < LPP; ++j)
-                    if (j < n) sH[r + j * n] = Hrow[j];
-            }
-            H_dirty = true;
-            G.sync();
-        } else if (grad_obj < f0) {                                     // :962
-            f0 = grad_obj;                                              // :965
-            L = grad_step_length * grad_norm;                           // :966
-            type = DZO_STEP_GRADIENT_DESCENT;                           // :967
-            iter += 1;                                                  // :968
-            moved = true;
-            dx = -x;                                                    // :971
-            dg = -g;                                                    // :972
-            const double alpha = -grad_step_length;
-            x = x + alpha * g;                                          // :973
-            g = Obj::grad(G, x);                                        // :976
-            dx = dx + x;                                                // :977
-            dg = dg + g;                                                // :978
-            if (!waited) { mbar_wait(bar, 0); waited = true; }          // the bulk load must land before we overwrite
-            if (G.act) {                                                // :981 identity_matrix!
-#pragma unroll
-                for (int j = 0; j < LPP; ++j)
-                    if (j < n) sH[r + j * n] = (j == r) ? 1.0 : 0.0;
-            }
-            H_dirty = true;
-            d = g;                                                      // :984-986
-            G.sync();
-        } else {
-            term = true;                                                // :989
-        }
-    }
-
-    // ---- write back
-    if (moved && G.act) {
-        A.x[p * n + r] = x;
-        A.g[p * n + r] = g;
-        A.d[p * n + r] = d;
-        A.dx[p * n + r] = dx;
-        A.dg[p * n + r] = dg;
-    }
-    if (H_dirty) {
-        fence_proxy_async_smem();  // generic-proxy writes to sH -> visible to the bulk-copy engine
-        G.sync();
-        if (r == 0) {
-            bulk_s2g(A.H + p * nn, sH, (uint32_t)(nn * sizeof(double)));
-            bulk_commit();
-        }
-    }
-    if (r == 0) {
-        if (moved) {
-            A.f[p] = f0;
-            A.L[p] = L;
-            A.iter[p] = iter;
-            A.type[p] = type;
-            if (A.f_host) A.f_host[p] = f0;
-        }
-        if (term) {
-            A.term[p] = 1;
-            if (A.term_host) A.term_host[p] = 1;
-        }
-        if (A.probes) atomicAdd(A.probes, G.probes);
-        if (!waited) mbar_wait(bar, 0);  // never leave with an async copy still targeting our smem
-        if (H_dirty) bulk_wait_read0();
-    }
-}
-
 // ----------------------------------------------------------------------------- resume kernel
 // State-rebuilding constructor legacy/DZOptimization.jl:819-862: x, H, dx, dg, L, type, iter were
 // copied in by the host; recompute f (:828), g (:830-831), d = H*g (:833-836), clear the flag (:849).
@@ -441,18 +257,6 @@ static __global__ void __launch_bounds__(kBatchedThreads) bfgs_batched_restore_k
     }
 }
 
-// identity_matrix! for every problem whose H is still implicit (hid != 0), then clear the flags: run before a
-// kernel that does not know about `hid` takes over a handle (A/B switch of the batched variant).
-static __global__ void materialize_identity_kernel(double* H, unsigned char* hid, int n, long long batch) {
-    const long long nn = (long long)n * n;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nn * batch) return;
-    const long long p = idx / nn;
-    if (!hid[p]) return;
-    const int e = (int)(idx - p * nn);
-    H[idx] = (e / n == e % n) ? 1.0 : 0.0;
-}
-
 // number of problems with has_terminated == false
 static __global__ void count_active_kernel(const unsigned char* term, long long batch, unsigned long long* out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -461,11 +265,6 @@ static __global__ void count_active_kernel(const unsigned char* term, long long 
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)v);
 }
 
-template <int LPP>
-inline size_t batched_step_smem(int n) {
-    constexpr int PPC = kBatchedThreads / LPP;
-    return 16 + sizeof(double) * ((size_t)PPC * n * n + (size_t)PPC * kBcBufs * LPP);
-}
 template <int LPP>
 inline size_t batched_init_smem() {
     constexpr int PPC = kBatchedThreads / LPP;

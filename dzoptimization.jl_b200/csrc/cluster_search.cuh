@@ -203,7 +203,8 @@ DZO_DEVINL void cluster_line_search(cg::cluster_group& cluster, ClusterRed& R, c
 // step! :891-960 up to (and including) the O(n) part of update_inverse_hessian! (:873-874).
 // Launch: grid = 8 CTAs (one cluster of 8), 512 threads each.
 static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
-    cluster_bfgs_search_kernel(LargeVecs a) {
+    cluster_bfgs_search_kernel(LargeVecs a_) {
+    const LargeVecs a = for_problem(a_, blockIdx.x / kClusterCtas);      // one cluster per problem
     __shared__ ClusterRed R;
     __shared__ LargeCtrl sc;
     cg::cluster_group cluster = cg::this_cluster();
@@ -308,7 +309,8 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
 
 // :876 on the cluster
 static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads, 1)
-    cluster_delta_kernel(LargeVecs a) {
+    cluster_delta_kernel(LargeVecs a_) {
+    const LargeVecs a = for_problem(a_, blockIdx.x / kClusterCtas);
     __shared__ ClusterRed R;
     cg::cluster_group cluster = cg::this_cluster();
     if (a.ctrl->kind != DZO_STEP_BFGS) return;

@@ -101,8 +101,6 @@ struct dzo_bfgs {
     unsigned long long* counter = nullptr;
     unsigned char* hid = nullptr;        // batched hybrid kernel: H of problem p is an implicit identity (batched_hybrid.cuh, LAZY)
     unsigned long long* stats = nullptr; // batched hybrid kernel: running step-kind counters (HK_COUNT words)
-    unsigned* tilectr = nullptr;         // batched hybrid kernel: tile counter of the persistent grid (zero between launches)
-    int sm_count = 0;
     // large path
     double *sd = nullptr, *t = nullptr, *partial = nullptr;
     unsigned* tile_counters = nullptr;
@@ -154,7 +152,7 @@ static void free_handle(dzo_bfgs* o) {
     if (o->arena) { o->t = nullptr; o->d = nullptr; o->flags_t = nullptr; o->flags_d = nullptr; }   // live inside the arena
     void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->H, o->f, o->L, o->iter, o->type, o->term, o->counter,
                     o->sd, o->t, o->partial, o->tile_counters, o->ctrl, o->flags_t, o->flags_d, o->done, o->arena,
-                    o->hid, o->stats, o->tilectr};
+                    o->hid, o->stats};
     if (o->own_stream) {
         for (void* p : ptrs) {
             if (!p) continue;
@@ -213,10 +211,10 @@ static int any_nan(dzo_bfgs* o, const double* f, long long count, bool* out) {
 static BatchedArgs batched_args(const dzo_bfgs* o, int ksteps) {
     BatchedArgs A;
     A.x = o->x; A.g = o->g; A.d = o->d; A.dx = o->dx; A.dg = o->dg; A.H = o->H; A.f = o->f; A.L = o->L;
-    A.iter = o->iter; A.type = o->type; A.term = o->term; A.probes = nullptr;
+    A.iter = o->iter; A.type = o->type; A.term = o->term;
     A.f_host = o->f_host; A.term_host = o->term_host;
     A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps; A.prefetch_rounds = g_tuning.batched_prefetch;
-    A.hid = o->hid; A.stats = o->stats; A.tile_counter = nullptr;
+    A.hid = o->hid; A.stats = o->stats;
     return A;
 }
 
@@ -240,20 +238,6 @@ static int launch_batched_restore(dzo_bfgs* o) {
     constexpr int PPC = kBatchedThreads / LPP;
     const unsigned grid = (unsigned)((o->batch + PPC - 1) / PPC);
     bfgs_batched_restore_kernel<LPP, RosenbrockSmall><<<grid, kBatchedThreads, batched_init_smem<LPP>(), o->stream>>>(batched_args(o, 0));
-    DZO_CUDA(cudaGetLastError());
-    return DZO_OK;
-}
-template <int LPP>
-static int launch_batched_step(dzo_bfgs* o, int k) {
-    constexpr int PPC = kBatchedThreads / LPP;
-    const unsigned grid = (unsigned)((o->batch + PPC - 1) / PPC);
-    const size_t smem = batched_step_smem<LPP>((int)o->n);
-    static bool attr_set[64] = {};
-    if (!attr_set[o->device & 63]) {
-        DZO_CUDA(cudaFuncSetAttribute(bfgs_batched_step_kernel<LPP, RosenbrockSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set[o->device & 63] = true;
-    }
-    bfgs_batched_step_kernel<LPP, RosenbrockSmall><<<grid, kBatchedThreads, smem, o->stream>>>(batched_args(o, k));
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;
 }
@@ -284,74 +268,16 @@ static int batched_restore(dzo_bfgs* o) {
     if (o->objective != DZO_OBJ_ROSENBROCK) return generic_launch(o, 2, 0, 0.0);
     DZO_LPP_DISPATCH(o, launch_batched_restore, o)
 }
-template <int N>
-static int launch_hybrid_step(dzo_bfgs* o, int k) {
-    const unsigned grid = (unsigned)((o->batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
-    const size_t smem = hybrid_smem<N>();
-    static bool attr_set[64] = {};
-    if (!attr_set[o->device & 63]) {
-        DZO_CUDA(cudaFuncSetAttribute(bfgs_batched_hybrid_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[o->device & 63] = true;
-    }
-    bfgs_batched_hybrid_kernel<N><<<grid, kHybridThreads, smem, o->stream>>>(batched_args(o, k));
-    DZO_CUDA(cudaGetLastError());
-    return DZO_OK;
-}
-template <int N, bool DUAL>
-static int launch_hybrid3_step_(dzo_bfgs* o, int k) {
-    unsigned grid = (unsigned)((o->batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
-    BatchedArgs args = batched_args(o, k);
-    const unsigned resident = (unsigned)(o->sm_count > 0 ? o->sm_count : 148) * 4u;   // 4 CTAs per SM (shared tile, registers)
-    if (g_tuning.batched_persistent && grid > resident) {   // persistent CTAs, tiles handed out to warps through a counter
-        grid = resident;
-        args.tile_counter = o->tilectr;
-    }
-    const size_t smem = hybrid_smem<N>();
-    static bool attr_set[64] = {};
-    if (!attr_set[o->device & 63]) {
-        DZO_CUDA(cudaFuncSetAttribute(bfgs_batched_hybrid3_kernel<N, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[o->device & 63] = true;
-    }
-    bfgs_batched_hybrid3_kernel<N, DUAL><<<grid, kHybridThreads, smem, o->stream>>>(args);
-    DZO_CUDA(cudaGetLastError());
-    return DZO_OK;
-}
-template <int N>
-static int launch_hybrid3_step(dzo_bfgs* o, int k) {
-    return g_tuning.batched_dual ? launch_hybrid3_step_<N, true>(o, k) : launch_hybrid3_step_<N, false>(o, k);
-}
-static bool hybrid_n(int64_t n) { return n == 2 || n == 4 || n == 8 || n == 16; }
-// a kernel that does not know about implicit identities takes over: write them out, drop the lazy mode for good
-static int materialize_identities(dzo_bfgs* o) {
-    if (!o->hid) return DZO_OK;
-    const long long total = (long long)o->n * o->n * o->batch;
-    materialize_identity_kernel<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(o->H, o->hid, (int)o->n, o->batch);
-    DZO_CUDA(cudaGetLastError());
-    DZO_CUDA(cudaStreamSynchronize(o->stream));
-    if (o->pooled) cudaFreeAsync(o->hid, o->own_stream); else cudaFree(o->hid);
-    o->hid = nullptr;
-    return DZO_OK;
-}
+static bool hybrid_n(int64_t n) { return n >= 2 && n <= 32 && n % 2 == 0; }
+// step! of a batched handle: ONE launch of bfgs_batched_hybrid_kernel<n> (Rosenbrock; every even n <= 32), or the generic
+// one-thread-per-problem kernel (Riesz)
 static int batched_step(dzo_bfgs* o, int k) {
     if (o->objective != DZO_OBJ_ROSENBROCK) return generic_launch(o, 0, k, 0.0);
-    if (g_tuning.batched_variant == 0 && hybrid_n(o->n)) {   // thread-per-problem dual line search + lanes-per-problem H update
-        switch (o->n) {
-            case 2: return launch_hybrid3_step<2>(o, k);
-            case 4: return launch_hybrid3_step<4>(o, k);
-            case 8: return launch_hybrid3_step<8>(o, k);
-            default: return launch_hybrid3_step<16>(o, k);
-        }
-    }
-    DZO_TRY(materialize_identities(o));
-    if (g_tuning.batched_variant == 2 && hybrid_n(o->n)) {   // second-generation kernel (round 1), kept as the A/B baseline
-        switch (o->n) {
-            case 2: return launch_hybrid_step<2>(o, k);
-            case 4: return launch_hybrid_step<4>(o, k);
-            case 8: return launch_hybrid_step<8>(o, k);
-            default: return launch_hybrid_step<16>(o, k);
-        }
-    }
-    DZO_LPP_DISPATCH(o, launch_batched_step, o, k)
+    const BatchedArgs args = batched_args(o, k);
+    const cudaError_t e = (o->n <= 16) ? hybrid_launch_n2_16((int)o->n, args, o->stream, o->device)
+                                       : hybrid_launch_n18_32((int)o->n, args, o->stream, o->device);
+    if (e != cudaSuccess) return fail(DZO_ERR_CUDA, "batched step! launch failed: %s", cudaGetErrorString(e));
+    return DZO_OK;
 }
 
 // ---- large-path launches
@@ -392,9 +318,9 @@ static int sweep_threads(int64_t rows, int64_t n) {
     while (t > 64 && ((rows + 2 * t - 1) / (2 * t)) * nchunks < 4 * 148) t >>= 1;   // (8 GPUs, n=16384: 64 and 128 measured equal)
     return t;
 }
-static dim3 sweep_grid(int64_t rows, int64_t n) {
+static dim3 sweep_grid(int64_t rows, int64_t n, int64_t batch = 1) {
     const int64_t r = 2 * sweep_threads(rows, n);
-    return dim3((unsigned)((rows + r - 1) / r), (unsigned)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK), 1);
+    return dim3((unsigned)((rows + r - 1) / r), (unsigned)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK), (unsigned)batch);
 }
 static void launch_gemv(dim3 grid, int threads, cudaStream_t st, const SweepArgs& a) {
     switch (g_tuning.sweep_unroll) {
@@ -427,7 +353,7 @@ static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind, 
     a.v = v; a.out = out;
     if (need_kind < 0) a.ctrl = nullptr; else a.need_kind = need_kind;
     if (fused_t) a.peers = peer_set(o, true);      // rows go straight into every peer's t; no collective call
-    launch_gemv(sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), o->stream, a);
+    launch_gemv(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), o->stream, a);
     DZO_CUDA(cudaGetLastError());
     return fused_t ? DZO_OK : allgather_rows(o, out);
 }
@@ -440,18 +366,18 @@ static int large_step_once(dzo_bfgs* o) {
     const bool cluster = (g_tuning.search_variant == 0) || o->fused;   // 8-CTA cluster with DSMEM reductions vs one CTA
                                                                         // (the peer-flag waits live in the cluster kernels)
     if (o->riesz) { /* search stage already enqueued above (cooperative Riesz kernel) */ }
-    else if (cluster) cluster_bfgs_search_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);   // :891-950, :873-874
-    else vec_bfgs_search_kernel<<<1, 1024, 0, o->stream>>>(v);
+    else if (cluster) cluster_bfgs_search_kernel<<<kClusterCtas * (unsigned)o->batch, kClusterThreads, 0, o->stream>>>(v);   // :891-950, :873-874
+    else vec_bfgs_search_kernel<<<(unsigned)o->batch, 1024, 0, o->stream>>>(v);
     DZO_CUDA(cudaGetLastError());
     DZO_TRY(large_gemv(o, o->dg, o->t, DZO_STEP_BFGS, o->fused));               // :875
-    if (cluster) cluster_delta_kernel<<<kClusterCtas, kClusterThreads, 0, o->stream>>>(v);         // :876
-    else vec_delta_kernel<<<1, 1024, 0, o->stream>>>(v);
+    if (cluster) cluster_delta_kernel<<<kClusterCtas * (unsigned)o->batch, kClusterThreads, 0, o->stream>>>(v);         // :876
+    else vec_delta_kernel<<<(unsigned)o->batch, 1024, 0, o->stream>>>(v);
     DZO_CUDA(cudaGetLastError());
     SweepArgs a = sweep_args(o);
     a.v = o->g; a.out = o->d;
     a.need_kind = DZO_STEP_GRADIENT_DESCENT + 100;   // this launch also serves identity_matrix! (:981) after a GD step
     if (o->fused) a.peers = peer_set(o, false);
-    launch_update(sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), o->stream, a);   // :878-886 + :958-960
+    launch_update(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), o->stream, a);   // :878-886 + :958-960
     DZO_CUDA(cudaGetLastError());
     if (!o->fused) DZO_TRY(allgather_rows(o, o->d));
     else {
@@ -544,8 +470,10 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     DZO_TRY(check_problem(objective, constraint, obj_param, n, batch));
     if (objective == DZO_OBJ_RIESZ && (obj_param > 4 || nranks != 1))
         return fail(DZO_ERR_UNSUPPORTED, "BFGSOptimizer with the Riesz objective: dim <= 4, one GPU");
-    if (batch > 1 && n > DZO_SMALL_N_MAX)
-        return fail(DZO_ERR_UNSUPPORTED, "batched mode needs n <= %d; larger n runs one problem per handle", DZO_SMALL_N_MAX);
+    if (batch > 1 && n > DZO_SMALL_N_MAX && (objective != DZO_OBJ_ROSENBROCK || nranks != 1))
+        return fail(DZO_ERR_UNSUPPORTED, "a batch of n > %d problems: DZO_OBJ_ROSENBROCK on one GPU (one thread-block cluster per problem)", DZO_SMALL_N_MAX);
+    if (batch > 1 && n > DZO_SMALL_N_MAX && (double)n * (double)n * (double)batch * 8.0 > 160e9)
+        return fail(DZO_ERR_ALLOC, "batch of %lld inverse Hessians of n = %lld does not fit one GPU", (long long)batch, (long long)n);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(DZO_ERR_INVALID_ARGUMENT, "bad rank/nranks");
     if (nranks > 1 && (n <= DZO_SMALL_N_MAX || n % (2 * nranks)))
         return fail(DZO_ERR_INVALID_ARGUMENT, "row sharding needs n > %d and n divisible by 2*nranks", DZO_SMALL_N_MAX);
@@ -579,25 +507,24 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     if (o->small) {
         if ((rc = dmalloc(&o->H, nb * (size_t)n)) || (rc = dmalloc(&o->f, (size_t)batch)) || (rc = dmalloc(&o->L, (size_t)batch)) ||
             (rc = dmalloc(&o->iter, (size_t)batch)) || (rc = dmalloc(&o->type, (size_t)batch)) || (rc = dmalloc(&o->term, (size_t)batch)) ||
-            (rc = dmalloc(&o->stats, (size_t)HK_COUNT)) || (rc = dmalloc(&o->tilectr, (size_t)1)))
+            (rc = dmalloc(&o->stats, (size_t)HK_COUNT)))
             return bail(rc);
-        if (cudaMemsetAsync(o->stats, 0, HK_COUNT * sizeof(unsigned long long), o->stream) != cudaSuccess ||
-            cudaMemsetAsync(o->tilectr, 0, sizeof(unsigned), o->stream) != cudaSuccess)
+        if (cudaMemsetAsync(o->stats, 0, HK_COUNT * sizeof(unsigned long long), o->stream) != cudaSuccess)
             return bail(fail(DZO_ERR_CUDA, "memset failed"));
-        cudaDeviceGetAttribute(&o->sm_count, cudaDevAttrMultiProcessorCount, device);
         // implicit identities (constructor and identity_matrix! after a GD step write no H): hybrid kernel only
-        if (objective == DZO_OBJ_ROSENBROCK && hybrid_n(n) && g_tuning.batched_variant == 0 && g_tuning.batched_lazy)
+        if (objective == DZO_OBJ_ROSENBROCK && hybrid_n(n) && g_tuning.batched_lazy)
             if ((rc = dmalloc(&o->hid, (size_t)batch))) return bail(rc);
     } else {
         const size_t nchunks = (size_t)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK);
         const size_t rblocks = (size_t)((o->rows + kSweepMinRows - 1) / kSweepMinRows);
-        if ((rc = dmalloc(&o->H, (size_t)o->rows * (size_t)n)) || (rc = dmalloc(&o->sd, (size_t)n)) ||
-            (!use_arena && (rc = dmalloc(&o->t, (size_t)n))) ||
-            (rc = dmalloc(&o->partial, nchunks * (size_t)o->rows)) || (rc = dmalloc(&o->tile_counters, rblocks)) ||
-            (rc = dmalloc(&o->ctrl, 1)) || (!use_arena && (rc = dmalloc(&o->flags_t, (size_t)kMaxPeers))) ||
+        const size_t B = (size_t)batch;     // > 1: a batch of medium-n problems, every array holds B consecutive copies
+        if ((rc = dmalloc(&o->H, (size_t)o->rows * (size_t)n * B)) || (rc = dmalloc(&o->sd, (size_t)n * B)) ||
+            (!use_arena && (rc = dmalloc(&o->t, (size_t)n * B))) ||
+            (rc = dmalloc(&o->partial, nchunks * (size_t)o->rows * B)) || (rc = dmalloc(&o->tile_counters, rblocks * B)) ||
+            (rc = dmalloc(&o->ctrl, B)) || (!use_arena && (rc = dmalloc(&o->flags_t, (size_t)kMaxPeers))) ||
             (!use_arena && (rc = dmalloc(&o->flags_d, (size_t)kMaxPeers))) || (rc = dmalloc(&o->done, 1)))
             return bail(rc);
-        if (cudaMemsetAsync(o->tile_counters, 0, rblocks * sizeof(unsigned), o->stream) != cudaSuccess ||
+        if (cudaMemsetAsync(o->tile_counters, 0, rblocks * B * sizeof(unsigned), o->stream) != cudaSuccess ||
             cudaMemsetAsync(o->flags_t, 0, kMaxPeers * 8, o->stream) != cudaSuccess ||
             cudaMemsetAsync(o->flags_d, 0, kMaxPeers * 8, o->stream) != cudaSuccess ||
             cudaMemsetAsync(o->done, 0, sizeof(unsigned), o->stream) != cudaSuccess)
@@ -621,10 +548,10 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
             if ((rc = riesz_bfgs_attach(n, obj_param, constraint, device, &o->riesz))) return bail(rc);
             if ((rc = riesz_bfgs_launch(o->riesz, 6, o->stream, o->x, o->g, o->d, o->dx, o->dg, o->sd, o->ctrl, L0))) return bail(rc);
         } else
-            vec_bfgs_init_kernel<<<1, 1024, 0, o->stream>>>(large_vecs(o), L0);
+            vec_bfgs_init_kernel<<<(unsigned)batch, 1024, 0, o->stream>>>(large_vecs(o), L0);
         SweepArgs a = sweep_args(o);
         a.ctrl = nullptr;
-        identity_kernel<<<sweep_grid(o->rows, o->n), sweep_threads(o->rows, o->n), 0, o->stream>>>(a);   // :781-783
+        identity_kernel<<<sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), 0, o->stream>>>(a);   // :781-783
     }
     if (cudaStreamSynchronize(o->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "constructor kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -634,9 +561,11 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
         if (o->small) {
             if ((rc = any_nan(o, o->f, batch, &bad))) return bail(rc);
         } else {
-            LargeCtrl c;
-            cudaMemcpy(&c, o->ctrl, sizeof c, cudaMemcpyDeviceToHost);
-            bad = (c.f != c.f);
+            for (int64_t q = 0; q < batch && !bad; ++q) {
+                LargeCtrl c;
+                cudaMemcpy(&c, o->ctrl + q, sizeof c, cudaMemcpyDeviceToHost);
+                bad = (c.f != c.f);
+            }
         }
         if (bad) return bail(fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the initial point"));
     }
@@ -745,6 +674,16 @@ static int read_back(dzo_bfgs* o, void* dst, const void* src, size_t bytes) {
     return DZO_OK;
 }
 static int read_ctrl(dzo_bfgs* o, LargeCtrl* c) { return read_back(o, c, o->ctrl, sizeof *c); }
+// scalar field of a (batch of) large-n handle(s): one control block per problem
+template <class T, class F>
+static int ctrl_field(dzo_bfgs* o, T* out, F pick) {
+    for (int64_t q = 0; q < o->batch; ++q) {
+        LargeCtrl c;
+        DZO_TRY(read_back(o, &c, o->ctrl + q, sizeof c));
+        out[q] = (T)pick(c);
+    }
+    return DZO_OK;
+}
 
 #define DZO_VEC_GETTER(name, field)                                                       \
     int name(dzo_bfgs* o, double* out) {                                                  \
@@ -770,7 +709,7 @@ int dzo_bfgs_get_inverse_hessian(dzo_bfgs* o, int64_t problem, double* out) {
         }
     }
     if (o->small) return read_back(o, out, o->H + (size_t)problem * o->n * o->n, (size_t)o->n * o->n * 8);
-    return read_back(o, out, o->H, (size_t)o->rows * (size_t)o->n * 8);
+    return read_back(o, out, o->H + (size_t)problem * (size_t)o->rows * (size_t)o->n, (size_t)o->rows * (size_t)o->n * 8);
 }
 // the mirrored fields are already in the caller's buffer once the stream has drained
 static int mirror_sync(dzo_bfgs* o) {
@@ -808,33 +747,40 @@ int dzo_bfgs_get_objective(dzo_bfgs* o, double* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     if (o->small && out == o->f_host) return mirror_sync(o);
     if (o->small) return read_back(o, out, o->f, (size_t)o->batch * 8);
-    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.f; return DZO_OK;
+    return ctrl_field(o, out, [](const LargeCtrl& c) { return c.f; });
 }
 int dzo_bfgs_get_step_length(dzo_bfgs* o, double* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     if (o->small) return read_back(o, out, o->L, (size_t)o->batch * 8);
-    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.L; return DZO_OK;
+    return ctrl_field(o, out, [](const LargeCtrl& c) { return c.L; });
 }
 int dzo_bfgs_get_step_type(dzo_bfgs* o, int32_t* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     if (o->small) return read_back(o, out, o->type, (size_t)o->batch * 4);
-    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.type; return DZO_OK;
+    return ctrl_field(o, out, [](const LargeCtrl& c) { return c.type; });
 }
 int dzo_bfgs_get_iteration_count(dzo_bfgs* o, int64_t* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     if (o->small) return read_back(o, out, o->iter, (size_t)o->batch * 8);
-    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.iter; return DZO_OK;
+    return ctrl_field(o, out, [](const LargeCtrl& c) { return c.iter; });
 }
 int dzo_bfgs_get_terminated(dzo_bfgs* o, uint8_t* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     if (o->small && out == o->term_host) return mirror_sync(o);
     if (o->small) return read_back(o, out, o->term, (size_t)o->batch);
-    LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = (uint8_t)(c.term != 0); return DZO_OK;
+    return ctrl_field(o, out, [](const LargeCtrl& c) { return c.term != 0; });
 }
 int dzo_bfgs_count_active(dzo_bfgs* o, int64_t* out) {
     if (!o || !out) return fail(DZO_ERR_INVALID_ARGUMENT, "null pointer");
     if (!o->small) {
-        LargeCtrl c; DZO_TRY(read_ctrl(o, &c)); *out = c.term ? 0 : 1; return DZO_OK;
+        int64_t active = 0;
+        for (int64_t q = 0; q < o->batch; ++q) {
+            LargeCtrl c;
+            DZO_TRY(read_back(o, &c, o->ctrl + q, sizeof c));
+            active += c.term ? 0 : 1;
+        }
+        *out = active;
+        return DZO_OK;
     }
     DZO_TRY(use_device(o->device));
     DZO_CUDA(cudaMemsetAsync(o->counter, 0, 8, o->stream));
@@ -907,20 +853,26 @@ int dzo_bfgs_set_state(dzo_bfgs* o, const double* point, const double* inverse_h
         if (o->f_host || o->term_host) DZO_CUDA(cudaStreamSynchronize(o->stream));
         return DZO_OK;
     }
-    // large: the caller passes the full n x n matrix; keep rows [row0, row0+rows) of every column
+    // large: the caller passes the full n x n matrix (per problem); keep rows [row0, row0+rows) of every column
     DZO_CUDA(cudaMemcpy2DAsync(o->H, (size_t)o->rows * 8, inverse_hessian + o->row0, (size_t)o->n * 8, (size_t)o->rows * 8,
-                               (size_t)o->n, cudaMemcpyHostToDevice, o->stream));
-    LargeCtrl c;
-    DZO_CUDA(cudaMemcpyAsync(&c, o->ctrl, sizeof c, cudaMemcpyDeviceToHost, o->stream));
-    DZO_CUDA(cudaStreamSynchronize(o->stream));
-    c.L = last_step_length[0]; c.type = last_step_type[0]; c.iter = iteration_count[0];              // :848, :855-856
-    DZO_CUDA(cudaMemcpyAsync(o->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, o->stream));
-    vec_bfgs_restore_kernel<<<1, 1024, 0, o->stream>>>(large_vecs(o));
+                               (size_t)o->n * (size_t)o->batch, cudaMemcpyHostToDevice, o->stream));   // (batch > 1: rows == n)
+    for (int64_t q = 0; q < o->batch; ++q) {
+        LargeCtrl c;
+        DZO_CUDA(cudaMemcpyAsync(&c, o->ctrl + q, sizeof c, cudaMemcpyDeviceToHost, o->stream));
+        DZO_CUDA(cudaStreamSynchronize(o->stream));
+        c.L = last_step_length[q]; c.type = last_step_type[q]; c.iter = iteration_count[q];          // :848, :855-856
+        DZO_CUDA(cudaMemcpyAsync(o->ctrl + q, &c, sizeof c, cudaMemcpyHostToDevice, o->stream));
+        DZO_CUDA(cudaStreamSynchronize(o->stream));
+    }
+    vec_bfgs_restore_kernel<<<(unsigned)o->batch, 1024, 0, o->stream>>>(large_vecs(o));
     DZO_CUDA(cudaGetLastError());
     DZO_TRY(large_gemv(o, o->g, o->d, -1));                                                          // :833-836
     DZO_CUDA(cudaStreamSynchronize(o->stream));
-    DZO_TRY(read_ctrl(o, &c));
-    if (c.f != c.f) return fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the restored point");
+    for (int64_t q = 0; q < o->batch; ++q) {
+        LargeCtrl c;
+        DZO_TRY(read_back(o, &c, o->ctrl + q, sizeof c));
+        if (c.f != c.f) return fail(DZO_ERR_NAN_OBJECTIVE, "objective is NaN at the restored point");
+    }
     return DZO_OK;
 }
 
@@ -1227,7 +1179,6 @@ int dzo_set_tuning(const char* key, int value) {
     if (!key) return fail(DZO_ERR_INVALID_ARGUMENT, "null key");
     g_tuning.epoch += 1;                                  // captured step graphs are rebuilt
     if (!strcmp(key, "use_graph")) { g_tuning.use_graph = value; return DZO_OK; }
-    if (!strcmp(key, "batched_variant")) { g_tuning.batched_variant = value; return DZO_OK; }
     if (!strcmp(key, "search_variant")) { g_tuning.search_variant = value; return DZO_OK; }
     if (!strcmp(key, "riesz_profile")) { g_tuning.riesz_profile = value; return DZO_OK; }
     if (!strcmp(key, "riesz_esplit")) { g_tuning.riesz_esplit = value; return DZO_OK; }
@@ -1240,8 +1191,6 @@ int dzo_set_tuning(const char* key, int value) {
     }
     if (!strcmp(key, "batched_prefetch")) { g_tuning.batched_prefetch = value; return DZO_OK; }
     if (!strcmp(key, "batched_lazy")) { g_tuning.batched_lazy = value; return DZO_OK; }
-    if (!strcmp(key, "batched_dual")) { g_tuning.batched_dual = value; return DZO_OK; }
-    if (!strcmp(key, "batched_persistent")) { g_tuning.batched_persistent = value; return DZO_OK; }
     return fail(DZO_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
 }
 

@@ -65,13 +65,8 @@ struct Tuning {
     int riesz_gvariant = 0;   // Riesz gradient: 0 = (32 rows x 128 sources) warp items, 1 = symmetric 128 x 128 CTA tiles (each pair
                               // weight computed once; measured 0.183 vs 0.177 ms per GD step at N = 4096, so not the default)
     int riesz_profile = 0;    // 1: the cooperative Riesz kernel logs (phase id, %globaltimer) events of its leader thread
-    int batched_variant = 0;  // 0 = third-generation hybrid kernel for n in {2,4,8,16}, 1 = lanes-per-problem kernel everywhere,
-                              // 2 = second-generation hybrid kernel (round 1; A/B baseline)
-    int batched_lazy = 1;     // hybrid kernel: keep H = I implicit (no HBM traffic for identity_matrix!); read at create time
-    int batched_persistent = 0;  // hybrid kernel: 1 = persistent CTAs (4 per SM), tiles of 32 problems handed out to warps through a
-                                 // counter (measured 0.80 vs 0.74 ms per 1M-problem launch: instruction-cache thrash; default off)
-    int batched_dual = 0;     // hybrid kernel: 1 = both line searches of a step side by side in one thread (one probe of each
-                              // per iteration), 0 = one per-thread state machine over both searches
+    int batched_lazy = 1;     // batched kernel: keep H = I implicit (no HBM traffic for identity_matrix!); read at create time
+                              // (1M x n=16: 0.74 ms per launch with, 0.86 ms without)
 };
 extern Tuning g_tuning;
 

@@ -202,9 +202,18 @@ struct LargeVecs {
     const unsigned long long* flags_d;   // d = H'*g slabs of step `calls`
     int nranks;
 };
+// batch > 1 with n > 32 ("run multiple optimizers in parallel" for medium n): problem q's vectors and control block are
+// q * n doubles / q blocks further; a kernel instance (a CTA, or a cluster) serves one problem
+DZO_DEVINL LargeVecs for_problem(LargeVecs a, long long q) {
+    const long long o = q * a.n;
+    a.x += o; a.g += o; a.d += o; a.dx += o; a.dg += o; a.sd += o; a.t += o;
+    a.ctrl += q;
+    return a;
+}
 
 // Constructor, legacy/DZOptimization.jl:762-810 (x already holds copy(x0)).
-static __global__ void __launch_bounds__(1024, 1) vec_bfgs_init_kernel(LargeVecs a, double initial_step_length) {
+static __global__ void __launch_bounds__(1024, 1) vec_bfgs_init_kernel(LargeVecs a_, double initial_step_length) {
+    const LargeVecs a = for_problem(a_, blockIdx.x);
     __shared__ double sm[132];
     const long long n = a.n, m = n >> 1;
     ProbeFlags fl;
@@ -229,7 +238,8 @@ static __global__ void __launch_bounds__(1024, 1) vec_bfgs_init_kernel(LargeVecs
 }
 
 // set_state (:819-862): recompute f and g at the restored point; d = H*g follows as a GEMV.
-static __global__ void __launch_bounds__(1024, 1) vec_bfgs_restore_kernel(LargeVecs a) {
+static __global__ void __launch_bounds__(1024, 1) vec_bfgs_restore_kernel(LargeVecs a_) {
+    const LargeVecs a = for_problem(a_, blockIdx.x);
     __shared__ double sm[132];
     const long long n = a.n, m = n >> 1;
     ProbeFlags fl;
@@ -246,7 +256,8 @@ static __global__ void __launch_bounds__(1024, 1) vec_bfgs_restore_kernel(LargeV
 }
 
 // step! :891-960 up to (and including) the O(n) part of update_inverse_hessian! (:873-874).
-static __global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVecs a) {
+static __global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVecs a_) {
+    const LargeVecs a = for_problem(a_, blockIdx.x);
     __shared__ double sm[2 * 132];
     __shared__ LargeCtrl sc;
     const long long n = a.n, m = n >> 1;
@@ -353,7 +364,8 @@ static __global__ void __launch_bounds__(1024, 1) vec_bfgs_search_kernel(LargeVe
 }
 
 // :876  delta_norm = step_length*overlap + dot(delta_gradient, scratch)
-static __global__ void __launch_bounds__(1024, 1) vec_delta_kernel(LargeVecs a) {
+static __global__ void __launch_bounds__(1024, 1) vec_delta_kernel(LargeVecs a_) {
+    const LargeVecs a = for_problem(a_, blockIdx.x);
     __shared__ double sm[132];
     if (a.ctrl->kind != DZO_STEP_BFGS) return;
     const double s = cta_tree_dot(a.dg, a.t, a.n, sm);
@@ -418,6 +430,20 @@ struct SweepArgs {
     int nchunks;
     PeerSet peers;          // fused all-gather over peer memory (nranks == 1: plain local store)
 };
+// batch > 1: blockIdx.z selects the problem (its n x n matrix, vectors, chunk partials, tile counters, control block)
+DZO_DEVINL SweepArgs sweep_for_problem(SweepArgs a) {
+    const long long q = blockIdx.z;
+    if (q == 0) return a;
+    a.H += q * a.ld * a.n;
+    if (a.v) a.v += q * a.n;
+    if (a.s) a.s += q * a.n;
+    if (a.t) a.t += q * a.n;
+    if (a.out) a.out += q * a.n;
+    if (a.partial) a.partial += q * (long long)a.nchunks * a.rows;
+    a.counters += q * gridDim.x;
+    if (a.ctrl) a.ctrl += q;
+    return a;
+}
 
 // store one finished row: locally and, when sharded with the fused gather, into every peer's copy
 DZO_DEVINL void sweep_store_row(const SweepArgs& a, long long gi, double r) {
@@ -484,7 +510,8 @@ DZO_DEVINL void sweep_finish_rows(const SweepArgs& a, long long i0, double acc0,
 // 1024-column chunk: a warp reads 512 contiguous bytes of every column (H is column-major),
 // and each thread's accumulator is exactly the sequential chunk partial of the oracle.
 template <int U>
-static __global__ void __launch_bounds__(kSweepMaxThreads) gemv_kernel(SweepArgs a) {
+static __global__ void __launch_bounds__(kSweepMaxThreads) gemv_kernel(SweepArgs a_) {
+    const SweepArgs a = sweep_for_problem(a_);
     if (a.ctrl && a.ctrl->kind != a.need_kind) return;
     __shared__ double sv[DZO_GEMV_CHUNK];
     const long long c0 = (long long)blockIdx.y * DZO_GEMV_CHUNK;
@@ -530,7 +557,8 @@ static __global__ void __launch_bounds__(kSweepMaxThreads) gemv_kernel(SweepArgs
 DZO_DEVINL void identity_tile(const SweepArgs& a);
 
 template <int U>
-static __global__ void __launch_bounds__(kSweepMaxThreads) update_gemv_kernel(SweepArgs a) {
+static __global__ void __launch_bounds__(kSweepMaxThreads) update_gemv_kernel(SweepArgs a_) {
+    const SweepArgs a = sweep_for_problem(a_);
     if (a.need_kind == DZO_STEP_GRADIENT_DESCENT + 100 && a.ctrl->kind == DZO_STEP_GRADIENT_DESCENT) {
         identity_tile(a);   // :981 -- step! resets H after a gradient-descent step; same launch, same tiling
         return;
@@ -620,7 +648,8 @@ DZO_DEVINL void identity_tile(const SweepArgs& a) {
         }
     }
 }
-static __global__ void __launch_bounds__(kSweepMaxThreads) identity_kernel(SweepArgs a) {
+static __global__ void __launch_bounds__(kSweepMaxThreads) identity_kernel(SweepArgs a_) {
+    const SweepArgs a = sweep_for_problem(a_);
     if (a.ctrl && a.ctrl->kind != a.need_kind) return;
     identity_tile(a);
 }

@@ -166,7 +166,8 @@ def test_readme_rosenbrock_n2(gpu, orc):
         assert_bitwise(opt.inverse_hessian(p), ref.inverse_hessian(p), "H")
 
 
-@pytest.mark.parametrize("n,batch", [(4, 300), (16, 2000), (30, 70), (32, 129)])
+@pytest.mark.parametrize("n,batch", [(2, 517), (4, 300), (6, 777), (8, 64), (10, 333), (12, 1000), (14, 95), (16, 2000), (18, 130),
+                                     (20, 257), (22, 33), (24, 500), (26, 31), (28, 200), (30, 70), (32, 129)])
 def test_batched_trace(gpu, orc, n, batch):
     dz = gpu
     EF = dz.ExampleFunctions
@@ -372,8 +373,8 @@ def test_batch_sizes_not_multiple_of_the_warp(gpu, orc):
 
 
 def test_tuning_variants_do_not_change_any_bit(gpu, orc):
-    """the A/B knobs (columns in flight, CTA size of the sweeps, line-search kernel, prefetch distance,
-    batched kernel generation) only change scheduling: every variant reproduces the oracle bit for bit."""
+    """the A/B knobs (columns in flight, CTA size of the sweeps, line-search kernel, prefetch distance, implicit
+    identities) only change scheduling and layout: every variant reproduces the oracle bit for bit."""
     dz = gpu
     EF = dz.ExampleFunctions
     n = 2100
@@ -392,20 +393,15 @@ def test_tuning_variants_do_not_change_any_bit(gpu, orc):
     xb = _x0(orc, 16 * 100, 20).reshape(100, 16)
     rb = orc.BFGS(ROSEN, xb, 1.0)
     rb.step(8)
-    for key, values in (("batched_prefetch", (0, 1, 5, 3)), ("batched_variant", (1, 2, 0)), ("batched_lazy", (0, 1)), ("batched_dual", (1, 0)), ("batched_persistent", (1, 0))):
+    for key, values in (("batched_prefetch", (0, 1, 5, 3)), ("batched_lazy", (0, 1))):
         for v in values:
             dz.set_tuning(key, v)
             b = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, xb, 1.0, batched=True)
             b.step(8)
             assert_bitwise(b.current_point, rb.point, f"{key}={v}: batched point")
             assert_bitwise(b.inverse_hessian(99), rb.inverse_hessian(99), f"{key}={v}: batched H")
-            # switching the kernel generation in the middle of a run (implicit identities get materialised)
-            dz.set_tuning("batched_variant", 2); b.step(3)
-            dz.set_tuning("batched_variant", 0); b.step(3)
-            r2 = orc.BFGS(ROSEN, xb, 1.0); r2.step(14)
-            assert_bitwise(b.current_point, r2.point, f"{key}={v}: after switching kernels")
             for p in range(0, 100, 9):
-                assert_bitwise(b.inverse_hessian(p), r2.inverse_hessian(p), f"{key}={v}: H after switching kernels")
+                assert_bitwise(b.inverse_hessian(p), rb.inverse_hessian(p), f"{key}={v}: batched H[{p}]")
             b.close()
 
 
@@ -592,33 +588,36 @@ def test_secant_condition_after_every_bfgs_step(gpu, orc, n, batched):
     assert seen > (100 if batched else 5)
 
 
-def test_persistent_grid_equals_one_tile_per_warp(gpu, orc):
-    """Above 148 x 4 CTAs worth of problems the hybrid kernel runs as a persistent grid whose warps fetch tiles of 32
-    problems from a counter; results (and the step-kind counters) must not depend on who processed which tile, the
-    counter must be back at zero after every launch (three launches in a row), ragged last tile included."""
+@pytest.mark.parametrize("n,batch", [(34, 50), (64, 40), (256, 12), (1100, 5)])
+def test_batched_medium_n_trace(gpu, orc, n, batch):
+    """README.md:12 "run multiple optimizers in parallel" for 32 < n: one handle, `batch` independent problems, every
+    kernel instance (a thread-block cluster for the O(n) stage, blockIdx.z of the n^2 sweeps) serves one problem.  Same
+    TREE summation order as a single large-n problem; every field of every problem equals the oracle's after every step!."""
     dz = gpu
     EF = dz.ExampleFunctions
-    n, batch = 16, 148 * 4 * 128 + 32 * 7 + 5
-    x0 = _x0(orc, n * batch, 99).reshape(batch, n)
-    dz.set_tuning("batched_persistent", 0)
-    a = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
-    dz.set_tuning("batched_persistent", 1)
+    x0 = _x0(orc, n * batch, 4400 + n).reshape(batch, n)
+    x0[1] = 1.0                                                  # one problem starts at the minimiser and terminates at once
+    opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+    ref = orc.BFGS(ROSEN, x0, 1.0, order=orc.TREE, nthreads=8)
+    assert opt.summation_order == TREE
+    _compare_state(opt, ref, True, "ctor")
+    for it in range(8):
+        dz.step_(opt); ref.step(1)
+        _compare_state(opt, ref, True, f"n={n} iter {it}")
+    opt.step(5); ref.step(5)
+    _compare_state(opt, ref, True, "after 5 more steps in one call")
+    assert opt.count_active() == ref.count_active() < batch
+    for p in (0, 1, batch - 1):
+        assert_bitwise(opt.inverse_hessian(p), ref.inverse_hessian(p), f"H[{p}]")
+    # a single-problem handle on problem 3 walks the same trajectory (the batch dimension changes no bit)
+    one = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0[3], 1.0)
+    one.step(13)
+    assert_bitwise(one.current_point, opt.current_point[3], "batched vs single handle")
+    # resume (set_state) of the whole batch
+    H = np.stack([opt.inverse_hessian(p) for p in range(batch)])
     b = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
-    for it in range(3):
-        dz.set_tuning("batched_persistent", 0); a.step(1)
-        dz.set_tuning("batched_persistent", 1); b.step(1)
-        assert_bitwise(b.current_point, a.current_point, f"iter {it}: point")
-        assert_bitwise(b.next_step_direction, a.next_step_direction, f"iter {it}: direction")
-        assert_bitwise(b.current_objective_value, a.current_objective_value, f"iter {it}: objective")
-        assert a.step_kind_counts() == b.step_kind_counts()
-    dz.set_tuning("batched_persistent", 0); a.step(7)
-    dz.set_tuning("batched_persistent", 1); b.step(7)                      # k fused steps per tile
-    assert_bitwise(b.current_point, a.current_point, "fused: point")
-    assert np.array_equal(b.iteration_count, a.iteration_count)
-    sel = np.arange(0, batch, batch // 2000)
-    ref = orc.BFGS(ROSEN, x0[sel], 1.0, order=orc.SEQ, nthreads=8)
-    ref.step(10)
-    assert_bitwise(b.current_point[sel], ref.point, "spot check against the oracle")
-    for p in (0, batch - 1, 75776):
-        assert_bitwise(b.inverse_hessian(p), a.inverse_hessian(p), f"H[{p}]")
-    dz.set_tuning("batched_persistent", 0)
+    b.set_state(opt.current_point, H, opt.delta_point, opt.delta_gradient, opt.last_step_length, opt.last_step_type,
+                opt.iteration_count)
+    b.step(2); opt.step(2); ref.step(2)
+    _compare_state(b, ref, True, "resumed batch")
+    _compare_state(opt, ref, True, "original batch")

@@ -2,7 +2,7 @@
 
     python tools/batched_ab.py [--batch 1000000] [--steps 20] [--warmup 5] [--configs v0l1p2,v0l0p2,v2l0p2,...]
 
-A config is v<batched_variant>l<batched_lazy>p<batched_prefetch>[d<batched_dual>][s<batched_persistent>].  Prints one JSON line per config: ms per step!,
+A config is l<batched_lazy>p<batched_prefetch>.  Prints one JSON line per config: ms per step!,
 the step kinds counted on the device, the algorithmic bytes of that mix and the fraction of the HBM copy peak."""
 import argparse
 import json
@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--repeat", type=int, default=2)
-    ap.add_argument("--configs", default="v2l0p2,v0l0p2,v0l1p2,v0l1p3,v0l1p2d1")
+    ap.add_argument("--configs", default="l0p3,l1p2,l1p3,l1p4")
     args = ap.parse_args()
     import torch
     import bench
@@ -36,12 +36,10 @@ def main():
     torch.cuda.set_stream(stream)
     for rep in range(args.repeat):
         for cfg in args.configs.split(","):
-            m = re.fullmatch(r"v(\d)l(\d)p(\d+)(?:d(\d))?(?:s(\d))?", cfg)
-            v, lz, pf = (int(g) for g in m.groups()[:3])
-            dual = int(m.group(4) or 0)
-            dz.set_tuning("batched_persistent", int(m.group(5) if m.group(5) is not None else 1))
-            dz.set_tuning("batched_variant", v); dz.set_tuning("batched_lazy", lz); dz.set_tuning("batched_prefetch", pf)
-            dz.set_tuning("batched_dual", dual)
+            m = re.fullmatch(r"l(\d)p(\d+)", cfg)
+            lz, pf = (int(g) for g in m.groups())
+            v = 0
+            dz.set_tuning("batched_lazy", lz); dz.set_tuning("batched_prefetch", pf)
             opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
             opt.set_stream(stream.cuda_stream)
             opt.step(args.warmup)
