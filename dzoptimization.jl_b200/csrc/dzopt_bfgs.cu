@@ -674,6 +674,7 @@ static int read_back(dzo_bfgs* o, void* dst, const void* src, size_t bytes) {
     return DZO_OK;
 }
 static int read_ctrl(dzo_bfgs* o, LargeCtrl* c) { return read_back(o, c, o->ctrl, sizeof *c); }
+}  // extern "C" (templates need C++ linkage)
 // scalar field of a (batch of) large-n handle(s): one control block per problem
 template <class T, class F>
 static int ctrl_field(dzo_bfgs* o, T* out, F pick) {
@@ -684,6 +685,7 @@ static int ctrl_field(dzo_bfgs* o, T* out, F pick) {
     }
     return DZO_OK;
 }
+extern "C" {
 
 #define DZO_VEC_GETTER(name, field)                                                       \
     int name(dzo_bfgs* o, double* out) {                                                  \
