@@ -46,6 +46,7 @@ BATCH = 1_000_000
 LARGE_N = 16384
 SHARDED_N = 65536
 SHARDED_CHECK_N = 8192
+STEPS_PER_BATCH = 25            # timed step! calls per batch (a batch converges within ~100 calls: see device_timed)
 METRIC = "batched BFGS problem-steps/s (1M x n=16)"
 UNIT = "problem-steps/s"
 
@@ -188,24 +189,28 @@ def cpu_leg(orc, steps, warmup, sample_batch, flags):
     """Oracle (port of the reference path) on every host thread; bounded sample of the workload.  Timed twice, the
     faster pass is reported (the direction that favours the CPU arm)."""
     threads = os.cpu_count() or 1
-    x0 = x0_batch(orc, sample_batch, 2024)
+    nb = -(-steps // STEPS_PER_BATCH)
+    x0s = [x0_batch(orc, sample_batch, 2024 + 1000 * b) for b in range(nb)]      # same batches as the GPU arm (rank 0)
     best = None
     for _ in range(2):
-        ref = orc.BFGS(orc.OBJ_ROSENBROCK, x0, 1.0, order=orc.SEQ, nthreads=threads)
-        ref.step(warmup)
-        active0 = ref.count_active()
+        refs = [orc.BFGS(orc.OBJ_ROSENBROCK, x0, 1.0, order=orc.SEQ, nthreads=threads) for x0 in x0s]
+        for ref in refs:
+            ref.step(warmup)
+        active0 = refs[0].count_active()
         t0 = time.perf_counter()
         done = 0
-        for _ in range(steps):
+        for i in range(steps):
+            ref = refs[i // STEPS_PER_BATCH]
             done += ref.count_active()
             ref.step(1)
         dt = time.perf_counter() - t0
-        ref.close()
+        for ref in refs:
+            ref.close()
         if best is None or dt < best[0]:
             best = (dt, done, active0)
     dt, done, active0 = best
     return {"value": done / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{sample_batch} of the {BATCH} problems (same PCG stream), {steps} step! calls after {warmup} warm-up, "
+            "sample": f"{sample_batch} of the {BATCH} problems of each batch (same PCG streams), {steps} step! calls over {nb} batch(es) after {warmup} warm-up each, "
                       f"{active0} active at start, best of 2 passes; oracle/dzo_oracle.c built here with '{flags}' "
                       f"(bit-identical to the -O2 checker build), OpenMP over problems, threads pinned",
             "seconds": dt, "ms_per_step": 1e3 * dt / steps}
@@ -315,57 +320,69 @@ def run_gpu(args):
         o.set_stream(stream.cuda_stream)
         return o
 
-    def device_timed(x0_host, batch):
-        """K back-to-back step! launches after W warm-up steps; returns (ms max over ranks, per-rank kind counts)."""
-        opt = make(x0_host)
-        opt.step(W)
-        opt.step_kind_counts(reset=True)
+    def device_timed(x0_list):
+        """K back-to-back step! launches after W warm-up steps per batch.  A batch of this workload converges within ~100
+        step! calls, so K > STEPS_PER_BATCH launches walk through ceil(K / STEPS_PER_BATCH) independent batches of the same
+        synthetic workload (each constructed and warmed up before the clock starts): every timed launch is a step! in
+        the regime the metric is quoted on, however long the timed region.  Returns (ms max over ranks, kind counts of
+        this rank summed over the batches, clock sampler)."""
+        opts = [make(x) for x in x0_list]
+        for o in opts:
+            o.step(W)
+            o.step_kind_counts(reset=True)
         barrier()
         with ClockSampler(local_rank) as clk:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             ev0.record(stream)
-            for _ in range(K):
-                opt.step_async(1)
+            for i in range(K):
+                opts[i // STEPS_PER_BATCH].step_async(1)
             ev1.record(stream)
             barrier()
             ms = ev0.elapsed_time(ev1)
-        kinds = opt.step_kind_counts()
-        opt.close()
+        kinds = {}
+        for o in opts:
+            for k, v in o.step_kind_counts().items():
+                kinds[k] = kinds.get(k, 0) + v
+            o.close()
         return max_over_ranks(ms), kinds, clk
 
-    def e2e_timed(x0_host, read_point):
-        """the README loop through the public API with HOST buffers (constructor H2D + per-step field reads)"""
+    def e2e_timed(x0_list, read_point):
+        """the README loop through the public API with HOST buffers (constructor H2D + per-step field reads), once per
+        batch of the timed region"""
         barrier()
         barrier()
         t1 = time.perf_counter()
-        e2 = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
-                              device=local_rank)       # H2D of x0 inside the timed region
-        e2.reuse_host_buffers(True)                     # cached page-locked field arrays; has_converged / objective become
-                                                        # zero-copy mirrors the step kernel writes over PCIe while it runs
-        e2.step(W)                                      # same starting state as the device-timed arm
-        flags = obj = None
-        for _ in range(K):
-            dz.step_(e2)
-            flags = e2.has_converged                    # D2H, what `while !opt.has_converged[]` reads
-            obj = e2.current_objective_value            # D2H
-        point_bytes = 0
-        if read_point:
-            point_bytes = e2.current_point.nbytes       # the answer itself (D2H, n x batch doubles)
-        torch.cuda.synchronize()
+        steps_total, d2h, point_bytes, left = 0.0, 0, 0, K
+        for x0_host in x0_list:
+            e2 = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
+                                  device=local_rank)       # H2D of x0 inside the timed region
+            e2.reuse_host_buffers(True)                     # cached page-locked field arrays; has_converged / objective become
+                                                            # zero-copy mirrors the step kernel writes over PCIe while it runs
+            e2.step(W)                                      # same starting state as the device-timed arm
+            flags = obj = None
+            for _ in range(min(left, STEPS_PER_BATCH)):
+                dz.step_(e2)
+                flags = e2.has_converged                    # D2H, what `while !opt.has_converged[]` reads
+                obj = e2.current_objective_value            # D2H
+            left -= STEPS_PER_BATCH
+            if read_point:
+                point_bytes += e2.current_point.nbytes      # the answer itself (D2H, n x batch doubles)
+            torch.cuda.synchronize()
+            # every step! of an active problem either moves it (iteration_count + 1) or terminates it; the
+            # warm-up steps of this arm are inside its timed region and count as work too
+            steps_total += float(e2.iteration_count.sum() + flags.sum())
+            d2h = flags.nbytes + obj.nbytes
+            e2.close()
         secs = time.perf_counter() - t1
-        # every step! of an active problem either moves it (iteration_count + 1) or terminates it; the
-        # warm-up steps of this arm are inside its timed region and count as work too
-        steps_total = float(e2.iteration_count.sum() + flags.sum())
-        d2h = flags.nbytes + obj.nbytes
-        e2.close()
         return max_over_ranks(secs), sum_over_ranks(steps_total), d2h, point_bytes
 
     # ================================================================== main metric: weak scaling, 1M problems per GPU
-    x0 = x0_batch(dz, BATCH, 2024 + rank)
-    x0_pinned = torch.from_numpy(x0).pin_memory()
-    x0_host = x0_pinned.numpy()
-    ms, kinds, clk = device_timed(x0_host, BATCH)
+    nbatches = -(-K // STEPS_PER_BATCH)
+    x0_hosts = [torch.from_numpy(x0_batch(dz, BATCH, 2024 + rank + 1000 * b)).pin_memory().numpy() for b in range(nbatches)]
+    x0_host = x0_hosts[0]
+    x0 = x0_host
+    ms, kinds, clk = device_timed(x0_hosts)
     launches += K
     active_steps = float(sum(kinds[k] for k in ("bfgs_read_h", "bfgs_identity_h", "gradient_descent", "terminate")))
     total_problem_steps = sum_over_ranks(active_steps)
@@ -381,7 +398,7 @@ def run_gpu(args):
     if rank == 0:
         rp = make(x0_host)
         per_step = []
-        for i in range(W + K):
+        for i in range(W + min(K, STEPS_PER_BATCH)):
             rp.step_kind_counts(reset=True)
             rp.step(1)
             c = rp.step_kind_counts()
@@ -415,11 +432,11 @@ def run_gpu(args):
     w_opt.step(1)
     _ = w_opt.has_converged, w_opt.current_objective_value, w_opt.current_point
     w_opt.close()
-    e2e_s, e2e_steps, d2h, _ = e2e_timed(x0_host, read_point=False)
+    e2e_s, e2e_steps, d2h, _ = e2e_timed(x0_hosts, read_point=False)
     e2e_value = e2e_steps / e2e_s
-    e2p_s, e2p_steps, _, point_bytes = e2e_timed(x0_host, read_point=True)
-    launches += 2 * (K + W + 1)
-    h2d = x0.nbytes / (K + W)
+    e2p_s, e2p_steps, _, point_bytes = e2e_timed(x0_hosts, read_point=True)
+    launches += 2 * (K + nbatches * (W + 1))
+    h2d = nbatches * x0.nbytes / (K + nbatches * W)
 
     # ================================================================== strong scaling: the SAME 1M problems over N GPUs
     strong = None
@@ -429,15 +446,17 @@ def run_gpu(args):
         hi = BATCH if rank == world - 1 else lo + share
         xs_all = x0_batch(dz, BATCH, 2024)                 # the single-GPU problem set (seed 2024), every rank its slice
         xs = torch.from_numpy(np.ascontiguousarray(xs_all[lo:hi])).pin_memory().numpy()
-        s_ms, s_kinds, _ = device_timed(xs, hi - lo)
+        xs_list = [xs] + [torch.from_numpy(np.ascontiguousarray(x0_batch(dz, BATCH, 2024 + 1000 * b)[lo:hi])).pin_memory().numpy()
+                          for b in range(1, nbatches)]
+        s_ms, s_kinds, _ = device_timed(xs_list)
         launches += K
         s_active = float(sum(s_kinds[k] for k in KINDS[:4]))
         s_total = sum_over_ranks(s_active)
         s_bytes = batched_bytes(s_kinds, N_SMALL, lazy)
         w2 = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, xs, 1.0, batched=True, device=local_rank)
         w2.reuse_host_buffers(True); w2.step(1); _ = w2.has_converged, w2.current_objective_value; w2.close()
-        se_s, se_steps, _, _ = e2e_timed(xs, read_point=False)
-        launches += K + W + 1
+        se_s, se_steps, _, _ = e2e_timed(xs_list, read_point=False)
+        launches += K + nbatches * (W + 1)
         strong = {"batch_total": BATCH, "batch_per_gpu": hi - lo, "n_gpus": world, "ms_per_step": s_ms / K,
                   "problem_steps_per_s": s_total / (s_ms * 1e-3),
                   "per_gpu_achieved_gbs": s_bytes / K / (s_ms / K * 1e-3) / 1e9,
@@ -482,6 +501,10 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "batched BFGS 1,000,000 x n=16 extended Rosenbrock per GPU (BASELINE configs[1])",
                        "batch_per_gpu": BATCH, "n": N_SMALL, "initial_step_length": 1.0,
+                       "batches_in_timed_region": nbatches, "steps_per_batch": STEPS_PER_BATCH,
+                       "batches_note": "a batch converges within ~100 step! calls; K > %d timed launches walk through "
+                                       "independent batches of the same workload (PCG seed 2024 + rank + 1000 b), each "
+                                       "constructed and warmed up W steps before the clock starts (e2e: inside it)" % STEPS_PER_BATCH,
                        "l2": "state per GPU = 2.9 GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "active_fraction_in_timed_region": active_frac, "timed_region_ms": ms,
                        "parallelism": f"independent problems, {world} GPU(s), no collective"},
@@ -505,7 +528,7 @@ def run_gpu(args):
                          "traffic_detail": traffic,
                          "peak_source": peak_src},
             "per_step_kinds": {"columns": list(KINDS[:4]) + ["idle"], "rows": per_step,
-                               "note": f"rows 0..{W - 1} are the warm-up steps, rows {W}..{W + K - 1} the timed ones"},
+                               "note": f"batch 0: rows 0..{W - 1} are the warm-up steps, rows {W}..{W + min(K, STEPS_PER_BATCH) - 1} the timed ones"},
         }
         if traffic and per_step and traffic.get("timed_step_index") is not None:
             row = per_step[W + int(traffic["timed_step_index"])]
@@ -865,7 +888,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=150,
-                    help="default: the timed region of the headline is >= 100 ms (about 0.8 ms per step!)")
+                    help="default: the timed region of the headline is >= 100 ms (about 0.7 ms per step!), six batches")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-large", action="store_true")

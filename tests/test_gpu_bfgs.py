@@ -618,6 +618,13 @@ def test_batched_medium_n_trace(gpu, orc, n, batch):
     b = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
     b.set_state(opt.current_point, H, opt.delta_point, opt.delta_gradient, opt.last_step_length, opt.last_step_type,
                 opt.iteration_count)
-    b.step(2); opt.step(2); ref.step(2)
-    _compare_state(b, ref, True, "resumed batch")
+    # the oracle's own state-rebuilding constructor (:819-862): it recomputes d = H*g (:834-836), so a problem whose
+    # d = copy(g) held a -0.0 (problem 1, terminated at the minimiser) legitimately resumes with +0.0
+    Hr = np.stack([ref.inverse_hessian(p) for p in range(batch)])
+    rb = orc.BFGS(ROSEN, x0, 1.0, order=orc.TREE, nthreads=8)
+    rb.set_state(ref.point, Hr, ref.delta_point, ref.delta_gradient, ref.step_length, ref.step_type, ref.iteration_count)
+    _compare_state(b, rb, True, "resumed batch vs the oracle's set_state")
+    b.step(2); opt.step(2); ref.step(2); rb.step(2)
+    _compare_state(b, rb, True, "resumed batch")
     _compare_state(opt, ref, True, "original batch")
+    assert_bitwise(b.current_point, opt.current_point, "resumed trajectory")
