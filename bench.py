@@ -349,33 +349,58 @@ def run_gpu(args):
 
     def e2e_timed(x0_list, read_point):
         """the README loop through the public API with HOST buffers (constructor H2D + per-step field reads), once per
-        batch of the timed region"""
+        batch of the timed region.  Also returns this rank's host-side phase times (ms): constructor, warm-up call,
+        step! calls, field reads, final point read."""
         barrier()
         barrier()
-        t1 = time.perf_counter()
-        steps_total, d2h, point_bytes, left = 0.0, 0, 0, K
+        ph = {"constructor": 0.0, "warmup_call": 0.0, "step_calls": 0.0, "field_reads": 0.0, "point_read": 0.0}
+        now = time.perf_counter
+        t1 = now()
+        opts, flags_last, d2h, point_bytes, left = [], [], 0, 0, K
         for x0_host in x0_list:
+            ta = now()
             e2 = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
                                   device=local_rank)       # H2D of x0 inside the timed region
             e2.reuse_host_buffers(True)                     # cached page-locked field arrays; has_converged / objective become
                                                             # zero-copy mirrors the step kernel writes over PCIe while it runs
+            tb = now()
             e2.step(W)                                      # same starting state as the device-timed arm
+            tc = now()
+            ph["constructor"] += tb - ta
+            ph["warmup_call"] += tc - tb
             flags = obj = None
             for _ in range(min(left, STEPS_PER_BATCH)):
+                td = now()
                 dz.step_(e2)
+                te = now()
                 flags = e2.has_converged                    # D2H, what `while !opt.has_converged[]` reads
                 obj = e2.current_objective_value            # D2H
+                tf = now()
+                ph["step_calls"] += te - td
+                ph["field_reads"] += tf - te
             left -= STEPS_PER_BATCH
             if read_point:
+                tg = now()
                 point_bytes += e2.current_point.nbytes      # the answer itself (D2H, n x batch doubles)
-            torch.cuda.synchronize()
-            # every step! of an active problem either moves it (iteration_count + 1) or terminates it; the
-            # warm-up steps of this arm are inside its timed region and count as work too
-            steps_total += float(e2.iteration_count.sum() + flags.sum())
+                ph["point_read"] += now() - tg
             d2h = flags.nbytes + obj.nbytes
+            opts.append(e2)
+            flags_last.append(flags)
+        torch.cuda.synchronize()
+        secs = now() - t1
+        # every step! of an active problem either moves it (iteration_count + 1) or terminates it; the
+        # warm-up steps of this arm are inside its timed region and count as work too
+        steps_total = 0.0
+        for e2, flags in zip(opts, flags_last):
+            steps_total += float(e2.iteration_count.sum() + flags.sum())
             e2.close()
-        secs = time.perf_counter() - t1
-        return max_over_ranks(secs), sum_over_ranks(steps_total), d2h, point_bytes
+        ph = {k: 1e3 * v for k, v in ph.items()}
+        ph["total"] = 1e3 * secs
+        if distributed:
+            box = [None] * world
+            dist.all_gather_object(box, ph)
+            ph = {"per_rank": box}
+        return max_over_ranks(secs), sum_over_ranks(steps_total), d2h, point_bytes, ph
 
     # ================================================================== main metric: weak scaling, 1M problems per GPU
     nbatches = -(-K // STEPS_PER_BATCH)
@@ -424,17 +449,12 @@ def run_gpu(args):
         launches += 1
 
     # ---- end to end through the public API with host buffers
-    # untimed warm-up pass of the same code path: fills the device memory pool and the recycled page-locked
+    # one untimed pass of the same code path first: fills the device memory pool and the recycled page-locked
     # field buffers (page-locking costs 10-40 ms on this virtualised host), like the W warm-up steps do for kernels
-    w_opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0_host, 1.0, batched=True,
-                             device=local_rank)
-    w_opt.reuse_host_buffers(True)
-    w_opt.step(1)
-    _ = w_opt.has_converged, w_opt.current_objective_value, w_opt.current_point
-    w_opt.close()
-    e2e_s, e2e_steps, d2h, _ = e2e_timed(x0_hosts, read_point=False)
+    _, _, _, _, e2e_first_pass = e2e_timed(x0_hosts, read_point=True)
+    e2e_s, e2e_steps, d2h, _, e2e_phases = e2e_timed(x0_hosts, read_point=False)
     e2e_value = e2e_steps / e2e_s
-    e2p_s, e2p_steps, _, point_bytes = e2e_timed(x0_hosts, read_point=True)
+    e2p_s, e2p_steps, _, point_bytes, _ = e2e_timed(x0_hosts, read_point=True)
     launches += 2 * (K + nbatches * (W + 1))
     h2d = nbatches * x0.nbytes / (K + nbatches * W)
 
@@ -453,9 +473,8 @@ def run_gpu(args):
         s_active = float(sum(s_kinds[k] for k in KINDS[:4]))
         s_total = sum_over_ranks(s_active)
         s_bytes = batched_bytes(s_kinds, N_SMALL, lazy)
-        w2 = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, xs, 1.0, batched=True, device=local_rank)
-        w2.reuse_host_buffers(True); w2.step(1); _ = w2.has_converged, w2.current_objective_value; w2.close()
-        se_s, se_steps, _, _ = e2e_timed(xs_list, read_point=False)
+        e2e_timed(xs_list, read_point=False)               # untimed pass of the same code path (see above)
+        se_s, se_steps, _, _, _ = e2e_timed(xs_list, read_point=False)
         launches += K + nbatches * (W + 1)
         strong = {"batch_total": BATCH, "batch_per_gpu": hi - lo, "n_gpus": world, "ms_per_step": s_ms / K,
                   "problem_steps_per_s": s_total / (s_ms * 1e-3),
@@ -510,6 +529,7 @@ def run_gpu(args):
                        "parallelism": f"independent problems, {world} GPU(s), no collective"},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_phases_ms": e2e_phases, "untimed_first_pass_host_phases_ms": e2e_first_pass,
                     "with_point_readback": {"value": e2p_steps / e2p_s, "unit": UNIT, "extra_d2h_bytes_total": point_bytes,
                                             "what": "the same loop followed by ONE current_point read (the answer)"},
                     "what": "BFGSOptimizer(host x0) + W+K x [step!; has_converged[]; current_objective_value[]] via the C ABI; the two fields reach the host as zero-copy mirrors (dzo_bfgs_mirror_fields): the step kernel stores them into page-locked host memory, the reads only synchronise"},

@@ -38,7 +38,10 @@
 
 namespace dzo {
 
-constexpr int kHybridWarps = 4;
+#ifndef DZO_HYBRID_WARPS
+#define DZO_HYBRID_WARPS 4              // warps per CTA (A/B knob of tools/build_variant.sh; 16 / 8 warps per SM in total either way)
+#endif
+constexpr int kHybridWarps = DZO_HYBRID_WARPS;
 constexpr int kHybridThreads = 32 * kHybridWarps;
 
 template <int N>
@@ -51,7 +54,8 @@ struct HybridCfg {
                                                             // 16-byte aligned rows (phase 2 reads pairs with one 128-bit load)
     static constexpr int SLOT = STRIDE - 2;
     static constexpr bool PINGPONG = (N <= 16);             // two register tiles of n doubles each
-    static constexpr int CTAS_PER_SM = (N <= 16) ? 4 : 2;   // what the shared tile (14 KB ... 26 KB per warp) allows
+    static constexpr int CTAS_PER_SM = ((N <= 16) ? 16 : 8) / kHybridWarps;   // 16 / 8 warps per SM: what the shared tile
+                                                                              // (14 KB ... 26 KB per warp) allows
 };
 
 template <int N>

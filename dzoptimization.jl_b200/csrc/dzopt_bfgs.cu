@@ -1184,6 +1184,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "search_variant")) { g_tuning.search_variant = value; return DZO_OK; }
     if (!strcmp(key, "riesz_profile")) { g_tuning.riesz_profile = value; return DZO_OK; }
     if (!strcmp(key, "riesz_esplit")) { g_tuning.riesz_esplit = value; return DZO_OK; }
+    if (!strcmp(key, "riesz_pair")) { g_tuning.riesz_pair = value; return DZO_OK; }
     if (!strcmp(key, "riesz_gvariant")) { g_tuning.riesz_gvariant = value; return DZO_OK; }
     if (!strcmp(key, "sharded_variant")) { g_tuning.sharded_variant = value; return DZO_OK; }
     if (!strcmp(key, "sweep_unroll")) { g_tuning.sweep_unroll = value; return DZO_OK; }

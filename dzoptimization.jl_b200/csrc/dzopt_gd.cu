@@ -36,7 +36,7 @@ struct dzo_gd {
     int n_e_items = 0;
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
-    int esplit = 2, gcnt_off = 0;
+    int esplit = 2, gcnt_off = 0, ecnt_stride = 0, espec = 0;
     int2* g_jobs = nullptr;
     int n_g_jobs = 0, gvariant = 0;
     unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
@@ -118,7 +118,7 @@ struct RieszWork {
     int n_e_items = 0;
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
-    int esplit = 2, gcnt_off = 0;
+    int esplit = 2, gcnt_off = 0, ecnt_stride = 0, espec = 0;
     int2* g_jobs = nullptr;
     int n_g_jobs = 0, gvariant = 0;
     int grid = 0;
@@ -128,13 +128,15 @@ struct RieszWork {
         kernel = riesz_kernel_for(dim);
         if (!kernel) return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
         const int nseg = (N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
-        DZO_TRY(dmalloc(&segE, (size_t)nseg * N));
-        DZO_TRY(dmalloc(&rowE, (size_t)2 * N));              // double-buffered by evaluation parity
-        DZO_CUDA(cudaMemset(rowE, 0, (size_t)2 * N * sizeof(double)));
+        DZO_TRY(dmalloc(&segE, (size_t)2 * nseg * N));       // two probes of a paired evaluation
+        DZO_TRY(dmalloc(&rowE, (size_t)4 * N));              // [phase parity][probe]
+        DZO_CUDA(cudaMemset(rowE, 0, (size_t)4 * N * sizeof(double)));
         esplit = (g_tuning.riesz_esplit == 2) ? 2 : 1;   // measured: 2 lanes per row is 11 % slower (the loops are issue-bound, not latency-bound)
-        gcnt_off = (N + 15) / 16;
-        DZO_TRY(dmalloc(&rbcnt, (size_t)2 * gcnt_off));      // items finished per row block: energy | gradient
-        DZO_CUDA(cudaMemset(rbcnt, 0, (size_t)2 * gcnt_off * sizeof(unsigned)));
+        espec = g_tuning.riesz_pair ? 1 : 0;
+        ecnt_stride = (N + 15) / 16;
+        gcnt_off = 2 * ecnt_stride;
+        DZO_TRY(dmalloc(&rbcnt, (size_t)3 * ecnt_stride));   // items finished per row block: energy probe 0 | probe 1 | gradient
+        DZO_CUDA(cudaMemset(rbcnt, 0, (size_t)3 * ecnt_stride * sizeof(unsigned)));
         DZO_TRY(dmalloc(&segG, (size_t)nseg * N * dim));
         DZO_TRY(dmalloc(&fbox, 4));
         DZO_TRY(dmalloc(&counter, 1));
@@ -170,6 +172,7 @@ struct RieszWork {
     void fill(RieszGdArgs& a) const {
         a.segE = segE; a.rowE = rowE; a.segG = segG; a.e_items = e_items; a.n_e_items = n_e_items;
         a.counter = counter; a.fbox = fbox; a.rbcnt = rbcnt; a.dscale = 1.0; a.esplit = esplit; a.gcnt_off = gcnt_off;
+        a.ecnt_stride = ecnt_stride; a.espec = espec;
         a.g_jobs = g_jobs; a.n_g_jobs = n_g_jobs; a.gvariant = gvariant;
     }
     int launch(RieszGdArgs& a, cudaStream_t stream) const {
@@ -185,6 +188,7 @@ static RieszGdArgs riesz_args(const dzo_gd* o, int mode, int k) {
     a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg;
     a.segE = o->segE; a.rowE = o->rowE; a.segG = o->segG; a.e_items = o->e_items; a.n_e_items = o->n_e_items;
     a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox; a.rbcnt = o->rbcnt; a.dscale = 1.0; a.esplit = o->esplit; a.gcnt_off = o->gcnt_off;
+    a.ecnt_stride = o->ecnt_stride; a.espec = o->espec;
     a.g_jobs = o->g_jobs; a.n_g_jobs = o->n_g_jobs; a.gvariant = o->gvariant;
     a.N = (int)(o->n / o->dim); a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.max_increases = o->max_increases;
     a.ksteps = k; a.mode = mode;
@@ -256,6 +260,7 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
         o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->esplit = w.esplit; o->gcnt_off = w.gcnt_off; o->grid = w.grid;
+        o->ecnt_stride = w.ecnt_stride; o->espec = w.espec;
         o->g_jobs = w.g_jobs; o->n_g_jobs = w.n_g_jobs; o->gvariant = w.gvariant;
     }
     if (!o->small && objective == DZO_OBJ_ROSENBROCK) {       // one 8-CTA cluster up to n = DZO_TREE_BLOCK, the whole grid above

@@ -35,9 +35,9 @@ struct GdCtrl {
 
 struct RieszGdArgs {
     double *x, *g, *d, *dx, *dg;  // dim x N column-major (point j contiguous)
-    double *segE;                 // [nseg][N]       energy segment partials
-    double *rowE;                 // [2][N]          row energies, double-buffered by the parity of the evaluation count
-    unsigned* rbcnt;              // [2][nrb]        items finished per 32-row block (energy | gradient); zero between uses
+    double *segE;                 // [2][nseg][N]    energy segment partials (probe 0 | probe 1 of a paired evaluation)
+    double *rowE;                 // [2][2][N]       row energies [parity of the phase count][probe]
+    unsigned* rbcnt;              // items finished per 32-row block (energy probe 0 | energy probe 1 | gradient); zero between uses
     double *segG;                 // [nseg][N][DIM]  gradient segment partials
     const int2* e_items;          // (row block, segment) items of the strict lower triangle
     int n_e_items;
@@ -49,6 +49,9 @@ struct RieszGdArgs {
     int gvariant;                 // 0: (32 rows x 128 sources) warp items; 1: symmetric 128 x 128 CTA tiles
     int esplit;                   // 1: energy items of 32 rows x 128 sources, one lane per row; 2: 16 rows, two lanes per row
     int gcnt_off;                 // offset of the gradient counters inside rbcnt
+    int ecnt_stride;              // offset of the second probe's energy counters inside rbcnt (paired evaluations)
+    int espec;                    // 1: the bracketing search evaluates the probe it needs and the one it will most likely
+                                  //    need next in ONE phase (paired evaluation; esplit = 1 only)
     double dscale;                // the direction actually used is dscale * dir[e] (1.0, or alpha with dir = g: see mode 0)
     int N, sphere, max_increases, ksteps;
     double initial_step_length;
@@ -65,7 +68,7 @@ struct RieszGdArgs {
 constexpr int kRieszProfCap = 8192;  // events of the optional phase log
 // phase ids: 1 step begin, 2 energy begin, 3 leader's own energy items done, 4 first energy barrier passed,
 // 5 energy end (rows + tree + barrier), 6 line search end, 7 point update + barrier, 8 leader's own gradient items
-// done, 9 gradient barrier passed, 10 gradient rows + barrier, 11 step end
+// done, 9 gradient barrier passed, 10 gradient rows + barrier, 11 step end, 12 paired energy begin, 13 both norms done
 DZO_DEVINL void riesz_prof_mark(const RieszGdArgs& a, int id) {
     if (a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
@@ -113,10 +116,20 @@ struct RieszDev {
     // ---- riesz_energy (legacy/ExampleFunctions.jl:30-45), phase 1: segment partials
     // The warp that finishes the LAST item of a 32-row block (per-block counter, threadfence pattern) adds that
     // block's segment partials in ascending order and stores the row energies: no grid barrier between the two.
-    static DZO_DEVINL void energy_segments(const RieszGdArgs& a, const double* dir, double alpha, int pmode, int par, double* wsm) {
+    // PAIRED evaluation (npr = 2): the items of two probes (alpha0, alpha1) share one phase.  One probe occupies fewer than
+    // half of the grid's warps (2112 items for 4736 warps at N = 4096), so the second one rides in the idle warps; every
+    // probe's arithmetic is what it would be alone.
+    static DZO_DEVINL void energy_segments(const RieszGdArgs& a, const double* dir, double alpha0, double alpha1, int npr, int pmode,
+                                           int par, double* wsm) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
-        for (int idx = blockIdx.x + gridDim.x * warp; idx < a.n_e_items; idx += gridDim.x * kRieszSegWarps) {
+        const int nseg_all = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
+        for (int idx2 = blockIdx.x + gridDim.x * warp; idx2 < npr * a.n_e_items; idx2 += gridDim.x * kRieszSegWarps) {
+            const int pr = (npr == 2) ? (idx2 & 1) : 0;                 // probes interleaved: both get heavy items first
+            const int idx = (npr == 2) ? (idx2 >> 1) : idx2;
+            const double alpha = pr ? alpha1 : alpha0;
+            double* segE = a.segE + (long long)pr * nseg_all * a.N;
+            unsigned* rbcnt = a.rbcnt + pr * a.ecnt_stride;
             const int2 it = a.e_items[idx];
             const int i0 = it.y * DZO_RIESZ_SEG;
             const int cnt = min(DZO_RIESZ_SEG, a.N - i0);
@@ -171,7 +184,7 @@ struct RieszDev {
                         }
                         seg += ieee_rsqrt_operators(dist_sq);
                     }
-                    a.segE[(long long)it.y * a.N + j] = seg;
+                    segE[(long long)it.y * a.N + j] = seg;
                 }
             }
             __threadfence();
@@ -180,7 +193,7 @@ struct RieszDev {
             if (lane == 0) {
                 const int jmax = min(a.N, it.x * 32 + 32) - 1;
                 const unsigned expected = (unsigned)((jmax + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG);
-                last = (atomicAdd(&a.rbcnt[it.x], 1u) == expected - 1u);
+                last = (atomicAdd(&rbcnt[it.x], 1u) == expected - 1u);
             }
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {
@@ -188,12 +201,12 @@ struct RieszDev {
                 if (j < a.N) {
                     double ej = 0.0;
                     for (int s0 = 0; s0 < j; s0 += DZO_RIESZ_SEG) {
-                        const double seg = __ldcg(&a.segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
+                        const double seg = __ldcg(&segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
                         ej = (s0 == 0) ? seg : ej + seg;
                     }
-                    a.rowE[(long long)par * a.N + j] = ej;
+                    a.rowE[(long long)(2 * par + pr) * a.N + j] = ej;
                 }
-                if (lane == 0) a.rbcnt[it.x] = 0;      // next use is behind at least one grid barrier
+                if (lane == 0) rbcnt[it.x] = 0;        // next use is behind at least one grid barrier
             }
         }
     }
@@ -280,7 +293,7 @@ struct RieszDev {
                         const double sg = __ldcg(&a.segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
                         ej = (s0 == 0) ? sg : ej + sg;
                     }
-                    a.rowE[(long long)par * a.N + j] = ej;
+                    a.rowE[(long long)(2 * par) * a.N + j] = ej;
                 }
                 if (lane == 0) a.rbcnt[it.x] = 0;
             }
@@ -289,35 +302,57 @@ struct RieszDev {
 
     // phase 2 (after ONE grid barrier): every CTA runs the canonical tree over the row energies itself (32 KB from L2
     // at N = 4096), so the value is identical on every thread of the grid without a broadcast or a second barrier.
-    static DZO_DEVINL double energy_finish(const RieszGdArgs& a, int par, double* sm) {
-        const double* rowE = a.rowE + (long long)par * a.N;
-        double p[1][4];
+    template <int NPR>
+    static DZO_DEVINL void energy_finish(const RieszGdArgs& a, int par, double* sm, double (&f)[2]) {
+        double p[NPR][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double acc = 0.0;
-            for (int j = threadIdx.x + 1024 * q; j < a.N; j += DZO_TREE_WIDTH) acc += __ldcg(&rowE[j]);
-            p[0][q] = acc;
+        for (int pr = 0; pr < NPR; ++pr) {
+            const double* rowE = a.rowE + (long long)(2 * par + pr) * a.N;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double acc = 0.0;
+                for (int j = threadIdx.x + 1024 * q; j < a.N; j += DZO_TREE_WIDTH) acc += __ldcg(&rowE[j]);
+                p[pr][q] = acc;
+            }
         }
-        double out[1];
-        cta1024_tree_reduce<1>(p, sm, out);
-        return out[0];
+        double out[NPR];
+        cta1024_tree_reduce<NPR>(p, sm, out);
+#pragma unroll
+        for (int pr = 0; pr < NPR; ++pr) f[pr] = out[pr];
     }
 
-    // `epar` counts the evaluations of this launch (identical on every CTA); its parity selects the rowE buffer, so a
-    // CTA that is still reducing evaluation k cannot be overtaken by the row stores of evaluation k+1.
+    // `epar` counts the evaluation PHASES of this launch (identical on every CTA); its parity selects the rowE buffers, so
+    // a CTA that is still reducing phase k cannot be overtaken by the row stores of phase k+1.
     static DZO_DEVINL double energy(const RieszGdArgs& a, cg::grid_group& grid, int& epar, const double* dir, double alpha, int pmode,
                                     double* wsm, double* sm) {
         const int par = epar & 1;
         epar += 1;
         riesz_prof_mark(a, 2);
         if (a.esplit == 2) energy_segments_split(a, dir, alpha, pmode, par, wsm);
-        else energy_segments(a, dir, alpha, pmode, par, wsm);
+        else energy_segments(a, dir, alpha, 0.0, 1, pmode, par, wsm);
         riesz_prof_mark(a, 3);
         grid.sync();
         riesz_prof_mark(a, 4);
-        const double f = energy_finish(a, par, sm);
+        double f[2];
+        energy_finish<1>(a, par, sm, f);
         riesz_prof_mark(a, 5);
-        return f;
+        return f[0];
+    }
+    // f(alpha0) and f(alpha1) in one phase: one grid barrier and one (two-value) tree for both
+    static DZO_DEVINL void energy_pair(const RieszGdArgs& a, cg::grid_group& grid, int& epar, const double* dir, double alpha0,
+                                       double alpha1, double* wsm, double* sm, double& f0v, double& f1v) {
+        const int par = epar & 1;
+        epar += 1;
+        riesz_prof_mark(a, 12);
+        energy_segments(a, dir, alpha0, alpha1, 2, 0, par, wsm);
+        riesz_prof_mark(a, 3);
+        grid.sync();
+        riesz_prof_mark(a, 4);
+        double f[2];
+        energy_finish<2>(a, par, sm, f);
+        riesz_prof_mark(a, 5);
+        f0v = f[0];
+        f1v = f[1];
     }
 
     // ---- riesz_gradient! (:47-83) at the stored points + tangent projection (:361-374)
@@ -620,16 +655,31 @@ struct RieszDev {
             }
             if (capped) break;
             if (small && all_points(a, dir, sign * step, 0.0, 2)) break;       // :107-123
-            double fa = energy(a, grid, epar, dir, sign * step, 0, wsm, sm);         // :126
-            ++evals;
+            // probe(t, guess): f at t.  With paired evaluation the probe the search will most likely ask for next
+            // (`guess`: the doubled step while expanding -- 9 searches of 10 on config 5 --, the halved one while
+            // shrinking) is evaluated in the same phase and kept; asking for it later costs nothing.  Which values the
+            // search sees, and in which order, is unchanged.
+            const bool paired = (a.espec != 0) && (a.esplit != 2);
+            double spec_t = 0.0, spec_f = 0.0;
+            bool spec_valid = false;
+            auto probe = [&](double t, double guess) -> double {
+                ++evals;
+                if (spec_valid && spec_t == t) { spec_valid = false; return spec_f; }
+                if (!paired) return energy(a, grid, epar, dir, sign * t, 0, wsm, sm);
+                double ft;
+                energy_pair(a, grid, epar, dir, sign * t, sign * guess, wsm, sm, ft, spec_f);
+                spec_t = guess;
+                spec_valid = true;
+                return ft;
+            };
+            double fa = probe(step, step + step);                              // :126
             if (fa <= f0) {                                                    // :130
                 int num_increases = 0;
                 cap = DZO_LINESEARCH_CAP;
                 for (;;) {                                                     // :143-156
                     const double ds = step + step;
                     num_increases += 1;
-                    const double fb = energy(a, grid, epar, dir, sign * ds, 0, wsm, sm);
-                    ++evals;
+                    const double fb = probe(ds, ds + ds);
                     --cap;
                     if (((a.max_increases > 0) && (num_increases >= a.max_increases)) || !isfinite(fb) || fb > fa ||
                         all_points(a, dir, sign * ds, sign * step, 3) || cap == 0) {
@@ -643,8 +693,7 @@ struct RieszDev {
                 cap = DZO_LINESEARCH_CAP;
                 for (;;) {
                     const double hs = 0.5 * step;
-                    const double fb = energy(a, grid, epar, dir, sign * hs, 0, wsm, sm);
-                    ++evals;
+                    const double fb = probe(hs, 0.5 * hs);
                     --cap;
                     if (fb <= f0 || cap == 0) {
                         x1 = hs; f1 = fb; x2 = step; f2 = fa;
@@ -900,6 +949,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         riesz_prof_mark(a, 10);
         double dxdx, gg;
         cta_tree_norms2(a.dx, a.g, n, sm, dxdx, gg);
+        riesz_prof_mark(a, 13);
         const double step_length = sqrt(dxdx);                                 // :424
         const double inv_gradient_norm = 1.0 / sqrt(gg);                       // :438
         const bool ok = isfinite(inv_gradient_norm);

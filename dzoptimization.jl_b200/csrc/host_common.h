@@ -64,6 +64,8 @@ struct Tuning {
     int riesz_esplit = 1;     // lanes per row in the Riesz energy items (1 or 2), read when an optimizer is created
     int riesz_gvariant = 0;   // Riesz gradient: 0 = (32 rows x 128 sources) warp items, 1 = symmetric 128 x 128 CTA tiles (each pair
                               // weight computed once; measured 0.183 vs 0.177 ms per GD step at N = 4096, so not the default)
+    int riesz_pair = 1;       // Riesz line search: evaluate the probe it needs and the one it will most likely need next in one
+                              // phase (the second rides in warps the first leaves idle); read when an optimizer is created
     int riesz_profile = 0;    // 1: the cooperative Riesz kernel logs (phase id, %globaltimer) events of its leader thread
     int batched_lazy = 1;     // batched kernel: keep H = I implicit (no HBM traffic for identity_matrix!); read at create time
                               // (1M x n=16: 0.74 ms per launch with, 0.86 ms without)

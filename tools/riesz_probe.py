@@ -13,6 +13,8 @@ if os.environ.get('DZO_RIESZ_ESPLIT'):
     dz.set_tuning('riesz_esplit', int(os.environ['DZO_RIESZ_ESPLIT']))
 if os.environ.get('DZO_RIESZ_GVARIANT'):
     dz.set_tuning('riesz_gvariant', int(os.environ['DZO_RIESZ_GVARIANT']))
+if os.environ.get('DZO_RIESZ_PAIR'):
+    dz.set_tuning('riesz_pair', int(os.environ['DZO_RIESZ_PAIR']))
 p = 2.0 * orc.pcg_fill(3 * N, 3).reshape(N, 3) - 1.0
 p = p / np.sqrt((p * p).sum(axis=1, keepdims=True))
 o = dz.GradientDescentOptimizer(dz.SPHERE_CONSTRAINT, EF.riesz_energy, EF.riesz_gradient_, dz.QuadraticLineSearch(0), p, 1e-3)
