@@ -216,7 +216,16 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
     cluster.sync();          // every CTA has read ctrl (the leader rewrites it at the end) and initialised R
     // row-sharded mode: the direction slabs of the previous BFGS-type step are stored into this GPU's
     // memory by the peers' update kernels; wait for all of them (flag = that step's sequence number)
-    if (a.nranks > 1 && sc.kind == DZO_STEP_BFGS) peer_wait(a.flags_d, a.nranks, (unsigned long long)sc.calls, &a.ctrl->pad);
+    if (a.nranks > 1 && sc.kind == DZO_STEP_BFGS) {
+        peer_wait(a.flags_d, a.nranks, (unsigned long long)sc.calls, &a.ctrl->pad);
+        cluster.sync();                                                   // every CTA's wait is over before anyone looks
+    }
+    if (a.nranks > 1 && *reinterpret_cast<volatile int*>(&a.ctrl->pad) != 0) {
+        // a peer's rows never arrived (now or in an earlier step!): this step! is a no-op on every kernel of the chain, the
+        // optimizer state stays at the last consistent step and the host reports DZO_ERR_NCCL at the next sync
+        if (leader) a.ctrl->kind = DZO_STEP_NULL;
+        return;
+    }
     if (sc.term) {                                                        // :893
         if (leader) a.ctrl->kind = DZO_STEP_NULL;
         return;
@@ -327,7 +336,12 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
     double p[1] = {acc};
     unsigned fl = 0;
     cluster_tree_reduce<1>(cluster, R, p, fl);
-    if (cluster.block_rank() == 0 && threadIdx.x == 0) a.ctrl->delta_norm = a.ctrl->step_length * a.ctrl->overlap + p[0];
+    if (cluster.block_rank() == 0 && threadIdx.x == 0) {
+        if (a.nranks > 1 && *reinterpret_cast<volatile int*>(&a.ctrl->pad) != 0)
+            a.ctrl->kind = DZO_STEP_NULL;      // t is incomplete (a peer timed out): the update sweep must not touch H
+        else
+            a.ctrl->delta_norm = a.ctrl->step_length * a.ctrl->overlap + p[0];
+    }
 }
 
 // Row-sharded fused mode, last launch of a step!: the peers' rows of next_step_direction are stored into this GPU's

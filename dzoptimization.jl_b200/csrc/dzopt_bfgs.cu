@@ -11,6 +11,7 @@
 #include "host_common.h"
 #include "large_bfgs.cuh"
 #include "small_ops.cuh"
+#include "warp_search.cuh"
 
 namespace dzo {
 thread_local char g_err[512] = "";
@@ -358,8 +359,44 @@ static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind, 
     return fused_t ? DZO_OK : allgather_rows(o, out);
 }
 
+// medium n (32 < n <= 512), one GPU, Rosenbrock: the O(n) stage of every problem on one warp (warp_search.cuh)
+static int warp_vw(const dzo_bfgs* o) {
+    if (o->riesz || o->nranks != 1 || o->n > kWarpSearchMaxN || !g_tuning.warp_search) return 0;
+    int vw = 1;
+    while (64 * vw < o->n) vw <<= 1;
+    return vw;
+}
+static void launch_warp_search(const dzo_bfgs* o, int vw, const LargeVecs& v, bool delta) {
+    const unsigned grid = (unsigned)((o->batch + kWarpSearchWarps - 1) / kWarpSearchWarps);
+    const int threads = 32 * kWarpSearchWarps;
+#define DZO_WS(VW)                                                                                  \
+    if (delta) warp_delta_kernel<VW><<<grid, threads, 0, o->stream>>>(v, o->batch);                  \
+    else warp_bfgs_search_kernel<VW><<<grid, threads, 0, o->stream>>>(v, o->batch)
+    switch (vw) {
+        case 1: DZO_WS(1); break;
+        case 2: DZO_WS(2); break;
+        case 4: DZO_WS(4); break;
+        default: DZO_WS(8); break;
+    }
+#undef DZO_WS
+}
+
 static int large_step_once(dzo_bfgs* o) {
     const LargeVecs v = large_vecs(o);
+    const int vw = warp_vw(o);
+    if (vw) {
+        launch_warp_search(o, vw, v, false);                                            // :891-950, :873-874
+        DZO_CUDA(cudaGetLastError());
+        DZO_TRY(large_gemv(o, o->dg, o->t, DZO_STEP_BFGS, false));                      // :875
+        launch_warp_search(o, vw, v, true);                                             // :876
+        DZO_CUDA(cudaGetLastError());
+        SweepArgs a = sweep_args(o);
+        a.v = o->g; a.out = o->d;
+        a.need_kind = DZO_STEP_GRADIENT_DESCENT + 100;   // this launch also serves identity_matrix! (:981) after a GD step
+        launch_update(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), o->stream, a);   // :878-886 + :958-960
+        DZO_CUDA(cudaGetLastError());
+        return DZO_OK;
+    }
     if (o->riesz) {
         DZO_TRY(riesz_bfgs_launch(o->riesz, 5, o->stream, o->x, o->g, o->d, o->dx, o->dg, o->sd, o->ctrl, 0.0));
     }
@@ -410,6 +447,9 @@ static bool allocation_base(const void* p, unsigned long long* offset) {
     *offset = (unsigned long long)(uintptr_t)p - base;
     return true;
 }
+// Every rank issues BOTH collectives whatever happens locally: a local CUDA error only turns this rank's vote into
+// "cannot map", so the peers never block in a gather this rank skipped, and all ranks end in the same mode (fused, or the
+// NCCL all-gather fallback) or fail together.  The scratch buffers are released on every path.
 static int exchange_peer_memory(dzo_bfgs* o) {
     o->fused = false;
     IpcBundle mine;
@@ -417,16 +457,23 @@ static int exchange_peer_memory(dzo_bfgs* o) {
     mine.ok = (g_tuning.sharded_variant == 0) && o->arena && allocation_base(o->arena, &mine.offset) &&
               cudaIpcGetMemHandle(&mine.arena, o->arena) == cudaSuccess;
     cudaGetLastError();
-    IpcBundle* dev = nullptr;
-    DZO_CUDA(cudaMalloc((void**)&dev, sizeof(IpcBundle) * o->nranks));
-    DZO_CUDA(cudaMemcpyAsync(dev + o->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, o->stream));
-    int r = g_nccl.AllGather(dev + o->rank, dev, sizeof(IpcBundle), /*ncclInt8*/ 0, o->comm, o->stream);
-    if (r != 0) { cudaFree(dev); return fail(DZO_ERR_NCCL, "ncclAllGather of IPC handles failed"); }
+    // one scratch allocation: [nranks bundles][nranks votes]
+    const size_t bundles = sizeof(IpcBundle) * o->nranks;
+    char* dev = nullptr;
+    if (cudaMalloc((void**)&dev, bundles + sizeof(int) * o->nranks) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(DZO_ERR_ALLOC, "row-sharded constructor: scratch allocation failed (no collective was issued on any stream yet)");
+    }
+    IpcBundle* dev_b = reinterpret_cast<IpcBundle*>(dev);
+    int* dev_v = reinterpret_cast<int*>(dev + bundles);
     IpcBundle all[kMaxPeers];
-    DZO_CUDA(cudaMemcpyAsync(all, dev, sizeof(IpcBundle) * o->nranks, cudaMemcpyDeviceToHost, o->stream));
-    DZO_CUDA(cudaStreamSynchronize(o->stream));
-    cudaFree(dev);
-    bool ok = true;
+    memset(all, 0, sizeof all);
+    bool local_ok = cudaMemcpyAsync(dev_b + o->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, o->stream) == cudaSuccess;
+    const int r1 = g_nccl.AllGather(dev_b + o->rank, dev_b, sizeof(IpcBundle), /*ncclInt8*/ 0, o->comm, o->stream);
+    local_ok = local_ok && r1 == 0 &&
+               cudaMemcpyAsync(all, dev_b, bundles, cudaMemcpyDeviceToHost, o->stream) == cudaSuccess &&
+               cudaStreamSynchronize(o->stream) == cudaSuccess;
+    bool ok = local_ok;
     for (int p = 0; p < o->nranks; ++p) ok = ok && all[p].ok;
     const size_t nb = (size_t)o->n;
     for (int p = 0; p < o->nranks && ok; ++p) {
@@ -436,7 +483,7 @@ static int exchange_peer_memory(dzo_bfgs* o) {
         } else {
             void* mapped = nullptr;
             ok = cudaIpcOpenMemHandle(&mapped, all[p].arena, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
-            if (!ok) { cudaGetLastError(); break; }
+            if (!ok) break;
             o->peer_arena[p] = static_cast<char*>(mapped);
             base = o->peer_arena[p] + all[p].offset;
         }
@@ -445,17 +492,20 @@ static int exchange_peer_memory(dzo_bfgs* o) {
         o->peer_flags_t[p] = reinterpret_cast<unsigned long long*>(o->peer_d[p] + nb);
         o->peer_flags_d[p] = o->peer_flags_t[p] + kMaxPeers;
     }
-    // every rank must agree on the mode: one more tiny gather of the outcome
-    int* flag = nullptr;
-    DZO_CUDA(cudaMalloc((void**)&flag, sizeof(int) * o->nranks));
+    cudaGetLastError();
+    // every rank must agree on the mode: one more tiny gather of the outcome (issued even after a local failure)
     int okint = ok ? 1 : 0;
-    DZO_CUDA(cudaMemcpyAsync(flag + o->rank, &okint, sizeof(int), cudaMemcpyHostToDevice, o->stream));
-    r = g_nccl.AllGather(flag + o->rank, flag, sizeof(int), /*ncclInt8*/ 0, o->comm, o->stream);
     int res[kMaxPeers];
-    if (r == 0) cudaMemcpyAsync(res, flag, sizeof(int) * o->nranks, cudaMemcpyDeviceToHost, o->stream);
-    cudaStreamSynchronize(o->stream);
-    cudaFree(flag);
-    if (r != 0) return fail(DZO_ERR_NCCL, "ncclAllGather failed");
+    memset(res, 0, sizeof res);
+    bool vote_ok = cudaMemcpyAsync(dev_v + o->rank, &okint, sizeof(int), cudaMemcpyHostToDevice, o->stream) == cudaSuccess;
+    const int r2 = (r1 == 0) ? g_nccl.AllGather(dev_v + o->rank, dev_v, sizeof(int), /*ncclInt8*/ 0, o->comm, o->stream) : r1;
+    vote_ok = vote_ok && r2 == 0 &&
+              cudaMemcpyAsync(res, dev_v, sizeof(int) * o->nranks, cudaMemcpyDeviceToHost, o->stream) == cudaSuccess;
+    const bool drained = cudaStreamSynchronize(o->stream) == cudaSuccess;
+    cudaFree(dev);
+    cudaGetLastError();
+    if (r1 != 0 || r2 != 0) return fail(DZO_ERR_NCCL, "row-sharded constructor: ncclAllGather of the peer-memory handles failed");
+    if (!vote_ok || !drained) return fail(DZO_ERR_CUDA, "row-sharded constructor: exchanging the peer-memory handles failed");
     bool all_ok = true;
     for (int p = 0; p < o->nranks; ++p) all_ok = all_ok && res[p];
     o->fused = all_ok;
@@ -1185,6 +1235,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "riesz_profile")) { g_tuning.riesz_profile = value; return DZO_OK; }
     if (!strcmp(key, "riesz_esplit")) { g_tuning.riesz_esplit = value; return DZO_OK; }
     if (!strcmp(key, "riesz_pair")) { g_tuning.riesz_pair = value; return DZO_OK; }
+    if (!strcmp(key, "warp_search")) { g_tuning.warp_search = value; return DZO_OK; }
     if (!strcmp(key, "riesz_gvariant")) { g_tuning.riesz_gvariant = value; return DZO_OK; }
     if (!strcmp(key, "sharded_variant")) { g_tuning.sharded_variant = value; return DZO_OK; }
     if (!strcmp(key, "sweep_unroll")) { g_tuning.sweep_unroll = value; return DZO_OK; }

@@ -101,7 +101,10 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         // eight 512-thread CTAs per block of DZO_TREE_BLOCK elements, as many CTAs as are co-resident (cooperative launch)
         o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
         int per_sm = 0, sms = 0;
+        int per_sm_one = 0;               // the launch picks OWN = 1 or kGridOwnMax: size the grid for the tighter of the two
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_lbfgs_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_one, (const void*)grid_lbfgs_kernel_ptr(1), kClusterThreads, 0) != cudaSuccess ||
+            (per_sm = per_sm < per_sm_one ? per_sm : per_sm_one) < 0 ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
             return bail(fail(DZO_ERR_CUDA, "the grid-wide L-BFGS kernel does not fit on this device"));
@@ -402,7 +405,10 @@ int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constrain
     if (n > DZO_TREE_BLOCK) {
         o->nblocks = (int)((n + DZO_TREE_BLOCK - 1) / DZO_TREE_BLOCK);
         int per_sm = 0, sms = 0;
+        int per_sm_one = 0;               // OWN = 1 or kGridOwnMax is picked at launch: size the grid for the tighter of the two
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_one, (const void*)grid_legacy_kernel_ptr(1), kClusterThreads, 0) != cudaSuccess ||
+            (per_sm = per_sm < per_sm_one ? per_sm : per_sm_one) < 0 ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
             return bail(fail(DZO_ERR_CUDA, "the grid-wide legacy L-BFGS kernel does not fit on this device"));
@@ -548,7 +554,10 @@ int grid_gd_attach(int64_t n, int device, void** out, double** scal) {
         return DZO_OK;
     }
     int per_sm = 0, sms = 0;
+    int per_sm_one = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_one, (const void*)grid_legacy_kernel_ptr(1), kClusterThreads, 0) != cudaSuccess ||
+        (per_sm = per_sm < per_sm_one ? per_sm : per_sm_one) < 0 ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
         cudaGetLastError();
         delete h;

@@ -87,7 +87,7 @@ static __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kC
         DZO_OWN_ELEMENTS(e, n, v) a.d[e] = stuck ? 0.0 : a.g[e] * c;                            // :378-383
         if (leader) {
             LbfgsCtrl t;
-            t.f = f0; t.df = 0.0; t.iter = 0; t.stuck = stuck; t.count = 0; t.head = 0; t.pad = 0; t.evals = 1;
+            t.f = f0; t.df = 0.0; t.iter = 0; t.stuck = stuck; t.count = 0; t.head = 0; t.pad = 0; t.evals = 1; t.yy = 0.0;
             for (int i = 0; i < DZO_LBFGS_MAX_HISTORY; ++i) t.rho[i] = 0.0;
             *a.ctrl = t;
         }

@@ -204,7 +204,7 @@ def test_batched_to_convergence(gpu, orc):
     assert (opt.current_objective_value[at_global] < 1e-10).all()
 
 
-@pytest.mark.parametrize("n", [34, 2048, 4098, 16384])
+@pytest.mark.parametrize("n", [34, 64, 130, 500, 512, 514, 2048, 4098, 16384])
 def test_large_trace(gpu, orc, n):
     dz = gpu
     EF = dz.ExampleFunctions
@@ -588,7 +588,7 @@ def test_secant_condition_after_every_bfgs_step(gpu, orc, n, batched):
     assert seen > (100 if batched else 5)
 
 
-@pytest.mark.parametrize("n,batch", [(34, 50), (64, 40), (256, 12), (1100, 5)])
+@pytest.mark.parametrize("n,batch", [(34, 50), (64, 40), (128, 33), (256, 12), (512, 6), (1100, 5)])
 def test_batched_medium_n_trace(gpu, orc, n, batch):
     """README.md:12 "run multiple optimizers in parallel" for 32 < n: one handle, `batch` independent problems, every
     kernel instance (a thread-block cluster for the O(n) stage, blockIdx.z of the n^2 sweeps) serves one problem.  Same
@@ -628,3 +628,24 @@ def test_batched_medium_n_trace(gpu, orc, n, batch):
     _compare_state(b, rb, True, "resumed batch")
     _compare_state(opt, ref, True, "original batch")
     assert_bitwise(b.current_point, opt.current_point, "resumed trajectory")
+
+
+@pytest.mark.parametrize("n,batch", [(64, 9), (200, 5), (512, 3)])
+def test_warp_and_cluster_search_agree(gpu, orc, n, batch):
+    """32 < n <= 512: the O(n) stage of step! runs on one warp per problem (warp_search.cuh); the 8-CTA cluster kernel
+    (tuning knob warp_search = 0) must produce the same bits -- both are the oracle's DZO_ORDER_TREE."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    x0 = _x0(orc, n * batch, 5100 + n).reshape(batch, n)
+    x0[0, ::2] = -0.0                                            # signed zeros through the tree (+0.0 of the empty subtrees)
+    ref = orc.BFGS(ROSEN, x0, 1.0, order=orc.TREE, nthreads=8)
+    ref.step(9)
+    try:
+        for knob in (1, 0):
+            dz.set_tuning("warp_search", knob)
+            opt = dz.BFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, batched=True)
+            for _ in range(9):
+                dz.step_(opt)
+            _compare_state(opt, ref, True, f"warp_search={knob}")
+    finally:
+        dz.set_tuning("warp_search", 1)
