@@ -34,6 +34,8 @@
 //
 // legacy/DZOptimization.jl:891-994 (step!), :864-889 (update_inverse_hessian!), :49-216 (line search).
 #pragma once
+#include <cstdlib>
+
 #include "batched_bfgs.cuh"
 
 namespace dzo {
@@ -481,7 +483,8 @@ inline size_t hybrid_smem() { return sizeof(HybridSmem<N>) * kHybridWarps; }
 template <int N>
 inline cudaError_t hybrid_launch(const BatchedArgs& args, cudaStream_t stream, int device) {
     static bool attr_set[64] = {};
-    const size_t smem = hybrid_smem<N>();
+    static const size_t pad = getenv("DZO_HYBRID_SMEM_PAD") ? (size_t)atoi(getenv("DZO_HYBRID_SMEM_PAD")) : 0;   // occupancy experiments
+    const size_t smem = hybrid_smem<N>() + pad;
     if (!attr_set[device & 63]) {
         cudaError_t e = cudaFuncSetAttribute(bfgs_batched_hybrid_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -45,10 +45,14 @@ static int lbfgs_launch(dzo_lbfgs* o, int mode, int k, double L0) {
         g.x = o->x; g.dx = o->dx; g.g = o->g; g.dg = o->dg; g.d = o->d; g.S = o->S; g.Y = o->Y; g.ctrl = o->ctrl;
         g.part = o->part; g.fpart = o->fpart; g.n = o->n; g.m = o->m; g.ksteps = k; g.nblocks = o->nblocks;
         g.mode = mode; g.initial_step_length = L0;
+        const bool own1 = (8 * o->nblocks <= o->nclusters);       // one eighth per CTA: direction in registers, staged passes
+        g.stage = (own1 && g_tuning.grid_stage) ? 1 : 0;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3((unsigned)o->nclusters);
         cfg.blockDim = dim3(kClusterThreads);
+        cfg.dynamicSmemBytes = g.stage ? kGridStageBytes : 0;
+        if (g_tuning.grid_profile && mode == 0) g.stage |= 2;
         cfg.stream = o->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeCooperative;
@@ -56,7 +60,7 @@ static int lbfgs_launch(dzo_lbfgs* o, int mode, int k, double L0) {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         void* params[] = {&g};
-        DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_lbfgs_kernel_ptr(8 * o->nblocks <= o->nclusters ? 1 : kGridOwnMax), params));   // own = 1: direction in registers
+        DZO_CUDA(cudaLaunchKernelExC(&cfg, grid_lbfgs_kernel_ptr(own1 ? 1 : kGridOwnMax), params));
         return DZO_OK;
     }
     LbfgsArgs a;
@@ -103,7 +107,8 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         int per_sm = 0, sms = 0;
         int per_sm_one = 0;               // the launch picks OWN = 1 or kGridOwnMax: size the grid for the tighter of the two
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_lbfgs_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_one, (const void*)grid_lbfgs_kernel_ptr(1), kClusterThreads, 0) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)grid_lbfgs_kernel_ptr(1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGridStageBytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_one, (const void*)grid_lbfgs_kernel_ptr(1), kClusterThreads, kGridStageBytes) != cudaSuccess ||
             (per_sm = per_sm < per_sm_one ? per_sm : per_sm_one) < 0 ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
@@ -114,7 +119,7 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nclusters)
             return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d CTA shares; the grid-wide L-BFGS kernel holds at most %d",
                              (long long)n, 8 * o->nblocks, kGridOwnMax * o->nclusters));
-        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
+        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll) != cudaSuccess ||
             cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
         o->use_grid = true;
@@ -281,7 +286,7 @@ int dzo_adgd_create(dzo_adgd** out, int objective, int constraint, int64_t obj_p
         o->nctas = 8 * o->nblocks < resident ? 8 * o->nblocks : resident;
         if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nctas)
             return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld is too large for the grid-wide AdGD kernel", (long long)n));
-        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
+        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll) != cudaSuccess ||
             cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
     }
@@ -418,7 +423,7 @@ int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constrain
         if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nctas)
             return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d CTA shares; the grid-wide legacy L-BFGS kernel holds at most %d",
                              (long long)n, 8 * o->nblocks, kGridOwnMax * o->nctas));
-        if (cudaMalloc((void**)&o->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
+        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll) != cudaSuccess ||
             cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
         o->use_grid = true;
@@ -569,7 +574,7 @@ int grid_gd_attach(int64_t n, int device, void** out, double** scal) {
         delete h;
         return fail(DZO_ERR_UNSUPPORTED, "n = %lld is too large for the grid-wide GD kernel", (long long)n);
     }
-    if (cudaMalloc((void**)&h->part, sizeof(double) * 2 * kGridQ * kGridMaxParts) != cudaSuccess ||
+    if (cudaMalloc((void**)&h->part, grid_part_bytes()) != cudaSuccess || grid_part_init(h->part, g_tuning.grid_ll) != cudaSuccess ||
         cudaMalloc((void**)&h->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess ||
         cudaMalloc((void**)&h->lctrl, sizeof(LegacyCtrl)) != cudaSuccess || cudaMalloc((void**)&h->scal, 6 * sizeof(double)) != cudaSuccess) {
         grid_gd_detach(h);

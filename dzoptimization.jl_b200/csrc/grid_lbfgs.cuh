@@ -13,6 +13,8 @@
 // slower one still reads.  (A first version used one 8-CTA cluster per block with DSMEM for the CTA bits; only 15
 // such clusters are co-resident on a B200, one short of the 16 blocks of n = 2^20.)
 #pragma once
+#include <cstdio>
+
 #include "lbfgs_kernels.cuh"
 
 namespace dzo {
@@ -32,19 +34,78 @@ struct GridLbfgsArgs {
     int m, ksteps, nblocks;
     int mode;                                // 0 = steps, 1 = constructor
     double initial_step_length;
+    int stage;                               // 1: kGridStageBytes of dynamic shared memory are there (OWN == 1 launches)
 };
 
 struct GridCtx {
     cg::grid_group grid;
     int nctas, cta, nblocks;                 // eighth e of the vector (block e / 8, part e % 8) belongs to CTA e mod nctas
     int red;                                 // reductions so far (parity)
-    double* part;                            // global [2][kGridQ][kGridMaxParts]
+    double* part;                            // global [2][kGridQ][kGridMaxParts] (barrier mode), then the flagged lines below
     unsigned* fpart;                         // global [2][kGridMaxParts]
     double* s_warp;                          // shared [kGridQ][16]: warp partials
     unsigned* s_wflag;                       // shared [16]
     double* s_out;                           // shared [kGridQ]: totals of the last reduction
     unsigned* s_flags;
+    long long* prof = nullptr;               // optional (leader thread): cycles spent [0] in the CTA-level part of reductions,
+                                             // [1] polling for the other CTAs' lines, [2] in the final combine, [3] reductions
+    uint4* ll = nullptr;                     // flagged lines [2][kGridQ + 1][kGridMaxParts] (null: grid-barrier mode)
+    unsigned seq = 0;                        // sequence number of the next reduction (flag value of its lines)
 };
+
+// ---- reductions WITHOUT a grid barrier (round 2).  A CTA value travels as one 16-byte line {lo, tag, hi, tag}: two 8-byte
+// halves, each atomic and each carrying the sequence number of the reduction (the protocol NCCL calls LL); the flag bits
+// of the reduction ride in the top four bits of quantity 0's tag.  Every CTA owns an INBOX; a producer pushes its line
+// into the inbox of every CTA of the grid (148 fire-and-forget stores to 148 different addresses) and a consumer polls
+// only its own inbox until both tags of every line show the current sequence number.  The producer's store and the
+// consumer's load are the whole synchronisation: no atomic counter and no hot line -- a first version with ONE shared
+// set of lines polled by all 128 CTAs was slower than grid.sync() (0.175 vs 0.135 ms per L-BFGS step! at n = 2^20:
+// a thousand requests per line and poll round serialise in the L2 slice that owns it).  No other data crosses CTAs
+// between reductions (a thread only re-reads vector elements it wrote itself), so nothing else needs the barrier's fence.
+// Lines are double-buffered by the parity of the reduction count: the line of reduction r is overwritten by reduction
+// r + 2, which every CTA reaches only after it has consumed r + 1, i.e. after every CTA has finished reading r.  The
+// running sequence number lives behind the inboxes and survives across launches (stale lines never match).
+constexpr int kLLParts = 1024;                            // CTA values per quantity the inbox mode handles (n <= 8 Mi)
+constexpr int kLLMaxCtas = 192;                           // inboxes allocated (a B200 runs 148 CTAs of these kernels)
+constexpr size_t kGridBarrierBytes = sizeof(double) * 2 * kGridQ * kGridMaxParts;
+constexpr size_t kLLInboxLines = (size_t)2 * kGridQ * kLLParts;
+constexpr size_t kGridLineCount = kLLInboxLines * kLLMaxCtas;
+constexpr unsigned kLLSeqMask = 0x0fffffffu;
+inline size_t grid_part_bytes() { return kGridBarrierBytes + sizeof(uint4) * (kGridLineCount + 1); }
+// host: zero everything, sequence numbers start at 1; `enabled` = 0 keeps the grid-barrier reductions (A/B)
+inline cudaError_t grid_part_init(double* part, int enabled) {
+    cudaError_t e = cudaMemset(part, 0, grid_part_bytes());
+    if (e != cudaSuccess) return e;
+    const uint4 head = make_uint4(1u, 0u, 0u, enabled ? 1u : 0u);
+    return cudaMemcpy(reinterpret_cast<char*>(part) + kGridBarrierBytes + sizeof(uint4) * kGridLineCount, &head, sizeof head,
+                      cudaMemcpyHostToDevice);
+}
+DZO_DEVINL uint4* grid_seq_cell(double* part) {
+    return reinterpret_cast<uint4*>(reinterpret_cast<char*>(part) + kGridBarrierBytes) + kGridLineCount;
+}
+// every thread, before the kernel's first grid barrier
+DZO_DEVINL void grid_ctx_begin(GridCtx& c) {
+    const uint4 head = __ldcg(grid_seq_cell(c.part));
+    if (head.w && 8 * c.nblocks <= kLLParts && c.nctas <= kLLMaxCtas) {
+        c.ll = reinterpret_cast<uint4*>(reinterpret_cast<char*>(c.part) + kGridBarrierBytes);
+        c.seq = head.x;
+    }
+}
+// the leader, after the kernel's last reduction (every CTA read the cell before its first one)
+DZO_DEVINL void grid_ctx_end(const GridCtx& c) {
+    if (c.ll != nullptr && blockIdx.x == 0 && threadIdx.x == 0) grid_seq_cell(c.part)->x = c.seq;
+}
+DZO_DEVINL void ll_store(uint4* p, unsigned long long bits, unsigned seq) {
+    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)bits), "r"(seq), "r"((unsigned)(bits >> 32)), "r"(seq)
+                 : "memory");
+}
+DZO_DEVINL uint4 ll_load(const uint4* p) {
+    uint4 q;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+    return q;
+}
+DZO_DEVINL bool ll_ok(const uint4& q, unsigned seq) { return (q.y & kLLSeqMask) == seq && (q.w & kLLSeqMask) == seq; }
+DZO_DEVINL double ll_value(const uint4& q) { return __longlong_as_double((long long)(((unsigned long long)q.z << 32) | q.x)); }
 
 // Reduce K per-eighth accumulators (acc[k][j] = this thread's partial of quantity k for the j-th eighth its CTA owns)
 // and OR the flag words.  Returns the totals in out[k], the OR in flags; identical on every thread of the grid.
@@ -52,6 +113,12 @@ template <int K, int MAXB>
 DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[MAXB], double (&out)[K], unsigned& flags) {
     const int par = c.red & 1;
     c.red += 1;
+    const bool prof = (c.prof != nullptr && threadIdx.x == 0);
+    long long t_in = 0, t_local = 0, t_poll = 0;
+    if (prof) t_in = clock64();
+    const bool ll = (c.ll != nullptr);
+    const unsigned seq = c.seq;
+    if (ll) c.seq = ((seq + 1u) & kLLSeqMask) ? ((seq + 1u) & kLLSeqMask) : 1u;      // 28 bits, 0 is "never written"
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < MAXB; ++j) {
@@ -66,21 +133,29 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
             if (lane == 0) c.s_wflag[warp] = wf;
             __syncthreads();
             if (warp == 0) {
+                unsigned f = c.s_wflag[lane & 15];
+                f = __reduce_or_sync(0xffffffffu, f);
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     double v = c.s_warp[k * 16 + (lane & 15)];
 #pragma unroll
-                    for (int o = 1; o < 16; o <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);   // bits 5,6,7,8
-                    if (lane == 0) c.part[(par * kGridQ + k) * kGridMaxParts + e] = v;
+                    for (int o = 1; o < 16; o <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);   // bits 5,6,7,8 (every lane holds v)
+                    if (ll) {
+                        const unsigned tag = seq | ((k == 0) ? ((f & 0xfu) << 28) : 0u);   // flag words of these kernels use bits 0..2
+                        const size_t slot = (size_t)(par * kGridQ + k) * kLLParts + e;
+                        for (int dst = lane; dst < c.nctas; dst += 32)             // into every CTA's inbox
+                            ll_store(c.ll + (size_t)dst * kLLInboxLines + slot, (unsigned long long)__double_as_longlong(v), tag);
+                    } else if (lane == 0) {
+                        c.part[(par * kGridQ + k) * kGridMaxParts + e] = v;
+                    }
                 }
-                unsigned f = c.s_wflag[lane & 15];
-                f = __reduce_or_sync(0xffffffffu, f);
-                if (lane == 0) c.fpart[par * kGridMaxParts + e] = f;
+                if (!ll && lane == 0) c.fpart[par * kGridMaxParts + e] = f;
             }
             __syncthreads();                 // s_warp may be reused by the next owned eighth
         }
     }
-    c.grid.sync();
+    if (prof) t_local = clock64();
+    if (!ll) c.grid.sync();
     // warp 0 of every CTA fetches the CTA values side by side (one L2 round trip per 16 blocks -- a thread adding
     // them one load at a time would wait out a full L2 latency per value): lane l holds CTA values 4l .. 4l+3 of
     // the round, i.e. half a block; bits 9, 10 inside the lane, bit 11 across the lane pair, blocks in ascending order
@@ -91,25 +166,53 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
             const int e0 = 8 * b0 + 4 * lane;
             const bool in = (e0 < 8 * c.nblocks);
             double half[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const double* q = c.part + (par * kGridQ + k) * kGridMaxParts + e0;
-                const double c0 = in ? __ldcg(&q[0]) : 0.0, c1 = in ? __ldcg(&q[1]) : 0.0;
-                const double c2 = in ? __ldcg(&q[2]) : 0.0, c3 = in ? __ldcg(&q[3]) : 0.0;
-                half[k] = (c0 + c1) + (c2 + c3);                                  // bits 9, 10
-            }
             unsigned fv = 0;
-            if (in) {
-                const unsigned* fq = c.fpart + par * kGridMaxParts + e0;
-                fv = __ldcg(&fq[0]) | __ldcg(&fq[1]) | __ldcg(&fq[2]) | __ldcg(&fq[3]);
+            if (ll) {
+                // poll this lane's lines of the CTA's own inbox, one quantity at a time, until both tags of each carry the
+                // current sequence number
+                const uint4* inbox = c.ll + (size_t)c.cta * kLLInboxLines;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint4* q = inbox + ((size_t)(par * kGridQ + k) * kLLParts + e0);
+                    uint4 l0 = make_uint4(0, 0, 0, 0), l1 = l0, l2 = l0, l3 = l0;
+                    if (in) {
+                        unsigned long long t0 = 0;
+                        for (unsigned spins = 1;; ++spins) {
+                            l0 = ll_load(q + 0); l1 = ll_load(q + 1); l2 = ll_load(q + 2); l3 = ll_load(q + 3);
+                            const bool ok = ll_ok(l0, seq) & ll_ok(l1, seq) & ll_ok(l2, seq) & ll_ok(l3, seq);
+                            if (ok) break;
+                            if ((spins & 1023u) == 0u) {                            // a grid that lost a CTA must not hang the GPU
+                                const unsigned long long now = global_timer_ns();
+                                if (t0 == 0) t0 = now;
+                                else if (now - t0 > 5000000000ull) { grid_seq_cell(c.part)->y = 1u; break; }
+                            }
+                        }
+                    }
+                    half[k] = (ll_value(l0) + ll_value(l1)) + (ll_value(l2) + ll_value(l3));   // bits 9, 10 (lanes past the end: 0.0)
+                    if (k == 0) fv = (l0.y | l1.y | l2.y | l3.y) >> 28;
+                }
+                __syncwarp();
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const double* q = c.part + (par * kGridQ + k) * kGridMaxParts + e0;
+                    const double c0 = in ? __ldcg(&q[0]) : 0.0, c1 = in ? __ldcg(&q[1]) : 0.0;
+                    const double c2 = in ? __ldcg(&q[2]) : 0.0, c3 = in ? __ldcg(&q[3]) : 0.0;
+                    half[k] = (c0 + c1) + (c2 + c3);                                  // bits 9, 10
+                }
+                if (in) {
+                    const unsigned* fq = c.fpart + par * kGridMaxParts + e0;
+                    fv = __ldcg(&fq[0]) | __ldcg(&fq[1]) | __ldcg(&fq[2]) | __ldcg(&fq[3]);
+                }
             }
             f |= __reduce_or_sync(0xffffffffu, fv);
+            if (prof) t_poll = clock64();
             const int cnt = min(16, c.nblocks - b0);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const double blockv = half[k] + __shfl_down_sync(0xffffffffu, half[k], 1);   // bit 11 (valid on even lanes)
-                for (int i = 0; i < cnt; ++i) {
-                    const double x = __shfl_sync(0xffffffffu, blockv, 2 * i);
+                for (int i = 0; i < cnt; ++i) {      // (through shared memory instead of 16 shuffles: measured slower, legacy
+                    const double x = __shfl_sync(0xffffffffu, blockv, 2 * i);   //  L-BFGS 0.212 -> 0.230 ms per step!)
                     tot[k] = (b0 == 0 && i == 0) ? x : tot[k] + x;
                 }
             }
@@ -121,10 +224,15 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
         }
     }
     __syncthreads();
+    if (prof) {
+        const long long t_out = clock64();
+        c.prof[0] += t_local - t_in; c.prof[1] += t_poll - t_local; c.prof[2] += t_out - t_poll; c.prof[3] += 1;
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) out[k] = c.s_out[k];
     flags = *c.s_flags;
-    // the next write to s_out sits behind the next grid barrier
+    // the next write to s_out sits behind this CTA's own contribution to the next reduction, i.e. behind the
+    // __syncthreads every warp passes after reading s_out
 }
 
 constexpr int kGridOwnMax = 8;   // eighths one CTA may own: n <= nctas * 65536 elements (148 CTAs: 9.7 Mi)
@@ -182,8 +290,45 @@ struct DirRegs {
     }
 };
 
+// The two history vectors of the NEXT pass of compute_lbfgs_step_direction!, fetched while the reduction of the current
+// pass is in flight (OWN == 1 only): which vectors the next pass reads depends on loop indices, not on the reduced value,
+// so each thread copies its own 8 pairs of both with 16-byte cp.async (128 KB of shared memory per CTA, one CTA per SM)
+// right before it enters the reduction and finds them in shared memory afterwards -- the pass no longer waits out an
+// HBM round trip behind every reduction.  A thread only ever reads back what it copied itself: no barrier involved.
+constexpr size_t kGridStageBytes = (size_t)2 * 8 * kClusterThreads * sizeof(double2);
+template <int OWN>
+struct PassStage {
+    double2* buf;                          // [2 vectors][8 pairs][512 threads]
+    bool staged;
+    DZO_DEVINL void fetch(const GridCtx& c, long long m2, const double* A, const double* B) {
+        if constexpr (OWN == 1) {
+            if (buf != nullptr && c.cta < 8 * c.nblocks) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long long k = (long long)(c.cta >> 3) * kBlockPairs + (c.cta & 7) * 512 + threadIdx.x + (long long)DZO_TREE_WIDTH * i;
+                    if (k < m2) {
+                        cp_async16(&buf[(0 * 8 + i) * kClusterThreads + threadIdx.x], reinterpret_cast<const double2*>(A) + k);
+                        cp_async16(&buf[(1 * 8 + i) * kClusterThreads + threadIdx.x], reinterpret_cast<const double2*>(B) + k);
+                    }
+                }
+                cp_async_commit();
+                staged = true;
+            }
+        }
+    }
+    DZO_DEVINL void wait() {
+        if constexpr (OWN == 1) { if (staged) cp_async_wait_all(); }
+    }
+    DZO_DEVINL double2 get(int v, int i, const double* G, long long k) const {
+        if constexpr (OWN == 1) { if (staged) return buf[(v * 8 + i) * kClusterThreads + threadIdx.x]; }
+        return reinterpret_cast<const double2*>(G)[k];
+    }
+    DZO_DEVINL void done() { staged = false; }
+};
+
 template <int OWN>
 static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(GridLbfgsArgs a) {
+    extern __shared__ __align__(16) unsigned char grid_stage_raw[];
     constexpr int kGridOwn = OWN;          // the macros and arrays below size themselves by it
     __shared__ LbfgsCtrl sc;
     __shared__ double alpha[DZO_LBFGS_MAX_HISTORY];
@@ -192,6 +337,13 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
     __shared__ double s_out[kGridQ];
     __shared__ unsigned s_flags;
     GridCtx c{cg::this_grid(), (int)gridDim.x, (int)blockIdx.x, a.nblocks, 0, a.part, a.fpart, s_warp, s_wflag, s_out, &s_flags};
+    grid_ctx_begin(c);
+    __shared__ long long s_prof[4];
+    long long t_kernel = 0;
+    if ((a.stage & 2) && blockIdx.x == 0) {                    // measurement knob "grid_profile": cycle split of the leader CTA
+        if (threadIdx.x == 0) { s_prof[0] = s_prof[1] = s_prof[2] = s_prof[3] = 0; t_kernel = clock64(); }
+        c.prof = s_prof;
+    }
     const long long n = a.n, m2 = n >> 1;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
     if (threadIdx.x == 0) sc = *a.ctrl;
@@ -230,6 +382,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
             for (int i = 0; i < DZO_LBFGS_MAX_HISTORY; ++i) t.rho[i] = 0.0;
             *a.ctrl = t;
         }
+        grid_ctx_end(c);
         return;
     }
 
@@ -253,6 +406,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
             double out[1];
             unsigned f;
             DirRegs<OWN> D;
+            PassStage<OWN> St{(OWN == 1 && (a.stage & 1)) ? reinterpret_cast<double2*>(grid_stage_raw) : nullptr, false};
 #pragma unroll
             for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; fl[j] = 0; }
             {
@@ -265,6 +419,24 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                     acc[0][j] += ss.y * gg.y;
                 });
             }
+            // vectors of pass i of the first loop: y_p and (s_{p+1} | y_p of the last entry again for y_{cnt-1} . d)
+            auto first_loop_vectors = [&](int i, const double*& y, const double*& nxt) {
+                const int p = (head + i) % m;
+                const bool last = (i == cnt - 1);
+                const int pn = last ? p : (head + i + 1) % m;
+                y = a.Y + (long long)p * n;
+                nxt = last ? (a.Y + (long long)pn * n) : (a.S + (long long)pn * n);
+            };
+            // vectors of pass i of the second loop: s_p and (y_{p-1} | x for the fused first trial)
+            auto second_loop_vectors = [&](int i, const double*& sp, const double*& other) {
+                sp = a.S + (long long)((head + i) % m) * n;
+                other = (i > 0) ? (a.Y + (long long)((head + i - 1) % m) * n) : a.x;
+            };
+            {
+                const double *fy, *fn;
+                first_loop_vectors(0, fy, fn);
+                St.fetch(c, m2, fy, fn);
+            }
             grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
             double al = out[0] / sc.rho[head];
             const double cc = -sc.rho[head] / sc.yy;                                            // :443 (dot(y_0, y_0) cached)
@@ -273,59 +445,74 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                 const int p = (head + i) % m;
                 if (threadIdx.x == 0) alpha[i] = al;
                 const double na = -al;
-                const double* y = a.Y + (long long)p * n;
+                const double *y, *nxt;
+                first_loop_vectors(i, y, nxt);
                 const bool last = (i == cnt - 1);
                 const int pn = last ? p : (head + i + 1) % m;
-                const double* nxt = last ? (a.Y + (long long)pn * n) : (a.S + (long long)pn * n);
 #pragma unroll
                 for (int j = 0; j < kGridOwn; ++j) acc[0][j] = 0.0;
+                St.wait();
                 own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
                     double2 dd = D.get(a.d, q, k);
-                    const double2 yy = reinterpret_cast<const double2*>(y)[k];
-                    const double2 nn = reinterpret_cast<const double2*>(nxt)[k];
+                    const double2 yy = St.get(0, q, y, k);
+                    const double2 nn = St.get(1, q, nxt, k);
                     dd.x += na * yy.x; dd.y += na * yy.y;                                       // :440
                     if (last) { dd.x *= cc; dd.y *= cc; }                                       // :443
                     D.set(a.d, q, k, dd, false);
                     acc[0][j] += nn.x * dd.x;                                                   // s_{i+1} . d (:439) or y_{cnt-1} . d (:446)
                     acc[0][j] += nn.y * dd.y;
                 });
+                St.done();
+                {
+                    const double *fa, *fb;
+                    if (!last) first_loop_vectors(i + 1, fa, fb);
+                    else second_loop_vectors(cnt - 1, fa, fb);
+                    St.fetch(c, m2, fa, fb);
+                }
                 grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
                 if (last) beta = out[0] / sc.rho[p];
                 else al = out[0] / sc.rho[pn];
             }
             __syncthreads();   // alpha[] visible
             for (int i = cnt - 1; i >= 0; --i) {
-                const int p = (head + i) % m;
                 const double na = -(alpha[i] + beta);
-                const double* sp = a.S + (long long)p * n;
+                const double *sp, *other;
+                second_loop_vectors(i, sp, other);
 #pragma unroll
                 for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; fl[j] = 0; }
+                St.wait();
                 if (i > 0) {
                     const int pn = (head + i - 1) % m;
-                    const double* yn = a.Y + (long long)pn * n;
                     own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
                         double2 dd = D.get(a.d, q, k);
-                        const double2 ss = reinterpret_cast<const double2*>(sp)[k];
-                        const double2 yy = reinterpret_cast<const double2*>(yn)[k];
+                        const double2 ss = St.get(0, q, sp, k);
+                        const double2 yy = St.get(1, q, other, k);
                         dd.x += na * ss.x; dd.y += na * ss.y;                                   // :447
                         D.set(a.d, q, k, dd, false);
                         acc[0][j] += yy.x * dd.x;                                               // y_{i-1} . d  (:446)
                         acc[0][j] += yy.y * dd.y;
                     });
+                    St.done();
+                    {
+                        const double *fa, *fb;
+                        second_loop_vectors(i - 1, fa, fb);
+                        St.fetch(c, m2, fa, fb);
+                    }
                     grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
                     beta = out[0] / sc.rho[pn];
                 } else {
                     // last correction fused with the first trial of take_backtracking_step!(opt, 1, d)  (:124-138)
                     own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
                         double2 dd = D.get(a.d, q, k);
-                        const double2 ss = reinterpret_cast<const double2*>(sp)[k];
-                        const double2 xx = reinterpret_cast<const double2*>(a.x)[k];
+                        const double2 ss = St.get(0, q, sp, k);
+                        const double2 xx = St.get(1, q, other, k);
                         dd.x += na * ss.x; dd.y += na * ss.y;                                   // :447
                         D.set(a.d, q, k, dd, true);                                             // step_direction as the host reads it
                         const double w0 = xx.x + step * dd.x, w1 = xx.y + step * dd.y;         // :124 axpy!
                         if (!julia_isequal(w0, xx.x) || !julia_isequal(w1, xx.y)) fl[j] |= 1u;  // :128
                         acc[0][j] += RosenbrockVec::term(w0, w1);                               // :138
                     });
+                    St.done();
                     grid_reduce<1, kGridOwn>(c, acc, fl, pr_out, pr_flags);
                     have_probe = true;
                 }
@@ -406,6 +593,10 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
         __syncthreads();
     }
     if (leader) *a.ctrl = sc;
+    grid_ctx_end(c);
+    if (c.prof != nullptr && threadIdx.x == 0)
+        printf("grid_lbfgs profile (CTA 0, cycles): kernel %lld, %lld reductions: CTA-level %lld, waiting for the grid %lld, final combine %lld\n",
+               clock64() - t_kernel, s_prof[3], s_prof[0], s_prof[1], s_prof[2]);
 }
 
 }  // namespace dzo
@@ -429,6 +620,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_adgd_kernel(Gr
     __shared__ double s_out[kGridQ];
     __shared__ unsigned s_flags;
     GridCtx c{cg::this_grid(), (int)gridDim.x, (int)blockIdx.x, ga.nblocks, 0, ga.part, ga.fpart, s_warp, s_wflag, s_out, &s_flags};
+    grid_ctx_begin(c);
     const long long m2 = a.n >> 1;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
     if (threadIdx.x == 0 && a.mode == 0) sc = *a.ctrl;
@@ -459,6 +651,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_adgd_kernel(Gr
             t.cur = t.prev = t.stuck ? 0.0 : a.initial_step_length / gnorm;                     // :235-236
             *a.ctrl = t;
         }
+        grid_ctx_end(c);
         return;
     }
     const double inv_sqrt_two = sqrt(0.5);
@@ -529,5 +722,6 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_adgd_kernel(Gr
         __syncthreads();
     }
     if (leader) *a.ctrl = sc;
+    grid_ctx_end(c);
 }
 }  // namespace dzo

@@ -160,6 +160,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
     __shared__ double s_out[kGridQ];
     __shared__ unsigned s_flags;
     GridCtx c{cg::this_grid(), (int)gridDim.x, (int)blockIdx.x, ga.nblocks, 0, ga.part, ga.fpart, s_warp, s_wflag, s_out, &s_flags};
+    grid_ctx_begin(c);
     const long long n = a.n, m2 = n >> 1;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
     LegacyDecor D;
@@ -205,6 +206,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
             for (int i = 0; i < DZO_LBFGS_MAX_HISTORY; ++i) { t.rho[i] = 0.0; t.alpha[i] = 0.0; }
             *a.ctrl = t;
         }
+        grid_ctx_end(c);
         return;
     }
 
@@ -392,6 +394,7 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
         __syncthreads();
     }
     if (leader) *a.ctrl = sc;
+    grid_ctx_end(c);
 }
 
 }  // namespace dzo

@@ -64,6 +64,11 @@ struct Tuning {
     int riesz_esplit = 1;     // lanes per row in the Riesz energy items (1 or 2), read when an optimizer is created
     int riesz_gvariant = 0;   // Riesz gradient: 0 = (32 rows x 128 sources) warp items, 1 = symmetric 128 x 128 CTA tiles (each pair
                               // weight computed once; measured 0.183 vs 0.177 ms per GD step at N = 4096, so not the default)
+    int grid_ll = 1;          // grid-wide kernels (L-BFGS / AdGD / GD above n = 65536): 1 = reductions through flagged 16-byte lines
+                              // (no grid barrier), 0 = one grid.sync per reduction; read when an optimizer is created
+    int grid_profile = 0;     // 1: the grid-wide live L-BFGS kernel prints the cycle split of its leader CTA (measurement only)
+    int grid_stage = 1;       // live L-BFGS grid kernel with one eighth per CTA: fetch the next pass's history vectors into shared
+                              // memory (cp.async) while the current reduction is in flight
     int warp_search = 1;      // O(n) stage of step! for 32 < n <= 512: 1 = one warp per problem (warp_search.cuh), 0 = 8-CTA cluster
     int riesz_pair = 1;       // Riesz line search: evaluate the probe it needs and the one it will most likely need next in one
                               // phase (the second rides in warps the first leaves idle); read when an optimizer is created
