@@ -400,8 +400,10 @@ static int large_step_once(dzo_bfgs* o) {
     if (o->riesz) {
         DZO_TRY(riesz_bfgs_launch(o->riesz, 5, o->stream, o->x, o->g, o->d, o->dx, o->dg, o->sd, o->ctrl, 0.0));
     }
-    const bool cluster = (g_tuning.search_variant == 0) || o->fused;   // 8-CTA cluster with DSMEM reductions vs one CTA
-                                                                        // (the peer-flag waits live in the cluster kernels)
+    // 8-CTA cluster with DSMEM reductions (a single problem: lowest latency) vs one 1024-thread CTA per problem (a batch:
+    // only ~18 clusters are co-resident on a B200, but 148+ CTAs -- n = 1024 x 256 problems spent a quarter of the step!
+    // call queueing for clusters); the peer-flag waits of the row-sharded mode live in the cluster kernels
+    const bool cluster = o->fused || (g_tuning.search_variant == 0 && o->batch < 4) || g_tuning.search_variant == 2;
     if (o->riesz) { /* search stage already enqueued above (cooperative Riesz kernel) */ }
     else if (cluster) cluster_bfgs_search_kernel<<<kClusterCtas * (unsigned)o->batch, kClusterThreads, 0, o->stream>>>(v);   // :891-950, :873-874
     else vec_bfgs_search_kernel<<<(unsigned)o->batch, 1024, 0, o->stream>>>(v);

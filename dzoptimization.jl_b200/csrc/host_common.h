@@ -60,7 +60,8 @@ struct Tuning {
                               // update kernel 0.79 (U=8), 0.96 (U=16), 0.84 (U=24), 0.87 (U=32) of HBM peak
     int sweep_threads = 0;    // threads per sweep CTA (0 = pick from the slab shape)
     int sharded_variant = 0;  // row-sharded gathers: 0 = fused into the producing kernels over peer memory, 1 = ncclAllGather
-    int search_variant = 0;   // large-n O(n) stage: 0 = 8-CTA cluster + DSMEM reductions, 1 = single 1024-thread CTA
+    int search_variant = 0;   // large-n O(n) stage: 0 = 8-CTA cluster + DSMEM reductions for one problem, one 1024-thread CTA per
+                              // problem for a batch of >= 4; 1 = always single CTA; 2 = always cluster
     int riesz_esplit = 1;     // lanes per row in the Riesz energy items (1 or 2), read when an optimizer is created
     int riesz_gvariant = 0;   // Riesz gradient: 0 = (32 rows x 128 sources) warp items, 1 = symmetric 128 x 128 CTA tiles (each pair
                               // weight computed once; measured 0.183 vs 0.177 ms per GD step at N = 4096, so not the default)
