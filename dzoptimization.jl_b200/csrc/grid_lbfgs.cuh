@@ -51,6 +51,7 @@ struct GridCtx {
                                              // [1] polling for the other CTAs' lines, [2] in the final combine, [3] reductions
     uint4* ll = nullptr;                     // flagged lines [2][kGridQ + 1][kGridMaxParts] (null: grid-barrier mode)
     unsigned seq = 0;                        // sequence number of the next reduction (flag value of its lines)
+    unsigned backoff = 0;                    // ns a consumer sleeps after a poll that found a line missing
 };
 
 // ---- reductions WITHOUT a grid barrier (round 2).  A CTA value travels as one 16-byte line {lo, tag, hi, tag}: two 8-byte
@@ -65,6 +66,15 @@ struct GridCtx {
 // Lines are double-buffered by the parity of the reduction count: the line of reduction r is overwritten by reduction
 // r + 2, which every CTA reaches only after it has consumed r + 1, i.e. after every CTA has finished reading r.  The
 // running sequence number lives behind the inboxes and survives across launches (stale lines never match).
+#ifndef DZO_LL_SYS
+#define DZO_LL_SYS 0            // 1: ld.volatile / st.cg lines (A/B)
+#endif
+#ifndef DZO_LL_COMBINE_SMEM
+#define DZO_LL_COMBINE_SMEM 0   // 1: final combine through shared memory instead of a chain of shuffles (A/B)
+#endif
+#ifndef DZO_EARLY_FETCH
+#define DZO_EARLY_FETCH 0       // 1: staged fetch issued before the reduction instead of behind the CTA's line stores (A/B)
+#endif
 constexpr int kLLParts = 1024;                            // CTA values per quantity the inbox mode handles (n <= 8 Mi)
 constexpr int kLLMaxCtas = 192;                           // inboxes allocated (a B200 runs 148 CTAs of these kernels)
 constexpr size_t kGridBarrierBytes = sizeof(double) * 2 * kGridQ * kGridMaxParts;
@@ -73,10 +83,10 @@ constexpr size_t kGridLineCount = kLLInboxLines * kLLMaxCtas;
 constexpr unsigned kLLSeqMask = 0x0fffffffu;
 inline size_t grid_part_bytes() { return kGridBarrierBytes + sizeof(uint4) * (kGridLineCount + 1); }
 // host: zero everything, sequence numbers start at 1; `enabled` = 0 keeps the grid-barrier reductions (A/B)
-inline cudaError_t grid_part_init(double* part, int enabled) {
+inline cudaError_t grid_part_init(double* part, int enabled, int backoff_ns = 0) {
     cudaError_t e = cudaMemset(part, 0, grid_part_bytes());
     if (e != cudaSuccess) return e;
-    const uint4 head = make_uint4(1u, 0u, 0u, enabled ? 1u : 0u);
+    const uint4 head = make_uint4(1u, 0u, (unsigned)backoff_ns, enabled ? 1u : 0u);
     return cudaMemcpy(reinterpret_cast<char*>(part) + kGridBarrierBytes + sizeof(uint4) * kGridLineCount, &head, sizeof head,
                       cudaMemcpyHostToDevice);
 }
@@ -89,6 +99,7 @@ DZO_DEVINL void grid_ctx_begin(GridCtx& c) {
     if (head.w && 8 * c.nblocks <= kLLParts && c.nctas <= kLLMaxCtas) {
         c.ll = reinterpret_cast<uint4*>(reinterpret_cast<char*>(c.part) + kGridBarrierBytes);
         c.seq = head.x;
+        c.backoff = head.z;
     }
 }
 // the leader, after the kernel's last reduction (every CTA read the cell before its first one)
@@ -96,12 +107,22 @@ DZO_DEVINL void grid_ctx_end(const GridCtx& c) {
     if (c.ll != nullptr && blockIdx.x == 0 && threadIdx.x == 0) grid_seq_cell(c.part)->x = c.seq;
 }
 DZO_DEVINL void ll_store(uint4* p, unsigned long long bits, unsigned seq) {
-    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)bits), "r"(seq), "r"((unsigned)(bits >> 32)), "r"(seq)
+    #if DZO_LL_SYS
+    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};"
+#else
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};"
+#endif
+                 ::"l"(p), "r"((unsigned)bits), "r"(seq), "r"((unsigned)(bits >> 32)), "r"(seq)
                  : "memory");
 }
 DZO_DEVINL uint4 ll_load(const uint4* p) {
     uint4 q;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+    #if DZO_LL_SYS
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+#else
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+#endif
+                 : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
     return q;
 }
 DZO_DEVINL bool ll_ok(const uint4& q, unsigned seq) { return (q.y & kLLSeqMask) == seq && (q.w & kLLSeqMask) == seq; }
@@ -109,11 +130,21 @@ DZO_DEVINL double ll_value(const uint4& q) { return __longlong_as_double((long l
 
 // Reduce K per-eighth accumulators (acc[k][j] = this thread's partial of quantity k for the j-th eighth its CTA owns)
 // and OR the flag words.  Returns the totals in out[k], the OR in flags; identical on every thread of the grid.
-template <int K, int MAXB>
-DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[MAXB], double (&out)[K], unsigned& flags) {
+// `after_store` runs on every thread once the CTA's own lines are on their way to the other CTAs and before the CTA
+// starts waiting for theirs: the place to issue memory traffic that should overlap the reduction (the staged fetch of
+// the next pass) -- issued earlier it would sit in the SM's request queue AHEAD of the lines everybody else is waiting for.
+template <int K, int MAXB, class F>
+DZO_DEVINL void grid_reduce_then(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[MAXB], double (&out)[K], unsigned& flags,
+                                 F&& after_store) {
+#if DZO_EARLY_FETCH
+    after_store();
+#endif
     const int par = c.red & 1;
     c.red += 1;
-    const bool prof = (c.prof != nullptr && threadIdx.x == 0);
+#ifndef DZO_GRID_PROF
+#define DZO_GRID_PROF 1
+#endif
+    const bool prof = DZO_GRID_PROF && (c.prof != nullptr && threadIdx.x == 0);
     long long t_in = 0, t_local = 0, t_poll = 0;
     if (prof) t_in = clock64();
     const bool ll = (c.ll != nullptr);
@@ -154,6 +185,9 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
             __syncthreads();                 // s_warp may be reused by the next owned eighth
         }
     }
+#if !DZO_EARLY_FETCH
+    after_store();
+#endif
     if (prof) t_local = clock64();
     if (!ll) c.grid.sync();
     // warp 0 of every CTA fetches the CTA values side by side (one L2 round trip per 16 blocks -- a thread adding
@@ -175,17 +209,24 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
                 for (int k = 0; k < K; ++k) {
                     const uint4* q = inbox + ((size_t)(par * kGridQ + k) * kLLParts + e0);
                     uint4 l0 = make_uint4(0, 0, 0, 0), l1 = l0, l2 = l0, l3 = l0;
-                    if (in) {
-                        unsigned long long t0 = 0;
-                        for (unsigned spins = 1;; ++spins) {
+                    // The loop is left by the WHOLE warp at once (vote).  With per-lane exits the lanes dropped out of the
+                    // spin loop one by one and the warp reached the combine below diverged: the same binary measured 0.20 ms
+                    // per L-BFGS step! (n = 2^20) with the shuffle combine and 0.13 ms with a shared-memory combine that
+                    // needs no collective; with the vote both run at 0.106 - 0.109 ms (profiles/r02_grid_lbfgs_variants_*).
+                    unsigned long long t0 = 0;
+                    for (unsigned spins = 1;; ++spins) {
+                        bool ok = true;
+                        if (in) {
                             l0 = ll_load(q + 0); l1 = ll_load(q + 1); l2 = ll_load(q + 2); l3 = ll_load(q + 3);
-                            const bool ok = ll_ok(l0, seq) & ll_ok(l1, seq) & ll_ok(l2, seq) & ll_ok(l3, seq);
-                            if (ok) break;
-                            if ((spins & 1023u) == 0u) {                            // a grid that lost a CTA must not hang the GPU
-                                const unsigned long long now = global_timer_ns();
-                                if (t0 == 0) t0 = now;
-                                else if (now - t0 > 5000000000ull) { grid_seq_cell(c.part)->y = 1u; break; }
-                            }
+                            ok = ll_ok(l0, seq) & ll_ok(l1, seq) & ll_ok(l2, seq) & ll_ok(l3, seq);
+                        }
+                        if (__all_sync(0xffffffffu, ok)) break;
+                        if (c.backoff) __nanosleep(c.backoff);
+                        if ((spins & 1023u) == 0u) {                                // a grid that lost a CTA must not hang the GPU
+                            const unsigned long long now = global_timer_ns();
+                            if (t0 == 0) t0 = now;
+                            const bool give_up = (now - t0 > 5000000000ull);
+                            if (__any_sync(0xffffffffu, give_up)) { if (lane == 0) grid_seq_cell(c.part)->y = 1u; break; }
                         }
                     }
                     half[k] = (ll_value(l0) + ll_value(l1)) + (ll_value(l2) + ll_value(l3));   // bits 9, 10 (lanes past the end: 0.0)
@@ -209,6 +250,20 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
             if (prof) t_poll = clock64();
             const int cnt = min(16, c.nblocks - b0);
 #pragma unroll
+#if DZO_LL_COMBINE_SMEM
+            for (int k = 0; k < K; ++k) {
+                const double blockv = half[k] + __shfl_down_sync(0xffffffffu, half[k], 1);   // bit 11 (valid on even lanes)
+                if (!(lane & 1)) c.s_warp[k * 16 + (lane >> 1)] = blockv;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                for (int i = 0; i < cnt; ++i) {
+                    const double x = c.s_warp[k * 16 + i];
+                    tot[k] = (b0 == 0 && i == 0) ? x : tot[k] + x;
+                }
+            __syncwarp();
+#else
             for (int k = 0; k < K; ++k) {
                 const double blockv = half[k] + __shfl_down_sync(0xffffffffu, half[k], 1);   // bit 11 (valid on even lanes)
                 for (int i = 0; i < cnt; ++i) {      // (through shared memory instead of 16 shuffles: measured slower, legacy
@@ -216,6 +271,7 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
                     tot[k] = (b0 == 0 && i == 0) ? x : tot[k] + x;
                 }
             }
+#endif
         }
         if (lane == 0) {
 #pragma unroll
@@ -233,6 +289,10 @@ DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[M
     flags = *c.s_flags;
     // the next write to s_out sits behind this CTA's own contribution to the next reduction, i.e. behind the
     // __syncthreads every warp passes after reading s_out
+}
+template <int K, int MAXB>
+DZO_DEVINL void grid_reduce(GridCtx& c, double (&acc)[K][MAXB], unsigned (&fl)[MAXB], double (&out)[K], unsigned& flags) {
+    grid_reduce_then<K, MAXB>(c, acc, fl, out, flags, [] {});
 }
 
 constexpr int kGridOwnMax = 8;   // eighths one CTA may own: n <= nctas * 65536 elements (148 CTAs: 9.7 Mi)
@@ -432,12 +492,11 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                 sp = a.S + (long long)((head + i) % m) * n;
                 other = (i > 0) ? (a.Y + (long long)((head + i - 1) % m) * n) : a.x;
             };
-            {
+            grid_reduce_then<1, kGridOwn>(c, acc, fl, out, f, [&] {
                 const double *fy, *fn;
                 first_loop_vectors(0, fy, fn);
                 St.fetch(c, m2, fy, fn);
-            }
-            grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
+            });
             double al = out[0] / sc.rho[head];
             const double cc = -sc.rho[head] / sc.yy;                                            // :443 (dot(y_0, y_0) cached)
             double beta = 0.0;
@@ -463,13 +522,12 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                     acc[0][j] += nn.y * dd.y;
                 });
                 St.done();
-                {
+                grid_reduce_then<1, kGridOwn>(c, acc, fl, out, f, [&] {
                     const double *fa, *fb;
                     if (!last) first_loop_vectors(i + 1, fa, fb);
                     else second_loop_vectors(cnt - 1, fa, fb);
                     St.fetch(c, m2, fa, fb);
-                }
-                grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
+                });
                 if (last) beta = out[0] / sc.rho[p];
                 else al = out[0] / sc.rho[pn];
             }
@@ -493,12 +551,11 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_lbfgs_kernel(G
                         acc[0][j] += yy.y * dd.y;
                     });
                     St.done();
-                    {
+                    grid_reduce_then<1, kGridOwn>(c, acc, fl, out, f, [&] {
                         const double *fa, *fb;
                         second_loop_vectors(i - 1, fa, fb);
                         St.fetch(c, m2, fa, fb);
-                    }
-                    grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
+                    });
                     beta = out[0] / sc.rho[pn];
                 } else {
                     // last correction fused with the first trial of take_backtracking_step!(opt, 1, d)  (:124-138)

@@ -10,13 +10,17 @@ if os.environ.get('DZO_GRID_PROFILE'):
     dz.set_tuning('grid_profile', int(os.environ['DZO_GRID_PROFILE']))
 if os.environ.get('DZO_GRID_STAGE'):
     dz.set_tuning('grid_stage', int(os.environ['DZO_GRID_STAGE']))
+if os.environ.get('DZO_GRID_BACKOFF'):
+    dz.set_tuning('grid_ll_backoff', int(os.environ['DZO_GRID_BACKOFF']))
 if os.environ.get('DZO_GRID_LL'):
     dz.set_tuning('grid_ll', int(os.environ['DZO_GRID_LL']))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 50
-x0 = 4.0 * orc.pcg_fill(n, 1) - 2.0
+x0 = 4.0 * orc.pcg_fill(n, int(os.environ.get('DZO_SEED', '1'))) - 2.0
 o = dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, m)
+if os.environ.get('DZO_SETSTREAM'):
+    _st = torch.cuda.Stream(); torch.cuda.set_stream(_st); o.set_stream(_st.cuda_stream)
 o.step(12)
 for rep in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -6,6 +6,8 @@ import torch
 import dzopt_b200 as dz
 import oracle as orc
 EF = dz.ExampleFunctions
+if os.environ.get('DZO_GRID_BACKOFF'):
+    dz.set_tuning('grid_ll_backoff', int(os.environ['DZO_GRID_BACKOFF']))
 if os.environ.get('DZO_GRID_LL'):
     dz.set_tuning('grid_ll', int(os.environ['DZO_GRID_LL']))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
