@@ -84,6 +84,46 @@ DZO_DEVINL void cta1024_tree_reduce(double (&p)[K][4], double* sm, double (&out)
     __syncthreads();  // sm may be reused immediately by the caller
 }
 
+// The same tree inside ONE CTA of NT = 512 or 1024 threads: thread tid emulates the VT = 4096 / NT virtual threads
+// v = tid + NT*q, so lane bits are tree bits 4..0, the warp index bits 5.. and q the top bits.  p[k][q] is the partial of
+// quantity k on virtual thread v; `sm` needs K*132 doubles.  NT = 1024 is cta1024_tree_reduce, bit for bit.
+template <int K, int NT>
+DZO_DEVINL void cta_tree_reduce(double (&p)[K][4096 / NT], double* sm, double (&out)[K]) {
+    constexpr int VT = 4096 / NT, W = NT / 32;
+    static_assert(NT == 512 || NT == 1024, "canonical tree on one CTA: 512 or 1024 threads");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int q = 0; q < VT; ++q) {
+            const double s = warp_butterfly_desc(p[k][q]);           // bits 4,3,2,1,0
+            if (lane == 0) sm[k * 132 + q * W + warp] = s;
+        }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double r[VT];
+#pragma unroll
+            for (int q = 0; q < VT; ++q) {
+                double v = sm[k * 132 + q * W + (lane & (W - 1))];
+#pragma unroll
+                for (int o = 1; o < W; o <<= 1) v = v + __shfl_xor_sync(0xffffffffu, v, o);     // warp-index bits, ascending
+                r[q] = v;
+            }
+#pragma unroll
+            for (int w = 1; w < VT; w <<= 1)                         // q bits, ascending
+#pragma unroll
+                for (int i = 0; i < VT; i += 2 * w) r[i] = r[i] + r[i + w];
+            if (lane == 0) sm[k * 132 + 128] = r[0];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = sm[k * 132 + 128];
+    __syncthreads();  // sm may be reused immediately by the caller
+}
+
 // ----------------------------------------------------------------------------- PTX: mbarrier + bulk async copy (TMA 1-D)
 DZO_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -40,7 +40,7 @@ struct dzo_gd {
     int2* g_jobs = nullptr;
     int n_g_jobs = 0, gvariant = 0;
     unsigned long long* prof = nullptr;   // phase log (tuning knob "riesz_profile")
-    int grid = 0;
+    int grid = 0, nt = 512;
     // Rosenbrock, n > 32: cluster kernel up to n = DZO_TREE_BLOCK, cooperative grid above (DZO_ORDER_TREE_BLOCKED)
     void* gridgd = nullptr;
     double* gscal = nullptr;              // { f, df, L, iteration_count, has_terminated, evals } (owned by gridgd)
@@ -96,17 +96,17 @@ static std::vector<int2> energy_items(int N, int rows) {
 
 // one translation unit per instance (riesz_dim<N>.cu)
 namespace dzo {
-void* riesz_kernel_dim1();
-void* riesz_kernel_dim2();
-void* riesz_kernel_dim3();
-void* riesz_kernel_dim4();
+void* riesz_kernel_dim1(int nt);
+void* riesz_kernel_dim2(int nt);
+void* riesz_kernel_dim3(int nt);
+void* riesz_kernel_dim4(int nt);
 }
-static void* riesz_kernel_for(int dim) {
+static void* riesz_kernel_for(int dim, int nt) {
     switch (dim) {
-        case 1: return riesz_kernel_dim1();
-        case 2: return riesz_kernel_dim2();
-        case 3: return riesz_kernel_dim3();
-        case 4: return riesz_kernel_dim4();
+        case 1: return riesz_kernel_dim1(nt);
+        case 2: return riesz_kernel_dim2(nt);
+        case 3: return riesz_kernel_dim3(nt);
+        case 4: return riesz_kernel_dim4(nt);
         default: return nullptr;
     }
 }
@@ -121,11 +121,14 @@ struct RieszWork {
     int esplit = 2, gcnt_off = 0, ecnt_stride = 0, espec = 0;
     int2* g_jobs = nullptr;
     int n_g_jobs = 0, gvariant = 0;
-    int grid = 0;
+    int grid = 0, nt = 512;
     void* kernel = nullptr;
     size_t smem = 0;
     int init(int N, int dim, int device) {
-        kernel = riesz_kernel_for(dim);
+        // threads per CTA: 512 (128 registers: twice the pair terms in flight per lane) unless the symmetric-tile gradient
+        // variant, which is written for 32 warps, or the tuning knob asks for the 1024-thread kernel
+        nt = (g_tuning.riesz_threads == 1024 || g_tuning.riesz_gvariant) ? 1024 : 512;
+        kernel = riesz_kernel_for(dim, nt);
         if (!kernel) return fail(DZO_ERR_UNSUPPORTED, "device Riesz kernels support 1 <= dim <= 4");
         const int nseg = (N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
         DZO_TRY(dmalloc(&segE, (size_t)2 * nseg * N));       // two probes of a paired evaluation
@@ -152,12 +155,12 @@ struct RieszWork {
         DZO_TRY(dmalloc(&g_jobs, jobs.size()));
         if (!jobs.empty())
             DZO_CUDA(cudaMemcpy(g_jobs, jobs.data(), jobs.size() * sizeof(int2), cudaMemcpyHostToDevice));
-        smem = riesz_gd_smem(dim);
+        smem = riesz_gd_smem(dim, nt);
         DZO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaDeviceProp prop;
         DZO_CUDA(cudaGetDeviceProperties(&prop, device));
         int per_sm = 0;
-        DZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 1024, smem));
+        DZO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem));
         if (per_sm < 1) return fail(DZO_ERR_CUDA, "riesz_gd_kernel does not fit on an SM");
         if (!prop.cooperativeLaunch) return fail(DZO_ERR_UNSUPPORTED, "device lacks cooperative launch");
         grid = prop.multiProcessorCount;   // one persistent CTA per SM
@@ -177,7 +180,7 @@ struct RieszWork {
     }
     int launch(RieszGdArgs& a, cudaStream_t stream) const {
         void* params[] = {&a};
-        DZO_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(1024), params, smem, stream));
+        DZO_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(nt), params, smem, stream));
         return DZO_OK;
     }
 };
@@ -215,8 +218,8 @@ static int gd_launch(dzo_gd* o, int mode, int k, double L0) {
             a.prof = o->prof;
         }
         void* params[] = {&a};
-        DZO_CUDA(cudaLaunchCooperativeKernel(riesz_kernel_for((int)o->dim), dim3(o->grid), dim3(1024), params,
-                                             riesz_gd_smem((int)o->dim), o->stream));
+        DZO_CUDA(cudaLaunchCooperativeKernel(riesz_kernel_for((int)o->dim, o->nt), dim3(o->grid), dim3(o->nt), params,
+                                             riesz_gd_smem((int)o->dim, o->nt), o->stream));
         return DZO_OK;
     }
     if (o->gridgd)
@@ -260,7 +263,7 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
         o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->esplit = w.esplit; o->gcnt_off = w.gcnt_off; o->grid = w.grid;
-        o->ecnt_stride = w.ecnt_stride; o->espec = w.espec;
+        o->ecnt_stride = w.ecnt_stride; o->espec = w.espec; o->nt = w.nt;
         o->g_jobs = w.g_jobs; o->n_g_jobs = w.n_g_jobs; o->gvariant = w.gvariant;
     }
     if (!o->small && objective == DZO_OBJ_ROSENBROCK) {       // one 8-CTA cluster up to n = DZO_TREE_BLOCK, the whole grid above

@@ -82,7 +82,6 @@ DZO_DEVINL void riesz_prof_mark(const RieszGdArgs& a, int id) {
     }
 }
 
-constexpr int kRieszSegWarps = 32;   // warps per CTA, each with a private staging buffer
 #ifndef DZO_RIESZ_BATCH
 #define DZO_RIESZ_BATCH 4
 #endif
@@ -92,8 +91,15 @@ constexpr int kRieszSegWarps = 32;   // warps per CTA, each with a private stagi
 constexpr int kRieszBatch = DZO_RIESZ_BATCH;            // energy pair terms whose sqrt / reciprocal chains run interleaved
 constexpr int kRieszGradBatch = DZO_RIESZ_GRAD_BATCH;   // same for the gradient (sqrt, reciprocal, division per term)
 
-template <int DIM>
+// NT = threads per CTA.  512 (default): 16 warps of up to 128 registers, so eight energy / four gradient pair terms run
+// interleaved per lane -- one energy evaluation is 2112 warp items, i.e. at most ONE per warp on either CTA size, and what
+// fills the FP64 pipe is chains in flight per warp, not warps (1024 threads: 64 registers, four / two terms).
+template <int DIM, int NT>
 struct RieszDev {
+    static constexpr int W = NT / 32;                       // warps per CTA, each with a private staging buffer
+    static constexpr int VT = 4096 / NT;                    // virtual threads of the canonical tree per thread
+    static constexpr int EB = (NT == 512) ? 2 * kRieszBatch : kRieszBatch;           // energy pair terms in flight per lane
+    static constexpr int GB = (NT == 512) ? 2 * kRieszGradBatch : kRieszGradBatch;   // gradient pair terms in flight per lane
     // trial point of point j: w = x_j + alpha*d_j, then constraint_function! (normalise) [pmode 0];
     // pmode 2: the stored point itself (already constrained).
     static DZO_DEVINL void trial_point(const RieszGdArgs& a, const double* dir, int j, double alpha, int pmode,
@@ -124,7 +130,7 @@ struct RieszDev {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
         const int nseg_all = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
-        for (int idx2 = blockIdx.x + gridDim.x * warp; idx2 < npr * a.n_e_items; idx2 += gridDim.x * kRieszSegWarps) {
+        for (int idx2 = blockIdx.x + gridDim.x * warp; idx2 < npr * a.n_e_items; idx2 += gridDim.x * W) {
             const int pr = (npr == 2) ? (idx2 & 1) : 0;                 // probes interleaved: both get heavy items first
             const int idx = (npr == 2) ? (idx2 >> 1) : idx2;
             const double alpha = pr ? alpha1 : alpha0;
@@ -148,14 +154,14 @@ struct RieszDev {
                     double wj[DIM];
                     trial_point(a, dir, j, alpha, pmode, wj);
                     double seg = 0.0;
-                    // the sqrt / reciprocal chains of kRieszBatch sources run interleaved (ieee_fast.cuh); only the
+                    // the sqrt / reciprocal chains of EB sources run interleaved (ieee_fast.cuh); only the
                     // adds are ordered
                     int i = 0;
-                    for (; i + kRieszBatch <= lim; i += kRieszBatch) {
-                        double ds[kRieszBatch], t[kRieszBatch];
+                    for (; i + EB <= lim; i += EB) {
+                        double ds[EB], t[EB];
                         bool safe = true;
 #pragma unroll
-                        for (int u = 0; u < kRieszBatch; ++u) {
+                        for (int u = 0; u < EB; ++u) {
                             double dist_sq = 0.0;
 #pragma unroll
                             for (int k = 0; k < DIM; ++k) {
@@ -167,13 +173,13 @@ struct RieszDev {
                         }
                         if (safe) {
 #pragma unroll
-                            for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));
+                            for (int u = 0; u < EB; ++u) t[u] = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));
                         } else {
 #pragma unroll
-                            for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_rsqrt_operators(ds[u]);
+                            for (int u = 0; u < EB; ++u) t[u] = ieee_rsqrt_operators(ds[u]);
                         }
 #pragma unroll
-                        for (int u = 0; u < kRieszBatch; ++u) seg += t[u];     // rsqrt(dist_sq)  :41
+                        for (int u = 0; u < EB; ++u) seg += t[u];     // rsqrt(dist_sq)  :41
                     }
                     for (; i < lim; ++i) {
                         double dist_sq = 0.0;
@@ -212,7 +218,7 @@ struct RieszDev {
     }
 
     // Two lanes per row (esplit = 2): an item is 16 rows x 128 sources; lane l < 16 takes the even sources of row l,
-    // lane l + 16 the odd ones, kRieszBatch terms each per round, and lane l adds the 2*kRieszBatch values in source
+    // lane l + 16 the odd ones, EB terms each per round, and lane l adds the 2*EB values in source
     // order (the odd ones arrive by shuffle).  Twice as many items as with one lane per row, so nearly every warp of
     // the grid has one (2112 -> 4224 items for 4736 warps at N = 4096) and the serial chain per lane halves.
     static DZO_DEVINL void energy_segments_split(const RieszGdArgs& a, const double* dir, double alpha, int pmode, int par,
@@ -220,7 +226,7 @@ struct RieszDev {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int half = lane >> 4;
         double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
-        for (int idx = blockIdx.x + gridDim.x * warp; idx < a.n_e_items; idx += gridDim.x * kRieszSegWarps) {
+        for (int idx = blockIdx.x + gridDim.x * warp; idx < a.n_e_items; idx += gridDim.x * W) {
             const int2 it = a.e_items[idx];                  // (16-row block, segment)
             const int i0 = it.y * DZO_RIESZ_SEG;
             const int cnt = min(DZO_RIESZ_SEG, a.N - i0);
@@ -242,11 +248,11 @@ struct RieszDev {
                 for (int k = 0; k < DIM; ++k) wj[k] = 0.0;
             }
             double seg = 0.0;
-            for (int base = 0; base < lim_max; base += 2 * kRieszBatch) {
-                double ds[kRieszBatch], t[kRieszBatch];
+            for (int base = 0; base < lim_max; base += 2 * EB) {
+                double ds[EB], t[EB];
                 bool safe = true;
 #pragma unroll
-                for (int u = 0; u < kRieszBatch; ++u) {
+                for (int u = 0; u < EB; ++u) {
                     const int i = base + 2 * u + half;
                     double dist_sq = 0.0;
                     if (i < lim) {
@@ -263,13 +269,13 @@ struct RieszDev {
                 }
                 if (safe) {
 #pragma unroll
-                    for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));
+                    for (int u = 0; u < EB; ++u) t[u] = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));
                 } else {
 #pragma unroll
-                    for (int u = 0; u < kRieszBatch; ++u) t[u] = ieee_rsqrt_operators(ds[u]);
+                    for (int u = 0; u < EB; ++u) t[u] = ieee_rsqrt_operators(ds[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < kRieszBatch; ++u) {
+                for (int u = 0; u < EB; ++u) {
                     const double odd = __shfl_down_sync(0xffffffffu, t[u], 16);
                     if (base + 2 * u < lim) seg += t[u];                          // rsqrt(dist_sq)  :41 (even source)
                     if (base + 2 * u + 1 < lim) seg += odd;                       //                     (odd source)
@@ -304,19 +310,32 @@ struct RieszDev {
     // at N = 4096), so the value is identical on every thread of the grid without a broadcast or a second barrier.
     template <int NPR>
     static DZO_DEVINL void energy_finish(const RieszGdArgs& a, int par, double* sm, double (&f)[2]) {
-        double p[NPR][4];
+        // row j -> virtual thread j mod 4096, ascending; all loads of a round of 4096 rows are issued before the first
+        // add (one loop per accumulator made every load wait out its own L2 round trip)
+        double p[NPR][VT];
 #pragma unroll
-        for (int pr = 0; pr < NPR; ++pr) {
-            const double* rowE = a.rowE + (long long)(2 * par + pr) * a.N;
+        for (int pr = 0; pr < NPR; ++pr)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                double acc = 0.0;
-                for (int j = threadIdx.x + 1024 * q; j < a.N; j += DZO_TREE_WIDTH) acc += __ldcg(&rowE[j]);
-                p[pr][q] = acc;
+            for (int q = 0; q < VT; ++q) p[pr][q] = 0.0;
+        for (int base = 0; base < a.N; base += DZO_TREE_WIDTH) {
+            double v[NPR][VT];
+#pragma unroll
+            for (int pr = 0; pr < NPR; ++pr) {
+                const double* rowE = a.rowE + (long long)(2 * par + pr) * a.N;
+#pragma unroll
+                for (int q = 0; q < VT; ++q) {
+                    const int j = base + threadIdx.x + NT * q;
+                    v[pr][q] = (j < a.N) ? __ldcg(&rowE[j]) : 0.0;
+                }
             }
+#pragma unroll
+            for (int pr = 0; pr < NPR; ++pr)
+#pragma unroll
+                for (int q = 0; q < VT; ++q)
+                    if (base + threadIdx.x + NT * q < a.N) p[pr][q] += v[pr][q];
         }
         double out[NPR];
-        cta1024_tree_reduce<NPR>(p, sm, out);
+        cta_tree_reduce<NPR, NT>(p, sm, out);
 #pragma unroll
         for (int pr = 0; pr < NPR; ++pr) f[pr] = out[pr];
     }
@@ -363,7 +382,7 @@ struct RieszDev {
         double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
         const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
         const int nrb = (a.N + 31) / 32;
-        for (int idx = blockIdx.x + gridDim.x * warp; idx < nrb * nseg; idx += gridDim.x * kRieszSegWarps) {
+        for (int idx = blockIdx.x + gridDim.x * warp; idx < nrb * nseg; idx += gridDim.x * W) {
             const int rb = idx / nseg, s = idx - rb * nseg;
             const int i0 = s * DZO_RIESZ_SEG;
             const int cnt = min(DZO_RIESZ_SEG, a.N - i0);
@@ -378,11 +397,11 @@ struct RieszDev {
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) { xj[k] = a.x[(long long)j * DIM + k]; part[k] = 0.0; }
                 int i = 0;
-                for (; i + kRieszGradBatch <= cnt; i += kRieszGradBatch) {
-                    double ds[kRieszGradBatch], c[kRieszGradBatch];
+                for (; i + GB <= cnt; i += GB) {
+                    double ds[GB], c[GB];
                     bool safe = true;
 #pragma unroll
-                    for (int u = 0; u < kRieszGradBatch; ++u) {
+                    for (int u = 0; u < GB; ++u) {
                         double dist_sq = 0.0;
 #pragma unroll
                         for (int k = 0; k < DIM; ++k) {
@@ -394,16 +413,16 @@ struct RieszDev {
                     }
                     if (safe) {
 #pragma unroll
-                        for (int u = 0; u < kRieszGradBatch; ++u) {
+                        for (int u = 0; u < GB; ++u) {
                             const double inv_dist = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));   // :61
                             c[u] = ieee_fast_div(inv_dist, ds[u]);                          // :62
                         }
                     } else {
 #pragma unroll
-                        for (int u = 0; u < kRieszGradBatch; ++u) c[u] = ieee_inv_cubed_operators(ds[u]);
+                        for (int u = 0; u < GB; ++u) c[u] = ieee_inv_cubed_operators(ds[u]);
                     }
 #pragma unroll
-                    for (int u = 0; u < kRieszGradBatch; ++u) {
+                    for (int u = 0; u < GB; ++u) {
                         if (i0 + i + u == j) continue;                         // :55, :69 (i != j)
 #pragma unroll
                         for (int k = 0; k < DIM; ++k) {
@@ -600,14 +619,16 @@ struct RieszDev {
     }
 
     static DZO_DEVINL void gradient(const RieszGdArgs& a, double* wsm, bool with_delta) {
-        if (a.gvariant == 1) gradient_tiles(a, wsm, with_delta);
-        else gradient_segments(a, wsm, with_delta);
+        if constexpr (NT == 1024) {
+            if (a.gvariant == 1) { gradient_tiles(a, wsm, with_delta); return; }
+        }
+        gradient_segments(a, wsm, with_delta);
     }
 
     // every CTA scans all points (N/1024 per thread): cheap, avoids a grid barrier
     static DZO_DEVINL bool all_points(const RieszGdArgs& a, const double* dir, double alpha, double alpha_ref, int what) {
         int bad = 0;
-        for (int j = threadIdx.x; j < a.N; j += 1024) {
+        for (int j = threadIdx.x; j < a.N; j += NT) {
             if (what == 0) {            // step_is_zero: all(dir == 0)  :71-85
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) bad |= !(a.dscale * dir[(long long)j * DIM + k] == 0.0);
@@ -726,72 +747,80 @@ struct RieszDev {
 // dx . dx and g . g in one pass over the canonical tree (every CTA computes both itself).  The loop runs over rounds
 // of 4096 pairs with the four virtual threads of a thread side by side, so the 16 loads of a round are in flight
 // together (two L2 round trips at n = 12288 instead of six); each accumulator still sees its pairs in ascending order.
+template <int NT>
 DZO_DEVINL void cta_tree_norms2(const double* __restrict__ v, const double* __restrict__ w, long long n, double* sm,
                                 double& vv, double& ww) {
-    double p[2][4];
+    constexpr int VT = 4096 / NT;
+    double p[2][VT];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { p[0][q] = 0.0; p[1][q] = 0.0; }
-    if ((n & 1) == 0 && n <= 4 * DZO_TREE_WIDTH) {
-        // at most two rounds (config 5: n = 12288): every pair as ONE 16-byte load and all of a thread's loads in flight
-        // together -- one L2 round trip for the whole pass (ncu / phase log: this pass was 14 us of a 166 us step)
+    for (int q = 0; q < VT; ++q) { p[0][q] = 0.0; p[1][q] = 0.0; }
+    if ((n & 1) == 0) {
+        // every pair as ONE 16-byte load and all of a thread's loads of a round in flight together: one L2 round trip per
+        // 4096 pairs (config 5, n = 12288: two) -- the phase log had this pass at 14 us of a 166 us step with 8-byte loads
         const double2* v2 = reinterpret_cast<const double2*>(v);
         const double2* w2 = reinterpret_cast<const double2*>(w);
         const long long m = n >> 1;
-        double2 a[2][4], b[2][4];
+        for (long long base = 0; base < m; base += DZO_TREE_WIDTH) {
+            double2 a[VT], b[VT];
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long k = (long long)r * DZO_TREE_WIDTH + threadIdx.x + 1024 * q;
+            for (int q = 0; q < VT; ++q) {
+                const long long k = base + threadIdx.x + NT * q;
                 const bool in = k < m;
-                a[r][q] = in ? __ldcg(&v2[k]) : make_double2(0.0, 0.0);
-                b[r][q] = in ? __ldcg(&w2[k]) : make_double2(0.0, 0.0);
+                a[q] = in ? __ldcg(&v2[k]) : make_double2(0.0, 0.0);
+                b[q] = in ? __ldcg(&w2[k]) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-        for (int r = 0; r < 2; ++r)                       // ascending pairs per accumulator, as in the general loop
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long k = (long long)r * DZO_TREE_WIDTH + threadIdx.x + 1024 * q;
+            for (int q = 0; q < VT; ++q) {
+                const long long k = base + threadIdx.x + NT * q;
                 if (k < m) {
-                    p[0][q] += a[r][q].x * a[r][q].x; p[1][q] += b[r][q].x * b[r][q].x;
-                    p[0][q] += a[r][q].y * a[r][q].y; p[1][q] += b[r][q].y * b[r][q].y;
+                    p[0][q] += a[q].x * a[q].x; p[1][q] += b[q].x * b[q].x;
+                    p[0][q] += a[q].y * a[q].y; p[1][q] += b[q].y * b[q].y;
                 }
             }
+        }
     } else {
         for (long long base = 0; 2 * base < n; base += DZO_TREE_WIDTH) {
-            double a0[4], a1[4], b0[4], b1[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long k = base + threadIdx.x + 1024 * q;
-                const bool in0 = 2 * k < n, in1 = 2 * k + 1 < n;
-                a0[q] = in0 ? v[2 * k] : 0.0;
-                b0[q] = in0 ? w[2 * k] : 0.0;
-                a1[q] = in1 ? v[2 * k + 1] : 0.0;
-                b1[q] = in1 ? w[2 * k + 1] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const long long k = base + threadIdx.x + 1024 * q;
-                if (2 * k < n) { p[0][q] += a0[q] * a0[q]; p[1][q] += b0[q] * b0[q]; }
-                if (2 * k + 1 < n) { p[0][q] += a1[q] * a1[q]; p[1][q] += b1[q] * b1[q]; }
+            for (int q = 0; q < VT; ++q) {
+                const long long k = base + threadIdx.x + NT * q;
+                if (2 * k < n) { p[0][q] += v[2 * k] * v[2 * k]; p[1][q] += w[2 * k] * w[2 * k]; }
+                if (2 * k + 1 < n) { p[0][q] += v[2 * k + 1] * v[2 * k + 1]; p[1][q] += w[2 * k + 1] * w[2 * k + 1]; }
             }
         }
     }
     double out[2];
-    cta1024_tree_reduce<2>(p, sm, out);
+    cta_tree_reduce<2, NT>(p, sm, out);
     vv = out[0];
     ww = out[1];
 }
+// v . w over the canonical tree on one CTA of NT threads (cta_tree_dot of large_bfgs.cuh is the 1024-thread case)
+template <int NT>
+DZO_DEVINL double cta_tree_dot_nt(const double* __restrict__ v, const double* __restrict__ w, long long n, double* sm) {
+    constexpr int VT = 4096 / NT;
+    double p[1][VT];
+#pragma unroll
+    for (int q = 0; q < VT; ++q) {
+        double acc = 0.0;
+        for (long long k = threadIdx.x + NT * q; 2 * k < n; k += DZO_TREE_WIDTH) {
+            acc += v[2 * k] * w[2 * k];
+            if (2 * k + 1 < n) acc += v[2 * k + 1] * w[2 * k + 1];
+        }
+        p[0][q] = acc;
+    }
+    double out[1];
+    cta_tree_reduce<1, NT>(p, sm, out);
+    return out[0];
+}
 
-template <int DIM>
-static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a) {
+template <int DIM, int NT>
+static __global__ void __launch_bounds__(NT, 1) riesz_gd_kernel(RieszGdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);          // 2 x 132 doubles: tree reduction scratch
-    double* wsm = sm + 272;                                    // 32 warps x 128 x DIM staging
+    double* wsm = sm + 272;                                    // (NT / 32) warps x 128 x DIM staging
     cg::grid_group grid = cg::this_grid();
-    using R = RieszDev<DIM>;
+    using R = RieszDev<DIM, NT>;
     const long long n = (long long)a.N * DIM;
-    const long long gtid = (long long)blockIdx.x * 1024 + threadIdx.x, gsize = (long long)gridDim.x * 1024;
+    const long long gtid = (long long)blockIdx.x * NT + threadIdx.x, gsize = (long long)gridDim.x * NT;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
     int epar = 0;                                               // energy evaluations of this launch (rowE parity)
 
@@ -852,7 +881,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         long long evals = 0;
         grid.sync();                       // every CTA holds the control block before the leader may rewrite it
         double gg, dd;
-        cta_tree_norms2(a.g, a.d, n, sm, gg, dd);
+        cta_tree_norms2<NT>(a.g, a.d, n, sm, gg, dd);
         const double grad_norm = sqrt(gg);                                     // :921
         const double bfgs_norm = sqrt(dd);                                     // :928
         double grad_step_length, grad_obj, bfgs_step_length, bfgs_obj;
@@ -891,7 +920,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         grid.sync();
         double overlap = 0.0;
         if (kind == DZO_STEP_BFGS) {
-            overlap = cta_tree_dot(a.d, a.dg, n, sm);                          // :873
+            overlap = cta_tree_dot_nt<NT>(a.d, a.dg, n, sm);                          // :873
             const double inv_overlap = 1.0 / overlap;                          // :874
             for (long long e = gtid; e < n; e += gsize) a.sd[e] = a.d[e] * inv_overlap;
         } else {
@@ -923,7 +952,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         const double f0 = R::energy(a, grid, epar, a.x, 0.0, 2, wsm, sm);      // :343
         R::gradient(a, wsm, false);                                   // :347-348
         grid.sync();
-        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot(a.g, a.g, n, sm));   // :352
+        const double inv_gradient_norm = 1.0 / sqrt(cta_tree_dot_nt<NT>(a.g, a.g, n, sm));   // :352
         if (isfinite(inv_gradient_norm)) {                                     // :354-357
             const double alpha = -a.initial_step_length * inv_gradient_norm;
             for (long long e = gtid; e < n; e += gsize) a.d[e] = a.g[e] * alpha;
@@ -976,7 +1005,7 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
         grid.sync();
         riesz_prof_mark(a, 10);
         double dxdx, gg;
-        cta_tree_norms2(a.dx, a.g, n, sm, dxdx, gg);
+        cta_tree_norms2<NT>(a.dx, a.g, n, sm, dxdx, gg);
         riesz_prof_mark(a, 13);
         const double step_length = sqrt(dxdx);                                 // :424
         const double inv_gradient_norm = 1.0 / sqrt(gg);                       // :438
@@ -1002,9 +1031,9 @@ static __global__ void __launch_bounds__(1024, 1) riesz_gd_kernel(RieszGdArgs a)
     }
 }
 
-inline size_t riesz_gd_smem(int dim) {
-    const size_t staging = (size_t)kRieszSegWarps * DZO_RIESZ_SEG * dim;                                  // per-warp source staging
-    const size_t tile = (size_t)DZO_RIESZ_SEG * (DZO_RIESZ_SEG + 1) + 2 * (size_t)DZO_RIESZ_SEG * dim;     // gradient tile + 2 point sets
+inline size_t riesz_gd_smem(int dim, int nt) {
+    const size_t staging = (size_t)(nt / 32) * DZO_RIESZ_SEG * dim;                                        // per-warp source staging
+    const size_t tile = (nt == 1024) ? (size_t)DZO_RIESZ_SEG * (DZO_RIESZ_SEG + 1) + 2 * (size_t)DZO_RIESZ_SEG * dim : 0;   // gradient tile + 2 point sets (gvariant 1)
     return sizeof(double) * (272 + (staging > tile ? staging : tile));
 }
 

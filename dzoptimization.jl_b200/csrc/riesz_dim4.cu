@@ -1,6 +1,6 @@
-// riesz_dim4.cu -- instantiates riesz_gd_kernel<4> in its own translation unit (each instance takes ptxas about a
+// riesz_dim4.cu -- instantiates riesz_gd_kernel<4, 512 | 1024> in its own translation unit (each instance takes ptxas about a
 // minute; four units compile in parallel).  dzopt_gd.cu launches it through the pointer returned here.
 #include "gd_kernels.cuh"
 namespace dzo {
-void* riesz_kernel_dim4() { return (void*)riesz_gd_kernel<4>; }
+void* riesz_kernel_dim4(int nt) { return nt == 512 ? (void*)riesz_gd_kernel<4, 512> : (void*)riesz_gd_kernel<4, 1024>; }
 }
