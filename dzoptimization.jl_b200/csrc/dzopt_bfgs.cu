@@ -1243,6 +1243,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "grid_stage")) { g_tuning.grid_stage = value; return DZO_OK; }
     if (!strcmp(key, "grid_profile")) { g_tuning.grid_profile = value; return DZO_OK; }
     if (!strcmp(key, "grid_ll_backoff")) { g_tuning.grid_ll_backoff = value; return DZO_OK; }
+    if (!strcmp(key, "grid_ll_first_seq")) { g_tuning.grid_ll_first_seq = value; return DZO_OK; }
     if (!strcmp(key, "riesz_gvariant")) { g_tuning.riesz_gvariant = value; return DZO_OK; }
     if (!strcmp(key, "sharded_variant")) { g_tuning.sharded_variant = value; return DZO_OK; }
     if (!strcmp(key, "sweep_unroll")) { g_tuning.sweep_unroll = value; return DZO_OK; }

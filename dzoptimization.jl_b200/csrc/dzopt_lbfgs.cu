@@ -119,7 +119,7 @@ int dzo_lbfgs_create(dzo_lbfgs** out, int objective, int constraint, int64_t obj
         if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nclusters)
             return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d CTA shares; the grid-wide L-BFGS kernel holds at most %d",
                              (long long)n, 8 * o->nblocks, kGridOwnMax * o->nclusters));
-        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff) != cudaSuccess ||
+        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff, (unsigned)g_tuning.grid_ll_first_seq) != cudaSuccess ||
             cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
         o->use_grid = true;
@@ -286,7 +286,7 @@ int dzo_adgd_create(dzo_adgd** out, int objective, int constraint, int64_t obj_p
         o->nctas = 8 * o->nblocks < resident ? 8 * o->nblocks : resident;
         if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nctas)
             return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld is too large for the grid-wide AdGD kernel", (long long)n));
-        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff) != cudaSuccess ||
+        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff, (unsigned)g_tuning.grid_ll_first_seq) != cudaSuccess ||
             cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
     }
@@ -423,7 +423,7 @@ int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constrain
         if (o->nblocks > kGridMaxBlocks || 8 * o->nblocks > kGridOwnMax * o->nctas)
             return bail(fail(DZO_ERR_UNSUPPORTED, "n = %lld needs %d CTA shares; the grid-wide legacy L-BFGS kernel holds at most %d",
                              (long long)n, 8 * o->nblocks, kGridOwnMax * o->nctas));
-        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff) != cudaSuccess ||
+        if (cudaMalloc((void**)&o->part, grid_part_bytes()) != cudaSuccess || grid_part_init(o->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff, (unsigned)g_tuning.grid_ll_first_seq) != cudaSuccess ||
             cudaMalloc((void**)&o->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess)
             return bail(fail(DZO_ERR_ALLOC, "cudaMalloc failed"));
         o->use_grid = true;
@@ -574,7 +574,7 @@ int grid_gd_attach(int64_t n, int device, void** out, double** scal) {
         delete h;
         return fail(DZO_ERR_UNSUPPORTED, "n = %lld is too large for the grid-wide GD kernel", (long long)n);
     }
-    if (cudaMalloc((void**)&h->part, grid_part_bytes()) != cudaSuccess || grid_part_init(h->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff) != cudaSuccess ||
+    if (cudaMalloc((void**)&h->part, grid_part_bytes()) != cudaSuccess || grid_part_init(h->part, g_tuning.grid_ll, g_tuning.grid_ll_backoff, (unsigned)g_tuning.grid_ll_first_seq) != cudaSuccess ||
         cudaMalloc((void**)&h->fpart, sizeof(unsigned) * 2 * kGridMaxParts) != cudaSuccess ||
         cudaMalloc((void**)&h->lctrl, sizeof(LegacyCtrl)) != cudaSuccess || cudaMalloc((void**)&h->scal, 6 * sizeof(double)) != cudaSuccess) {
         grid_gd_detach(h);

@@ -83,10 +83,10 @@ constexpr size_t kGridLineCount = kLLInboxLines * kLLMaxCtas;
 constexpr unsigned kLLSeqMask = 0x0fffffffu;
 inline size_t grid_part_bytes() { return kGridBarrierBytes + sizeof(uint4) * (kGridLineCount + 1); }
 // host: zero everything, sequence numbers start at 1; `enabled` = 0 keeps the grid-barrier reductions (A/B)
-inline cudaError_t grid_part_init(double* part, int enabled, int backoff_ns = 0) {
+inline cudaError_t grid_part_init(double* part, int enabled, int backoff_ns = 0, unsigned first_seq = 1u) {
     cudaError_t e = cudaMemset(part, 0, grid_part_bytes());
     if (e != cudaSuccess) return e;
-    const uint4 head = make_uint4(1u, 0u, (unsigned)backoff_ns, enabled ? 1u : 0u);
+    const uint4 head = make_uint4(first_seq ? (first_seq & kLLSeqMask) : 1u, 0u, (unsigned)backoff_ns, enabled ? 1u : 0u);
     return cudaMemcpy(reinterpret_cast<char*>(part) + kGridBarrierBytes + sizeof(uint4) * kGridLineCount, &head, sizeof head,
                       cudaMemcpyHostToDevice);
 }
@@ -100,6 +100,16 @@ DZO_DEVINL void grid_ctx_begin(GridCtx& c) {
         c.ll = reinterpret_cast<uint4*>(reinterpret_cast<char*>(c.part) + kGridBarrierBytes);
         c.seq = head.x;
         c.backoff = head.z;
+        if (c.seq > (kLLSeqMask >> 1)) {
+            // Half of the 28-bit tag range is used up: start over at 1 with clean inboxes, so that a line left behind by a
+            // reduction long ago (a quantity or parity that has not come up since) can never carry the current tag again.
+            // Every CTA clears its own inbox; the kernel's first grid barrier (right behind this call) separates the
+            // clearing from the first line any producer stores.  Uniform: every CTA read the same counter.
+            uint4* mine = c.ll + (size_t)c.cta * kLLInboxLines;
+            for (size_t i = threadIdx.x; i < kLLInboxLines; i += blockDim.x) mine[i] = make_uint4(0u, 0u, 0u, 0u);
+            __threadfence();
+            c.seq = 1u;
+        }
     }
 }
 // the leader, after the kernel's last reduction (every CTA read the cell before its first one)

@@ -67,6 +67,7 @@ struct Tuning {
                               // weight computed once; measured 0.183 vs 0.177 ms per GD step at N = 4096, so not the default)
     int grid_ll = 1;          // grid-wide kernels (L-BFGS / AdGD / GD above n = 65536): 1 = reductions through flagged 16-byte lines
                               // (no grid barrier), 0 = one grid.sync per reduction; read when an optimizer is created
+    int grid_ll_first_seq = 1; // first sequence number of a new handle's flagged lines (tests start near the recycling threshold 2^27)
     int grid_ll_backoff = 0;  // ns a consumer sleeps after a poll that found a line missing (0 = poll back to back)
     int grid_profile = 0;     // 1: the grid-wide live L-BFGS kernel prints the cycle split of its leader CTA (measurement only)
     int grid_stage = 1;       // live L-BFGS grid kernel with one eighth per CTA: fetch the next pass's history vectors into shared

@@ -111,12 +111,14 @@ def test_error_paths_need_no_gpu(dz):
     assert lib.dzo_pairwise_energy(9, 0, 4, dp, dp, dp, None, C.byref(e), 0) == -1    # unknown potential
 
 
-def test_bench_reference_arm_contract():
-    """bench.py --impl reference runs without a GPU and prints ONE JSON line with the contract's keys."""
+@pytest.mark.parametrize("steps", [3, 27])
+def test_bench_reference_arm_contract(steps):
+    """bench.py --impl reference runs without a GPU and prints ONE JSON line with the contract's keys (27 steps: the timed
+    region crosses into a second batch of the workload, bench.py STEPS_PER_BATCH = 25)."""
     import json
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", str(steps), "--warmup", "3"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -126,6 +128,7 @@ def test_bench_reference_arm_contract():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["steps"] == steps and ("%d batch(es)" % (-(-steps // 25))) in d["cpu_baseline"]["sample"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
 

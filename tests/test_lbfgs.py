@@ -266,3 +266,38 @@ def test_gpu_adgd_grid_wide_trace(gpu, orc, n):
         compare(f"n={n} iter {it}")
     opt.step(40); ref.step(40)
     compare("fused")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["recycle", "barrier", "no-stage"])
+def test_gpu_grid_reduction_variants(gpu, orc, variant):
+    """The grid-wide kernels reduce through flagged 16-byte lines in per-CTA inboxes (grid_lbfgs.cuh).  (recycle) a handle
+    whose line tags start just below the recycling threshold 2^27 crosses it between launches -- every CTA clears its
+    inbox and the tags start over at 1; (barrier) the grid.sync() reductions kept for A/B; (no-stage) passes read from
+    global memory instead of the staged copies.  All three walk the oracle's trajectory bit for bit."""
+    dz = gpu
+    EF = dz.ExampleFunctions
+    n, m = 200000, 4
+    x0 = _x0(orc, n, 11)
+    knobs = {"recycle": ("grid_ll_first_seq", (1 << 27) - 40, 1), "barrier": ("grid_ll", 0, 1), "no-stage": ("grid_stage", 0, 1)}
+    key, value, default = knobs[variant]
+    try:
+        dz.set_tuning(key, value)
+        opt = dz.LBFGSOptimizer(None, EF.rosenbrock_function, EF.rosenbrock_gradient_, x0, 1.0, m)
+        leg = dz.LegacyLBFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, dz.QuadraticLineSearch(0), x0, 1.0, m)
+    finally:
+        dz.set_tuning(key, default)
+    ref = orc.LBFGS(ROSEN, x0, 1.0, m, orc.TREE_BLOCKED)
+    for it in range(10):                                   # ~10 reductions per launch: the threshold falls inside this loop
+        dz.step_(opt); ref.step(1)
+        assert_bitwise(opt.current_point, ref.point, f"{variant} iter {it}: point")
+        assert_bitwise(opt.step_direction, ref.direction, f"{variant} iter {it}: direction")
+        assert float(opt.current_objective_value[()]) == ref.objective
+    opt.step(20); ref.step(20)
+    assert_bitwise(opt.current_point, ref.point, f"{variant}: fused steps")
+    # the legacy kernel shares the reduction code: compare two handles created with and without the knob
+    leg2 = dz.LegacyLBFGSOptimizer(EF.rosenbrock_function, EF.rosenbrock_gradient_, dz.QuadraticLineSearch(0), x0, 1.0, m)
+    for _ in range(6):
+        dz.step_(leg); dz.step_(leg2)
+    leg.step(6); leg2.step(6)
+    assert_bitwise(leg.current_point, leg2.current_point, f"{variant}: legacy L-BFGS")
