@@ -185,6 +185,32 @@ def pin_host_threads():
     return threads
 
 
+def bind_to_gpu_numa_node(torch, index):
+    """Multi-rank runs: keep this rank's host threads -- and with them the first-touch placement of its page-locked x0 and
+    field buffers -- on the NUMA node its GPU hangs off (what `numactl --cpunodebind` does for a user).  Round-2 phase
+    timers of an 8-rank run: constructors (128 MB of x0 over PCIe each) took 6.5 ms on ranks 0-3 and 4.4 ms on ranks 4-7
+    against 2.9 ms alone.  Returns a description for the JSON line, or None when sysfs does not say."""
+    try:
+        props = torch.cuda.get_device_properties(index)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 def cpu_leg(orc, steps, warmup, sample_batch, flags):
     """Oracle (port of the reference path) on every host thread; bounded sample of the workload.  Timed twice, the
     faster pass is reported (the direction that favours the CPU arm)."""
@@ -269,7 +295,10 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     distributed = world > 1
     torch.cuda.set_device(local_rank)
+    numa = None
     if distributed:
+        if not args.no_numa_bind:
+            numa = bind_to_gpu_numa_node(torch, local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import dzopt_b200 as dz
@@ -283,7 +312,8 @@ def run_gpu(args):
     orc = None
     cpu_flags = None
     if want_cpu:
-        pin_host_threads()
+        if not distributed:
+            pin_host_threads()      # (multi-rank runs keep the NUMA binding; their only oracle use is the small sharded check)
         orc = oracle_mod()
         cpu_flags = orc.use_native_build()
     peak, peak_src = load_peaks()
@@ -526,7 +556,8 @@ def run_gpu(args):
                                        "constructed and warmed up W steps before the clock starts (e2e: inside it)" % STEPS_PER_BATCH,
                        "l2": "state per GPU = 2.9 GB >> 126 MB L2 (inputs larger than L2, no flush needed)",
                        "active_fraction_in_timed_region": active_frac, "timed_region_ms": ms,
-                       "parallelism": f"independent problems, {world} GPU(s), no collective"},
+                       "parallelism": f"independent problems, {world} GPU(s), no collective",
+                       "host_numa_binding_rank0": numa},
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "host_phases_ms": e2e_phases, "untimed_first_pass_host_phases_ms": e2e_first_pass,
@@ -913,6 +944,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-large", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: leave the ranks' CPU affinity alone (A/B)")
     ap.add_argument("--cpu-sample", type=int, default=50_000)
     ap.add_argument("--tune", action="append", default=[], help="key=value passed to dzo_set_tuning (A/B runs)")
     args = ap.parse_args()
