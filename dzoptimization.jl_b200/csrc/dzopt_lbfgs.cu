@@ -356,10 +356,13 @@ static int legacy_launch(dzo_legacy_lbfgs* o, int mode, int k, double L0) {
     if (o->use_grid) {
         GridLegacyArgs ga;
         ga.a = a; ga.part = o->part; ga.fpart = o->fpart; ga.nblocks = o->nblocks;
+        const bool own1 = (8 * o->nblocks <= o->nctas);
+        ga.stage = (own1 && g_tuning.grid_stage) ? 1 : 0;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof cfg);
         cfg.gridDim = dim3((unsigned)o->nctas);
         cfg.blockDim = dim3(kClusterThreads);
+        cfg.dynamicSmemBytes = ga.stage ? kGridStageBytes : 0;
         cfg.stream = o->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeCooperative;
@@ -412,7 +415,8 @@ int dzo_legacy_lbfgs_create(dzo_legacy_lbfgs** out, int objective, int constrain
         int per_sm = 0, sms = 0;
         int per_sm_one = 0;               // OWN = 1 or kGridOwnMax is picked at launch: size the grid for the tighter of the two
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)grid_legacy_kernel_ptr(kGridOwnMax), kClusterThreads, 0) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_one, (const void*)grid_legacy_kernel_ptr(1), kClusterThreads, 0) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)grid_legacy_kernel_ptr(1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGridStageBytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_one, (const void*)grid_legacy_kernel_ptr(1), kClusterThreads, kGridStageBytes) != cudaSuccess ||
             (per_sm = per_sm < per_sm_one ? per_sm : per_sm_one) < 0 ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || per_sm < 1 || sms < 1) {
             cudaGetLastError();
@@ -600,6 +604,7 @@ int grid_gd_launch(void* p, int mode, int k, cudaStream_t stream, double* x, dou
         DZO_CUDA(cudaGetLastError());
         return DZO_OK;
     }
+    ga.stage = 0;                              // (GD has no history passes to stage)
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)h->nctas);

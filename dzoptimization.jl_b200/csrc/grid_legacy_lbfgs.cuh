@@ -16,6 +16,7 @@ struct GridLegacyArgs {
     double* part;                            // [2][kGridQ][kGridMaxParts]
     unsigned* fpart;                         // [2][kGridMaxParts]
     int nblocks;
+    int stage;                               // 1: kGridStageBytes of dynamic shared memory are there (OWN == 1 launches)
 };
 
 // bit 0: any(x != x + alpha*dir)   bit 1: any(dir != 0)
@@ -152,6 +153,7 @@ DZO_DEVINL void grid_legacy_line_search(GridCtx& c, long long m2, const LegacyDe
 
 template <int OWN>   // eighths one CTA may own (1: n <= CTAs * 8192); compiled in ONE translation unit (grid_legacy_tu.cu)
 static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_kernel(GridLegacyArgs ga) {
+    extern __shared__ __align__(16) unsigned char grid_stage_raw[];
     constexpr int kGridOwn = OWN;
     const LegacyArgs& a = ga.a;
     __shared__ LegacyCtrl sc;
@@ -327,6 +329,21 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
 #pragma unroll
         for (int j = 0; j < kGridOwn; ++j) { acc[0][j] = 0.0; fl[j] = 0; }
         DirRegs<OWN> Dr;                       // OWN == 1: the direction lives in registers across the 2m + 1 passes
+        PassStage<OWN> St{(OWN == 1 && ga.stage) ? reinterpret_cast<double2*>(grid_stage_raw) : nullptr, false};
+        // the two vectors a pass reads depend only on loop indices: the next pass's are fetched into shared memory while
+        // the reduction of the current one is in flight (grid_lbfgs.cuh: PassStage)
+        auto first_loop_vectors = [&](long long it, const double*& y, const double*& nxt) {
+            const int cc = (int)((it - 1) % m);
+            const bool last = (it == hist_begin);
+            const int cn = last ? (int)((hist_begin - 1) % m) : (int)((it - 2) % m);
+            y = a.Y + (long long)cc * n;
+            nxt = last ? (a.Y + (long long)cn * n) : (a.S + (long long)cn * n);
+        };
+        auto second_loop_vectors = [&](long long it, const double*& sp, const double*& nxt) {
+            const int cc = (int)((it - 1) % m);
+            sp = a.S + (long long)cc * n;
+            nxt = (it == hist_end) ? a.g : (a.Y + (long long)((it) % m) * n);                    // Y of it+1, or g for :683-684
+        };
         {
             const double* s0 = a.S + (long long)((hist_end - 1) % m) * n;
             own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {                          // :656 d = g, and d . S_c of the first stage
@@ -336,50 +353,67 @@ static __global__ void __launch_bounds__(kClusterThreads, 1) grid_legacy_lbfgs_k
                 acc[0][j] += gg.x * ss.x; acc[0][j] += gg.y * ss.y;
             });
         }
-        grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
+        grid_reduce_then<1, kGridOwn>(c, acc, fl, out, f, [&] {
+            const double *fa, *fb;
+            first_loop_vectors(hist_end, fa, fb);
+            St.fetch(c, m2, fa, fb);
+        });
         const double gamma = delta_overlap / q4[3];                                             // :669-670
         for (long long it = hist_end; it >= hist_begin; --it) {                                 // :659-666
             const int cc = (int)((it - 1) % m);
             const double alpha = sc.rho[cc] * out[0];
             if (threadIdx.x == 0) sc.alpha[cc] = alpha;
-            const double* y = a.Y + (long long)cc * n;
+            const double *y, *nxt;
+            first_loop_vectors(it, y, nxt);
             const bool last = (it == hist_begin);
-            // next stage: first loop continues with S of it-1, or the second loop starts with Y of hist_begin
-            const int cn = last ? (int)((hist_begin - 1) % m) : (int)((it - 2) % m);
-            const double* nxt = last ? (a.Y + (long long)cn * n) : (a.S + (long long)cn * n);
 #pragma unroll
             for (int j = 0; j < kGridOwn; ++j) acc[0][j] = 0.0;
+            St.wait();
             own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
                 double2 dd = Dr.get(a.d, q, k);
-                const double2 yy = reinterpret_cast<const double2*>(y)[k];
-                const double2 nn = reinterpret_cast<const double2*>(nxt)[k];
+                const double2 yy = St.get(0, q, y, k);
+                const double2 nn = St.get(1, q, nxt, k);
                 dd.x += alpha * yy.x; dd.y += alpha * yy.y;
                 if (last) { dd.x *= gamma; dd.y *= gamma; }                                     // :669-670 scale!
                 Dr.set(a.d, q, k, dd, false);
                 acc[0][j] += dd.x * nn.x; acc[0][j] += dd.y * nn.y;
             });
-            grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
+            St.done();
+            grid_reduce_then<1, kGridOwn>(c, acc, fl, out, f, [&] {
+                const double *fa, *fb;
+                if (!last) first_loop_vectors(it - 1, fa, fb);
+                else second_loop_vectors(hist_begin, fa, fb);
+                St.fetch(c, m2, fa, fb);
+            });
         }
         __syncthreads();                       // sc.alpha[] visible
         double gradient_overlap = 0.0;
         for (long long it = hist_begin; it <= hist_end; ++it) {                                 // :673-680
             const int cc = (int)((it - 1) % m);
             const double beta = sc.alpha[cc] - sc.rho[cc] * out[0];
-            const double* sp = a.S + (long long)cc * n;
+            const double *sp, *nxt;
+            second_loop_vectors(it, sp, nxt);
             const bool last = (it == hist_end);
-            const double* nxt = last ? a.g : (a.Y + (long long)((it) % m) * n);                 // Y of it+1, or g for :683-684
 #pragma unroll
             for (int j = 0; j < kGridOwn; ++j) acc[0][j] = 0.0;
+            St.wait();
             own_pairs_idx<OWN>(c, m2, [&](int j, int q, long long k) {
                 double2 dd = Dr.get(a.d, q, k);
-                const double2 ss = reinterpret_cast<const double2*>(sp)[k];
-                const double2 nn = reinterpret_cast<const double2*>(nxt)[k];
+                const double2 ss = St.get(0, q, sp, k);
+                const double2 nn = St.get(1, q, nxt, k);
                 dd.x += beta * ss.x; dd.y += beta * ss.y;
                 if (last) { dd.x = -dd.x; dd.y = -dd.y; }                                       // :683 negate!
                 Dr.set(a.d, q, k, dd, last);                                                    // the finished direction goes to memory
                 acc[0][j] += dd.x * nn.x; acc[0][j] += dd.y * nn.y;
             });
-            grid_reduce<1, kGridOwn>(c, acc, fl, out, f);
+            St.done();
+            grid_reduce_then<1, kGridOwn>(c, acc, fl, out, f, [&] {
+                if (!last) {
+                    const double *fa, *fb;
+                    second_loop_vectors(it + 1, fa, fb);
+                    St.fetch(c, m2, fa, fb);
+                }
+            });
             if (last) gradient_overlap = out[0];                                                // :684
         }
         if (!isfinite(gradient_overlap)) {                                                      // :687-688

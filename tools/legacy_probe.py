@@ -6,6 +6,8 @@ import torch
 import dzopt_b200 as dz
 import oracle as orc
 EF = dz.ExampleFunctions
+if os.environ.get('DZO_GRID_STAGE'):
+    dz.set_tuning('grid_stage', int(os.environ['DZO_GRID_STAGE']))
 if os.environ.get('DZO_GRID_BACKOFF'):
     dz.set_tuning('grid_ll_backoff', int(os.environ['DZO_GRID_BACKOFF']))
 if os.environ.get('DZO_GRID_LL'):
