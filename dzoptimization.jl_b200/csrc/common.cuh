@@ -216,12 +216,20 @@ DZO_DEVINL unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// Lane p < nranks of warp 0 watches rank p's flag; the warp leaves the loop as a whole (vote), so it reaches the shuffles
+// of the reductions that follow converged (grid_lbfgs.cuh: per-lane exits from a poll loop cost 3 us per reduction there).
 DZO_DEVINL void peer_wait(const unsigned long long* local_flags, int nranks, unsigned long long seq, int* timeout_flag) {
-    if (nranks > 1 && threadIdx.x < nranks) {
+    if (nranks > 1 && threadIdx.x < 32) {
         const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(local_flags + threadIdx.x) < seq) {
+        for (;;) {
+            const bool ok = ((int)threadIdx.x >= nranks) || (ld_acquire_sys(local_flags + threadIdx.x) >= seq);
+            if (__all_sync(0xffffffffu, ok)) break;
             __nanosleep(64);
-            if (global_timer_ns() - t0 > kPeerTimeoutNs) { atomicExch(timeout_flag, 1); break; }
+            const bool give_up = (global_timer_ns() - t0 > kPeerTimeoutNs);
+            if (__any_sync(0xffffffffu, give_up)) {
+                if (threadIdx.x == 0) atomicExch(timeout_flag, 1);
+                break;
+            }
         }
     }
     __syncthreads();
