@@ -407,6 +407,37 @@ static __global__ void vec_rosenbrock_gradient_kernel(const double* x, long long
 }
 
 // ============================================================================= n^2 sweeps
+// cache operators of the update sweep's streaming H accesses (compile-time A/B knobs of tools/build_variant.sh; measured at
+// n = 16384, fraction of the copy peak: loads __ldcs 0.943, __ldcg 0.949, __ldlu 0.948, plain 0.930 (with plain stores);
+// stores __stcs 0.943, __stcg 0.942, __stwt 0.943, plain 0.919 -- profiles/r02_update_sweep_cache_operators.jsonl)
+#ifndef DZO_SWEEP_LD
+#define DZO_SWEEP_LD 1      // 0 __ldcs, 1 __ldcg, 2 plain, 3 __ldlu
+#endif
+#ifndef DZO_SWEEP_ST
+#define DZO_SWEEP_ST 0      // 0 __stcs, 1 plain, 2 __stcg, 3 __stwt
+#endif
+DZO_DEVINL double2 sweep_ld(const double2* p) {
+#if DZO_SWEEP_LD == 1
+    return __ldcg(p);
+#elif DZO_SWEEP_LD == 2
+    return *p;
+#elif DZO_SWEEP_LD == 3
+    return __ldlu(p);
+#else
+    return __ldcs(p);
+#endif
+}
+DZO_DEVINL void sweep_st(double2* p, double2 v) {
+#if DZO_SWEEP_ST == 1
+    *p = v;
+#elif DZO_SWEEP_ST == 2
+    __stcg(p, v);
+#elif DZO_SWEEP_ST == 3
+    __stwt(p, v);
+#else
+    __stcs(p, v);
+#endif
+}
 // A sweep CTA has blockDim.x in {32, 64, 128, 256} threads, each owning two adjacent rows: the host picks
 // the size so that even a thin row slab (row-sharded mode) yields enough tiles to fill the GPU.
 constexpr int kSweepMaxThreads = 256;
@@ -586,13 +617,13 @@ static __global__ void __launch_bounds__(kSweepMaxThreads) update_gemv_kernel(Sw
             double2 h[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                h[u] = __ldcs(reinterpret_cast<const double2*>(base + (long long)(j + u) * a.ld));
+                h[u] = sweep_ld(reinterpret_cast<const double2*>(base + (long long)(j + u) * a.ld));
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const double sj = ss[j + u], tj = st[j + u], gj = sg[j + u];
                 h[u].x = h[u].x + (delta * (si0 * sj) - (ti0 * sj + si0 * tj));   // :882-884
                 h[u].y = h[u].y + (delta * (si1 * sj) - (ti1 * sj + si1 * tj));
-                __stcs(reinterpret_cast<double2*>(base + (long long)(j + u) * a.ld), h[u]);
+                sweep_st(reinterpret_cast<double2*>(base + (long long)(j + u) * a.ld), h[u]);
                 acc0 += h[u].x * gj;                                               // :958-960
                 acc1 += h[u].y * gj;
             }
