@@ -1238,6 +1238,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "riesz_esplit")) { g_tuning.riesz_esplit = value; return DZO_OK; }
     if (!strcmp(key, "riesz_pair")) { g_tuning.riesz_pair = value; return DZO_OK; }
     if (!strcmp(key, "riesz_threads")) { g_tuning.riesz_threads = value; return DZO_OK; }
+    if (!strcmp(key, "riesz_bar")) { g_tuning.riesz_bar = value; return DZO_OK; }
     if (!strcmp(key, "warp_search")) { g_tuning.warp_search = value; return DZO_OK; }
     if (!strcmp(key, "grid_ll")) { g_tuning.grid_ll = value; return DZO_OK; }
     if (!strcmp(key, "grid_stage")) { g_tuning.grid_stage = value; return DZO_OK; }

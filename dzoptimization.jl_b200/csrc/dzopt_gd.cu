@@ -36,6 +36,7 @@ struct dzo_gd {
     int n_e_items = 0;
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
+    unsigned long long* bar = nullptr;
     int esplit = 2, gcnt_off = 0, ecnt_stride = 0, espec = 0;
     int2* g_jobs = nullptr;
     int n_g_jobs = 0, gvariant = 0;
@@ -49,7 +50,7 @@ struct dzo_gd {
 static void free_gd(dzo_gd* o) {
     if (!o) return;
     cudaSetDevice(o->device);
-    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter, o->rbcnt, o->prof, o->g_jobs,
+    void* ptrs[] = {o->x, o->g, o->d, o->dx, o->dg, o->ctrl, o->segE, o->rowE, o->segG, o->fbox, o->e_items, o->counter, o->rbcnt, o->prof, o->g_jobs, o->bar,
                     o->f, o->df, o->L, o->iter, o->term};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -118,6 +119,7 @@ struct RieszWork {
     int n_e_items = 0;
     unsigned* counter = nullptr;
     unsigned* rbcnt = nullptr;
+    unsigned long long* bar = nullptr;
     int esplit = 2, gcnt_off = 0, ecnt_stride = 0, espec = 0;
     int2* g_jobs = nullptr;
     int n_g_jobs = 0, gvariant = 0;
@@ -140,6 +142,10 @@ struct RieszWork {
         gcnt_off = 2 * ecnt_stride;
         DZO_TRY(dmalloc(&rbcnt, (size_t)3 * ecnt_stride));   // items finished per row block: energy probe 0 | probe 1 | gradient
         DZO_CUDA(cudaMemset(rbcnt, 0, (size_t)3 * ecnt_stride * sizeof(unsigned)));
+        if (g_tuning.riesz_bar) {
+            DZO_TRY(dmalloc(&bar, riesz_bar_bytes() / sizeof(unsigned long long)));
+            DZO_CUDA(cudaMemset(bar, 0, riesz_bar_bytes()));
+        }
         DZO_TRY(dmalloc(&segG, (size_t)nseg * N * dim));
         DZO_TRY(dmalloc(&fbox, 4));
         DZO_TRY(dmalloc(&counter, 1));
@@ -167,15 +173,15 @@ struct RieszWork {
         return DZO_OK;
     }
     void release() {
-        void* ptrs[] = {segE, rowE, segG, fbox, e_items, counter, rbcnt, g_jobs};
+        void* ptrs[] = {segE, rowE, segG, fbox, e_items, counter, rbcnt, g_jobs, bar};
         for (void* p : ptrs)
             if (p) cudaFree(p);
-        segE = rowE = segG = fbox = nullptr; e_items = nullptr; counter = nullptr; rbcnt = nullptr; g_jobs = nullptr;
+        segE = rowE = segG = fbox = nullptr; e_items = nullptr; counter = nullptr; rbcnt = nullptr; g_jobs = nullptr; bar = nullptr;
     }
     void fill(RieszGdArgs& a) const {
         a.segE = segE; a.rowE = rowE; a.segG = segG; a.e_items = e_items; a.n_e_items = n_e_items;
         a.counter = counter; a.fbox = fbox; a.rbcnt = rbcnt; a.dscale = 1.0; a.esplit = esplit; a.gcnt_off = gcnt_off;
-        a.ecnt_stride = ecnt_stride; a.espec = espec;
+        a.ecnt_stride = ecnt_stride; a.espec = espec; a.bar = bar;
         a.g_jobs = g_jobs; a.n_g_jobs = n_g_jobs; a.gvariant = gvariant;
     }
     int launch(RieszGdArgs& a, cudaStream_t stream) const {
@@ -191,7 +197,7 @@ static RieszGdArgs riesz_args(const dzo_gd* o, int mode, int k) {
     a.x = o->x; a.g = o->g; a.d = o->d; a.dx = o->dx; a.dg = o->dg;
     a.segE = o->segE; a.rowE = o->rowE; a.segG = o->segG; a.e_items = o->e_items; a.n_e_items = o->n_e_items;
     a.ctrl = o->ctrl; a.counter = o->counter; a.fbox = o->fbox; a.rbcnt = o->rbcnt; a.dscale = 1.0; a.esplit = o->esplit; a.gcnt_off = o->gcnt_off;
-    a.ecnt_stride = o->ecnt_stride; a.espec = o->espec;
+    a.ecnt_stride = o->ecnt_stride; a.espec = o->espec; a.bar = o->bar;
     a.g_jobs = o->g_jobs; a.n_g_jobs = o->n_g_jobs; a.gvariant = o->gvariant;
     a.N = (int)(o->n / o->dim); a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.max_increases = o->max_increases;
     a.ksteps = k; a.mode = mode;
@@ -263,7 +269,7 @@ int dzo_gd_create(dzo_gd** out, int objective, int constraint, int64_t obj_param
         if ((rc = w.init((int)(n / obj_param), (int)obj_param, device))) { w.release(); return bail(rc); }
         o->segE = w.segE; o->rowE = w.rowE; o->segG = w.segG; o->fbox = w.fbox; o->e_items = w.e_items;
         o->n_e_items = w.n_e_items; o->counter = w.counter; o->rbcnt = w.rbcnt; o->esplit = w.esplit; o->gcnt_off = w.gcnt_off; o->grid = w.grid;
-        o->ecnt_stride = w.ecnt_stride; o->espec = w.espec; o->nt = w.nt;
+        o->ecnt_stride = w.ecnt_stride; o->espec = w.espec; o->nt = w.nt; o->bar = w.bar;
         o->g_jobs = w.g_jobs; o->n_g_jobs = w.n_g_jobs; o->gvariant = w.gvariant;
     }
     if (!o->small && objective == DZO_OBJ_ROSENBROCK) {       // one 8-CTA cluster up to n = DZO_TREE_BLOCK, the whole grid above

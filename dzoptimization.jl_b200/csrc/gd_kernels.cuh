@@ -50,6 +50,8 @@ struct RieszGdArgs {
     int esplit;                   // 1: energy items of 32 rows x 128 sources, one lane per row; 2: 16 rows, two lanes per row
     int gcnt_off;                 // offset of the gradient counters inside rbcnt
     int ecnt_stride;              // offset of the second probe's energy counters inside rbcnt (paired evaluations)
+    unsigned long long* bar;      // flag-word barrier of the k-step mode (null: cooperative-groups grid.sync everywhere):
+                                  //   [kRieszBarStride CTAs][kRieszBarStride sources] arrival counters, then the running count
     int espec;                    // 1: the bracketing search evaluates the probe it needs and the one it will most likely
                                   //    need next in ONE phase (paired evaluation; esplit = 1 only)
     double dscale;                // the direction actually used is dscale * dir[e] (1.0, or alpha with dir = g: see mode 0)
@@ -90,6 +92,54 @@ DZO_DEVINL void riesz_prof_mark(const RieszGdArgs& a, int id) {
 #endif
 constexpr int kRieszBatch = DZO_RIESZ_BATCH;            // energy pair terms whose sqrt / reciprocal chains run interleaved
 constexpr int kRieszGradBatch = DZO_RIESZ_GRAD_BATCH;   // same for the gradient (sqrt, reciprocal, division per term)
+
+// Grid-wide barrier of the k-step mode without an atomic counter (round 2; the same idea as the flagged lines of
+// grid_lbfgs.cuh; tuning knob "riesz_bar", OFF by default: measured 4 % slower than grid.sync() on config 5 -- where a
+// reduction's VALUES have to travel anyway the inboxes win, for a bare barrier one atomic counter is cheaper): every CTA owns an inbox of 64-bit arrival counters, one per CTA of the grid.  Arriving = storing the
+// barrier's running number into MY word of every CTA's inbox (relaxed stores behind __syncthreads + one fence per lane of
+// warp 0, so every thread's writes of the phase are visible first); waiting = warp 0 polling its own inbox (relaxed
+// loads, warp-uniform exit) until every word has reached the number, then a fence (acquire side: it also drops the SM's
+// stale L1 lines), then __syncthreads.  No word
+// is written by two CTAs and no line is polled by two: nothing serialises in an L2 slice the way one shared counter does.
+// The running number lives behind the inboxes and survives across launches (64 bits: no wrap).
+constexpr int kRieszBarStride = 192;                     // CTAs the barrier buffer is laid out for (a B200 runs 148)
+struct RieszBar {
+    cg::grid_group g;
+    unsigned long long* base;                            // null: g.sync()
+    unsigned long long seq;
+    int nctas, cta;
+    DZO_DEVINL void sync() {
+        if (base == nullptr) { g.sync(); return; }
+        seq += 1;
+        __syncthreads();                                     // every thread's writes of the phase happen before ...
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            __threadfence();                                 // ... this fence (cumulative), which orders them before the arrival words
+            for (int dst = lane; dst < nctas; dst += 32)
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(base + (size_t)dst * kRieszBarStride + cta), "l"(seq) : "memory");
+            const unsigned long long* mine = base + (size_t)cta * kRieszBarStride;
+            unsigned long long t0 = 0;
+            for (unsigned spins = 1;; ++spins) {
+                bool ok = true;
+                for (int src = lane; src < nctas; src += 32) {
+                    unsigned long long v;
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + src) : "memory");
+                    ok &= (v >= seq);
+                }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if ((spins & 1023u) == 0u) {                 // a grid that lost a CTA must not hang the GPU
+                    const unsigned long long now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    if (__any_sync(0xffffffffu, now - t0 > 5000000000ull)) break;
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    DZO_DEVINL unsigned long long* count_cell() const { return base + (size_t)kRieszBarStride * kRieszBarStride; }
+};
+inline size_t riesz_bar_bytes() { return sizeof(unsigned long long) * ((size_t)kRieszBarStride * kRieszBarStride + 8); }
 
 // NT = threads per CTA.  512 (default): 16 warps of up to 128 registers, so eight energy / four gradient pair terms run
 // interleaved per lane -- one energy evaluation is 2112 warp items, i.e. at most ONE per warp on either CTA size, and what
@@ -342,7 +392,7 @@ struct RieszDev {
 
     // `epar` counts the evaluation PHASES of this launch (identical on every CTA); its parity selects the rowE buffers, so
     // a CTA that is still reducing phase k cannot be overtaken by the row stores of phase k+1.
-    static DZO_DEVINL double energy(const RieszGdArgs& a, cg::grid_group& grid, int& epar, const double* dir, double alpha, int pmode,
+    static DZO_DEVINL double energy(const RieszGdArgs& a, RieszBar& grid, int& epar, const double* dir, double alpha, int pmode,
                                     double* wsm, double* sm) {
         const int par = epar & 1;
         epar += 1;
@@ -358,7 +408,7 @@ struct RieszDev {
         return f[0];
     }
     // f(alpha0) and f(alpha1) in one phase: one grid barrier and one (two-value) tree for both
-    static DZO_DEVINL void energy_pair(const RieszGdArgs& a, cg::grid_group& grid, int& epar, const double* dir, double alpha0,
+    static DZO_DEVINL void energy_pair(const RieszGdArgs& a, RieszBar& grid, int& epar, const double* dir, double alpha0,
                                        double alpha1, double* wsm, double* sm, double& f0v, double& f1v) {
         const int par = epar & 1;
         epar += 1;
@@ -655,7 +705,7 @@ struct RieszDev {
     }
 
     // QuadraticLineSearch (:191-216) over find_three_point_bracket (:49-172), first trial step t1
-    static DZO_DEVINL void line_search(const RieszGdArgs& a, cg::grid_group& grid, int& epar, const double* dir, double f0, double t1,
+    static DZO_DEVINL void line_search(const RieszGdArgs& a, RieszBar& grid, int& epar, const double* dir, double f0, double t1,
                                        double sign, double* wsm, double* sm, double& t_best, double& f_best,
                                        long long& evals) {
         double x1 = 0.0, f1 = f0, x2 = 0.0, f2 = f0;
@@ -817,7 +867,11 @@ static __global__ void __launch_bounds__(NT, 1) riesz_gd_kernel(RieszGdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);          // 2 x 132 doubles: tree reduction scratch
     double* wsm = sm + 272;                                    // (NT / 32) warps x 128 x DIM staging
-    cg::grid_group grid = cg::this_grid();
+    // mode 0 (k step! calls) synchronises through the flag-word barrier when the host provides its buffer; every other
+    // mode keeps grid.sync().  Every CTA reads the running count before its first barrier; the leader stores it back at
+    // the end (it cannot get there before every CTA has arrived at every barrier, i.e. has read the count).
+    RieszBar grid{cg::this_grid(), (a.mode == 0 && (int)gridDim.x <= kRieszBarStride) ? a.bar : nullptr, 0ull, (int)gridDim.x, (int)blockIdx.x};
+    if (grid.base != nullptr) grid.seq = __ldcg(grid.count_cell());
     using R = RieszDev<DIM, NT>;
     const long long n = (long long)a.N * DIM;
     const long long gtid = (long long)blockIdx.x * NT + threadIdx.x, gsize = (long long)gridDim.x * NT;
@@ -1029,6 +1083,7 @@ static __global__ void __launch_bounds__(NT, 1) riesz_gd_kernel(RieszGdArgs a) {
         a.dscale = alpha;
         riesz_prof_mark(a, 11);
     }
+    if (grid.base != nullptr && leader) *grid.count_cell() = grid.seq;
 }
 
 inline size_t riesz_gd_smem(int dim, int nt) {

@@ -75,6 +75,9 @@ struct Tuning {
     int warp_search = 1;      // O(n) stage of step! for 32 < n <= 512: 1 = one warp per problem (warp_search.cuh), 0 = 8-CTA cluster
     int riesz_threads = 512;  // threads per CTA of the cooperative Riesz kernel (512: 128 registers, 8 / 4 pair terms in flight per
                               // lane; 1024: 64 registers, 4 / 2); read when an optimizer is created
+    int riesz_bar = 0;        // cooperative Riesz kernel, k-step mode: 1 = flag-word barrier (per-CTA inboxes) instead of grid.sync().
+                              // Measured SLOWER (0.152-0.157 vs 0.146-0.151 ms per GD step!; a pure barrier of 148 CTAs is
+                              // cheaper through one atomic counter than through 148 x 148 words), so off; read at create time
     int riesz_pair = 1;       // Riesz line search: evaluate the probe it needs and the one it will most likely need next in one
                               // phase (the second rides in warps the first leaves idle); read when an optimizer is created
     int riesz_profile = 0;    // 1: the cooperative Riesz kernel logs (phase id, %globaltimer) events of its leader thread

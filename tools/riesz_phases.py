@@ -7,6 +7,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import dzopt_b200 as dz
 import oracle as orc
 EF = dz.ExampleFunctions
+if os.environ.get('DZO_RIESZ_BAR'):
+    dz.set_tuning('riesz_bar', int(os.environ['DZO_RIESZ_BAR']))
 if os.environ.get('DZO_RIESZ_THREADS'):
     dz.set_tuning('riesz_threads', int(os.environ['DZO_RIESZ_THREADS']))
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
