@@ -328,7 +328,7 @@ def test_errors(gpu):
 
 
 # ----------------------------------------------------------------------------- degenerate starts (state, never an error)
-@pytest.mark.parametrize("n,batched", [(16, True), (2048, False)])
+@pytest.mark.parametrize("n,batched", [(16, True), (2048, False), (100, False), (300, False)])
 def test_degenerate_starts(gpu, orc, n, batched):
     dz = gpu
     EF = dz.ExampleFunctions
@@ -432,11 +432,11 @@ def test_batched_awkward_inputs(gpu, orc, n, L0):
     _compare_state(opt, ref, True, "fused")
 
 
+@pytest.mark.parametrize("n", [2050, 70, 260, 700])     # cluster / one warp per problem (1, 8 virtual warps) / cluster
 @pytest.mark.parametrize("L0", [1.0, 1e-12, 1e6, 1e-300])
-def test_large_awkward_inputs(gpu, orc, L0):
+def test_large_awkward_inputs(gpu, orc, L0, n):
     dz = gpu
     EF = dz.ExampleFunctions
-    n = 2050
     u = orc.pcg_fill(n, 99)
     pick = (orc.pcg_fill(n, 98) * 40).astype(int)
     special = np.array([0.0, -0.0, 1.0, -1.0, 1e-8, -1e-8, 1e3, -1e3, 1e-160, 1e-300])
