@@ -191,6 +191,14 @@ static int dmalloc_on(cudaStream_t stream, T** p, size_t count, bool pooled = tr
 }
 #define dmalloc(p, count) dmalloc_on(o->own_stream, p, count, o->pooled)
 
+// problem-major matrices [p][e] -> batch-innermost [e][p] (set_state of the generic batched kernel)
+static __global__ void h_to_batch_inner_kernel(const double* in, double* out, long long nn, long long batch) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // t = e * batch + p: coalesced stores
+    if (t >= nn * batch) return;
+    const long long e = t / batch, p = t - e * batch;
+    out[t] = in[p * nn + e];
+}
+
 // any(isnan(f)) on the device: 4 bytes come back instead of the whole objective vector
 static __global__ void any_nan_kernel(const double* f, long long count, int* flag) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,6 +265,7 @@ static int generic_launch(dzo_bfgs* o, int mode, int k, double L0) {
     a.iter = o->iter; a.type = o->type; a.term = o->term; a.n = (int)o->n; a.dim = (int)o->dim;
     a.objective = o->objective; a.sphere = (o->constraint == DZO_CONSTRAINT_SPHERE); a.ksteps = k; a.batch = o->batch;
     a.initial_step_length = L0; a.mode = mode;
+    a.hs = o->batch;                          // batch-innermost inverse Hessians (gd_batched.cuh)
     bfgs_generic_kernel<<<(unsigned)((o->batch + 63) / 64), 64, 0, o->stream>>>(a);
     DZO_CUDA(cudaGetLastError());
     return DZO_OK;
@@ -762,6 +771,13 @@ int dzo_bfgs_get_inverse_hessian(dzo_bfgs* o, int64_t problem, double* out) {
             return DZO_OK;
         }
     }
+    if (o->small && o->objective != DZO_OBJ_ROSENBROCK) {
+        // generic batched kernel: element e of problem p lives at H[e * batch + p]
+        DZO_TRY(use_device(o->device));
+        DZO_CUDA(cudaMemcpy2DAsync(out, 8, o->H + problem, (size_t)o->batch * 8, 8, (size_t)o->n * o->n, cudaMemcpyDeviceToHost, o->stream));
+        DZO_CUDA(cudaStreamSynchronize(o->stream));
+        return DZO_OK;
+    }
     if (o->small) return read_back(o, out, o->H + (size_t)problem * o->n * o->n, (size_t)o->n * o->n * 8);
     return read_back(o, out, o->H + (size_t)problem * (size_t)o->rows * (size_t)o->n, (size_t)o->rows * (size_t)o->n * 8);
 }
@@ -894,6 +910,16 @@ int dzo_bfgs_set_state(dzo_bfgs* o, const double* point, const double* inverse_h
     DZO_CUDA(cudaMemcpyAsync(o->dx, delta_point, nb, cudaMemcpyHostToDevice, o->stream));       // :853
     DZO_CUDA(cudaMemcpyAsync(o->dg, delta_gradient, nb, cudaMemcpyHostToDevice, o->stream));    // :854
     if (o->small) {
+        if (o->objective != DZO_OBJ_ROSENBROCK) {
+            // generic batched kernel: scatter the caller's problem-major matrices into the batch-innermost layout
+            double* tmp = nullptr;
+            DZO_TRY(dmalloc_on(o->stream, &tmp, (size_t)o->n * o->n * (size_t)o->batch, o->pooled));
+            DZO_CUDA(cudaMemcpyAsync(tmp, inverse_hessian, nb * (size_t)o->n, cudaMemcpyHostToDevice, o->stream));
+            const long long total = (long long)o->n * o->n * o->batch;
+            h_to_batch_inner_kernel<<<(unsigned)((total + 255) / 256), 256, 0, o->stream>>>(tmp, o->H, (long long)o->n * o->n, o->batch);
+            DZO_CUDA(cudaGetLastError());
+            if (o->pooled) cudaFreeAsync(tmp, o->stream); else { cudaStreamSynchronize(o->stream); cudaFree(tmp); }
+        } else
         DZO_CUDA(cudaMemcpyAsync(o->H, inverse_hessian, nb * (size_t)o->n, cudaMemcpyHostToDevice, o->stream));  // :832
         DZO_CUDA(cudaMemcpyAsync(o->L, last_step_length, (size_t)o->batch * 8, cudaMemcpyHostToDevice, o->stream));
         DZO_CUDA(cudaMemcpyAsync(o->type, last_step_type, (size_t)o->batch * 4, cudaMemcpyHostToDevice, o->stream));

@@ -271,8 +271,13 @@ static __global__ void __launch_bounds__(128) gd_batched_kernel(GdBatchedArgs a)
 
 // ----------------------------------------------------------------------------- generic batched BFGS, one thread per problem
 // step!(::BFGSOptimizer) :891-994 for objectives the warp-resident kernels do not cover (Riesz energy with or
-// without the sphere constraint, n <= 32).  A literal transcription: the thread walks its own n x n inverse
-// Hessian in global memory.  Slow next to the hybrid kernel, but bitwise the sequential reference order.
+// without the sphere constraint, n <= 32).  A literal transcription, bitwise the sequential reference order.  The
+// inverse Hessians are stored BATCH-INNERMOST (element (i, j) of problem p at H[(i + j*n) * batch + p]): the threads of a
+// warp walk their matrices in lockstep, so every access is 32 consecutive doubles (round 2: with the problem-major layout
+// every thread streamed its own 4.6 KB matrix; 200 k problems of 8 points x 3: 9.05 -> 6.58 ms per step! call).  The
+// rank-2 update and d = H*g share one sweep (each d[i] still accumulates its columns in ascending order).  What is left
+// is the thread-per-problem line search itself (divergent probe counts, vectors in local memory): still "correct, not
+// tuned" next to the warp-resident Rosenbrock kernel.
 struct BfgsGenericArgs {
     double *x, *g, *d, *dx, *dg, *H, *f, *L;
     long long* iter;
@@ -282,6 +287,7 @@ struct BfgsGenericArgs {
     long long batch;
     double initial_step_length;
     int mode;   // 0 = steps, 1 = constructor, 2 = resume (recompute f, g, d = H*g)
+    long long hs;   // stride between consecutive elements of one problem's matrix: batch (batch-innermost) or 1 (problem-major)
 };
 
 static __global__ void __launch_bounds__(64) bfgs_generic_kernel(BfgsGenericArgs a) {
@@ -289,7 +295,8 @@ static __global__ void __launch_bounds__(64) bfgs_generic_kernel(BfgsGenericArgs
     if (p >= a.batch) return;
     SmallProblem P{a.n, a.dim > 0 ? a.dim : 1, a.objective, a.sphere};
     const int n = a.n;
-    double* H = a.H + p * n * n;
+    const long long hs = a.hs;
+    double* H = a.H + ((hs == 1) ? p * n * n : p);          // element (i, j) at H[(i + j * n) * hs]
     double x[kGdSmallMax], g[kGdSmallMax], d[kGdSmallMax], w[kGdSmallMax], ref[kGdSmallMax];
     for (int i = 0; i < n; ++i) x[i] = a.x[p * n + i];
     if (a.mode == 1 || a.mode == 2) {
@@ -302,13 +309,13 @@ static __global__ void __launch_bounds__(64) bfgs_generic_kernel(BfgsGenericArgs
         }
         if (a.mode == 1) {
             for (int j = 0; j < n; ++j)
-                for (int i = 0; i < n; ++i) H[i + j * n] = (i == j) ? 1.0 : 0.0;    // :781-783
+                for (int i = 0; i < n; ++i) H[(i + j * n) * hs] = (i == j) ? 1.0 : 0.0;    // :781-783
             for (int i = 0; i < n; ++i) { a.d[p * n + i] = g[i]; a.dx[p * n + i] = 0.0; a.dg[p * n + i] = 0.0; }   // :784
             a.L[p] = a.initial_step_length; a.iter[p] = 0; a.type[p] = DZO_STEP_NULL;
         } else {
             for (int i = 0; i < n; ++i) {                          // :833-836 d = H*g
                 double acc = 0.0;
-                for (int j = 0; j < n; ++j) acc += H[i + j * n] * g[j];
+                for (int j = 0; j < n; ++j) acc += H[(i + j * n) * hs] * g[j];
                 a.d[p * n + i] = acc;
             }
         }
@@ -346,27 +353,27 @@ static __global__ void __launch_bounds__(64) bfgs_generic_kernel(BfgsGenericArgs
             for (int i = 0; i < n; ++i) overlap += d[i] * dgv[i];
             const double inv_overlap = 1.0 / overlap;
             for (int i = 0; i < n; ++i) d[i] *= inv_overlap;       // :874
-            for (int i = 0; i < n; ++i) {                          // :875
-                double acc = 0.0;
-                for (int j = 0; j < n; ++j) acc += H[i + j * n] * dgv[j];
-                tv[i] = acc;
+            for (int i = 0; i < n; ++i) tv[i] = 0.0;               // :875, column by column: tv[i] still sums j ascending
+            for (int j = 0; j < n; ++j) {
+                const double vj = dgv[j];
+                for (int i = 0; i < n; ++i) tv[i] += H[(i + j * n) * hs] * vj;
             }
             double dot = 0.0;
             for (int i = 0; i < n; ++i) dot += dgv[i] * tv[i];
             const double delta_norm = alpha * overlap + dot;       // :876
-            for (int j = 0; j < n; ++j) {                          // :878-886
-                const double sj = d[j], tj = tv[j];
-                for (int i = 0; i < n; ++i) H[i + j * n] += (delta_norm * (d[i] * sj) - (tv[i] * sj + d[i] * tj));
-            }
-            for (int i = 0; i < n; ++i) {                          // :958-960 (into w, then d)
-                double acc = 0.0;
-                for (int j = 0; j < n; ++j) acc += H[i + j * n] * g[j];
-                w[i] = acc;
+            for (int i = 0; i < n; ++i) w[i] = 0.0;
+            for (int j = 0; j < n; ++j) {                          // :878-886 fused with :958-960 (d = H*g, into w)
+                const double sj = d[j], tj = tv[j], gj = g[j];
+                for (int i = 0; i < n; ++i) {
+                    const double h = H[(i + j * n) * hs] + (delta_norm * (d[i] * sj) - (tv[i] * sj + d[i] * tj));
+                    H[(i + j * n) * hs] = h;
+                    w[i] += h * gj;
+                }
             }
             for (int i = 0; i < n; ++i) d[i] = w[i];
         } else {
             for (int j = 0; j < n; ++j)
-                for (int i = 0; i < n; ++i) H[i + j * n] = (i == j) ? 1.0 : 0.0;    // :981
+                for (int i = 0; i < n; ++i) H[(i + j * n) * hs] = (i == j) ? 1.0 : 0.0;    // :981
             for (int i = 0; i < n; ++i) d[i] = g[i];               // :984-986
         }
     }
