@@ -255,10 +255,17 @@ struct RieszDev {
             if (last) {
                 __threadfence();
                 if (j < a.N) {
+                    // segments below row j in ascending order, eight loads in flight at a time (see gradient_row)
+                    const int ns = (j + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
                     double ej = 0.0;
-                    for (int s0 = 0; s0 < j; s0 += DZO_RIESZ_SEG) {
-                        const double seg = __ldcg(&segE[(long long)(s0 / DZO_RIESZ_SEG) * a.N + j]);
-                        ej = (s0 == 0) ? seg : ej + seg;
+                    constexpr int CB = 8;
+                    for (int s0 = 0; s0 < ns; s0 += CB) {
+                        double v[CB];
+#pragma unroll
+                        for (int u = 0; u < CB; ++u) v[u] = (s0 + u < ns) ? __ldcg(&segE[(long long)(s0 + u) * a.N + j]) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < CB; ++u)
+                            if (s0 + u < ns) ej = (s0 + u == 0) ? v[u] : ej + v[u];
                     }
                     a.rowE[(long long)(2 * par + pr) * a.N + j] = ej;
                 }
@@ -427,13 +434,20 @@ struct RieszDev {
     // ---- riesz_gradient! (:47-83) at the stored points + tangent projection (:361-374)
     // As for the energy, the warp finishing the last segment item of a 32-row block combines that block's rows
     // (ascending segment order), projects, and writes g (and dg = g_new - g_old when with_delta).
+    // RP row blocks per item.  RP = 2 (an item stages its 128 sources once and runs two rows per lane side by side: 2048
+    // items for the 2368 warps of 512-thread CTAs instead of 4096) was measured and is NOT used: a double item took 50 us
+    // where two single items took 43 -- the pair loops are pipe-bound, not latency-bound, and the extra predicates cost
+    // more than the shared staging saves (profiles/README.md).
     static DZO_DEVINL void gradient_segments(const RieszGdArgs& a, double* wsm, bool with_delta) {
+        constexpr int RP = 1;
+        constexpr int GBR = GB;                                      // sources per batch and row: RP * GBR chains per lane
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         double* buf = wsm + warp * (DZO_RIESZ_SEG * DIM);
         const int nseg = (a.N + DZO_RIESZ_SEG - 1) / DZO_RIESZ_SEG;
         const int nrb = (a.N + 31) / 32;
-        for (int idx = blockIdx.x + gridDim.x * warp; idx < nrb * nseg; idx += gridDim.x * W) {
-            const int rb = idx / nseg, s = idx - rb * nseg;
+        const int nrbp = (nrb + RP - 1) / RP;
+        for (int idx = blockIdx.x + gridDim.x * warp; idx < nrbp * nseg; idx += gridDim.x * W) {
+            const int rbp = idx / nseg, s = idx - rbp * nseg;
             const int i0 = s * DZO_RIESZ_SEG;
             const int cnt = min(DZO_RIESZ_SEG, a.N - i0);
             __syncwarp();
@@ -441,73 +455,97 @@ struct RieszDev {
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) buf[q * DIM + k] = a.x[(long long)(i0 + q) * DIM + k];
             __syncwarp();
-            const int j = rb * 32 + lane;
-            if (j < a.N) {
-                double xj[DIM], part[DIM];
+            int j[RP];
+            bool row[RP];
+            double xj[RP][DIM], part[RP][DIM];
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) { xj[k] = a.x[(long long)j * DIM + k]; part[k] = 0.0; }
-                int i = 0;
-                for (; i + GB <= cnt; i += GB) {
-                    double ds[GB], c[GB];
-                    bool safe = true;
+            for (int r = 0; r < RP; ++r) {
+                j[r] = (rbp * RP + r) * 32 + lane;
+                row[r] = (rbp * RP + r) < nrb && j[r] < a.N;
 #pragma unroll
-                    for (int u = 0; u < GB; ++u) {
+                for (int k = 0; k < DIM; ++k) { xj[r][k] = row[r] ? a.x[(long long)j[r] * DIM + k] : 0.0; part[r][k] = 0.0; }
+            }
+            int i = 0;
+            for (; i + GBR <= cnt; i += GBR) {
+                double ds[RP][GBR], c[RP][GBR];
+                bool safe = true;
+#pragma unroll
+                for (int r = 0; r < RP; ++r)
+#pragma unroll
+                    for (int u = 0; u < GBR; ++u) {
                         double dist_sq = 0.0;
 #pragma unroll
                         for (int k = 0; k < DIM; ++k) {
-                            const double dist = buf[(i + u) * DIM + k] - xj[k];
+                            const double dist = buf[(i + u) * DIM + k] - xj[r][k];
                             dist_sq += dist * dist;
                         }
-                        ds[u] = (i0 + i + u == j) ? 1.0 : dist_sq;             // the skipped self term (:55, :69) rides along as 1.0
-                        safe &= ieee_fast_safe(ds[u]);
+                        // the skipped self term (:55, :69) and the rows past the end ride along as 1.0
+                        ds[r][u] = (!row[r] || i0 + i + u == j[r]) ? 1.0 : dist_sq;
+                        safe &= ieee_fast_safe(ds[r][u]);
                     }
-                    if (safe) {
+                if (safe) {
 #pragma unroll
-                        for (int u = 0; u < GB; ++u) {
-                            const double inv_dist = ieee_fast_rcp(ieee_fast_sqrt(ds[u]));   // :61
-                            c[u] = ieee_fast_div(inv_dist, ds[u]);                          // :62
+                    for (int r = 0; r < RP; ++r)
+#pragma unroll
+                        for (int u = 0; u < GBR; ++u) {
+                            const double inv_dist = ieee_fast_rcp(ieee_fast_sqrt(ds[r][u]));   // :61
+                            c[r][u] = ieee_fast_div(inv_dist, ds[r][u]);                          // :62
                         }
-                    } else {
+                } else {
 #pragma unroll
-                        for (int u = 0; u < GB; ++u) c[u] = ieee_inv_cubed_operators(ds[u]);
-                    }
+                    for (int r = 0; r < RP; ++r)
 #pragma unroll
-                    for (int u = 0; u < GB; ++u) {
-                        if (i0 + i + u == j) continue;                         // :55, :69 (i != j)
+                        for (int u = 0; u < GBR; ++u) c[r][u] = ieee_inv_cubed_operators(ds[r][u]);
+                }
+#pragma unroll
+                for (int r = 0; r < RP; ++r)
+#pragma unroll
+                    for (int u = 0; u < GBR; ++u) {
+                        if (!row[r] || i0 + i + u == j[r]) continue;           // :55, :69 (i != j)
 #pragma unroll
                         for (int k = 0; k < DIM; ++k) {
-                            const double dist = buf[(i + u) * DIM + k] - xj[k];
-                            part[k] += dist * c[u];                            // :65
+                            const double dist = buf[(i + u) * DIM + k] - xj[r][k];
+                            part[r][k] += dist * c[r][u];                      // :65
                         }
                     }
-                }
-                for (; i < cnt; ++i) {
-                    if (i0 + i == j) continue;
+            }
+            for (; i < cnt; ++i) {
+#pragma unroll
+                for (int r = 0; r < RP; ++r) {
+                    if (!row[r] || i0 + i == j[r]) continue;
                     double dist_sq = 0.0;
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) {
-                        const double dist = buf[i * DIM + k] - xj[k];
+                        const double dist = buf[i * DIM + k] - xj[r][k];
                         dist_sq += dist * dist;
                     }
                     const double inv_dist_cubed = ieee_inv_cubed_operators(dist_sq);
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) {
-                        const double dist = buf[i * DIM + k] - xj[k];
-                        part[k] += dist * inv_dist_cubed;
+                        const double dist = buf[i * DIM + k] - xj[r][k];
+                        part[r][k] += dist * inv_dist_cubed;
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < DIM; ++k) a.segG[((long long)s * a.N + j) * DIM + k] = part[k];
             }
+#pragma unroll
+            for (int r = 0; r < RP; ++r)
+                if (row[r])
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) a.segG[((long long)s * a.N + j[r]) * DIM + k] = part[r][k];
             __threadfence();
             __syncwarp();
-            unsigned last = 0;
-            if (lane == 0) last = (atomicAdd(&a.rbcnt[a.gcnt_off + rb], 1u) == (unsigned)nseg - 1u);
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {
-                __threadfence();
-                if (j < a.N) gradient_row(a, j, nseg, with_delta);
-                if (lane == 0) a.rbcnt[a.gcnt_off + rb] = 0;
+#pragma unroll
+            for (int r = 0; r < RP; ++r) {
+                const int rb = rbp * RP + r;
+                if (rb >= nrb) continue;                                       // uniform over the warp
+                unsigned last = 0;
+                if (lane == 0) last = (atomicAdd(&a.rbcnt[a.gcnt_off + rb], 1u) == (unsigned)nseg - 1u);
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    __threadfence();
+                    if (row[r]) gradient_row(a, j[r], nseg, with_delta);
+                    if (lane == 0) a.rbcnt[a.gcnt_off + rb] = 0;
+                }
             }
         }
     }
@@ -650,9 +688,23 @@ struct RieszDev {
             acc[k] = __ldcg(&a.segG[((long long)0 * a.N + j) * DIM + k]);
             xj[k] = a.x[(long long)j * DIM + k];
         }
-        for (int s = 1; s < nseg; ++s)
+        // segments in ascending order; eight segments' partials are requested before the first add (one loop iteration
+        // per segment made the warp that finishes a row block wait out an L2 round trip per segment -- 32 of them at
+        // N = 4096 -- while the grid barrier waited for it)
+        constexpr int CB = 8;
+        for (int s0 = 1; s0 < nseg; s0 += CB) {
+            double v[CB][DIM];
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) acc[k] += __ldcg(&a.segG[((long long)s * a.N + j) * DIM + k]);
+            for (int u = 0; u < CB; ++u)
+#pragma unroll
+                for (int k = 0; k < DIM; ++k)
+                    v[u][k] = (s0 + u < nseg) ? __ldcg(&a.segG[((long long)(s0 + u) * a.N + j) * DIM + k]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < CB; ++u)
+                if (s0 + u < nseg)
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) acc[k] += v[u][k];
+        }
         if (a.sphere) {
             double overlap = 0.0;
 #pragma unroll
