@@ -756,6 +756,22 @@ struct RieszDev {
         return __syncthreads_or(bad) == 0;
     }
 
+    // step_is_zero (all(dir == 0), :71-85) and !point_changed (all(x == x + alpha*dir), :73-80) from one set of loads
+    static DZO_DEVINL void first_checks(const RieszGdArgs& a, const double* dir, double alpha, bool& zero_step, bool& unchanged) {
+        int nonzero = 0, moved = 0;
+        for (int j = threadIdx.x; j < a.N; j += NT) {
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const double dd = a.dscale * dir[(long long)j * DIM + k];
+                const double xx = a.x[(long long)j * DIM + k];
+                nonzero |= !(dd == 0.0);
+                moved |= (xx != xx + alpha * dd);
+            }
+        }
+        zero_step = __syncthreads_or(nonzero) == 0;
+        unchanged = __syncthreads_or(moved) == 0;
+    }
+
     // QuadraticLineSearch (:191-216) over find_three_point_bracket (:49-172), first trial step t1
     static DZO_DEVINL void line_search(const RieszGdArgs& a, RieszBar& grid, int& epar, const double* dir, double f0, double t1,
                                        double sign, double* wsm, double* sm, double& t_best, double& f_best,
@@ -764,10 +780,11 @@ struct RieszDev {
         do {
             if (!isfinite(f0)) break;                                          // :64-66
             if (!isfinite(t1) || t1 == 0.0) break;                             // [GLUE]
-            if (all_points(a, dir, 0.0, 0.0, 0)) break;                        // :71-85
             double step = t1;
             bool small = false;
-            bool unchanged = all_points(a, dir, sign * step, 0.0, 1);
+            bool zero_step, unchanged;                                         // :71-85 and :73-80 in ONE pass over the points
+            first_checks(a, dir, sign * step, zero_step, unchanged);
+            if (zero_step) break;
             int cap = DZO_LINESEARCH_CAP;
             bool capped = false;
             while (unchanged) {                                                // :91-101
