@@ -24,6 +24,7 @@ struct BatchedArgs {
     long long batch;
     int ksteps;
     int prefetch_rounds;  // hybrid kernel: phase-2 rounds whose H tiles are pulled into L2 ahead of use
+    int tile;             // hybrid kernel: problems per warp (0 or 32: a full warp; smaller for batches of a few waves)
     unsigned char* hid;          // optional (may be null): hid[p] != 0 <=> H of problem p is the identity and its copy in
                                  //   HBM is stale (identity_matrix! :981 / :781-783 not materialised; hybrid kernel only)
     unsigned long long* stats;   // optional (may be null): HK_COUNT running step-kind counters

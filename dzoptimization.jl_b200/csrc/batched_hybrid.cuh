@@ -182,11 +182,14 @@ __global__ void __launch_bounds__(kHybridThreads, HybridCfg<N>::CTAS_PER_SM) bfg
     constexpr int NP = C::NP, PPR = C::PPR, SLOT = C::SLOT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     HybridSmem<N>& S = reinterpret_cast<HybridSmem<N>*>(smem_raw)[warp];
-    const long long p0 = ((long long)blockIdx.x * kHybridWarps + warp) * 32;  // first problem of this warp's tile
+    // A tile is A.tile <= 32 consecutive problems (32 for a large batch; the host shrinks it when the batch would fill the
+    // GPU's warp slots only a few times over, so that the last wave of warps is as full as the first)
+    const int tile = (A.tile > 0 && A.tile < 32) ? A.tile : 32;
+    const long long p0 = ((long long)blockIdx.x * kHybridWarps + warp) * tile;  // first problem of this warp's tile
     if (p0 >= A.batch) return;
     const long long p = p0 + lane;
-    const bool valid = p < A.batch;
-    const int nprob = (int)((A.batch - p0 < 32) ? (A.batch - p0) : 32);
+    const int nprob = (int)((A.batch - p0 < tile) ? (A.batch - p0) : tile);
+    const bool valid = lane < nprob;
     const bool lazy = (A.hid != nullptr);
 
     // A tile starts cold: everything it needs first is requested at once -- the three vectors as 16-byte asynchronous
@@ -477,6 +480,7 @@ __global__ void __launch_bounds__(kHybridThreads, HybridCfg<N>::CTAS_PER_SM) bfg
 
 template <int N>
 inline size_t hybrid_smem() { return sizeof(HybridSmem<N>) * kHybridWarps; }
+inline int hybrid_warps_per_sm(int n) { return n <= 16 ? 16 : 8; }      // CTAS_PER_SM * kHybridWarps
 
 // host side of the launch, instantiated in two translation units (batched_hybrid_tu_{a,b}.cu) so that ptxas works on the
 // sixteen kernels in parallel
@@ -490,7 +494,8 @@ inline cudaError_t hybrid_launch(const BatchedArgs& args, cudaStream_t stream, i
         if (e != cudaSuccess) return e;
         attr_set[device & 63] = true;
     }
-    const unsigned grid = (unsigned)((args.batch + 32 * kHybridWarps - 1) / (32 * kHybridWarps));
+    const int tile = (args.tile > 0 && args.tile < 32) ? args.tile : 32;
+    const unsigned grid = (unsigned)((args.batch + (long long)tile * kHybridWarps - 1) / ((long long)tile * kHybridWarps));
     bfgs_batched_hybrid_kernel<N><<<grid, kHybridThreads, smem, stream>>>(args);
     return cudaGetLastError();
 }

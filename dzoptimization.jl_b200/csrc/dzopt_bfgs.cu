@@ -91,6 +91,7 @@ struct dzo_bfgs {
     int64_t dim = 0, n = 0, batch = 0;
     bool small = false;  // batched warp-resident path (n <= DZO_SMALL_N_MAX), SEQUENTIAL order
     int lpp = 0;
+    int tile = 32;                          // batched hybrid kernel: problems per warp (see create_common)
     // optimizer fields (device)
     double *x = nullptr, *g = nullptr, *d = nullptr, *dx = nullptr, *dg = nullptr, *H = nullptr;
     double *f = nullptr, *L = nullptr;
@@ -224,6 +225,7 @@ static BatchedArgs batched_args(const dzo_bfgs* o, int ksteps) {
     A.f_host = o->f_host; A.term_host = o->term_host;
     A.n = (int)o->n; A.batch = o->batch; A.ksteps = ksteps; A.prefetch_rounds = g_tuning.batched_prefetch;
     A.hid = o->hid; A.stats = o->stats;
+    A.tile = o->tile;
     return A;
 }
 
@@ -543,6 +545,21 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
     if (!o) return fail(DZO_ERR_ALLOC, "out of memory");
     o->device = device; o->objective = objective; o->constraint = constraint; o->dim = obj_param;
     o->n = n; o->batch = batch; o->small = (n <= DZO_SMALL_N_MAX); o->lpp = pick_lpp(n);
+    o->tile = 32;
+    if (o->small && objective == DZO_OBJ_ROSENBROCK && hybrid_n(n) && g_tuning.batched_tile != 32) {
+        // problems per warp of the batched kernel: a batch that fills the resident warps of the GPU at most three times over
+        // is spread evenly over that many full waves (125 k problems: 2 waves of 27 instead of 1.65 waves of 32)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        const long long slots = (long long)sms * hybrid_warps_per_sm((int)n);
+        const long long tiles32 = (batch + 31) / 32;
+        const long long waves = (tiles32 + slots - 1) / slots;
+        if (g_tuning.batched_tile > 0) o->tile = g_tuning.batched_tile < 32 ? g_tuning.batched_tile : 32;
+        else if (waves <= 3) {
+            const long long t = (batch + waves * slots - 1) / (waves * slots);
+            o->tile = (int)(t < 1 ? 1 : (t > 32 ? 32 : t));
+        }
+    }
     o->rank = rank; o->nranks = nranks; o->rows = n / nranks; o->row0 = o->rows * rank;
     o->pooled = (nranks == 1);        // sharded handles use cudaMalloc: CUDA IPC cannot export pool memory
     if (nranks > kMaxPeers) { delete o; return fail(DZO_ERR_INVALID_ARGUMENT, "at most %d ranks", kMaxPeers); }
@@ -1265,6 +1282,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "riesz_pair")) { g_tuning.riesz_pair = value; return DZO_OK; }
     if (!strcmp(key, "riesz_threads")) { g_tuning.riesz_threads = value; return DZO_OK; }
     if (!strcmp(key, "riesz_bar")) { g_tuning.riesz_bar = value; return DZO_OK; }
+    if (!strcmp(key, "batched_tile")) { g_tuning.batched_tile = value; return DZO_OK; }
     if (!strcmp(key, "warp_search")) { g_tuning.warp_search = value; return DZO_OK; }
     if (!strcmp(key, "grid_ll")) { g_tuning.grid_ll = value; return DZO_OK; }
     if (!strcmp(key, "grid_stage")) { g_tuning.grid_stage = value; return DZO_OK; }

@@ -30,6 +30,8 @@ def main():
     import dzopt_b200 as dz
     EF = dz.ExampleFunctions
     peak, _ = bench.load_peaks()
+    if os.environ.get("DZO_BATCHED_TILE"):
+        dz.set_tuning("batched_tile", int(os.environ["DZO_BATCHED_TILE"]))
     n = args.n
     x0 = (4.0 * dz.pcg_fill(args.batch * n, 2024) - 2.0).reshape(args.batch, n)
     stream = torch.cuda.Stream()
