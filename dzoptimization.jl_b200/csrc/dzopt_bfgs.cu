@@ -322,16 +322,19 @@ static SweepArgs sweep_args(const dzo_bfgs* o) {
     a.peers.nranks = 1;
     return a;
 }
-// threads per sweep CTA (each thread owns 2 rows): the largest size that still gives >= 4 tiles per SM
-static int sweep_threads(int64_t rows, int64_t n) {
+// threads per sweep CTA (each thread owns 2 rows): the largest size that still gives >= 4 tiles per SM -- counting the
+// problems of a batch (blockIdx.z), whose tiles fill the GPU by themselves -- but never a CTA more than twice as tall as
+// the slab (batches of n = 256 problems: 128 threads 0.495 ms per step! call, 64 threads 0.558; n = 64: 64 threads)
+static int sweep_threads(int64_t rows, int64_t n, int64_t batch = 1) {
     if (g_tuning.sweep_threads > 0) return g_tuning.sweep_threads;
     const int64_t nchunks = (n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK;
     int t = kSweepThreads;
-    while (t > 64 && ((rows + 2 * t - 1) / (2 * t)) * nchunks < 4 * 148) t >>= 1;   // (8 GPUs, n=16384: 64 and 128 measured equal)
+    while (t > 64 && ((rows + 2 * t - 1) / (2 * t)) * nchunks * batch < 4 * 148) t >>= 1;   // (8 GPUs, n=16384: 64 and 128 measured equal)
+    while (t > 64 && t > rows) t >>= 1;
     return t;
 }
 static dim3 sweep_grid(int64_t rows, int64_t n, int64_t batch = 1) {
-    const int64_t r = 2 * sweep_threads(rows, n);
+    const int64_t r = 2 * sweep_threads(rows, n, batch);
     return dim3((unsigned)((rows + r - 1) / r), (unsigned)((n + DZO_GEMV_CHUNK - 1) / DZO_GEMV_CHUNK), (unsigned)batch);
 }
 static void launch_gemv(dim3 grid, int threads, cudaStream_t st, const SweepArgs& a) {
@@ -365,7 +368,7 @@ static int large_gemv(dzo_bfgs* o, const double* v, double* out, int need_kind, 
     a.v = v; a.out = out;
     if (need_kind < 0) a.ctrl = nullptr; else a.need_kind = need_kind;
     if (fused_t) a.peers = peer_set(o, true);      // rows go straight into every peer's t; no collective call
-    launch_gemv(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), o->stream, a);
+    launch_gemv(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n, o->batch), o->stream, a);
     DZO_CUDA(cudaGetLastError());
     return fused_t ? DZO_OK : allgather_rows(o, out);
 }
@@ -404,7 +407,7 @@ static int large_step_once(dzo_bfgs* o) {
         SweepArgs a = sweep_args(o);
         a.v = o->g; a.out = o->d;
         a.need_kind = DZO_STEP_GRADIENT_DESCENT + 100;   // this launch also serves identity_matrix! (:981) after a GD step
-        launch_update(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), o->stream, a);   // :878-886 + :958-960
+        launch_update(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n, o->batch), o->stream, a);   // :878-886 + :958-960
         DZO_CUDA(cudaGetLastError());
         return DZO_OK;
     }
@@ -427,7 +430,7 @@ static int large_step_once(dzo_bfgs* o) {
     a.v = o->g; a.out = o->d;
     a.need_kind = DZO_STEP_GRADIENT_DESCENT + 100;   // this launch also serves identity_matrix! (:981) after a GD step
     if (o->fused) a.peers = peer_set(o, false);
-    launch_update(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), o->stream, a);   // :878-886 + :958-960
+    launch_update(sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n, o->batch), o->stream, a);   // :878-886 + :958-960
     DZO_CUDA(cudaGetLastError());
     if (!o->fused) DZO_TRY(allgather_rows(o, o->d));
     else {
@@ -629,7 +632,7 @@ static int create_common(dzo_bfgs** out, int objective, int constraint, int64_t 
             vec_bfgs_init_kernel<<<(unsigned)batch, 1024, 0, o->stream>>>(large_vecs(o), L0);
         SweepArgs a = sweep_args(o);
         a.ctrl = nullptr;
-        identity_kernel<<<sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n), 0, o->stream>>>(a);   // :781-783
+        identity_kernel<<<sweep_grid(o->rows, o->n, o->batch), sweep_threads(o->rows, o->n, o->batch), 0, o->stream>>>(a);   // :781-783
     }
     if (cudaStreamSynchronize(o->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return bail(fail(DZO_ERR_CUDA, "constructor kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
