@@ -11,6 +11,7 @@
 #include "host_common.h"
 #include "large_bfgs.cuh"
 #include "small_ops.cuh"
+#include "small_sweeps.cuh"
 #include "warp_search.cuh"
 
 namespace dzo {
@@ -398,6 +399,26 @@ static void launch_warp_search(const dzo_bfgs* o, int vw, const LargeVecs& v, bo
 static int large_step_once(dzo_bfgs* o) {
     const LargeVecs v = large_vecs(o);
     const int vw = warp_vw(o);
+    if (vw && o->batch > 1 && o->n <= kSmallSweepMaxN && g_tuning.small_sweeps) {
+        // a batch of small matrices: the n^2 sweeps on one warp per problem too (small_sweeps.cuh)
+        const unsigned grid = (unsigned)((o->batch + kSmallSweepWarps - 1) / kSmallSweepWarps);
+        const int threads = 32 * kSmallSweepWarps;
+        SmallSweepArgs sa;
+        sa.H = o->H; sa.s = o->sd; sa.t = o->t; sa.ctrl = o->ctrl; sa.n = o->n; sa.batch = o->batch;
+        launch_warp_search(o, vw, v, false);                                            // :891-950, :873-874
+        DZO_CUDA(cudaGetLastError());
+        sa.v = o->dg; sa.out = o->t;                                                    // :875
+        if (o->n <= 64) warp_gemv_kernel<2, 16><<<grid, threads, 0, o->stream>>>(sa);
+        else warp_gemv_kernel<4, 8><<<grid, threads, 0, o->stream>>>(sa);
+        DZO_CUDA(cudaGetLastError());
+        launch_warp_search(o, vw, v, true);                                             // :876
+        DZO_CUDA(cudaGetLastError());
+        sa.v = o->g; sa.out = o->d;                                                     // :878-886 + :958-960, :981
+        if (o->n <= 64) warp_update_gemv_kernel<2, 16><<<grid, threads, 0, o->stream>>>(sa);
+        else warp_update_gemv_kernel<4, 8><<<grid, threads, 0, o->stream>>>(sa);
+        DZO_CUDA(cudaGetLastError());
+        return DZO_OK;
+    }
     if (vw) {
         launch_warp_search(o, vw, v, false);                                            // :891-950, :873-874
         DZO_CUDA(cudaGetLastError());
@@ -1286,6 +1307,7 @@ int dzo_set_tuning(const char* key, int value) {
     if (!strcmp(key, "riesz_threads")) { g_tuning.riesz_threads = value; return DZO_OK; }
     if (!strcmp(key, "riesz_bar")) { g_tuning.riesz_bar = value; return DZO_OK; }
     if (!strcmp(key, "batched_tile")) { g_tuning.batched_tile = value; return DZO_OK; }
+    if (!strcmp(key, "small_sweeps")) { g_tuning.small_sweeps = value; return DZO_OK; }
     if (!strcmp(key, "warp_search")) { g_tuning.warp_search = value; return DZO_OK; }
     if (!strcmp(key, "grid_ll")) { g_tuning.grid_ll = value; return DZO_OK; }
     if (!strcmp(key, "grid_stage")) { g_tuning.grid_stage = value; return DZO_OK; }

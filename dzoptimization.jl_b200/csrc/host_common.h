@@ -81,6 +81,7 @@ struct Tuning {
     int riesz_pair = 1;       // Riesz line search: evaluate the probe it needs and the one it will most likely need next in one
                               // phase (the second rides in warps the first leaves idle); read when an optimizer is created
     int riesz_profile = 0;    // 1: the cooperative Riesz kernel logs (phase id, %globaltimer) events of its leader thread
+    int small_sweeps = 1;     // batches of 32 < n <= 64 problems: n^2 sweeps on one warp per problem (small_sweeps.cuh); 0 = tiled kernels
     int batched_tile = 0;     // batched kernel, problems per warp: 0 = automatic (32, fewer for batches of at most three waves of
                               // warps), 32 = always a full warp, 1..31 = forced; read when an optimizer is created
     int batched_lazy = 1;     // batched kernel: keep H = I implicit (no HBM traffic for identity_matrix!); read at create time
