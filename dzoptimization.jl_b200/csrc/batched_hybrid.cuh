@@ -172,7 +172,9 @@ DZO_DEVINL void hs_probe(const double* X, const double* Dir, double a, double ar
 // step kinds as counted for the roofline (include/dzopt.h, dzo_bfgs_get_step_kind_counts)
 enum : int { HK_BFGS_READ = 0, HK_BFGS_IDENT = 1, HK_GD = 2, HK_TERMINATE = 3, HK_IDLE = 4, HK_IDLE_WARP = 5, HK_COUNT = 6 };
 
-template <int N>
+// VTILE: problems per warp taken from A.tile (small batches) instead of the compile-time 32 -- a second instantiation
+// because the run-time tile costs the n = 16 kernel two more spilled registers (0.699 -> 0.706 ms per 1 M-problem launch)
+template <int N, bool VTILE>
 __global__ void __launch_bounds__(kHybridThreads, HybridCfg<N>::CTAS_PER_SM) bfgs_batched_hybrid_kernel(BatchedArgs A) {
     using C = HybridCfg<N>;
     static_assert(HK_COUNT <= 32, "one counter per lane");
@@ -184,12 +186,12 @@ __global__ void __launch_bounds__(kHybridThreads, HybridCfg<N>::CTAS_PER_SM) bfg
     HybridSmem<N>& S = reinterpret_cast<HybridSmem<N>*>(smem_raw)[warp];
     // A tile is A.tile <= 32 consecutive problems (32 for a large batch; the host shrinks it when the batch would fill the
     // GPU's warp slots only a few times over, so that the last wave of warps is as full as the first)
-    const int tile = (A.tile > 0 && A.tile < 32) ? A.tile : 32;
+    const int tile = VTILE ? A.tile : 32;
     const long long p0 = ((long long)blockIdx.x * kHybridWarps + warp) * tile;  // first problem of this warp's tile
     if (p0 >= A.batch) return;
     const long long p = p0 + lane;
+    const bool valid = VTILE ? (lane < tile && p < A.batch) : (p < A.batch);
     const int nprob = (int)((A.batch - p0 < tile) ? (A.batch - p0) : tile);
-    const bool valid = lane < nprob;
     const bool lazy = (A.hid != nullptr);
 
     // A tile starts cold: everything it needs first is requested at once -- the three vectors as 16-byte asynchronous
@@ -490,13 +492,16 @@ inline cudaError_t hybrid_launch(const BatchedArgs& args, cudaStream_t stream, i
     static const size_t pad = getenv("DZO_HYBRID_SMEM_PAD") ? (size_t)atoi(getenv("DZO_HYBRID_SMEM_PAD")) : 0;   // occupancy experiments
     const size_t smem = hybrid_smem<N>() + pad;
     if (!attr_set[device & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(bfgs_batched_hybrid_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(bfgs_batched_hybrid_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bfgs_batched_hybrid_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set[device & 63] = true;
     }
-    const int tile = (args.tile > 0 && args.tile < 32) ? args.tile : 32;
+    const bool vtile = (args.tile > 0 && args.tile < 32);
+    const int tile = vtile ? args.tile : 32;
     const unsigned grid = (unsigned)((args.batch + (long long)tile * kHybridWarps - 1) / ((long long)tile * kHybridWarps));
-    bfgs_batched_hybrid_kernel<N><<<grid, kHybridThreads, smem, stream>>>(args);
+    if (vtile) bfgs_batched_hybrid_kernel<N, true><<<grid, kHybridThreads, smem, stream>>>(args);
+    else bfgs_batched_hybrid_kernel<N, false><<<grid, kHybridThreads, smem, stream>>>(args);
     return cudaGetLastError();
 }
 cudaError_t hybrid_launch_n2_16(int n, const BatchedArgs& args, cudaStream_t stream, int device);    // batched_hybrid_tu_a.cu
