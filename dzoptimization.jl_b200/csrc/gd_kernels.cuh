@@ -2,7 +2,7 @@
 // with device objectives, TREE summation order.
 //
 // (1) Riesz energy on the sphere (legacy/ExampleFunctions.jl:30-83; config 5: N = 4096 points,
-//     n = 12288): ONE cooperative persistent kernel (one 1024-thread CTA per SM) runs k whole
+//     n = 12288): ONE cooperative persistent kernel (one 512-thread CTA per SM; NT template parameter) runs k whole
 //     step! calls -- the bracketing line search with its data-dependent number of O(N^2) energy
 //     evaluations, the point update, the O(N^2) gradient and the O(n) bookkeeping -- with grid-wide
 //     barriers between phases and no host round trip.  Pair work is cut into (32 rows x 128
